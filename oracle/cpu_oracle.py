@@ -1,0 +1,170 @@
+"""ctypes front-end of oracle/mkb_oracle.c -- the CPU restatement of the reference hot path.
+
+TEST INFRASTRUCTURE ONLY (see the header of mkb_oracle.c).  Function names and argument
+order mirror the reference's Cython modules so parity tests read like the reference's:
+
+  moleculekit/occupancy_utils/occupancy_utils.pyx:34   calculate_occupancy
+  moleculekit/distance_utils/distance_utils.pyx:59     contacts_trajectory
+  moleculekit/distance_utils/distance_utils.pyx:98     get_collisions
+  moleculekit/distance_utils/distance_utils.pyx:126    dist_trajectory
+  moleculekit/distance_utils/distance_utils.pyx:211    dist_trajectory_reduction
+  moleculekit/distance_utils/distance_utils.pyx:286    dist_trajectory_reduction_pairs
+  moleculekit/distance_utils/distance_utils.pyx:355+   cdist / pdist / squareform
+
+Parity status: PINNED (oracle/pin_oracle.py; tests/test_oracle_golden.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "mkb_oracle.c")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(BUILD, "libmkb_oracle.so")
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """gcc -O3 -ffp-contract=off (no FMA contraction: the reference binary has none)."""
+    if (not force) and os.path.isfile(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    cmd = ["gcc", "-O3", "-ffp-contract=off", "-fno-fast-math", "-fvisibility=hidden",
+           "-shared", "-fPIC", SRC, "-o", LIB, "-lm"]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.oracle_contacts_trajectory.restype = C.c_int64
+        _lib.oracle_get_collisions.restype = C.c_int64
+        _lib.oracle_squareform_dim.restype = C.c_int64
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def calculate_occupancy(centers, coords, sigmas, results):
+    centers = np.ascontiguousarray(centers, dtype=np.float64)
+    coords = _f32(coords)
+    sigmas = np.ascontiguousarray(sigmas, dtype=np.float64)
+    assert results.dtype == np.float64 and results.flags["C_CONTIGUOUS"]
+    M, N, Cn = centers.shape[0], coords.shape[0], sigmas.shape[1]
+    assert results.shape == (M, Cn) and sigmas.shape[0] == N
+    lib().oracle_calculate_occupancy(_p(centers), _p(coords), _p(sigmas), _p(results),
+                                     C.c_int64(M), C.c_int64(N), C.c_int64(Cn))
+
+
+def dist_trajectory(coords, box, sel1, sel2, digitized_chains, selfdist, pbc, results):
+    coords, box = _f32(coords), _f32(box)
+    sel1, sel2, ch = _u32(sel1), _u32(sel2), _u32(digitized_chains)
+    assert results.dtype == np.float32 and results.flags["C_CONTIGUOUS"]
+    F = coords.shape[2]
+    lib().oracle_dist_trajectory(_p(coords), _p(box), _p(sel1), C.c_int64(len(sel1)),
+                                 _p(sel2), C.c_int64(len(sel2)), _p(ch),
+                                 C.c_int(bool(selfdist)), C.c_int(bool(pbc)), _p(results),
+                                 C.c_int64(F), C.c_int64(results.shape[1]))
+
+
+def contacts_trajectory(coords, box, sel1, sel2, digitized_chains, selfdist, pbc, dist_threshold=5):
+    """Returns a list (per frame) of flat lists [a0, b0, a1, b1, ...] like the reference."""
+    coords, box = _f32(coords), _f32(box)
+    sel1, sel2, ch = _u32(sel1), _u32(sel2), _u32(digitized_chains)
+    F = coords.shape[2]
+    counts = np.zeros(F, dtype=np.int64)
+    args = (_p(coords), _p(box), _p(sel1), C.c_int64(len(sel1)), _p(sel2), C.c_int64(len(sel2)),
+            _p(ch), C.c_int(bool(selfdist)), C.c_int(bool(pbc)), C.c_float(dist_threshold),
+            C.c_int64(F), _p(counts))
+    total = lib().oracle_contacts_trajectory(*args, None)
+    pairs = np.zeros((max(total, 1), 2), dtype=np.uint32)
+    lib().oracle_contacts_trajectory(*args, _p(pairs))
+    out, s = [], 0
+    for f in range(F):
+        out.append(pairs[s:s + counts[f]].reshape(-1).tolist())
+        s += counts[f]
+    return out
+
+
+def get_collisions(coords1, coords2, dist_threshold):
+    c1, c2 = _f32(coords1), _f32(coords2)
+    n = lib().oracle_get_collisions(_p(c1), C.c_int64(len(c1)), _p(c2), C.c_int64(len(c2)),
+                                    C.c_float(dist_threshold), None)
+    pairs = np.zeros((max(n, 1), 2), dtype=np.uint32)
+    lib().oracle_get_collisions(_p(c1), C.c_int64(len(c1)), _p(c2), C.c_int64(len(c2)),
+                                C.c_float(dist_threshold), _p(pairs))
+    return pairs[:n].reshape(-1).tolist()
+
+
+def _csr(groups):
+    off = np.zeros(len(groups) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(g) for g in groups])
+    atoms = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=np.int32) for g in groups])
+                                 if len(groups) else np.zeros(0, np.int32), dtype=np.int32)
+    return off, atoms
+
+
+def dist_trajectory_reduction(coords, box, groups1, groups2, digitized_chains1, digitized_chains2,
+                              selfdist, pbc, masses, reduction1, reduction2, results):
+    coords, box, masses = _f32(coords), _f32(box), _f32(masses)
+    o1, a1 = _csr(groups1)
+    o2, a2 = _csr(groups2)
+    c1, c2 = _u32(digitized_chains1), _u32(digitized_chains2)
+    F = coords.shape[2]
+    lib().oracle_dist_trajectory_reduction(_p(coords), _p(box), _p(o1), _p(a1), C.c_int64(len(groups1)),
+                                           _p(o2), _p(a2), C.c_int64(len(groups2)), _p(c1), _p(c2),
+                                           C.c_int(bool(selfdist)), C.c_int(bool(pbc)), _p(masses),
+                                           C.c_int(reduction1), C.c_int(reduction2), _p(results),
+                                           C.c_int64(F), C.c_int64(results.shape[1]))
+    return results
+
+
+def dist_trajectory_reduction_pairs(coords, box, groups1, groups2, digitized_chains1, digitized_chains2,
+                                    pbc, masses, reduction1, reduction2, results):
+    coords, box, masses = _f32(coords), _f32(box), _f32(masses)
+    o1, a1 = _csr(groups1)
+    o2, a2 = _csr(groups2)
+    c1, c2 = _u32(digitized_chains1), _u32(digitized_chains2)
+    F = coords.shape[2]
+    lib().oracle_dist_trajectory_reduction_pairs(_p(coords), _p(box), _p(o1), _p(a1), _p(o2), _p(a2),
+                                                 C.c_int64(len(groups1)), _p(c1), _p(c2),
+                                                 C.c_int(bool(pbc)), _p(masses),
+                                                 C.c_int(reduction1), C.c_int(reduction2), _p(results),
+                                                 C.c_int64(F), C.c_int64(results.shape[1]))
+    return results
+
+
+def cdist(coords1, coords2, results):
+    c1, c2 = _f32(coords1), _f32(coords2)
+    lib().oracle_cdist(_p(c1), C.c_int64(c1.shape[0]), _p(c2), C.c_int64(c2.shape[0]),
+                       C.c_int64(c1.shape[1]), _p(results))
+
+
+def pdist(coords, results):
+    c = _f32(coords)
+    lib().oracle_pdist(_p(c), C.c_int64(c.shape[0]), C.c_int64(c.shape[1]), _p(results))
+
+
+def squareform(distances):
+    d = _f32(distances)
+    m = lib().oracle_squareform_dim(C.c_int64(len(d)))
+    out = np.zeros((m, m), dtype=np.float32)
+    lib().oracle_squareform(_p(d), C.c_int64(len(d)), _p(out))
+    return out

@@ -1,0 +1,318 @@
+/*
+ * mkb_oracle.c -- CPU restatement of the moleculekit voxel/distance hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and the cpu_baseline /
+ * --impl reference legs of bench.py may load this library.  The product path
+ * (moleculekit_b200/) never links, imports or calls it and has no CPU fallback.
+ *
+ * Parity is PINNED: oracle/pin_oracle.py checks every function below bit-for-bit against the
+ * reference's own Cython kernels compiled from /root/reference (oracle/_ref, see
+ * oracle/build_ref.py) and against the reference's golden vectors (tests/golden/).
+ *
+ * Each function cites the reference file:line it restates (paths relative to
+ * /root/reference/moleculekit/).  Arithmetic notes that matter for bit parity:
+ *   - occupancy is all-double (coords are float, promoted), strict "< 25" gate, "value > old"
+ *     update (NaN never stored), sigma == 0 skipped.
+ *   - distances are all-float with every operation individually rounded (x86-64 baseline has
+ *     no FMA; compile this file with -ffp-contract=off), roundf = half away from zero.
+ * Build: gcc -O3 -ffp-contract=off -fno-fast-math -shared -fPIC mkb_oracle.c -o libmkb_oracle.so -lm
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define EXPORT __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------
+ * occupancy_utils/occupancy_utils.pyx:34-61  calculate_occupancy
+ * centers (M,3) f64, coords (N,3) f32, sigmas (N,C) f64, results (M,C) f64 accumulated in place.
+ * ------------------------------------------------------------------------------------------ */
+EXPORT void oracle_calculate_occupancy(const double *centers, const float *coords,
+                                       const double *sigmas, double *results,
+                                       int64_t n_centers, int64_t n_atoms, int64_t n_channels)
+{
+    for (int64_t a = 0; a < n_atoms; ++a) {
+        const double ax = (double)coords[3 * a + 0];
+        const double ay = (double)coords[3 * a + 1];
+        const double az = (double)coords[3 * a + 2];
+        const double *sig = sigmas + a * n_channels;
+        for (int64_t c = 0; c < n_centers; ++c) {
+            const double dx = ax - centers[3 * c + 0];
+            const double dy = ay - centers[3 * c + 1];
+            const double dz = az - centers[3 * c + 2];
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < 25.0) {
+                double *res = results + c * n_channels;
+                for (int64_t h = 0; h < n_channels; ++h) {
+                    if (sig[h] == 0.0) continue;
+                    const double x = sig[h] / sqrt(d2);
+                    const double x3 = (x * x) * x;
+                    const double x12 = ((x3 * x3) * x3) * x3;
+                    const double v = 1.0 - exp(-x12);
+                    if (v > res[h]) res[h] = v;
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * distance_utils/distance_utils.pyx:34-54  _dist  (frame-minor coords (N,3,F), box (3,F))
+ * ------------------------------------------------------------------------------------------ */
+static inline float wrap1(float d, float b)
+{
+    /* d - b * roundf(d / b), each op rounded to float (pyx:50-52) */
+    float q = d / b;
+    float n = roundf(q);
+    float p = b * n;
+    return d - p;
+}
+
+static inline float pair_d2(const float *coords, const float *box, const uint32_t *chains,
+                            int64_t F, int64_t i, int64_t j, int64_t f, int pbc)
+{
+    float dx = coords[(i * 3 + 0) * F + f] - coords[(j * 3 + 0) * F + f];
+    float dy = coords[(i * 3 + 1) * F + f] - coords[(j * 3 + 1) * F + f];
+    float dz = coords[(i * 3 + 2) * F + f] - coords[(j * 3 + 2) * F + f];
+    if (pbc && chains[i] != chains[j]) {
+        dx = wrap1(dx, box[0 * F + f]);
+        dy = wrap1(dy, box[1 * F + f]);
+        dz = wrap1(dz, box[2 * F + f]);
+    }
+    float s = dx * dx;
+    s = s + dy * dy;
+    s = s + dz * dz;
+    return s;
+}
+
+/* distance_utils.pyx:126-155  dist_trajectory: results (F, P) f32, i-major / j-minor columns,
+ * selfdist starts j at i+1 (positions, not atom ids). */
+EXPORT void oracle_dist_trajectory(const float *coords, const float *box,
+                                   const uint32_t *sel1, int64_t n1,
+                                   const uint32_t *sel2, int64_t n2,
+                                   const uint32_t *chains, int selfdist, int pbc,
+                                   float *results, int64_t n_frames, int64_t n_cols)
+{
+    for (int64_t f = 0; f < n_frames; ++f) {
+        int64_t idx = 0;
+        for (int64_t i = 0; i < n1; ++i) {
+            const int64_t a = sel1[i];
+            for (int64_t j = selfdist ? i + 1 : 0; j < n2; ++j) {
+                const float d2 = pair_d2(coords, box, chains, n_frames, a, sel2[j], f, pbc);
+                results[f * n_cols + idx] = sqrtf(d2);
+                ++idx;
+            }
+        }
+    }
+}
+
+/* distance_utils.pyx:59-93  contacts_trajectory.  Two-call protocol: pairs == NULL -> only
+ * counts[f] (number of PAIRS of frame f) is written; else pairs receives (a, b) uint32 couples,
+ * frames concatenated, in (i asc, j asc) order.  thr2 = thr * thr in float (pyx:77). */
+EXPORT int64_t oracle_contacts_trajectory(const float *coords, const float *box,
+                                          const uint32_t *sel1, int64_t n1,
+                                          const uint32_t *sel2, int64_t n2,
+                                          const uint32_t *chains, int selfdist, int pbc,
+                                          float threshold, int64_t n_frames,
+                                          int64_t *counts, uint32_t *pairs)
+{
+    const float thr2 = threshold * threshold;
+    int64_t total = 0;
+    for (int64_t f = 0; f < n_frames; ++f) {
+        int64_t cnt = 0;
+        for (int64_t i = 0; i < n1; ++i) {
+            const uint32_t a = sel1[i];
+            for (int64_t j = selfdist ? i + 1 : 0; j < n2; ++j) {
+                const uint32_t b = sel2[j];
+                const float d2 = pair_d2(coords, box, chains, n_frames, a, b, f, pbc);
+                if (d2 <= thr2) {
+                    if (pairs) {
+                        pairs[2 * (total + cnt) + 0] = a;
+                        pairs[2 * (total + cnt) + 1] = b;
+                    }
+                    ++cnt;
+                }
+            }
+        }
+        if (counts) counts[f] = cnt;
+        total += cnt;
+    }
+    return total;
+}
+
+/* distance_utils.pyx:98-121  get_collisions: single frame, no pbc, LOCAL (i, j) indices. */
+EXPORT int64_t oracle_get_collisions(const float *c1, int64_t n1, const float *c2, int64_t n2,
+                                     float threshold, uint32_t *pairs)
+{
+    const float thr2 = threshold * threshold;
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n1; ++i)
+        for (int64_t j = 0; j < n2; ++j) {
+            const float dx = c1[3 * i + 0] - c2[3 * j + 0];
+            const float dy = c1[3 * i + 1] - c2[3 * j + 1];
+            const float dz = c1[3 * i + 2] - c2[3 * j + 2];
+            float s = dx * dx;
+            s = s + dy * dy;
+            s = s + dz * dz;
+            if (s <= thr2) {
+                if (pairs) {
+                    pairs[2 * cnt + 0] = (uint32_t)i;
+                    pairs[2 * cnt + 1] = (uint32_t)j;
+                }
+                ++cnt;
+            }
+        }
+    return cnt;
+}
+
+/* distance_utils.pyx:160-183  _calc_com: float accumulation in atom order, mul then add. */
+static void calc_com(const float *coords, int64_t F, int64_t f, const int32_t *atoms, int64_t n,
+                     const float *masses, float *com)
+{
+    float tm = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
+    for (int64_t k = 0; k < n; ++k) {
+        const int64_t a = atoms[k];
+        const float m = masses[a];
+        float t;
+        t = coords[(a * 3 + 0) * F + f] * m; cx = cx + t;
+        t = coords[(a * 3 + 1) * F + f] * m; cy = cy + t;
+        t = coords[(a * 3 + 2) * F + f] * m; cz = cz + t;
+        tm = tm + m;
+    }
+    com[0] = cx / tm;
+    com[1] = cy / tm;
+    com[2] = cz / tm;
+}
+
+/* distance_utils.pyx:188-206  _dist2 on two explicit points */
+static inline float point_d2(const float *p, const float *q, const float *box, int wrap)
+{
+    float dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+    if (wrap) {
+        dx = wrap1(dx, box[0]);
+        dy = wrap1(dy, box[1]);
+        dz = wrap1(dz, box[2]);
+    }
+    float s = dx * dx;
+    s = s + dy * dy;
+    s = s + dz * dz;
+    return s;
+}
+
+static float group_pair(const float *coords, int64_t F, int64_t f, const float *bx,
+                        const int32_t *g1, int64_t m1, const int32_t *g2, int64_t m2,
+                        const float *masses, int red1, int red2, int wrap)
+{
+    /* pyx:240-279 inner body: COM side collapses to one pseudo atom; mindist=-1 sentinel. */
+    float com1[3], com2[3];
+    if (red1 == 1) calc_com(coords, F, f, g1, m1, masses, com1);
+    if (red2 == 1) calc_com(coords, F, f, g2, m2, masses, com2);
+    const int64_t l1 = (red1 == 1) ? 1 : m1;
+    const int64_t l2 = (red2 == 1) ? 1 : m2;
+    float mind = -1.f;
+    for (int64_t a = 0; a < l1; ++a) {
+        float p[3];
+        if (red1 == 1) { p[0] = com1[0]; p[1] = com1[1]; p[2] = com1[2]; }
+        else { const int64_t x = g1[a]; p[0] = coords[(x*3+0)*F+f]; p[1] = coords[(x*3+1)*F+f]; p[2] = coords[(x*3+2)*F+f]; }
+        for (int64_t b = 0; b < l2; ++b) {
+            float q[3];
+            if (red2 == 1) { q[0] = com2[0]; q[1] = com2[1]; q[2] = com2[2]; }
+            else { const int64_t y = g2[b]; q[0] = coords[(y*3+0)*F+f]; q[1] = coords[(y*3+1)*F+f]; q[2] = coords[(y*3+2)*F+f]; }
+            const float d2 = point_d2(p, q, bx, wrap);
+            if (d2 < mind || mind < 0.f) mind = d2;
+        }
+    }
+    return sqrtf(mind);
+}
+
+/* distance_utils.pyx:211-281  dist_trajectory_reduction.  Groups are CSR: off (G+1), atoms. */
+EXPORT void oracle_dist_trajectory_reduction(const float *coords, const float *box,
+                                             const int64_t *off1, const int32_t *atoms1, int64_t G1,
+                                             const int64_t *off2, const int32_t *atoms2, int64_t G2,
+                                             const uint32_t *chains1, const uint32_t *chains2,
+                                             int selfdist, int pbc, const float *masses,
+                                             int red1, int red2, float *results,
+                                             int64_t n_frames, int64_t n_cols)
+{
+    for (int64_t f = 0; f < n_frames; ++f) {
+        const float bx[3] = { box[0 * n_frames + f], box[1 * n_frames + f], box[2 * n_frames + f] };
+        int64_t idx = 0;
+        for (int64_t a = 0; a < G1; ++a)
+            for (int64_t b = selfdist ? a + 1 : 0; b < G2; ++b) {
+                const int wrap = pbc && (chains1[a] != chains2[b]);
+                results[f * n_cols + idx] = group_pair(coords, n_frames, f, bx,
+                        atoms1 + off1[a], off1[a + 1] - off1[a],
+                        atoms2 + off2[b], off2[b + 1] - off2[b], masses, red1, red2, wrap);
+                ++idx;
+            }
+    }
+}
+
+/* distance_utils.pyx:286-350  dist_trajectory_reduction_pairs (group g of set 1 vs group g of set 2) */
+EXPORT void oracle_dist_trajectory_reduction_pairs(const float *coords, const float *box,
+                                                   const int64_t *off1, const int32_t *atoms1,
+                                                   const int64_t *off2, const int32_t *atoms2, int64_t G,
+                                                   const uint32_t *chains1, const uint32_t *chains2,
+                                                   int pbc, const float *masses,
+                                                   int red1, int red2, float *results,
+                                                   int64_t n_frames, int64_t n_cols)
+{
+    for (int64_t f = 0; f < n_frames; ++f) {
+        const float bx[3] = { box[0 * n_frames + f], box[1 * n_frames + f], box[2 * n_frames + f] };
+        for (int64_t g = 0; g < G; ++g) {
+            const int wrap = pbc && (chains1[g] != chains2[g]);
+            results[f * n_cols + g] = group_pair(coords, n_frames, f, bx,
+                    atoms1 + off1[g], off1[g + 1] - off1[g],
+                    atoms2 + off2[g], off2[g + 1] - off2[g], masses, red1, red2, wrap);
+        }
+    }
+}
+
+/* distance_utils.pyx:355-383  cdist: float accumulate over D in index order, sqrtf */
+EXPORT void oracle_cdist(const float *c1, int64_t n1, const float *c2, int64_t n2, int64_t D, float *out)
+{
+    for (int64_t i = 0; i < n1; ++i)
+        for (int64_t j = 0; j < n2; ++j) {
+            float s = 0.f;
+            for (int64_t k = 0; k < D; ++k) {
+                const float d = c1[i * D + k] - c2[j * D + k];
+                s = s + d * d;
+            }
+            out[i * n2 + j] = sqrtf(s);
+        }
+}
+
+/* distance_utils.pyx:388-416  pdist: condensed i<j */
+EXPORT void oracle_pdist(const float *c, int64_t n, int64_t D, float *out)
+{
+    int64_t t = 0;
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = i + 1; j < n; ++j) {
+            float s = 0.f;
+            for (int64_t k = 0; k < D; ++k) {
+                const float d = c[i * D + k] - c[j * D + k];
+                s = s + d * d;
+            }
+            out[t++] = sqrtf(s);
+        }
+}
+
+/* distance_utils.pyx:421-435  squareform: n' = int((sqrt(8n+1)+1)/2), symmetric fill */
+EXPORT int64_t oracle_squareform_dim(int64_t n)
+{
+    return (int64_t)((sqrt((double)(8 * n + 1)) + 1.0) / 2.0);
+}
+
+EXPORT void oracle_squareform(const float *d, int64_t n, float *out)
+{
+    const int64_t m = oracle_squareform_dim(n);
+    memset(out, 0, sizeof(float) * (size_t)(m * m));
+    int64_t k = 0;
+    for (int64_t i = 0; i < m; ++i)
+        for (int64_t j = i + 1; j < m; ++j) {
+            out[i * m + j] = d[k];
+            out[j * m + i] = d[k];
+            ++k;
+        }
+}

@@ -1,0 +1,74 @@
+"""pytest configuration: markers + shared fixtures.
+
+`-m "not gpu"`  : oracle vs golden vectors, host logic, C-ABI symbol checks, gloo sharding tests (CPU).
+`-m gpu`        : parity of the CUDA path (through the C-ABI) against the oracle and the goldens.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _npz(name):
+    with np.load(os.path.join(GOLDEN, name), allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def g_voxel3ptb():
+    return _npz("voxel_3ptb.npz")
+
+
+@pytest.fixture(scope="session")
+def g_voxelsmall():
+    return _npz("voxel_small.npz")
+
+
+@pytest.fixture(scope="session")
+def g_traj():
+    return _npz("traj20.npz")
+
+
+@pytest.fixture(scope="session")
+def g_3ptb():
+    return _npz("pdb_3ptb.npz")
+
+
+@pytest.fixture(scope="session")
+def g_5vl5():
+    return _npz("pdb_5vl5.npz")
+
+
+@pytest.fixture(scope="session")
+def g_raw():
+    return _npz("rawkernels.npz")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import cpu_oracle
+
+    cpu_oracle.build()
+    return cpu_oracle
+
+
+@pytest.fixture(scope="session")
+def refmods():
+    """The reference's own compiled kernels (oracle/_ref) when available, else None."""
+    from oracle import build_ref
+
+    try:
+        build_ref.build(verbose=False)
+    except Exception:
+        pass
+    return build_ref.load()

@@ -1,0 +1,275 @@
+"""Generate the committed golden fixtures in tests/golden/ from the REFERENCE itself.
+
+Runs only in the build container (needs /root/reference).  Two sources are used:
+
+ 1. the reference's own stored goldens under /root/reference/tests (3PTB_voxres_old.npy,
+    metricdistance/{distances,mindistances,selfmindistance}.npy, inline constants of
+    tests/test_metricdistance.py / tests/test_interactions.py), sliced/sparsified so they are small;
+ 2. outputs of the reference's compiled Cython kernels (oracle/_ref, built from the .pyx files in
+    place by oracle/build_ref.py) on seeded inputs, for cases the reference has no stored golden for
+    (arbitrary centres, multi-sigma atoms, ordered contact pairs, COM reductions, cdist/pdist).
+
+Reading PDB/XTC files needs the full reference Python package with its extensions built; as
+/root/reference is read-only that build lives in a scratch copy:
+
+    mkdir /tmp/refcopy && cd /tmp/refcopy && cp -r /root/reference/moleculekit /root/reference/setup.py . \
+      && chmod -R u+w . && python setup.py build_ext --inplace
+    cd /root/repo && PYTHONPATH=/tmp/refcopy LOCAL_PDB_REPO=/root/reference/tests/pdb python tests/golden/make_golden.py
+
+The fixtures carry only numbers (coordinates, masks, outputs) -- no reference source.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REFT = "/root/reference/tests"
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    from oracle import build_ref
+
+    assert build_ref.build(), "oracle/_ref could not be built (is /root/reference present?)"
+    occ_ref, dist_ref = build_ref.load()
+
+    from moleculekit.molecule import Molecule  # the reference (scratch build on PYTHONPATH)
+    from moleculekit.tools.voxeldescriptors import getCenters
+    from moleculekit.periodictable import periodictable
+
+    # ------------------------------------------------------------------ voxel: 3PTB (reference golden)
+    vd = os.path.join(REFT, "test_voxeldescriptors")
+    coords = np.load(os.path.join(vd, "3PTB_coords_inp.npy"))
+    sigmas = np.load(os.path.join(vd, "3PTB_channels_inp.npy"))
+    centers_inp = np.load(os.path.join(vd, "3PTB_centers_inp.npy"))
+    gold_feat, gold_centers, gold_nvox = np.load(os.path.join(vd, "3PTB_voxres_old.npy"), allow_pickle=True)
+    assert coords.dtype == np.float32 and sigmas.dtype == np.float64
+    # The orphan *_inp.npy inputs predate the current vdW table: their single metal atom (the Ca2+ ion,
+    # channels 6 and 7) carries sigma 1.37, whereas the stored golden was produced with today's
+    # periodictable["Ca"].vdw_radius = 2.31 (reference test: mol.element "CA" -> "Ca",
+    # tests/test_voxeldescriptors.py:71-86).  Patch that one row so inputs and golden agree.
+    metal = sigmas[:, 6] != 0
+    assert metal.sum() == 1
+    sigmas = sigmas.copy()
+    sigmas[metal] = np.where(sigmas[metal] != 0, periodictable["Ca"].vdw_radius, 0.0)
+
+    class _M:  # minimal duck for reference getCenters/boundingBox
+        def __init__(self, c):
+            self.c = c
+
+        def get(self, what, sel=None):
+            return self.c
+
+    centers, nvox = getCenters(_M(coords.copy()), buffer=8, voxelsize=1)
+    assert np.array_equal(centers, centers_inp) and np.array_equal(centers, gold_centers)
+    assert np.array_equal(nvox, gold_nvox) and list(nvox) == [60, 55, 65]
+    out = np.zeros((centers.shape[0], 8))
+    occ_ref.calculate_occupancy(centers, coords, sigmas, out)
+    assert np.allclose(out, gold_feat), "today's reference kernel no longer matches its stored golden"
+    assert np.array_equal(out != 0, gold_feat != 0)
+    nz = np.flatnonzero(gold_feat.reshape(-1))
+    np.savez_compressed(
+        os.path.join(HERE, "voxel_3ptb.npz"),
+        coords=coords, sigmas=sigmas, buffer=np.float64(8), voxelsize=np.float64(1),
+        nvoxels=np.asarray(nvox, dtype=np.int64), bb_min=centers[0].copy(),
+        centers_sha256=np.array(sha(centers)), centers_head=centers[:4], centers_tail=centers[-4:],
+        # the reference's stored golden (tests/test_voxeldescriptors/3PTB_voxres_old.npy), sparse, f32 values
+        gold_nz_idx=nz.astype(np.uint32), gold_nz_val=gold_feat.reshape(-1)[nz].astype(np.float32),
+        # today's reference kernel on the same inputs, bit pattern pinned by hash + f64 checksum
+        refkernel_sha256=np.array(sha(out)), refkernel_sum=np.float64(out.sum()),
+        refkernel_nnz=np.int64(np.count_nonzero(out)),
+    )
+
+    # ------------------------------------------------------------------ voxel: small seeded cases (_ref outputs)
+    rng = np.random.default_rng(1234)
+    cases = {}
+    # (a) arbitrary user centres, per-channel distinct sigmas, zero sigmas, negative sigma, coincident point
+    N, M, C = 48, 700, 8
+    xyz = (rng.normal(size=(N, 3)) * 4.0 + 20.0).astype(np.float32)
+    ctr = rng.uniform(8.0, 32.0, size=(M, 3))
+    ctr[0] = xyz[3].astype(np.float64)                      # d2 == 0 -> value 1
+    ctr[1] = xyz[5].astype(np.float64) + [3.0, 4.0, 0.0]    # d2 == 25 exactly?  (only if exact in fp) gate check
+    sg = rng.choice([0.0, 1.1, 1.52, 1.55, 1.7, 1.8, 2.0], size=(N, C), p=[.5, .1, .1, .1, .1, .05, .05])
+    sg[7, 2] = -1.7
+    o = np.zeros((M, C))
+    occ_ref.calculate_occupancy(ctr, xyz, sg, o)
+    cases["a"] = (xyz, ctr, sg, o)
+    # (b) lattice points and lattice atoms: many exact d2 == 25 ties (3-4-0 triangles), C = 3
+    g = np.arange(0, 9, dtype=np.float64)
+    ctr = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    xyz = rng.integers(0, 9, size=(20, 3)).astype(np.float32)
+    sg = rng.choice([0.0, 1.7, 3.4], size=(20, 3))
+    o = np.zeros((ctr.shape[0], 3))
+    occ_ref.calculate_occupancy(ctr, xyz, sg, o)
+    cases["b"] = (xyz, ctr, sg, o)
+    # (c) big coordinates (fp32 ulp ~ 1.5e-5) on a 0.5 A grid with f64 origin, C = 8 bool-like sigmas
+    xyz = (rng.normal(size=(60, 3)) * 3.0 + np.array([210.0, -180.0, 95.0])).astype(np.float32)
+    origin = np.array([210.0, -180.0, 95.0]) - 6.0 + 0.123456789
+    ii = np.arange(24) * 0.5
+    ctr = np.stack(np.meshgrid(ii, ii, ii, indexing="ij"), -1).reshape(-1, 3) + origin
+    rad = rng.choice([1.52, 1.55, 1.7, 1.8], size=60)
+    sg = rad[:, None] * (rng.random((60, 8)) < 0.4)
+    o = np.zeros((ctr.shape[0], 8))
+    occ_ref.calculate_occupancy(ctr, xyz, sg, o)
+    cases["c"] = (xyz, ctr, sg, o)
+    np.savez_compressed(os.path.join(HERE, "voxel_small.npz"),
+                        **{f"{k}_{n}": v for k, tup in cases.items()
+                           for n, v in zip(("coords", "centers", "sigmas", "out"), tup)})
+
+    # ------------------------------------------------------------------ trajectory (every 10th frame)
+    tr = os.path.join(REFT, "test_projections", "trajectory")
+    md = os.path.join(REFT, "test_projections", "metricdistance")
+    mol = Molecule(os.path.join(tr, "filtered.pdb"))
+    mol.read(os.path.join(tr, "traj.xtc"))
+    molskip = Molecule(os.path.join(tr, "filtered.pdb"))
+    molskip.read(os.path.join(tr, "traj.xtc"), skip=10)
+    assert np.array_equal(molskip.coords, mol.coords[:, :, ::10])
+    sels = ["protein and name CA", "resname MOL and noh", "protein and noh",
+            "protein and resid 1 to 50 and noh", "protein and resid 1 to 20 and noh", "protein"]
+    masks = np.stack([mol.atomselect(s) for s in sels])
+    from moleculekit.projections.metricdistance import MetricDistance, MetricSelfDistance
+
+    def strarr(a):
+        return np.array([str(x) for x in a])
+
+    fx = dict(
+        coords=molskip.coords, box=molskip.box, name=strarr(mol.name), resname=strarr(mol.resname),
+        resid=mol.resid.astype(np.int64), chain=strarr(mol.chain), segid=strarr(mol.segid),
+        element=strarr(mol.element), sel_strings=np.array(sels), sel_masks=masks,
+        # reference stored goldens, frames ::10 (tests/test_metricdistance.py:182-278)
+        gold_distances=np.load(os.path.join(md, "distances.npy"))[::10],
+        gold_mindistances=np.load(os.path.join(md, "mindistances.npy"))[::10],
+        gold_selfmindistance=np.load(os.path.join(md, "selfmindistance.npy"))[::10],
+    )
+    # sanity: the reference on the 20 skipped frames reproduces its goldens
+    d = MetricDistance("protein and name CA", "resname MOL and noh", metric="distances", periodic="selections").project(molskip)
+    assert np.allclose(d, fx["gold_distances"], atol=1e-3)
+    fx["ref_distances"] = d  # exact float32 output of today's kernel on these frames
+    fx["ref_mindistances"] = MetricDistance("protein and noh", "resname MOL and noh", periodic="selections",
+                                            groupsel1="residue", groupsel2="all").project(molskip)
+    fx["ref_selfmindistance"] = MetricSelfDistance("protein and resid 1 to 50 and noh", groupsel="residue").project(molskip)
+    fx["ref_chains_distances"] = MetricDistance("protein and resid 1 to 20 and noh", "resname MOL and noh",
+                                                periodic="chains").project(molskip)
+    fx["ref_com_com"] = MetricDistance("protein and resid 1 to 50 and noh", "resname MOL and noh", "selections",
+                                       groupsel1="residue", groupsel2="all", groupreduce1="com",
+                                       groupreduce2="com").project(molskip)
+    fx["ref_com_closest"] = MetricDistance("protein and resid 1 to 50 and noh", "resname MOL and noh", "selections",
+                                           groupsel1="residue", groupsel2="all", groupreduce1="com",
+                                           groupreduce2="closest").project(molskip)
+    # ordered contact pairs from the reference's contacts_trajectory (bit-exact target)
+    from moleculekit.distance import calculate_contacts
+
+    def pack(lst):
+        cnt = np.array([len(x) for x in lst], dtype=np.int64)
+        return cnt, (np.vstack(lst) if cnt.sum() else np.zeros((0, 2), np.uint32)).astype(np.uint32)
+
+    ca, lig, noh = masks[0], masks[1], masks[2]
+    fx["ct_ca_lig_sel8_cnt"], fx["ct_ca_lig_sel8_pairs"] = pack(calculate_contacts(molskip, ca, lig, "selections", 8))
+    fx["ct_ca_ca_none6_cnt"], fx["ct_ca_ca_none6_pairs"] = pack(calculate_contacts(molskip, ca, ca, None, 6))
+    fx["ct_noh_lig_chains5_cnt"], fx["ct_noh_lig_chains5_pairs"] = pack(calculate_contacts(molskip, noh, lig, "chains", 5))
+    np.savez_compressed(os.path.join(HERE, "traj20.npz"), **fx)
+
+    # ------------------------------------------------------------------ single-structure cases (3ptb, 5vl5)
+    def molfix(pdbid):
+        m = Molecule(pdbid)
+        return m, dict(coords=m.coords.copy(), box=m.box.copy(), element=strarr(m.element), resname=strarr(m.resname),
+                       resid=m.resid.astype(np.int64), name=strarr(m.name), chain=strarr(m.chain),
+                       segid=strarr(m.segid),
+                       masses=np.array([periodictable[e].mass for e in m.element], dtype=np.float32))
+
+    m3, f3 = molfix("3ptb")
+    f3["sel_protein"] = m3.atomselect("protein")
+    f3["sel_ben"] = m3.atomselect("resname BEN")
+    f3["sel_residue_1_2"] = m3.atomselect("residue 1 2")
+    f3["sel_residue_3_4"] = m3.atomselect("residue 3 4")
+    f3["sel_residue_1"] = m3.atomselect("residue 1"); f3["sel_residue_2"] = m3.atomselect("residue 2")
+    f3["sel_residue_3"] = m3.atomselect("residue 3"); f3["sel_residue_4"] = m3.atomselect("residue 4")
+    kw = dict(groupsel1="all", groupsel2="all")
+    f3["ref_com_com"] = MetricDistance("protein", "resname BEN", None, groupreduce1="com", groupreduce2="com", **kw).project(m3)
+    f3["ref_com_closest"] = MetricDistance("protein", "resname BEN", None, groupreduce1="com", groupreduce2="closest", **kw).project(m3)
+    f3["ref_closest_com"] = MetricDistance("protein", "resname BEN", None, groupreduce1="closest", groupreduce2="com", **kw).project(m3)
+    f3["ref_closest_closest"] = MetricDistance("protein", "resname BEN", None, groupreduce1="closest", groupreduce2="closest", **kw).project(m3)
+    f3["ref_pairs_residue"] = MetricDistance("residue 1 2", "residue 3 4", None, pairs=True, groupsel1="residue",
+                                             groupsel2="residue").project(m3)
+    from moleculekit.periodictable import METAL_ELEMENTS
+    metals = sorted(METAL_ELEMENTS)
+    lig_el = ["N", "O", "Cl", "F", "Br", "I", "CL", "BR", "S"]
+    s1, s2 = m3.atomselect("not protein"), m3.atomselect("protein")
+    f3["mc_sel1"] = s1 & np.isin(m3.element, metals)
+    f3["mc_sel2"] = s2 & np.isin(m3.element, lig_el)
+    f3["mc_expected"] = np.array([[1629, 383], [1629, 396], [1629, 420], [1629, 460]], dtype=np.uint32)  # tests/test_interactions.py:346-349
+    np.savez_compressed(os.path.join(HERE, "pdb_3ptb.npz"), **f3)
+
+    m5, f5 = molfix("5vl5")
+    s1, s2 = m5.atomselect("all"), m5.atomselect("resname S31 and not element Cu")
+    f5 = dict(coords=f5["coords"], box=f5["box"], element=f5["element"])
+    f5["mc_a_sel1"] = s1 & np.isin(m5.element, metals); f5["mc_a_sel2"] = s2 & np.isin(m5.element, lig_el)
+    f5["mc_b_sel1"] = s1 & np.isin(m5.element, lig_el); f5["mc_b_sel2"] = s2 & np.isin(m5.element, metals)
+    f5["mc_expected"] = np.array([[933, 922], [933, 932], [933, 934], [933, 935], [933, 937], [933, 944]],
+                                 dtype=np.uint32)  # tests/test_interactions.py:338-341
+    np.savez_compressed(os.path.join(HERE, "pdb_5vl5.npz"), **f5)
+
+    # ------------------------------------------------------------------ seeded raw-kernel cases (_ref outputs, bit-exact targets)
+    rng = np.random.default_rng(77)
+    N, F = 120, 7
+    L = np.array([18.0, 21.0, 16.5], dtype=np.float32)
+    c = np.empty((N, 3, F), dtype=np.float32)
+    c[:, :, 0] = rng.uniform(0, 1, size=(N, 3)) * L
+    for f in range(1, F):
+        c[:, :, f] = c[:, :, f - 1] + rng.normal(0, 1.5, size=(N, 3)).astype(np.float32)   # unwrapped walk, |n| up to ~3
+    bx = (L[:, None] * (1 + 0.01 * rng.normal(size=(3, F)))).astype(np.float32)
+    chains = rng.integers(0, 3, size=N).astype(np.uint32)
+    s1 = np.sort(rng.choice(N, 37, replace=False)).astype(np.uint32)
+    s2 = np.sort(rng.choice(N, 53, replace=False)).astype(np.uint32)
+    rk = dict(coords=c, box=bx, chains=chains, sel1=s1, sel2=s2)
+    r = np.zeros((F, 37 * 53), np.float32); dist_ref.dist_trajectory(c, bx, s1, s2, chains, False, True, r); rk["dist_pbc"] = r
+    r = np.zeros((F, 37 * 53), np.float32); dist_ref.dist_trajectory(c, bx, s1, s2, chains, False, False, r); rk["dist_nopbc"] = r
+    r = np.zeros((F, 37 * 36 // 2), np.float32); dist_ref.dist_trajectory(c, bx, s1, s1, chains, True, True, r); rk["dist_self_pbc"] = r
+    ct = dist_ref.contacts_trajectory(c, bx, s1, s2, chains, False, True, 6.5)
+    rk["ct_cnt"] = np.array([len(x) // 2 for x in ct], dtype=np.int64)
+    rk["ct_pairs"] = np.concatenate([np.array(x, dtype=np.uint32) for x in ct]).reshape(-1, 2)
+    ct = dist_ref.contacts_trajectory(c, bx, s1, s1, chains, True, True, 7.25)
+    rk["ct_self_cnt"] = np.array([len(x) // 2 for x in ct], dtype=np.int64)
+    rk["ct_self_pairs"] = np.concatenate([np.array(x, dtype=np.uint32) for x in ct]).reshape(-1, 2)
+    groups1 = [sorted(rng.choice(N, rng.integers(1, 9), replace=False).tolist()) for _ in range(11)]
+    groups2 = [sorted(rng.choice(N, rng.integers(1, 9), replace=False).tolist()) for _ in range(6)]
+    masses = rng.choice([1.00794, 12.0107, 14.0067, 15.9994, 32.065], size=N).astype(np.float32)
+    gc1 = np.array([chains[g[0]] for g in groups1], dtype=np.uint32)
+    gc2 = np.array([chains[g[0]] for g in groups2], dtype=np.uint32)
+    rk["g1_off"] = np.cumsum([0] + [len(g) for g in groups1]).astype(np.int64); rk["g1_atoms"] = np.concatenate(groups1).astype(np.int32)
+    rk["g2_off"] = np.cumsum([0] + [len(g) for g in groups2]).astype(np.int64); rk["g2_atoms"] = np.concatenate(groups2).astype(np.int32)
+    rk["masses"] = masses
+    for r1 in (0, 1):
+        for r2 in (0, 1):
+            r = np.zeros((F, 11 * 6), np.float32)
+            dist_ref.dist_trajectory_reduction(c, bx, groups1, groups2, gc1, gc2, False, True, masses, r1, r2, r)
+            rk[f"red_{r1}{r2}"] = r
+    r = np.zeros((F, 11 * 10 // 2), np.float32)
+    dist_ref.dist_trajectory_reduction(c, bx, groups1, groups1, gc1, gc1, True, True, masses, 0, 0, r); rk["red_self"] = r
+    r = np.zeros((F, 6), np.float32)
+    dist_ref.dist_trajectory_reduction_pairs(c, bx, groups1[:6], groups2, gc1[:6], gc2, True, masses, 0, 1, r); rk["red_pairs_01"] = r
+    for D in (1, 2, 3, 5):
+        a = rng.normal(size=(13, D)).astype(np.float32) * 5; b = rng.normal(size=(9, D)).astype(np.float32) * 5
+        r = np.zeros((13, 9), np.float32); dist_ref.cdist(a, b, r)
+        p = np.zeros(13 * 12 // 2, np.float32); dist_ref.pdist(a, p)
+        rk[f"cd{D}_a"], rk[f"cd{D}_b"], rk[f"cd{D}_out"], rk[f"pd{D}_out"] = a, b, r, p
+    rk["sq_out"] = np.array(dist_ref.squareform(rk["pd3_out"]))
+    rk["coll_out"] = np.array(dist_ref.get_collisions(rk["cd3_a"], rk["cd3_b"], 6.0), dtype=np.uint32).reshape(-1, 2)
+    np.savez_compressed(os.path.join(HERE, "rawkernels.npz"), **rk)
+
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+"""Pin the CPU oracle (oracle/mkb_oracle.c) against the reference.
+
+Sources of truth, strongest first:
+  * outputs of the reference's own compiled Cython kernels (oracle/_ref) -- live when present,
+    and frozen in tests/golden/*.npz (tests/golden/make_golden.py) otherwise;
+  * the reference's stored goldens (3PTB_voxres_old.npy, distances/mindistances/selfmindistance.npy).
+Integer / float32 outputs must be bit-identical; the float64 occupancy must be bit-identical to the
+reference kernel on the same libm (hash) and within allclose of the stored golden.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _grid_centers(bb_min, nvox, vs):
+    ix, iy, iz = [np.arange(n) * vs for n in nvox]
+    g = np.stack(np.meshgrid(ix, iy, iz, indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    return g + bb_min
+
+
+def test_occupancy_3ptb_golden(oracle, g_voxel3ptb):
+    g = g_voxel3ptb
+    centers = _grid_centers(g["bb_min"], g["nvoxels"], float(g["voxelsize"]))
+    assert _sha(centers) == str(g["centers_sha256"])
+    out = np.zeros((centers.shape[0], 8))
+    oracle.calculate_occupancy(centers, g["coords"], g["sigmas"], out)
+    # reference's stored golden (f32-rounded sparse copy): allclose like tests/test_voxeldescriptors.py:84
+    gold = np.zeros(out.size, dtype=np.float64)
+    gold[g["gold_nz_idx"]] = g["gold_nz_val"]
+    assert np.array_equal(np.flatnonzero(out.reshape(-1)), g["gold_nz_idx"])
+    assert np.allclose(out.reshape(-1), gold, rtol=1e-5, atol=1e-8)
+    # today's reference kernel: identical bit pattern (same glibc exp) or, failing that, 1e-12 checksum
+    assert int(g["refkernel_nnz"]) == np.count_nonzero(out)
+    if _sha(out) != str(g["refkernel_sha256"]):
+        assert abs(out.sum() - float(g["refkernel_sum"])) < 1e-9 * float(g["refkernel_sum"])
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_occupancy_small_golden(oracle, g_voxelsmall, case):
+    g = g_voxelsmall
+    out = np.zeros_like(g[f"{case}_out"])
+    oracle.calculate_occupancy(g[f"{case}_centers"], g[f"{case}_coords"], g[f"{case}_sigmas"], out)
+    assert np.array_equal(out != 0, g[f"{case}_out"] != 0)
+    assert np.allclose(out, g[f"{case}_out"], rtol=1e-14, atol=0)
+
+
+def test_occupancy_accumulates_and_ignores_nan(oracle):
+    rng = np.random.default_rng(0)
+    xyz = rng.normal(size=(10, 3)).astype(np.float32) * 3
+    ctr = rng.normal(size=(50, 3)) * 3
+    sg = np.full((10, 2), 1.7)
+    sg[0, 0] = np.nan
+    a = np.zeros((50, 2)); oracle.calculate_occupancy(ctr, xyz, sg, a)
+    assert not np.isnan(a).any()
+    b = np.full((50, 2), 0.5); oracle.calculate_occupancy(ctr, xyz, sg, b)
+    assert np.array_equal(b, np.maximum(a, 0.5))
+
+
+def test_dist_rawkernels_golden(oracle, g_raw):
+    g = g_raw
+    c, bx, ch, s1, s2 = g["coords"], g["box"], g["chains"], g["sel1"], g["sel2"]
+    F = c.shape[2]
+    r = np.zeros_like(g["dist_pbc"]); oracle.dist_trajectory(c, bx, s1, s2, ch, False, True, r)
+    assert np.array_equal(r.view(np.uint32), g["dist_pbc"].view(np.uint32))
+    r = np.zeros_like(g["dist_nopbc"]); oracle.dist_trajectory(c, bx, s1, s2, ch, False, False, r)
+    assert np.array_equal(r.view(np.uint32), g["dist_nopbc"].view(np.uint32))
+    r = np.zeros_like(g["dist_self_pbc"]); oracle.dist_trajectory(c, bx, s1, s1, ch, True, True, r)
+    assert np.array_equal(r.view(np.uint32), g["dist_self_pbc"].view(np.uint32))
+    ct = oracle.contacts_trajectory(c, bx, s1, s2, ch, False, True, 6.5)
+    assert [len(x) // 2 for x in ct] == g["ct_cnt"].tolist()
+    assert np.array_equal(np.concatenate([np.array(x, np.uint32) for x in ct]).reshape(-1, 2), g["ct_pairs"])
+    ct = oracle.contacts_trajectory(c, bx, s1, s1, ch, True, True, 7.25)
+    assert [len(x) // 2 for x in ct] == g["ct_self_cnt"].tolist()
+    assert np.array_equal(np.concatenate([np.array(x, np.uint32) for x in ct]).reshape(-1, 2), g["ct_self_pairs"])
+
+    def groups(off, atoms):
+        return [atoms[off[i]:off[i + 1]].tolist() for i in range(len(off) - 1)]
+
+    g1, g2 = groups(g["g1_off"], g["g1_atoms"]), groups(g["g2_off"], g["g2_atoms"])
+    gc1 = np.array([ch[x[0]] for x in g1], np.uint32); gc2 = np.array([ch[x[0]] for x in g2], np.uint32)
+    for r1 in (0, 1):
+        for r2 in (0, 1):
+            r = np.zeros((F, len(g1) * len(g2)), np.float32)
+            oracle.dist_trajectory_reduction(c, bx, g1, g2, gc1, gc2, False, True, g["masses"], r1, r2, r)
+            assert np.array_equal(r.view(np.uint32), g[f"red_{r1}{r2}"].view(np.uint32)), (r1, r2)
+    r = np.zeros_like(g["red_self"])
+    oracle.dist_trajectory_reduction(c, bx, g1, g1, gc1, gc1, True, True, g["masses"], 0, 0, r)
+    assert np.array_equal(r.view(np.uint32), g["red_self"].view(np.uint32))
+    r = np.zeros_like(g["red_pairs_01"])
+    oracle.dist_trajectory_reduction_pairs(c, bx, g1[:6], g2, gc1[:6], gc2, True, g["masses"], 0, 1, r)
+    assert np.array_equal(r.view(np.uint32), g["red_pairs_01"].view(np.uint32))
+    for D in (1, 2, 3, 5):
+        a, b = g[f"cd{D}_a"], g[f"cd{D}_b"]
+        r = np.zeros((len(a), len(b)), np.float32); oracle.cdist(a, b, r)
+        assert np.array_equal(r.view(np.uint32), g[f"cd{D}_out"].view(np.uint32))
+        p = np.zeros(len(a) * (len(a) - 1) // 2, np.float32); oracle.pdist(a, p)
+        assert np.array_equal(p.view(np.uint32), g[f"pd{D}_out"].view(np.uint32))
+    assert np.array_equal(oracle.squareform(g["pd3_out"]), g["sq_out"])
+    assert np.array_equal(np.array(oracle.get_collisions(g["cd3_a"], g["cd3_b"], 6.0), np.uint32).reshape(-1, 2),
+                          g["coll_out"])
+
+
+def test_dist_trajectory_fixture_golden(oracle, g_traj):
+    """tests/test_metricdistance.py:182-193 on every 10th frame + exact output of today's kernel."""
+    g = g_traj
+    sel = {s: m for s, m in zip(g["sel_strings"].tolist(), g["sel_masks"])}
+    s1 = np.where(sel["protein and name CA"])[0].astype(np.uint32)
+    s2 = np.where(sel["resname MOL and noh"])[0].astype(np.uint32)
+    ch = np.ones(g["coords"].shape[0], np.uint32); ch[s2] = 2
+    r = np.zeros((g["coords"].shape[2], len(s1) * len(s2)), np.float32)
+    oracle.dist_trajectory(g["coords"], g["box"], s1, s2, ch, False, True, r)
+    assert np.allclose(r, g["gold_distances"], atol=1e-3)
+    assert np.array_equal(r.view(np.uint32), g["ref_distances"].view(np.uint32))
+    ct = oracle.contacts_trajectory(g["coords"], g["box"], s1, s2, ch, False, True, 8)
+    assert [len(x) // 2 for x in ct] == g["ct_ca_lig_sel8_cnt"].tolist()
+    assert np.array_equal(np.concatenate([np.array(x, np.uint32) for x in ct]).reshape(-1, 2), g["ct_ca_lig_sel8_pairs"])
+
+
+def test_oracle_vs_live_reference(oracle, refmods):
+    """When oracle/_ref is present (it is in the build container and travels to the GPU box),
+    compare against the reference's own binaries on fresh random inputs."""
+    if refmods is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    occ_ref, dist_ref = refmods
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        N, M, C = 30 + 10 * trial, 400, 1 + 3 * trial
+        xyz = (rng.normal(size=(N, 3)) * 5).astype(np.float32)
+        ctr = rng.normal(size=(M, 3)) * 6
+        sg = rng.choice([0.0, 1.2, 1.7, 2.2], size=(N, C))
+        a = np.zeros((M, C)); occ_ref.calculate_occupancy(ctr, xyz, sg, a)
+        b = np.zeros((M, C)); oracle.calculate_occupancy(ctr, xyz, sg, b)
+        assert np.array_equal(a, b)
+    N, F = 64, 5
+    c = (rng.normal(size=(N, 3, F)) * 12).astype(np.float32)
+    bx = np.abs(rng.normal(size=(3, F)) * 2 + 15).astype(np.float32)
+    ch = rng.integers(0, 4, N).astype(np.uint32)
+    s1 = np.arange(0, 40, dtype=np.uint32); s2 = np.arange(20, 64, dtype=np.uint32)
+    for pbc in (False, True):
+        a = np.zeros((F, 40 * 44), np.float32); dist_ref.dist_trajectory(c, bx, s1, s2, ch, False, pbc, a)
+        b = np.zeros((F, 40 * 44), np.float32); oracle.dist_trajectory(c, bx, s1, s2, ch, False, pbc, b)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert dist_ref.contacts_trajectory(c, bx, s1, s2, ch, False, pbc, 9.0) == \
+            oracle.contacts_trajectory(c, bx, s1, s2, ch, False, pbc, 9.0)
