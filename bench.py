@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- voxel-channels/s of the 8-channel 1 A occupancy path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU kernel on the host cores
+
+A "step" = one pass of the hot path (bin atoms -> scan -> scatter -> tile fill) over one batch of synthetic
+pockets: BASELINE.json configs[2] (256 protein pockets x ~3000 atoms, 64^3 grid @ 1 A, 8 channels) PER GPU
+(weak scaling: ranks voxelise independent batches, no data-path collective).  One JSON line on stdout (rank 0).
+
+  value     voxel-channels/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the public host API (getVoxelDescriptorsBatch): pinned host buffers in,
+            pinned host features out, H2D + kernels + D2H inside the timed region
+  roofline  algorithmic bytes of the fill kernel / its mean launch duration (CUDA events inside the library,
+            recorded on the launch stream) against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's compiled Cython kernel (oracle/_ref, kind "reference") or the C port of it
+            (kind "port") on a bounded sample of the same pockets, one process per host core
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "voxel-channels/s (8-ch 1A protein grids)"
+UNIT = "voxel-channels/s"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c5"])
+    ap.add_argument("--batch", type=int, default=0, help="items per GPU (0 = the config's size)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def make_workload(kind: str, batch: int, rank: int):
+    from moleculekit_b200 import workloads
+
+    if kind == "c3":
+        return workloads.protein_pockets(B=batch or 256, seed=1000 + 100000 * rank)
+    if kind == "c2":
+        return workloads.ligand_poses(B=batch or 1024, seed=100000 * rank)
+    return workloads.fine_grids(B=batch or 8, seed=2000 + 100000 * rank)
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    kind, coords, sigmas, boxsize, center, voxelsize = args
+    sys.path.insert(0, ROOT)
+    from moleculekit_b200.tools.voxeldescriptors import _centers_from_spec, _grid_spec
+
+    bb_min, nvox = _grid_spec(None, 0, boxsize, center, voxelsize)
+    centers = _centers_from_spec(bb_min, nvox, voxelsize)
+    out = np.zeros((centers.shape[0], sigmas.shape[1]))
+    if kind == "reference":
+        from oracle import build_ref
+
+        fn = build_ref.load()[0].calculate_occupancy
+    else:
+        from oracle import cpu_oracle
+
+        fn = cpu_oracle.calculate_occupancy
+    t0 = time.perf_counter()
+    fn(centers, np.ascontiguousarray(coords, dtype=np.float32), np.ascontiguousarray(sigmas, dtype=np.float64), out)
+    return time.perf_counter() - t0, out.size
+
+
+def cpu_kind():
+    from oracle import build_ref, cpu_oracle
+
+    try:
+        build_ref.build(verbose=False)
+    except Exception:
+        pass
+    if build_ref.load() is not None:
+        return "reference"
+    cpu_oracle.build()
+    return "port"
+
+
+def cpu_sample(w, n_items: int, procs: int):
+    """Time the CPU kernel on the first n_items of the workload, one single-threaded process per item (the
+    reference kernel is single-threaded: OpenMP is commented out in its setup.py:48)."""
+    import multiprocessing as mp
+
+    kind = cpu_kind()
+    jobs = [(kind, w["coords"][b], w["sigmas"][b], w["boxsize"], w["centers"][b], w["voxelsize"])
+            for b in range(n_items)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(processes=procs) as pool:
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    vc = sum(r[1] for r in res)
+    return dict(value=vc / wall, unit=UNIT, cores=procs, kind=kind,
+                sample=f"{n_items} of the workload's items, kernel only (centres prebuilt), {procs} processes x 1 thread, "
+                       f"{sum(r[0] for r in res):.1f} core-seconds"), wall
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    w = make_workload(a.workload, a.batch, 0)
+    n_items = min(len(w["coords"]), max(1, min(procs, 64)))
+    for _ in range(a.warmup):
+        cpu_sample(w, n_items, procs)
+    walls, base = [], None
+    for _ in range(a.steps):
+        base, wall = cpu_sample(w, n_items, procs)
+        walls.append(wall)
+    vc_step = n_items * int(np.prod(np.ceil(np.array(w["boxsize"]) / w["voxelsize"]))) * 8
+    base["value"] = vc_step * len(walls) / sum(walls)
+    best = (base, sum(walls) / len(walls))
+    vals = walls
+    line = dict(impl="reference", metric=METRIC, value=base["value"], unit=UNIT, n_gpus=a.gpus, steps=len(vals),
+                warmup=a.warmup, ms_per_step=best[1] * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=w["name"], sample_items=n_items), cpu_baseline=base,
+                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            if t0 - 0.05 <= t <= t1 + 0.15:
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from moleculekit_b200 import _lib, workloads
+    from moleculekit_b200.tools import voxeldescriptors as vd
+
+    w = make_workload(a.workload, a.batch, rank)
+    batch = vd.VoxelBatch(w["coords"], w["sigmas"], boxsize=w["boxsize"], centers=w["centers"], voxelsize=w["voxelsize"])
+    n_vc = batch.total_voxels * batch.C
+    n_atoms = batch.coords.shape[0]
+    d_coords, d_sig = batch.to_device(dev)
+    out = torch.empty((batch.total_voxels, batch.C), dtype=torch.float32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing
+    _lib.set_timing(True, local)
+    for _ in range(max(a.warmup, 3)):
+        batch.run(d_coords, d_sig, out)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.25 if rank == 0 else 0.0)
+    barrier()
+    l0 = _lib.launch_count(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fill_ms, prep_ms = [], []
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(a.steps):
+        batch.run(d_coords, d_sig, out)
+        # reading the library's per-kernel events would synchronise; they are read after the loop for the LAST
+        # step and, below, in a second pass for every step
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = _lib.launch_count(local) - l0
+    ms_total = ev0.elapsed_time(ev1)
+    # per-kernel durations (one synchronising read per step, outside the aggregate timing above)
+    for _ in range(a.steps):
+        batch.run(d_coords, d_sig, out)
+        p, m = _lib.get_timing(local)
+        prep_ms.append(p); fill_ms.append(m)
+    t_wall2 = time.perf_counter()
+    clk = clocks.stop(t_wall0, t_wall2) if clocks else None
+    ms_step = ms_total / a.steps
+    if world > 1:
+        t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    value = world * n_vc / (ms_step * 1e-3)
+
+    # ---- end to end through the public host API (pinned host in, pinned host out)
+    e2e = None
+    if not a.no_e2e:
+        h_coords = vd.pinned_array(batch.coords.shape, np.float32); h_coords[:] = batch.coords
+        h_sig = vd.pinned_array(batch.sigmas.shape, np.float64); h_sig[:] = batch.sigmas
+        h_out = vd.pinned_array((batch.total_voxels, batch.C), np.float32)
+        kw = dict(boxsize=w["boxsize"], centers=w["centers"], voxelsize=w["voxelsize"], atom_offsets=batch.atom_offsets,
+                  device=dev, out=h_out)
+        for _ in range(2):
+            vd.getVoxelDescriptorsBatch(h_coords, h_sig, **kw)
+        barrier()
+        n_e2e = max(3, min(a.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            vd.getVoxelDescriptorsBatch(h_coords, h_sig, **kw)
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = dict(value=world * n_vc / dt, unit=UNIT, h2d_bytes_per_step=int(h_coords.nbytes + h_sig.nbytes),
+                   d2h_bytes_per_step=int(h_out.nbytes), ms_per_step=dt * 1e3, steps=n_e2e,
+                   api="moleculekit_b200.tools.voxeldescriptors.getVoxelDescriptorsBatch(out=pinned float32)")
+        del h_out
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = None, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured"
+    except Exception:
+        peak = HBM_FALLBACK_GBS
+    alg_bytes = workloads.occupancy_algorithmic_bytes(batch.total_voxels, n_atoms, batch.C)
+    fill_mean = float(np.mean(fill_ms))
+    achieved = alg_bytes / (fill_mean * 1e-3) / 1e9
+    roofline = dict(bound="hbm", kernel="occ_fill_kernel<8>", achieved=achieved, peak=peak, unit="GB/s",
+                    frac=achieved / peak, traffic=None, peak_source=f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
+                    algorithmic_bytes_per_launch=int(alg_bytes), kernel_ms_mean=fill_mean,
+                    kernel_ms_min=float(np.min(fill_ms)), prep_ms_mean=float(np.mean(prep_ms)),
+                    kernel_share_of_step=fill_mean / ms_step)
+    cpu = None
+    if not a.no_cpu and world == 1:
+        procs = os.cpu_count() or 1
+        n_items = min(batch.B, max(1, min(procs, 32)))
+        cpu, _ = cpu_sample(w, n_items, procs)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
+                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic",
+                config=dict(workload=w["name"] + " per GPU", items_per_gpu=batch.B, atoms_per_gpu=int(n_atoms),
+                            voxel_channels_per_gpu=int(n_vc),
+                            l2="no flush needed: each step streams %.2f GB of grid output, >> 126 MB L2" % (n_vc * 4 / 1e9),
+                            parallelism=f"batch sharded over {world} GPU(s), no collective"),
+                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

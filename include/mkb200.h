@@ -1,0 +1,157 @@
+/*
+ * mkb200.h -- C-ABI of libmkb200.so: the B200-native voxel-occupancy and trajectory-distance engine.
+ *
+ * This is the drop-in boundary for ONE hot path of Acellera/moleculekit:
+ *   moleculekit/occupancy_utils/occupancy_utils.pyx   (calculate_occupancy)
+ *   moleculekit/distance_utils/distance_utils.pyx     (dist_trajectory, contacts_trajectory,
+ *                                                      dist_trajectory_reduction[_pairs], cdist, pdist,
+ *                                                      squareform, get_collisions)
+ * The reference exposes these as Cython `def` functions over numpy memoryviews (no C header); each entry
+ * point below cites the reference function it replaces.  Conventions:
+ *   - plain C types only: pointers, sizes, scalars.  No torch / numpy types.
+ *   - bulk arrays are DEVICE pointers (the Python host obtains them from torch.Tensor.data_ptr());
+ *     small per-grid descriptors are HOST arrays (they size the launch); `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream).  All work is stream-ordered; nothing blocks the host
+ *     except where stated (mkb_contacts_count returns a host total).
+ *   - every function returns MKB_OK (0) or a negative mkb_status; mkb_last_error(h) gives the message.
+ *   - the caller owns every input/output array; the handle owns only scratch (cell lists, scan temp),
+ *     grown on demand and freed by mkb_destroy.  One handle per device; not thread-safe per handle.
+ *   - there is NO CPU fallback: without a CUDA device mkb_create fails with MKB_ERR_CUDA.
+ */
+#ifndef MKB200_H
+#define MKB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MKB_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    MKB_OK = 0,
+    MKB_ERR_BAD_ARG = -1,
+    MKB_ERR_CUDA = -2,
+    MKB_ERR_NOMEM = -3,
+    MKB_ERR_CAPACITY = -4
+} mkb_status;
+
+typedef struct mkb_ctx *mkb_handle_t;
+
+/* flags for the occupancy entry points */
+#define MKB_OCC_ACCUMULATE 1u /* out = max(out, value): the reference accumulates into the caller's buffer
+                                 (occupancy_utils.pyx:61); without it `out` is overwritten (caller passes zeros,
+                                 voxeldescriptors.py:531, so both agree) */
+
+/* output modes of the distance entry points (host post-ops of projections/util.py:74-84 fused in) */
+#define MKB_DIST_DISTANCES 0 /* float32 distances, optionally truncated */
+#define MKB_DIST_CONTACTS 1  /* uint8 (bool) = distance <= threshold, after optional truncate */
+
+int mkb_version(void);
+int mkb_create(int device, mkb_handle_t *out);
+int mkb_destroy(mkb_handle_t h);
+const char *mkb_last_error(mkb_handle_t h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t mkb_launch_count(mkb_handle_t h);
+/* Per-kernel device timing for the roofline report: when on, the occupancy and distance entry points record CUDA
+ * events on the launch stream before their preparation kernels, before the main kernel and after it.
+ * mkb_get_timing synchronises on the last event and returns the two intervals of the most recent call (ms). */
+int mkb_set_timing(mkb_handle_t h, int on);
+int mkb_get_timing(mkb_handle_t h, float *prep_ms, float *main_ms);
+
+/* One regular voxel grid: centre of voxel (ix,iy,iz) = fl(fl(i*voxelsize) + origin[d]) in float64, exactly
+ * as moleculekit/tools/voxeldescriptors.py:125-132,245 builds `centers`; flat voxel index
+ * (ix*ny + iy)*nz + iz (z fastest), channels minor. */
+typedef struct {
+    double origin[3];   /* bb_min of getCenters (voxeldescriptors.py:231-243) */
+    double voxelsize;   /* isotropic voxel edge, Angstrom */
+    int32_t dims[3];    /* nx, ny, nz */
+    int32_t reserved;
+    int64_t atom_begin; /* rows [atom_begin, atom_end) of coords/sigmas belong to this grid */
+    int64_t atom_end;
+    int64_t out_offset; /* first voxel of this grid in `out`, in voxels (row = C floats) */
+} mkb_grid_desc;
+
+/* K1+K2: batched occupancy on regular grids.
+ * Replaces calculate_occupancy (occupancy_utils.pyx:34-61) + the centre materialisation of getCenters for every
+ * grid of the batch in one launch sequence (bin atoms -> scan -> scatter -> fill).
+ *   coords  [n_atoms,3] float32 device      (reference: coords f32[:,:])
+ *   sigmas  [n_atoms,C] float64 device      (reference: sigmas f64[:,:]; 0 = channel off, NaN ignored)
+ *   grids   [B] HOST descriptors
+ *   out     [sum_b nx*ny*nz, C] float32 device (the reference's float64 results; the host wrapper upcasts)
+ * 1 <= C <= 32. */
+int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
+                             int64_t n_atoms, int32_t C, const mkb_grid_desc *grids, int32_t B,
+                             float *out, uint32_t flags);
+
+/* K1b: occupancy at arbitrary centres (the `usercenters` branch, voxeldescriptors.py:338-340 ->
+ * calculate_occupancy).  centers [M,3] float64 device; same arithmetic contract. */
+int mkb_occupancy_points(mkb_handle_t h, void *stream, const double *centers, int64_t M,
+                         const float *coords, const double *sigmas, int64_t n_atoms, int32_t C,
+                         float *out, uint32_t flags);
+
+/* Trajectory view shared by the distance entry points: coords is float32 (n_atoms, 3, F) frame-minor
+ * (moleculekit/molecule.py:144-146); element (a, d, f) lives at coords[(a*3 + d)*frame_stride + f], box (3, F) at
+ * box[d*frame_stride_box + f].  A frame shard [f0, f1) of a resident trajectory is (coords + f0, n_frames = f1 - f0,
+ * frame_stride = F). */
+typedef struct {
+    const float *coords;
+    const float *box;
+    int64_t n_atoms;
+    int64_t n_frames;
+    int64_t frame_stride;     /* elements between consecutive (atom, dim) rows of coords */
+    int64_t frame_stride_box; /* elements between consecutive rows of box */
+} mkb_traj;
+
+/* K3: dist_trajectory (distance_utils.pyx:126-155) with the truncate / contacts post-ops of
+ * pp_calcDistances (projections/util.py:74-84) fused into the store.
+ *   sel1 [n1], sel2 [n2], chains [n_atoms] uint32 device; out [n_frames, P] row-major, P = n1*n2 or n1*(n1-1)/2
+ *   when selfdist (then sel2 must equal sel1 as in the reference); float32 (mode 0) or uint8 (mode 1).
+ *   truncate: NaN = off.  Arithmetic: every float op individually rounded (no FMA), roundf half-away, sqrtf IEEE
+ *   -> bit-identical to the reference binary. */
+int mkb_dist_trajectory(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *sel1, int64_t n1,
+                        const uint32_t *sel2, int64_t n2, const uint32_t *chains, int32_t selfdist, int32_t pbc,
+                        int32_t mode, float truncate, float threshold, void *out);
+
+/* K4: contacts_trajectory (distance_utils.pyx:59-93), two calls.
+ * count: row_offsets [n_frames*n1 + 1] int64 device receives the exclusive scan of the per-(frame, i) contact
+ *        counts; *total_pairs (HOST) receives the grand total (this call synchronises the stream).
+ * fill : pairs [total_pairs, 2] uint32 device receives (sel1[i], sel2[j]) in the reference's order: frame-major,
+ *        then i ascending, then j ascending -- bit-exact index output.  thr2 = threshold*threshold in float
+ *        (pyx:77), compare `<=`. */
+int mkb_contacts_count(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *sel1, int64_t n1,
+                       const uint32_t *sel2, int64_t n2, const uint32_t *chains, int32_t selfdist, int32_t pbc,
+                       float threshold, int64_t *row_offsets, int64_t *total_pairs);
+int mkb_contacts_fill(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *sel1, int64_t n1,
+                      const uint32_t *sel2, int64_t n2, const uint32_t *chains, int32_t selfdist, int32_t pbc,
+                      float threshold, const int64_t *row_offsets, uint32_t *pairs);
+
+/* K5: dist_trajectory_reduction / dist_trajectory_reduction_pairs (distance_utils.pyx:211-350) with the same
+ * fused post-ops (projections/util.py:212-223).  Groups are CSR (offsets [G+1] int64, atoms int32), device.
+ * gchains1/2 [G1]/[G2] uint32 = chain id of each group's first atom (projections/util.py:174-179).
+ * red1/red2: 0 closest, 1 centre of mass (float accumulation in atom order, pyx:160-183).
+ * pairs != 0: group g of set 1 against group g of set 2 (G1 == G2), out [n_frames, G1];
+ * else out [n_frames, G1*G2] or [n_frames, G1*(G1-1)/2] when selfdist. */
+int mkb_dist_reduction(mkb_handle_t h, void *stream, const mkb_traj *t, const int64_t *g1_off,
+                       const int32_t *g1_atoms, int64_t G1, const int64_t *g2_off, const int32_t *g2_atoms,
+                       int64_t G2, const uint32_t *gchains1, const uint32_t *gchains2, int32_t selfdist,
+                       int32_t pbc, const float *masses, int32_t red1, int32_t red2, int32_t pairs, int32_t mode,
+                       float truncate, float threshold, void *out);
+
+/* K6: cdist / pdist / squareform / get_collisions (distance_utils.pyx:355-435, 98-121).  Row-major float32. */
+int mkb_cdist(mkb_handle_t h, void *stream, const float *a, int64_t n1, const float *b, int64_t n2, int32_t D,
+              float *out);
+int mkb_pdist(mkb_handle_t h, void *stream, const float *a, int64_t n, int32_t D, float *out);
+int mkb_squareform(mkb_handle_t h, void *stream, const float *d, int64_t n, int64_t dim, float *out);
+/* get_collisions: single frame, no pbc, LOCAL (i, j) indices; same two-call protocol as K4 with
+ * row_offsets [n1 + 1]. */
+int mkb_collisions_count(mkb_handle_t h, void *stream, const float *c1, int64_t n1, const float *c2, int64_t n2,
+                         float threshold, int64_t *row_offsets, int64_t *total_pairs);
+int mkb_collisions_fill(mkb_handle_t h, void *stream, const float *c1, int64_t n1, const float *c2, int64_t n2,
+                        float threshold, const int64_t *row_offsets, uint32_t *pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MKB200_H */

@@ -1,0 +1,125 @@
+// common.cuh -- handle, scratch and error plumbing shared by the mkb200 translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "mkb200.h"
+
+namespace mkb {
+
+enum ScratchSlot {
+    S_DESC = 0,     // device copy of per-grid descriptors
+    S_ITEM_CELL,    // per (grid, atom) item: cell id / slot
+    S_ITEM_SLOT,
+    S_CELL_COUNT,   // per cell counters, then exclusive offsets
+    S_CELL_START,
+    S_SCAN_TMP,     // cub temp storage
+    S_SORT_PX, S_SORT_PY, S_SORT_PZ, S_SORT_S2, S_SORT_MASK, S_SORT_SRC,
+    S_PT_S2,        // points path: per (atom, channel) sigma^2
+    S_PT_BUCKET,    // points path: bucket offsets
+    S_PT_ORDER,     // points path: atom order
+    S_ROWCNT,       // contacts: per-row counts
+    S_COM,          // reductions: centres of mass
+    S_NSLOTS
+};
+
+struct Scratch {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace mkb
+
+struct mkb_ctx {
+    int device = 0;
+    std::string err;
+    mkb::Scratch scratch[mkb::S_NSLOTS];
+    int64_t launches = 0;
+    int sm_count = 148;
+    // optional per-kernel timing (bench.py roofline): events recorded on the launch stream
+    bool timing = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before prep, before main kernel, after main kernel
+};
+
+namespace mkb {
+
+inline int fail(mkb_ctx *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define MKB_CUDA(h, expr)                                                                            \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return mkb::fail((h), MKB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                                    \
+    } while (0)
+
+// Grow-only scratch.  cudaFree synchronises the device, so a buffer still in use by in-flight work is never
+// pulled from under it.
+inline int scratch_get(mkb_ctx *h, ScratchSlot s, size_t bytes, void **out) {
+    Scratch &sc = h->scratch[s];
+    if (bytes > sc.cap) {
+        if (sc.ptr) MKB_CUDA(h, cudaFree(sc.ptr));
+        sc.ptr = nullptr;
+        sc.cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&sc.ptr, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(h, MKB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        sc.cap = want;
+    }
+    *out = sc.ptr;
+    return MKB_OK;
+}
+
+template <typename T>
+inline int scratch_get(mkb_ctx *h, ScratchSlot s, size_t count, T **out) {
+    void *p = nullptr;
+    int rc = scratch_get(h, s, count * sizeof(T), &p);
+    *out = static_cast<T *>(p);
+    return rc;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+#define MKB_ENTER(h)                                                        \
+    if (!(h)) return MKB_ERR_BAD_ARG;                                       \
+    mkb::DeviceGuard _guard((h)->device);                                   \
+    if (!_guard.ok) return mkb::fail((h), MKB_ERR_CUDA, "cudaSetDevice(%d) failed", (h)->device)
+
+#define MKB_LAUNCHED(h)                                                                                    \
+    do {                                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                               \
+        if (_e != cudaSuccess)                                                                             \
+            return mkb::fail((h), MKB_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                                          \
+        (h)->launches++;                                                                                   \
+    } while (0)
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace mkb

@@ -1,0 +1,603 @@
+// distance.cu -- K3/K4/K5/K6: trajectory distances, ordered contacts, group reductions, cdist/pdist for sm_100a.
+//
+// Replaces moleculekit/distance_utils/distance_utils.pyx (all functions) with the post-ops of
+// moleculekit/projections/util.py:74-84,212-223 fused into the stores.
+//
+// Data flow (not the reference's frame/i/j triple loop):
+//   gather   the selected atoms of the frame-minor trajectory (N,3,F) are transposed once, through shared memory,
+//            into frame-major float4 rows G[f][k] = (x, y, z, chain-id bits): reads are coalesced along frames, writes
+//            along atoms.  This is ~3 % extra traffic for the dense kernels and makes every later access coalesced.
+//   K3       CTA = (frame, 16 rows of sel1, 256 columns of sel2); a thread keeps its sel2 atom in registers, sel1 atoms
+//            arrive by L1 broadcast, stores are 128-byte coalesced rows of the (F, P) matrix; truncate / `<= threshold`
+//            are applied in the store (float32 or uint8 output).
+//   K4       one warp per (frame, i) row: ballot + popc gives the row count (pass 1) and, after a cub scan, the
+//            ORDERED position of every hit (pass 2) -> output order identical to the reference's nested loops.
+//   K5       COM pre-pass (one thread per (frame, group), sequential float sums in atom order = reference bits),
+//            then one warp per (frame, group pair) min-reduction.
+// Bit parity: the reference binary has no FMA and rounds every float op; so do we (__fmul_rn/__fadd_rn/..., roundf
+// half-away via an exactly-rounded quotient on the rare near-half cases, __fsqrt_rn).
+#include <cub/device/device_scan.cuh>
+
+#include <cmath>
+
+#include "common.cuh"
+
+namespace mkb {
+
+// d - b * roundf(d / b) with every op rounded to float (distance_utils.pyx:50-52).
+// Fast path: q~ = d * (1/b) differs from fl(d/b) by <= 2 ulp, and round-to-nearest-integer of q~ (magic-number add)
+// equals roundf(fl(d/b)) unless a half-integer lies within that error; those cases (and huge / non-finite quotients)
+// take the exact division + roundf.
+__device__ __forceinline__ float wrap_axis(float d, float b, float rb) {
+    const float q = __fmul_rn(d, rb);
+    float n = __fsub_rn(__fadd_rn(q, 12582912.0f), 12582912.0f);
+    const float fr = fabsf(__fsub_rn(q, n));
+    const float lim = fmaf(-6e-7f, fabsf(q), 0.5f);  // negative for |q| > 8e5 -> always exact path; NaN -> exact path
+    if (!(fr < lim)) n = roundf(__fdiv_rn(d, b));
+    return __fsub_rn(d, __fmul_rn(b, n));
+}
+
+__device__ __forceinline__ float sq3(float dx, float dy, float dz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+struct BoxF {
+    float bx, by, bz, rx, ry, rz;
+};
+
+__device__ __forceinline__ BoxF load_box(const float *box, long long stride, long long f) {
+    BoxF b;
+    b.bx = box[f];
+    b.by = box[stride + f];
+    b.bz = box[2 * stride + f];
+    b.rx = __frcp_rn(b.bx);
+    b.ry = __frcp_rn(b.by);
+    b.rz = __frcp_rn(b.bz);
+    return b;
+}
+
+// squared distance of two gathered atoms, distance_utils.pyx:34-54 (_dist) / :188-206 (_dist2)
+__device__ __forceinline__ float pair_d2(const float4 a, const float4 b, const BoxF &bx, bool wrap) {
+    float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+    if (wrap) {
+        dx = wrap_axis(dx, bx.bx, bx.rx);
+        dy = wrap_axis(dy, bx.by, bx.ry);
+        dz = wrap_axis(dz, bx.bz, bx.rz);
+    }
+    return sq3(dx, dy, dz);
+}
+
+// store with the fused host post-ops of projections/util.py:74-84: results[results > truncate] = truncate, then
+// (contacts) results <= threshold.  NaN distances stay NaN / compare false exactly like numpy.
+template <int MODE>
+__device__ __forceinline__ void store_dist(void *out, long long idx, float d, float truncate, float threshold) {
+    if (d > truncate) d = truncate;  // truncate = NaN disables (comparison false)
+    if (MODE == MKB_DIST_CONTACTS) reinterpret_cast<unsigned char *>(out)[idx] = (d <= threshold) ? 1 : 0;
+    else reinterpret_cast<float *>(out)[idx] = d;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gather + transpose: G[f][k] = (coords[idx[k], 0..2, f], chain bits) ; 32 frames x 32 atoms per CTA
+// ---------------------------------------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void gather_kernel(const float *__restrict__ coords, long long stride, long long n_frames,
+                              const IdxT *__restrict__ idx, long long n, const unsigned *__restrict__ tag,
+                              float4 *__restrict__ G) {
+    __shared__ float tile[3][32][33];
+    const long long f0 = (long long)blockIdx.x * 32, k0 = (long long)blockIdx.y * 32;
+    const int lane = threadIdx.x, row = threadIdx.y;  // blockDim = (32, 8)
+    for (int kk = row; kk < 32; kk += 8) {
+        const long long k = k0 + kk, f = f0 + lane;
+        if (k < n && f < n_frames) {
+            const long long a = (long long)idx[k];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) tile[d][kk][lane] = coords[(a * 3 + d) * stride + f];
+        }
+    }
+    __syncthreads();
+    for (int ff = row; ff < 32; ff += 8) {
+        const long long f = f0 + ff, k = k0 + lane;
+        if (k < n && f < n_frames) {
+            const unsigned t = tag ? tag[(long long)idx[k]] : 0u;
+            G[f * n + k] = make_float4(tile[0][lane][ff], tile[1][lane][ff], tile[2][lane][ff], __uint_as_float(t));
+        }
+    }
+}
+
+template <typename IdxT>
+static int launch_gather(mkb_ctx *h, cudaStream_t st, const mkb_traj *t, const IdxT *idx, int64_t n,
+                         const unsigned *tag, float4 *G) {
+    if (n == 0 || t->n_frames == 0) return MKB_OK;
+    dim3 grid((unsigned)cdiv(t->n_frames, 32), (unsigned)cdiv(n, 32));
+    if (grid.y > 65535) return fail(h, MKB_ERR_BAD_ARG, "selection too large (%lld atoms)", (long long)n);
+    gather_kernel<IdxT><<<grid, dim3(32, 8), 0, st>>>(t->coords, t->frame_stride, t->n_frames, idx, n, tag, G);
+    MKB_LAUNCHED(h);
+    return MKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: dense distances.  grid = (col tiles, row tiles, frames)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int K3_ROWS = 16;
+constexpr int K3_COLS = 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(K3_COLS) dist_kernel(const float4 *__restrict__ G1, const float4 *__restrict__ G2,
+                                                        long long n1, long long n2, const float *__restrict__ box,
+                                                        long long box_stride, int selfdist, int pbc, float truncate,
+                                                        float threshold, long long P, void *__restrict__ out,
+                                                        long long frame0) {
+    const long long f = frame0 + blockIdx.z;
+    const long long j = (long long)blockIdx.x * K3_COLS + threadIdx.x;
+    const long long i0 = (long long)blockIdx.y * K3_ROWS;
+    if (selfdist && (long long)(blockIdx.x + 1) * K3_COLS <= i0 + 1) return;  // tile entirely below the diagonal
+    if (j >= n2) return;
+    const float4 b = G2[f * n2 + j];
+    const unsigned cb = __float_as_uint(b.w);
+    const BoxF bx = load_box(box, box_stride, f);
+    const long long i1 = min(i0 + K3_ROWS, n1);
+    for (long long i = i0; i < i1; ++i) {
+        if (selfdist && j <= i) continue;
+        const float4 a = __ldg(G1 + f * n1 + i);
+        const bool wrap = pbc && (__float_as_uint(a.w) != cb);
+        const float d = __fsqrt_rn(pair_d2(a, b, bx, wrap));
+        const long long col = selfdist ? (i * n2 - (i * (i + 1)) / 2 + (j - i - 1)) : (i * n2 + j);
+        store_dist<MODE>(out, f * P + col, d, truncate, threshold);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4: ordered contacts.  One warp per (frame, i) row.  FILL = false: counts; FILL = true: ordered write.
+// ---------------------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256) contacts_kernel(const float4 *__restrict__ G1, const float4 *__restrict__ G2,
+                                                       long long n1, long long n2, long long n_frames,
+                                                       const float *__restrict__ box, long long box_stride,
+                                                       int selfdist, int pbc, float thr2,
+                                                       const unsigned *__restrict__ sel1,
+                                                       const unsigned *__restrict__ sel2,
+                                                       long long *__restrict__ row_counts,
+                                                       const long long *__restrict__ row_offsets,
+                                                       unsigned *__restrict__ pairs) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_frames * n1) return;
+    const long long f = row / n1, i = row - f * n1;
+    const float4 a = G1[f * n1 + i];
+    const unsigned ca = __float_as_uint(a.w);
+    const BoxF bx = load_box(box, box_stride, f);
+    const unsigned s1 = FILL ? sel1[i] : 0u;
+    long long pos = FILL ? row_offsets[row] : 0;
+    long long cnt = 0;
+    const long long jstart = selfdist ? i + 1 : 0;
+    for (long long jb = jstart - (jstart & 31); jb < n2; jb += 32) {  // aligned chunks keep loads coalesced
+        const long long j = jb + lane;
+        bool hit = false;
+        if (j >= jstart && j < n2) {
+            const float4 b = G2[f * n2 + j];
+            const bool wrap = pbc && (ca != __float_as_uint(b.w));
+            hit = pair_d2(a, b, bx, wrap) <= thr2;  // distance_utils.pyx:90
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (FILL) {
+            if (hit) {
+                const long long p = pos + __popc(bal & ((1u << lane) - 1u));
+                pairs[2 * p + 0] = s1;
+                pairs[2 * p + 1] = sel2[j];
+            }
+            pos += __popc(bal);
+        } else {
+            cnt += __popc(bal);
+        }
+    }
+    if (!FILL && lane == 0) row_counts[row] = cnt;
+}
+
+// get_collisions (distance_utils.pyx:98-121): single frame, row-major (n,3) inputs, local indices
+template <bool FILL>
+__global__ void __launch_bounds__(256) collisions_kernel(const float *__restrict__ c1, long long n1,
+                                                         const float *__restrict__ c2, long long n2, float thr2,
+                                                         long long *__restrict__ row_counts,
+                                                         const long long *__restrict__ row_offsets,
+                                                         unsigned *__restrict__ pairs) {
+    const int lane = threadIdx.x & 31;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n1) return;
+    const float ax = c1[3 * i], ay = c1[3 * i + 1], az = c1[3 * i + 2];
+    long long pos = FILL ? row_offsets[i] : 0, cnt = 0;
+    for (long long jb = 0; jb < n2; jb += 32) {
+        const long long j = jb + lane;
+        bool hit = false;
+        if (j < n2)
+            hit = sq3(__fsub_rn(ax, c2[3 * j]), __fsub_rn(ay, c2[3 * j + 1]), __fsub_rn(az, c2[3 * j + 2])) <= thr2;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (FILL) {
+            if (hit) {
+                const long long p = pos + __popc(bal & ((1u << lane) - 1u));
+                pairs[2 * p + 0] = (unsigned)i;
+                pairs[2 * p + 1] = (unsigned)j;
+            }
+            pos += __popc(bal);
+        } else {
+            cnt += __popc(bal);
+        }
+    }
+    if (!FILL && lane == 0) row_counts[i] = cnt;
+}
+
+__global__ void set_last_zero(long long *p, long long n) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) p[n] = 0;
+}
+
+static int scan_i64(mkb_ctx *h, cudaStream_t st, long long *in, long long *out, long long n) {
+    if (n >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "too many rows for one call (%lld)", n);
+    size_t tmp_bytes = 0;
+    MKB_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, st));
+    void *tmp = nullptr;
+    int rc = scratch_get(h, S_SCAN_TMP, tmp_bytes, &tmp);
+    if (rc) return rc;
+    MKB_CUDA(h, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)n, st));
+    h->launches++;
+    return MKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: group reductions
+// ---------------------------------------------------------------------------------------------------------
+// _calc_com (distance_utils.pyx:160-183): sequential float sums in atom order, product rounded before the add.
+__global__ void com_kernel(const float4 *__restrict__ G, long long nflat, long long n_frames,
+                           const long long *__restrict__ off, long long ngroups, const int *__restrict__ atoms,
+                           const float *__restrict__ masses, float4 *__restrict__ com) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_frames * ngroups) return;
+    const long long f = t / ngroups, g = t - f * ngroups;
+    float tm = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
+    for (long long k = off[g]; k < off[g + 1]; ++k) {
+        const float4 p = G[f * nflat + k];
+        const float m = masses[atoms[k]];
+        cx = __fadd_rn(cx, __fmul_rn(p.x, m));
+        cy = __fadd_rn(cy, __fmul_rn(p.y, m));
+        cz = __fadd_rn(cz, __fmul_rn(p.z, m));
+        tm = __fadd_rn(tm, m);
+    }
+    com[t] = make_float4(__fdiv_rn(cx, tm), __fdiv_rn(cy, tm), __fdiv_rn(cz, tm), 0.f);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) reduction_kernel(const float4 *__restrict__ G1, long long nflat1,
+                                                        const float4 *__restrict__ G2, long long nflat2,
+                                                        const float4 *__restrict__ com1,
+                                                        const float4 *__restrict__ com2,
+                                                        const long long *__restrict__ off1, long long NG1,
+                                                        const long long *__restrict__ off2, long long NG2,
+                                                        const unsigned *__restrict__ gch1,
+                                                        const unsigned *__restrict__ gch2, long long n_frames,
+                                                        const float *__restrict__ box, long long box_stride,
+                                                        int selfdist, int pbc, int red1, int red2, int pairs,
+                                                        float truncate, float threshold, long long P,
+                                                        void *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long per_frame = pairs ? NG1 : NG1 * NG2;
+    if (w >= n_frames * per_frame) return;
+    const long long f = w / per_frame, r = w - f * per_frame;
+    long long a, b, col;
+    if (pairs) { a = r; b = r; col = r; }
+    else {
+        a = r / NG2; b = r - a * NG2;
+        if (selfdist) { if (b <= a) return; col = a * NG2 - (a * (a + 1)) / 2 + (b - a - 1); }
+        else col = r;
+    }
+    const bool wrap = pbc && (gch1[a] != gch2[b]);
+    const BoxF bx = load_box(box, box_stride, f);
+    const long long s1 = off1[a], m1 = red1 ? 1 : off1[a + 1] - s1;
+    const long long s2 = off2[b], m2 = red2 ? 1 : off2[b + 1] - s2;
+    const long long total = m1 * m2;
+    float best = INFINITY;  // min over non-NaN candidates
+    float first = 0.f;      // d2 of the first pair: the reference always takes it (mindist = -1 sentinel, pyx:260-275)
+    for (long long p = lane; p < total; p += 32) {
+        const long long ia = p / m2, ib = p - ia * m2;
+        const float4 pa = red1 ? com1[f * NG1 + a] : G1[f * nflat1 + s1 + ia];
+        const float4 pb = red2 ? com2[f * NG2 + b] : G2[f * nflat2 + s2 + ib];
+        const float d2 = pair_d2(pa, pb, bx, wrap);
+        if (p == 0) first = d2;
+        if (d2 < best) best = d2;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    first = __shfl_sync(0xffffffffu, first, 0);
+    if (lane == 0) {
+        float m;
+        if (total <= 0) m = -1.f;             // empty group: sqrt(-1) = NaN like the reference
+        else if (first != first) m = first;   // a NaN first element sticks (all later `<` comparisons are false)
+        else m = best;
+        store_dist<MODE>(out, f * P + col, __fsqrt_rn(m), truncate, threshold);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6: cdist / pdist / squareform
+// ---------------------------------------------------------------------------------------------------------
+__global__ void cdist_kernel(const float *__restrict__ a, long long n1, const float *__restrict__ b, long long n2, int D,
+                             float *__restrict__ out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (j >= n2 || i >= n1) return;
+    float s = 0.f;
+    for (int k = 0; k < D; ++k) {
+        const float d = __fsub_rn(a[i * D + k], b[j * D + k]);
+        s = __fadd_rn(s, __fmul_rn(d, d));
+    }
+    out[i * n2 + j] = __fsqrt_rn(s);
+}
+
+__global__ void pdist_kernel(const float *__restrict__ a, long long n, int D, float *__restrict__ out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (j >= n || j <= i) return;
+    float s = 0.f;
+    for (int k = 0; k < D; ++k) {
+        const float d = __fsub_rn(a[i * D + k], a[j * D + k]);
+        s = __fadd_rn(s, __fmul_rn(d, d));
+    }
+    out[i * n - (i * (i + 1)) / 2 + (j - i - 1)] = __fsqrt_rn(s);
+}
+
+__global__ void squareform_kernel(const float *__restrict__ d, long long dim, float *__restrict__ out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (j >= dim || i >= dim) return;
+    float v = 0.f;
+    if (i != j) {
+        const long long lo = min(i, j), hi = max(i, j);
+        v = d[lo * dim - (lo * (lo + 1)) / 2 + (hi - lo - 1)];
+    }
+    out[i * dim + j] = v;
+}
+
+static int check_traj(mkb_ctx *h, const mkb_traj *t) {
+    if (!t) return fail(h, MKB_ERR_BAD_ARG, "null trajectory view");
+    if (t->n_atoms < 0 || t->n_frames < 0) return fail(h, MKB_ERR_BAD_ARG, "negative trajectory size");
+    if (t->n_frames > 0 && (!t->coords || !t->box)) return fail(h, MKB_ERR_BAD_ARG, "null coords/box");
+    if (t->frame_stride < t->n_frames || t->frame_stride_box < t->n_frames)
+        return fail(h, MKB_ERR_BAD_ARG, "frame_stride smaller than n_frames");
+    return MKB_OK;
+}
+
+}  // namespace mkb
+
+using namespace mkb;
+
+extern "C" int mkb_dist_trajectory(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *sel1, int64_t n1,
+                                   const uint32_t *sel2, int64_t n2, const uint32_t *chains, int32_t selfdist,
+                                   int32_t pbc, int32_t mode, float truncate, float threshold, void *out) {
+    MKB_ENTER(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_traj(h, t);
+    if (rc) return rc;
+    if (n1 < 0 || n2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative selection size");
+    if (mode != MKB_DIST_DISTANCES && mode != MKB_DIST_CONTACTS) return fail(h, MKB_ERR_BAD_ARG, "bad mode %d", mode);
+    if (selfdist && n1 != n2) return fail(h, MKB_ERR_BAD_ARG, "selfdist needs sel1 == sel2");
+    const long long P = selfdist ? (n1 * (n2 - 1)) / 2 : n1 * n2;
+    if (t->n_frames == 0 || P <= 0) return MKB_OK;
+    if (!sel1 || !sel2 || !chains || !out) return fail(h, MKB_ERR_BAD_ARG, "null argument");
+    float4 *G;
+    const long long F = t->n_frames;
+    if ((rc = scratch_get(h, S_SORT_PX, (size_t)(F * (n1 + n2)), &G))) return rc;
+    float4 *G1 = G, *G2 = G + F * n1;
+    if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[0], st));
+    if ((rc = launch_gather<uint32_t>(h, st, t, sel1, n1, chains, G1))) return rc;
+    if ((rc = launch_gather<uint32_t>(h, st, t, sel2, n2, chains, G2))) return rc;
+    if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
+    const unsigned gx = (unsigned)cdiv(n2, K3_COLS), gy = (unsigned)cdiv(n1, K3_ROWS);
+    if (gy > 65535) return fail(h, MKB_ERR_BAD_ARG, "sel1 too large for one call (%lld)", (long long)n1);
+    for (long long f0 = 0; f0 < F; f0 += 65535) {
+        const unsigned gz = (unsigned)std::min<long long>(65535, F - f0);
+        dim3 grid(gx, gy, gz);
+        if (mode == MKB_DIST_DISTANCES)
+            dist_kernel<MKB_DIST_DISTANCES><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box,
+                                                                      selfdist, pbc, truncate, threshold, P, out, f0);
+        else
+            dist_kernel<MKB_DIST_CONTACTS><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box,
+                                                                     selfdist, pbc, truncate, threshold, P, out, f0);
+        MKB_LAUNCHED(h);
+    }
+    if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));
+    return MKB_OK;
+}
+
+static int contacts_common(mkb_ctx *h, cudaStream_t st, const mkb_traj *t, const uint32_t *sel1, int64_t n1,
+                           const uint32_t *sel2, int64_t n2, const uint32_t *chains, float4 **G1, float4 **G2) {
+    int rc = check_traj(h, t);
+    if (rc) return rc;
+    if (n1 < 0 || n2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative selection size");
+    if (t->n_frames * n1 > 0 && (!sel1 || !sel2 || !chains)) return fail(h, MKB_ERR_BAD_ARG, "null argument");
+    float4 *G;
+    const long long F = t->n_frames;
+    if ((rc = scratch_get(h, S_SORT_PX, (size_t)std::max<long long>(F * (n1 + n2), 1), &G))) return rc;
+    *G1 = G;
+    *G2 = G + F * n1;
+    if ((rc = launch_gather<uint32_t>(h, st, t, sel1, n1, chains, *G1))) return rc;
+    if ((rc = launch_gather<uint32_t>(h, st, t, sel2, n2, chains, *G2))) return rc;
+    return MKB_OK;
+}
+
+extern "C" int mkb_contacts_count(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *sel1, int64_t n1,
+                                  const uint32_t *sel2, int64_t n2, const uint32_t *chains, int32_t selfdist,
+                                  int32_t pbc, float threshold, int64_t *row_offsets, int64_t *total_pairs) {
+    MKB_ENTER(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!row_offsets || !total_pairs) return fail(h, MKB_ERR_BAD_ARG, "null row_offsets/total_pairs");
+    float4 *G1, *G2;
+    int rc = contacts_common(h, st, t, sel1, n1, sel2, n2, chains, &G1, &G2);
+    if (rc) return rc;
+    const long long rows = t->n_frames * n1;
+    long long *counts;
+    if ((rc = scratch_get(h, S_ROWCNT, (size_t)rows + 1, &counts))) return rc;
+    const float thr2 = threshold * threshold;  // float product, distance_utils.pyx:77
+    if (rows > 0) {
+        contacts_kernel<false><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(
+            G1, G2, n1, n2, t->n_frames, t->box, t->frame_stride_box, selfdist, pbc, thr2, sel1, sel2, counts,
+            nullptr, nullptr);
+        MKB_LAUNCHED(h);
+    }
+    set_last_zero<<<1, 32, 0, st>>>(counts, rows);
+    MKB_LAUNCHED(h);
+    if ((rc = scan_i64(h, st, counts, (long long *)row_offsets, rows + 1))) return rc;
+    long long total = 0;
+    MKB_CUDA(h, cudaMemcpyAsync(&total, row_offsets + rows, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    MKB_CUDA(h, cudaStreamSynchronize(st));
+    *total_pairs = total;
+    return MKB_OK;
+}
+
+extern "C" int mkb_contacts_fill(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *sel1, int64_t n1,
+                                 const uint32_t *sel2, int64_t n2, const uint32_t *chains, int32_t selfdist,
+                                 int32_t pbc, float threshold, const int64_t *row_offsets, uint32_t *pairs) {
+    MKB_ENTER(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!row_offsets) return fail(h, MKB_ERR_BAD_ARG, "null row_offsets");
+    float4 *G1, *G2;
+    int rc = contacts_common(h, st, t, sel1, n1, sel2, n2, chains, &G1, &G2);
+    if (rc) return rc;
+    const long long rows = t->n_frames * n1;
+    if (rows == 0) return MKB_OK;
+    if (!pairs) return fail(h, MKB_ERR_BAD_ARG, "null pairs");
+    const float thr2 = threshold * threshold;
+    contacts_kernel<true><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(
+        G1, G2, n1, n2, t->n_frames, t->box, t->frame_stride_box, selfdist, pbc, thr2, sel1, sel2, nullptr,
+        (const long long *)row_offsets, pairs);
+    MKB_LAUNCHED(h);
+    return MKB_OK;
+}
+
+extern "C" int mkb_dist_reduction(mkb_handle_t h, void *stream, const mkb_traj *t, const int64_t *g1_off,
+                                  const int32_t *g1_atoms, int64_t NG1, const int64_t *g2_off,
+                                  const int32_t *g2_atoms, int64_t NG2, const uint32_t *gchains1,
+                                  const uint32_t *gchains2, int32_t selfdist, int32_t pbc, const float *masses,
+                                  int32_t red1, int32_t red2, int32_t pairs, int32_t mode, float truncate,
+                                  float threshold, void *out) {
+    MKB_ENTER(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_traj(h, t);
+    if (rc) return rc;
+    if (NG1 < 0 || NG2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative group count");
+    if (mode != MKB_DIST_DISTANCES && mode != MKB_DIST_CONTACTS) return fail(h, MKB_ERR_BAD_ARG, "bad mode %d", mode);
+    if (pairs && NG1 != NG2) return fail(h, MKB_ERR_BAD_ARG, "pairs mode needs as many groups in both sets");
+    if (selfdist && NG1 != NG2) return fail(h, MKB_ERR_BAD_ARG, "selfdist needs identical group sets");
+    const long long P = pairs ? NG1 : (selfdist ? (NG1 * (NG2 - 1)) / 2 : NG1 * NG2);
+    const long long F = t->n_frames;
+    if (F == 0 || P <= 0) return MKB_OK;
+    if (!g1_off || !g2_off || !g1_atoms || !g2_atoms || !gchains1 || !gchains2 || !masses || !out)
+        return fail(h, MKB_ERR_BAD_ARG, "null argument");
+    // group sizes live on the device; the flat lengths are the last offsets (tiny D2H, synchronising)
+    long long nf1 = 0, nf2 = 0;
+    MKB_CUDA(h, cudaMemcpyAsync(&nf1, g1_off + NG1, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    MKB_CUDA(h, cudaMemcpyAsync(&nf2, g2_off + NG2, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    MKB_CUDA(h, cudaStreamSynchronize(st));
+    if (nf1 < 0 || nf2 < 0) return fail(h, MKB_ERR_BAD_ARG, "bad group offsets");
+    float4 *G, *com;
+    if ((rc = scratch_get(h, S_SORT_PX, (size_t)std::max<long long>(F * (nf1 + nf2), 1), &G))) return rc;
+    if ((rc = scratch_get(h, S_COM, (size_t)(F * (NG1 + NG2)), &com))) return rc;
+    float4 *G1 = G, *G2 = G + F * nf1, *com1 = com, *com2 = com + F * NG1;
+    if ((rc = launch_gather<int32_t>(h, st, t, g1_atoms, nf1, nullptr, G1))) return rc;
+    if ((rc = launch_gather<int32_t>(h, st, t, g2_atoms, nf2, nullptr, G2))) return rc;
+    if (red1) {
+        com_kernel<<<(unsigned)cdiv(F * NG1, 128), 128, 0, st>>>(G1, nf1, F, (const long long *)g1_off, NG1, g1_atoms,
+                                                                masses, com1);
+        MKB_LAUNCHED(h);
+    }
+    if (red2) {
+        com_kernel<<<(unsigned)cdiv(F * NG2, 128), 128, 0, st>>>(G2, nf2, F, (const long long *)g2_off, NG2, g2_atoms,
+                                                                masses, com2);
+        MKB_LAUNCHED(h);
+    }
+    const long long per_frame = pairs ? NG1 : NG1 * NG2;
+    const long long warps = F * per_frame;
+    if (warps * 32 / 256 >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "too many group pairs for one call");
+    const unsigned nb = (unsigned)cdiv(warps * 32, 256);
+    if (mode == MKB_DIST_DISTANCES)
+        reduction_kernel<MKB_DIST_DISTANCES><<<nb, 256, 0, st>>>(
+            G1, nf1, G2, nf2, com1, com2, (const long long *)g1_off, NG1, (const long long *)g2_off, NG2, gchains1,
+            gchains2, F, t->box, t->frame_stride_box, selfdist, pbc, red1, red2, pairs, truncate, threshold, P, out);
+    else
+        reduction_kernel<MKB_DIST_CONTACTS><<<nb, 256, 0, st>>>(
+            G1, nf1, G2, nf2, com1, com2, (const long long *)g1_off, NG1, (const long long *)g2_off, NG2, gchains1,
+            gchains2, F, t->box, t->frame_stride_box, selfdist, pbc, red1, red2, pairs, truncate, threshold, P, out);
+    MKB_LAUNCHED(h);
+    return MKB_OK;
+}
+
+extern "C" int mkb_cdist(mkb_handle_t h, void *stream, const float *a, int64_t n1, const float *b, int64_t n2,
+                         int32_t D, float *out) {
+    MKB_ENTER(h);
+    if (n1 < 0 || n2 < 0 || D < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
+    if (n1 == 0 || n2 == 0) return MKB_OK;
+    if (!a || !b || !out) return fail(h, MKB_ERR_BAD_ARG, "null argument");
+    if (n1 > 65535) return fail(h, MKB_ERR_BAD_ARG, "cdist: at most 65535 rows per call");
+    cdist_kernel<<<dim3((unsigned)cdiv(n2, 128), (unsigned)n1), 128, 0, (cudaStream_t)stream>>>(a, n1, b, n2, D, out);
+    MKB_LAUNCHED(h);
+    return MKB_OK;
+}
+
+extern "C" int mkb_pdist(mkb_handle_t h, void *stream, const float *a, int64_t n, int32_t D, float *out) {
+    MKB_ENTER(h);
+    if (n < 0 || D < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
+    if (n < 2) return MKB_OK;
+    if (!a || !out) return fail(h, MKB_ERR_BAD_ARG, "null argument");
+    if (n > 65535) return fail(h, MKB_ERR_BAD_ARG, "pdist: at most 65535 points per call");
+    pdist_kernel<<<dim3((unsigned)cdiv(n, 128), (unsigned)n), 128, 0, (cudaStream_t)stream>>>(a, n, D, out);
+    MKB_LAUNCHED(h);
+    return MKB_OK;
+}
+
+extern "C" int mkb_squareform(mkb_handle_t h, void *stream, const float *d, int64_t n, int64_t dim, float *out) {
+    MKB_ENTER(h);
+    if (n < 0 || dim < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
+    if (dim == 0) return MKB_OK;
+    if (!out || (n > 0 && !d)) return fail(h, MKB_ERR_BAD_ARG, "null argument");
+    if (dim * (dim - 1) / 2 > n) return fail(h, MKB_ERR_BAD_ARG, "condensed vector too short for dim %lld", (long long)dim);
+    if (dim > 65535) return fail(h, MKB_ERR_BAD_ARG, "squareform: dim too large");
+    squareform_kernel<<<dim3((unsigned)cdiv(dim, 128), (unsigned)dim), 128, 0, (cudaStream_t)stream>>>(d, dim, out);
+    MKB_LAUNCHED(h);
+    return MKB_OK;
+}
+
+extern "C" int mkb_collisions_count(mkb_handle_t h, void *stream, const float *c1, int64_t n1, const float *c2,
+                                    int64_t n2, float threshold, int64_t *row_offsets, int64_t *total_pairs) {
+    MKB_ENTER(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n1 < 0 || n2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
+    if (!row_offsets || !total_pairs) return fail(h, MKB_ERR_BAD_ARG, "null row_offsets/total_pairs");
+    if (n1 > 0 && n2 > 0 && (!c1 || !c2)) return fail(h, MKB_ERR_BAD_ARG, "null coordinates");
+    long long *counts;
+    int rc;
+    if ((rc = scratch_get(h, S_ROWCNT, (size_t)n1 + 1, &counts))) return rc;
+    const float thr2 = threshold * threshold;
+    if (n1 > 0) {
+        collisions_kernel<false><<<(unsigned)cdiv(n1 * 32, 256), 256, 0, st>>>(c1, n1, c2, n2, thr2, counts, nullptr,
+                                                                               nullptr);
+        MKB_LAUNCHED(h);
+    }
+    set_last_zero<<<1, 32, 0, st>>>(counts, n1);
+    MKB_LAUNCHED(h);
+    if ((rc = scan_i64(h, st, counts, (long long *)row_offsets, n1 + 1))) return rc;
+    long long total = 0;
+    MKB_CUDA(h, cudaMemcpyAsync(&total, row_offsets + n1, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    MKB_CUDA(h, cudaStreamSynchronize(st));
+    *total_pairs = total;
+    return MKB_OK;
+}
+
+extern "C" int mkb_collisions_fill(mkb_handle_t h, void *stream, const float *c1, int64_t n1, const float *c2,
+                                   int64_t n2, float threshold, const int64_t *row_offsets, uint32_t *pairs) {
+    MKB_ENTER(h);
+    if (n1 < 0 || n2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
+    if (n1 == 0 || n2 == 0) return MKB_OK;
+    if (!c1 || !c2 || !row_offsets || !pairs) return fail(h, MKB_ERR_BAD_ARG, "null argument");
+    const float thr2 = threshold * threshold;
+    collisions_kernel<true><<<(unsigned)cdiv(n1 * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        c1, n1, c2, n2, thr2, nullptr, (const long long *)row_offsets, pairs);
+    MKB_LAUNCHED(h);
+    return MKB_OK;
+}

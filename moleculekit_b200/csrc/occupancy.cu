@@ -1,0 +1,617 @@
+// occupancy.cu -- K1/K1b/K2: voxel occupancy for sm_100a.
+//
+// Replaces moleculekit/occupancy_utils/occupancy_utils.pyx:34-61 (calculate_occupancy) and the grid-centre
+// materialisation of moleculekit/tools/voxeldescriptors.py:125-132,197-248 on the device.
+//
+// Algorithm (not a translation of the reference's atoms x centres double loop):
+//   value(c,h) = max_a [ d2 < 25 ] (1 - exp(-(sigma_ah^2/d2)^6)).   f(q) = 1 - exp(-q^6) is monotone in
+//   q = sigma^2/d2, so the max over atoms commutes with f: the hot loop only tracks max q per voxel-channel and the
+//   transcendental runs ONCE per voxel-channel in the epilogue.
+//   K2  bin atoms of every grid of the batch into 8-voxel cells (count -> cub scan -> scatter), positions kept as
+//       float64 voxel coordinates p' = (x - origin)/voxelsize.
+//   K1  one CTA (512 threads) per 8x8x8-voxel tile: gather the tile's halo atoms from <= (R+1)^2 contiguous cell rows
+//       into shared memory as float positions RELATIVE TO THE TILE CORNER (|rel| < 32, so fp32 keeps ~5e-7 voxel
+//       absolute accuracy wherever the molecule sits), then each warp owns a 2x4x4 voxel block, culls the list
+//       against its block with one ballot per 32 atoms and accumulates max q in registers (8 channels = 8 FMNMX).
+//       Pairs whose d2 falls within 4e-6 (relative) of the 5 A gate are re-evaluated in float64 with the reference's
+//       exact operation order, so the discontinuity at the gate is reproduced bit-for-bit.
+//       Output: coalesced 32-byte (8-channel) streaming stores, 4 lanes = one 128-byte line.
+// HBM-bound gather-accumulate: no tensor cores (max of a transcendental is not a contraction).
+#include <cub/device/device_scan.cuh>
+
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mkb {
+
+constexpr int TILE = 8;
+constexpr int FILL_THREADS = 512;
+constexpr int LIST_CAP = 1536;
+constexpr double CUTOFF_A = 5.0;      // occupancy_utils.pyx:53: dist2 < 25
+constexpr float GATE_BAND = 4e-6f;    // relative half-width of the float64 re-check band around the gate
+
+struct GridDev {
+    double origin[3];
+    double vs;
+    double inv_vs;
+    int dims[3];
+    int tiles[3];
+    int cells[3];
+    int cutv;    // halo in voxels: ceil(5 / vs)
+    int rcells;  // neighbour reach in cells: (TILE - 1 + 2 cutv) / TILE
+    float cut2v, cut2v_lo, cut2v_hi;  // (5/vs)^2 in voxel units and the re-check band
+    float pad0;
+    long long atom_begin, atom_end, out_offset;
+    long long item_base, tile_base, cell_base;
+};
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// 1 - exp(-q^6), q = sigma^2/d2  (== 1 - exp(-(sigma/r)^12), occupancy_utils.pyx:57-60), relative error ~1e-6.
+__device__ __forceinline__ float occ_value(float q) {
+    const float q2 = q * q;
+    const float q3 = q2 * q;
+    const float t = q3 * q3;
+    // small t: -expm1(-t) by Taylor (avoids the cancellation that costs 0.4 relative error in naive fp32)
+    float s = fmaf(t, 1.0f / 5040.0f, -1.0f / 720.0f);
+    s = fmaf(t, s, 1.0f / 120.0f);
+    s = fmaf(t, s, -1.0f / 24.0f);
+    s = fmaf(t, s, 1.0f / 6.0f);
+    s = fmaf(t, s, -0.5f);
+    s = fmaf(t, s, 1.0f);
+    s = s * t;
+    const float b = 1.0f - ex2_approx(t * -1.4426950408889634f);
+    return t < 0.25f ? s : b;
+}
+
+__device__ __forceinline__ int find_grid_item(const GridDev *g, int B, long long v) {
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (g[mid].item_base <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ int find_grid_tile(const GridDev *g, int B, long long v) {
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (g[mid].tile_base <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2a: per (grid, atom) item -> cell id + slot inside the cell (atomic counter).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void occ_bin_kernel(const float *__restrict__ coords, const GridDev *__restrict__ grids, int B,
+                               long long n_items, int *__restrict__ item_cell, unsigned *__restrict__ item_slot,
+                               unsigned *__restrict__ cell_count) {
+    const long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const int b = find_grid_item(grids, B, it);
+    const GridDev &g = grids[b];
+    const long long a = g.atom_begin + (it - g.item_base);
+    int c[3];
+    bool live = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double p = ((double)coords[3 * a + d] - g.origin[d]) * g.inv_vs;
+        // atoms farther than the 5 A halo from the grid cannot touch any voxel (NaN fails both tests)
+        live = live && (p >= -(double)g.cutv) && (p <= (double)(g.dims[d] - 1 + g.cutv));
+        int ci = live ? (int)floor((p + (double)g.cutv) * (1.0 / TILE)) : 0;
+        c[d] = min(max(ci, 0), g.cells[d] - 1);
+    }
+    if (!live) {
+        item_cell[it] = -1;
+        return;
+    }
+    const int cid = (c[0] * g.cells[1] + c[1]) * g.cells[2] + c[2];
+    item_cell[it] = cid;
+    item_slot[it] = atomicAdd(&cell_count[g.cell_base + cid], 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2b: scatter items into cell order (SoA).  sigma handling: the common case (moleculekit's boolean channels times
+// one vdW radius, voxeldescriptors.py:332-335) has ONE distinct non-zero sigma per atom -> one s2 and a channel
+// bit mask.  Atoms with several distinct sigmas are flagged (bit 31 of src) and take a per-channel path in K1.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void occ_scatter_kernel(const float *__restrict__ coords, const double *__restrict__ sigmas, int C,
+                                   const GridDev *__restrict__ grids, int B, long long n_items,
+                                   const int *__restrict__ item_cell, const unsigned *__restrict__ item_slot,
+                                   const unsigned *__restrict__ cell_start, double *__restrict__ px,
+                                   double *__restrict__ py, double *__restrict__ pz, float *__restrict__ s2,
+                                   unsigned *__restrict__ mask, unsigned *__restrict__ src) {
+    const long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const int cid = item_cell[it];
+    if (cid < 0) return;
+    const int b = find_grid_item(grids, B, it);
+    const GridDev &g = grids[b];
+    const long long a = g.atom_begin + (it - g.item_base);
+    const unsigned dst = cell_start[g.cell_base + cid] + item_slot[it];
+    px[dst] = ((double)coords[3 * a + 0] - g.origin[0]) * g.inv_vs;
+    py[dst] = ((double)coords[3 * a + 1] - g.origin[1]) * g.inv_vs;
+    pz[dst] = ((double)coords[3 * a + 2] - g.origin[2]) * g.inv_vs;
+    const double *sg = sigmas + a * C;
+    double first = 0.0;
+    unsigned m = 0;
+    bool multi = false;
+    for (int h = 0; h < C; ++h) {
+        const double s = sg[h];
+        if (s == 0.0 || s != s) continue;  // sigma == 0 skipped (pyx:56); NaN never wins the max (pyx:61)
+        if (m == 0) { first = s; m = 1u << h; }
+        else if (s == first) m |= 1u << h;
+        else multi = true;
+    }
+    const double sv = first * g.inv_vs;  // sigma in voxel units
+    s2[dst] = m ? fmaxf((float)(sv * sv), FLT_MIN) : 0.0f;
+    mask[dst] = m;
+    src[dst] = (unsigned)a | (multi ? 0x80000000u : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: tile fill.
+// ---------------------------------------------------------------------------------------------------------
+struct FillParams {
+    const GridDev *grids;
+    int B, C;
+    const double *px, *py, *pz;
+    const float *s2;
+    const unsigned *mask, *src;
+    const unsigned *cell_start;
+    const float *coords;
+    const double *sigmas;
+    float *out;
+    unsigned flags;
+    int vec_ok;
+};
+
+// float64 re-evaluation of the gate with the reference's exact operations (pyx:49-53; centres as built by
+// voxeldescriptors.py:125-132,245: fl(fl(i*vs) + origin)).
+__device__ __noinline__ bool exact_gate(const GridDev *g, const float *coords, unsigned a, int ix, int iy, int iz) {
+    const double cx = __dadd_rn(__dmul_rn((double)ix, g->vs), g->origin[0]);
+    const double cy = __dadd_rn(__dmul_rn((double)iy, g->vs), g->origin[1]);
+    const double cz = __dadd_rn(__dmul_rn((double)iz, g->vs), g->origin[2]);
+    const double dx = (double)coords[3ll * a + 0] - cx;
+    const double dy = (double)coords[3ll * a + 1] - cy;
+    const double dz = (double)coords[3ll * a + 2] - cz;
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    return d2 < CUTOFF_A * CUTOFF_A;
+}
+
+template <int CP>
+__global__ void __launch_bounds__(FILL_THREADS, (CP <= 8 ? 2 : 1)) occ_fill_kernel(const FillParams p) {
+    __shared__ float4 s_ent[LIST_CAP];   // x, y, z relative to the tile corner (voxel units), w = sigma^2 (voxel units)
+    __shared__ unsigned s_mask[LIST_CAP];
+    __shared__ unsigned s_src[LIST_CAP];
+    __shared__ int s_cnt;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile = blockIdx.x;
+    const GridDev *g = p.grids + find_grid_tile(p.grids, p.B, tile);
+
+    const int nx = g->dims[0], ny = g->dims[1], nz = g->dims[2];
+    const int local = (int)(tile - g->tile_base);
+    const int tzN = g->tiles[2], tyN = g->tiles[1];
+    const int tz = local % tzN, ty = (local / tzN) % tyN, tx = local / (tzN * tyN);
+
+    // warp -> 2x4x4 voxel block of the tile, lane -> voxel (z fastest so 4 lanes cover one 128-byte output line)
+    const int bx = warp >> 2, by = (warp >> 1) & 1, bz = warp & 1;
+    const int vx = bx * 2 + (lane >> 4), vy = by * 4 + ((lane >> 2) & 3), vz = bz * 4 + (lane & 3);
+    const float fvx = (float)vx, fvy = (float)vy, fvz = (float)vz;
+    const float bcx = (float)(bx * 2), bcy = (float)(by * 4), bcz = (float)(bz * 4);
+    const int ix = tx * TILE + vx, iy = ty * TILE + vy, iz = tz * TILE + vz;
+
+    const float cut2v = g->cut2v, cut_lo = g->cut2v_lo, cut_hi = g->cut2v_hi;
+    const int C = p.C;
+
+    float acc[CP];
+#pragma unroll
+    for (int h = 0; h < CP; ++h) acc[h] = 0.0f;
+    bool touched = false;
+
+    // cell rows feeding this tile: cells [tx, tx+R] x [ty, ty+R], each a contiguous z-run [tz, tz+R]
+    const int R = g->rcells;
+    const int cN1 = g->cells[1], cN2 = g->cells[2];
+    const int cx1 = min(tx + R, g->cells[0] - 1), cy1 = min(ty + R, cN1 - 1), cz1 = min(tz + R, cN2 - 1);
+    const int ncy = cy1 - ty + 1;
+    const int nrows = (cx1 - tx + 1) * ncy;
+    const double tox = (double)(tx * TILE), toy = (double)(ty * TILE), toz = (double)(tz * TILE);
+
+    int row = 0;
+    unsigned pos = 0, end = 0;
+    bool have_row = false, more = true;
+    while (more) {
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        int est = 0;
+        while (true) {
+            if (!have_row) {
+                if (row >= nrows) { more = false; break; }
+                const int rx = row / ncy, ry = row - rx * ncy;
+                const long long cb = g->cell_base + ((long long)(tx + rx) * cN1 + (ty + ry)) * cN2;
+                pos = __ldg(p.cell_start + cb + tz);
+                end = __ldg(p.cell_start + cb + cz1 + 1);
+                have_row = true;
+            }
+            if (pos >= end) { have_row = false; ++row; continue; }
+            const unsigned n_piece = min(end - pos, (unsigned)FILL_THREADS);
+            if (est + (int)n_piece > LIST_CAP) break;  // flush what we have, then resume from (row, pos)
+            bool pass = false;
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned m = 0, sr = 0;
+            if ((unsigned)tid < n_piece) {
+                const unsigned i = pos + tid;
+                e.x = (float)(p.px[i] - tox);
+                e.y = (float)(p.py[i] - toy);
+                e.z = (float)(p.pz[i] - toz);
+                e.w = p.s2[i];
+                m = p.mask[i];
+                sr = p.src[i];
+                const float ddx = fmaxf(fmaxf(-e.x, e.x - (float)(TILE - 1)), 0.f);
+                const float ddy = fmaxf(fmaxf(-e.y, e.y - (float)(TILE - 1)), 0.f);
+                const float ddz = fmaxf(fmaxf(-e.z, e.z - (float)(TILE - 1)), 0.f);
+                pass = (m != 0) && (ddx * ddx + ddy * ddy + ddz * ddz <= cut_hi);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_cnt, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) {
+                    const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                    s_ent[slot] = e;
+                    s_mask[slot] = m;
+                    s_src[slot] = sr;
+                }
+            }
+            pos += n_piece;
+            est += (int)n_piece;
+        }
+        __syncthreads();
+        const int n = s_cnt;
+
+        // ---- consume: each warp culls the tile list against its 2x4x4 block, then all lanes evaluate the survivors
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int j = c0 + lane;
+            bool hit = false;
+            if (j < n) {
+                const float4 e = s_ent[j];
+                const float rx = e.x - bcx, ry = e.y - bcy, rz = e.z - bcz;
+                const float ddx = fmaxf(fmaxf(-rx, rx - 1.f), 0.f);
+                const float ddy = fmaxf(fmaxf(-ry, ry - 3.f), 0.f);
+                const float ddz = fmaxf(fmaxf(-rz, rz - 3.f), 0.f);
+                hit = (ddx * ddx + ddy * ddy + ddz * ddz) <= cut_hi;
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, hit);
+            touched = touched || (bal != 0);
+            while (bal) {
+                const int k = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const int jj = c0 + k;
+                const float4 e = s_ent[jj];
+                const unsigned sr = s_src[jj];
+                const float dx = e.x - fvx, dy = e.y - fvy, dz = e.z - fvz;
+                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                bool in = d2 < cut2v;
+                if (d2 > cut_lo && d2 < cut_hi)  // within 4e-6 of the gate: decide exactly like the reference
+                    in = exact_gate(g, p.coords, sr & 0x7fffffffu, ix, iy, iz);
+                const float r = in ? rcp_approx(d2) : 0.0f;
+                if (!(sr & 0x80000000u)) {
+                    const unsigned cm = s_mask[jj];
+                    const float q = e.w * r;  // (sigma^2/d2); 0 outside the gate; +inf at d2 == 0 -> value 1
+#pragma unroll
+                    for (int h = 0; h < CP; ++h)
+                        if (cm & (1u << h)) acc[h] = fmaxf(acc[h], q);
+                } else {
+                    // several distinct sigmas on this atom: per-channel q (user-supplied float channels)
+                    const double *sg = p.sigmas + (long long)(sr & 0x7fffffffu) * C;
+                    const double ivs = g->inv_vs;
+#pragma unroll
+                    for (int h = 0; h < CP; ++h) {
+                        if (h < C) {
+                            const double s = sg[h] * ivs;
+                            const float sq = (s == 0.0 || s != s) ? 0.0f : fmaxf((float)(s * s), FLT_MIN);
+                            acc[h] = fmaxf(acc[h], sq * r);  // 0*inf = NaN is dropped by fmaxf
+                        }
+                    }
+                }
+            }
+        }
+        if (more) __syncthreads();  // list is about to be overwritten
+    }
+
+    // ---- epilogue: one transcendental per voxel-channel, streaming 32-byte stores
+    if (ix < nx && iy < ny && iz < nz) {
+        float v[CP];
+        if (touched) {
+#pragma unroll
+            for (int h = 0; h < CP; ++h) v[h] = occ_value(acc[h]);
+        } else {
+#pragma unroll
+            for (int h = 0; h < CP; ++h) v[h] = 0.0f;
+        }
+        float *o = p.out + (g->out_offset + ((long long)ix * ny + iy) * nz + iz) * C;
+        if (p.flags & MKB_OCC_ACCUMULATE) {
+#pragma unroll
+            for (int h = 0; h < CP; ++h)
+                if (h < C) { const float old = o[h]; v[h] = (v[h] > old) ? v[h] : old; }  // pyx:61 `value > old`
+        }
+        if (CP == 8 && p.vec_ok) {
+            __stcs(reinterpret_cast<float4 *>(o), make_float4(v[0], v[1], v[2], v[3]));
+            __stcs(reinterpret_cast<float4 *>(o) + 1, make_float4(v[4], v[5], v[6], v[7]));
+        } else {
+#pragma unroll
+            for (int h = 0; h < CP; ++h)
+                if (h < C) o[h] = v[h];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1b: arbitrary centres.  Atoms hashed into 5 A cells (count -> scan -> order); one thread per centre visits the
+// 27 neighbouring buckets.  Distances in float64 exactly as the reference (pyx:49-53), so the gate is exact.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cell_hash(long long cx, long long cy, long long cz, unsigned hmask) {
+    const unsigned long long h = (unsigned long long)cx * 73856093ull ^ (unsigned long long)cy * 19349663ull ^
+                                 (unsigned long long)cz * 83492791ull;
+    return (unsigned)((h ^ (h >> 23)) & hmask);
+}
+
+constexpr double PT_LIMIT = 1e12;  // beyond this nothing can be within 5 A in float32 coordinates that matter
+
+__global__ void pt_bin_kernel(const float *__restrict__ coords, long long n, unsigned hmask,
+                              int *__restrict__ item_bucket, unsigned *__restrict__ item_slot,
+                              unsigned *__restrict__ bucket_count) {
+    const long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const double x = coords[3 * a], y = coords[3 * a + 1], z = coords[3 * a + 2];
+    if (!(fabs(x) < PT_LIMIT && fabs(y) < PT_LIMIT && fabs(z) < PT_LIMIT)) { item_bucket[a] = -1; return; }
+    const unsigned bkt = cell_hash((long long)floor(x * (1.0 / CUTOFF_A)), (long long)floor(y * (1.0 / CUTOFF_A)),
+                                   (long long)floor(z * (1.0 / CUTOFF_A)), hmask);
+    item_bucket[a] = (int)bkt;
+    item_slot[a] = atomicAdd(&bucket_count[bkt], 1u);
+}
+
+__global__ void pt_order_kernel(long long n, const int *__restrict__ item_bucket, const unsigned *__restrict__ item_slot,
+                                const unsigned *__restrict__ bucket_start, unsigned *__restrict__ order) {
+    const long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int b = item_bucket[a];
+    if (b < 0) return;
+    order[bucket_start[b] + item_slot[a]] = (unsigned)a;
+}
+
+__global__ void pt_sigma_kernel(const double *__restrict__ sigmas, long long n, float *__restrict__ s2) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double s = sigmas[i];
+    s2[i] = (s == 0.0 || s != s) ? 0.0f : fmaxf((float)(s * s), FLT_MIN);
+}
+
+template <int CP>
+__global__ void __launch_bounds__(128) occ_points_kernel(const double *__restrict__ centers, long long M,
+                                                         const float *__restrict__ coords,
+                                                         const float *__restrict__ s2, int C, unsigned hmask,
+                                                         const unsigned *__restrict__ bucket_start,
+                                                         const unsigned *__restrict__ order, float *__restrict__ out,
+                                                         unsigned flags) {
+    const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const double cx = centers[3 * m], cy = centers[3 * m + 1], cz = centers[3 * m + 2];
+    float acc[CP];
+#pragma unroll
+    for (int h = 0; h < CP; ++h) acc[h] = 0.0f;
+    if (fabs(cx) < PT_LIMIT && fabs(cy) < PT_LIMIT && fabs(cz) < PT_LIMIT) {
+        const long long kx = (long long)floor(cx * (1.0 / CUTOFF_A)), ky = (long long)floor(cy * (1.0 / CUTOFF_A)),
+                        kz = (long long)floor(cz * (1.0 / CUTOFF_A));
+        for (int n = 0; n < 27; ++n) {
+            const unsigned bkt = cell_hash(kx + (n / 9) - 1, ky + ((n / 3) % 3) - 1, kz + (n % 3) - 1, hmask);
+            const unsigned s = bucket_start[bkt], e = bucket_start[bkt + 1];
+            for (unsigned i = s; i < e; ++i) {
+                const unsigned a = order[i];
+                const double dx = (double)coords[3ll * a + 0] - cx;
+                const double dy = (double)coords[3ll * a + 1] - cy;
+                const double dz = (double)coords[3ll * a + 2] - cz;
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (d2 < CUTOFF_A * CUTOFF_A) {
+                    const float r = rcp_approx((float)d2);
+                    const float *sa = s2 + (long long)a * C;
+#pragma unroll
+                    for (int h = 0; h < CP; ++h)
+                        if (h < C) acc[h] = fmaxf(acc[h], sa[h] * r);  // A^2/A^2: same q as the grid path
+                }
+            }
+        }
+    }
+    float *o = out + m * C;
+#pragma unroll
+    for (int h = 0; h < CP; ++h) {
+        if (h < C) {
+            float v = occ_value(acc[h]);
+            if (flags & MKB_OCC_ACCUMULATE) { const float old = o[h]; v = (v > old) ? v : old; }
+            o[h] = v;
+        }
+    }
+}
+
+static int scan_u32(mkb_ctx *h, cudaStream_t st, unsigned *in, unsigned *out, long long n) {
+    size_t tmp_bytes = 0;
+    MKB_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, st));
+    void *tmp = nullptr;
+    int rc = scratch_get(h, S_SCAN_TMP, tmp_bytes, &tmp);
+    if (rc) return rc;
+    MKB_CUDA(h, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)n, st));
+    h->launches++;
+    return MKB_OK;
+}
+
+}  // namespace mkb
+
+using namespace mkb;
+
+extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
+                                        int64_t n_atoms, int32_t C, const mkb_grid_desc *grids, int32_t B,
+                                        float *out, uint32_t flags) {
+    MKB_ENTER(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B < 0 || n_atoms < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
+    if (C < 1 || C > 32) return fail(h, MKB_ERR_BAD_ARG, "C=%d: 1..32 channels per call (split wider channel sets)", C);
+    if (B == 0) return MKB_OK;
+    if (!grids || !out) return fail(h, MKB_ERR_BAD_ARG, "null grids/out");
+    if (n_atoms >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "n_atoms must be < 2^31");
+    if (n_atoms > 0 && (!coords || !sigmas)) return fail(h, MKB_ERR_BAD_ARG, "null coords/sigmas");
+
+    std::vector<GridDev> gd((size_t)B);
+    long long items = 0, tiles = 0, cells = 0;
+    for (int b = 0; b < B; ++b) {
+        const mkb_grid_desc &s = grids[b];
+        GridDev &g = gd[b];
+        if (!(s.voxelsize > 0.0) || !std::isfinite(s.voxelsize))
+            return fail(h, MKB_ERR_BAD_ARG, "grid %d: voxelsize must be positive and finite", b);
+        if (s.atom_begin < 0 || s.atom_end < s.atom_begin || s.atom_end > n_atoms)
+            return fail(h, MKB_ERR_BAD_ARG, "grid %d: bad atom range [%lld, %lld)", b, (long long)s.atom_begin,
+                        (long long)s.atom_end);
+        if (s.out_offset < 0) return fail(h, MKB_ERR_BAD_ARG, "grid %d: negative out_offset", b);
+        const double cut = CUTOFF_A / s.voxelsize;
+        if (cut > 4096.0) return fail(h, MKB_ERR_BAD_ARG, "grid %d: voxelsize %g too small", b, s.voxelsize);
+        g.vs = s.voxelsize;
+        g.inv_vs = 1.0 / s.voxelsize;
+        g.cutv = (int)std::ceil(cut);
+        g.rcells = (TILE - 1 + 2 * g.cutv) / TILE;
+        g.cut2v = (float)(cut * cut);
+        g.cut2v_lo = g.cut2v * (1.0f - GATE_BAND);
+        g.cut2v_hi = g.cut2v * (1.0f + GATE_BAND);
+        g.pad0 = 0.f;
+        long long nt = 1, nc = 1;
+        for (int d = 0; d < 3; ++d) {
+            if (s.dims[d] <= 0) return fail(h, MKB_ERR_BAD_ARG, "grid %d: dims must be positive", b);
+            if (!std::isfinite(s.origin[d])) return fail(h, MKB_ERR_BAD_ARG, "grid %d: origin not finite", b);
+            g.origin[d] = s.origin[d];
+            g.dims[d] = s.dims[d];
+            g.tiles[d] = (s.dims[d] + TILE - 1) / TILE;
+            g.cells[d] = (s.dims[d] + 2 * g.cutv + TILE - 1) / TILE;
+            nt *= g.tiles[d];
+            nc *= g.cells[d];
+        }
+        g.atom_begin = s.atom_begin;
+        g.atom_end = s.atom_end;
+        g.out_offset = s.out_offset;
+        g.item_base = items;
+        g.tile_base = tiles;
+        g.cell_base = cells;
+        items += s.atom_end - s.atom_begin;
+        tiles += nt;
+        cells += nc;
+    }
+    if (tiles >= (1ll << 31) - 1) return fail(h, MKB_ERR_BAD_ARG, "too many tiles (%lld): split the batch", tiles);
+    if (cells >= (1ll << 31) - 2 || items >= (1ll << 31))
+        return fail(h, MKB_ERR_BAD_ARG, "batch too large (%lld cells, %lld atom items): split it", cells, items);
+
+    GridDev *d_grids;
+    int *item_cell;
+    unsigned *item_slot, *cell_count, *cell_start, *mask, *src;
+    double *px, *py, *pz;
+    float *s2;
+    int rc;
+    const size_t ni = (size_t)std::max<long long>(items, 1);
+    if ((rc = scratch_get(h, S_DESC, (size_t)B, &d_grids))) return rc;
+    if ((rc = scratch_get(h, S_ITEM_CELL, ni, &item_cell))) return rc;
+    if ((rc = scratch_get(h, S_ITEM_SLOT, ni, &item_slot))) return rc;
+    if ((rc = scratch_get(h, S_CELL_COUNT, (size_t)cells + 1, &cell_count))) return rc;
+    if ((rc = scratch_get(h, S_CELL_START, (size_t)cells + 1, &cell_start))) return rc;
+    if ((rc = scratch_get(h, S_SORT_PX, ni, &px))) return rc;
+    if ((rc = scratch_get(h, S_SORT_PY, ni, &py))) return rc;
+    if ((rc = scratch_get(h, S_SORT_PZ, ni, &pz))) return rc;
+    if ((rc = scratch_get(h, S_SORT_S2, ni, &s2))) return rc;
+    if ((rc = scratch_get(h, S_SORT_MASK, ni, &mask))) return rc;
+    if ((rc = scratch_get(h, S_SORT_SRC, ni, &src))) return rc;
+
+    if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[0], st));
+    MKB_CUDA(h, cudaMemcpyAsync(d_grids, gd.data(), sizeof(GridDev) * (size_t)B, cudaMemcpyHostToDevice, st));
+    MKB_CUDA(h, cudaMemsetAsync(cell_count, 0, sizeof(unsigned) * ((size_t)cells + 1), st));
+    if (items > 0) {
+        const int nb = (int)cdiv(items, 256);
+        occ_bin_kernel<<<nb, 256, 0, st>>>(coords, d_grids, B, items, item_cell, item_slot, cell_count);
+        MKB_LAUNCHED(h);
+    }
+    if ((rc = scan_u32(h, st, cell_count, cell_start, cells + 1))) return rc;
+    if (items > 0) {
+        const int nb = (int)cdiv(items, 256);
+        occ_scatter_kernel<<<nb, 256, 0, st>>>(coords, sigmas, C, d_grids, B, items, item_cell, item_slot, cell_start,
+                                               px, py, pz, s2, mask, src);
+        MKB_LAUNCHED(h);
+    }
+    FillParams fp;
+    fp.grids = d_grids; fp.B = B; fp.C = C;
+    fp.px = px; fp.py = py; fp.pz = pz; fp.s2 = s2; fp.mask = mask; fp.src = src;
+    fp.cell_start = cell_start; fp.coords = coords; fp.sigmas = sigmas; fp.out = out; fp.flags = flags;
+    fp.vec_ok = (C == 8 && ((uintptr_t)out % 16 == 0)) ? 1 : 0;
+    if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
+    if (C <= 8) occ_fill_kernel<8><<<(unsigned)tiles, FILL_THREADS, 0, st>>>(fp);
+    else if (C <= 16) occ_fill_kernel<16><<<(unsigned)tiles, FILL_THREADS, 0, st>>>(fp);
+    else occ_fill_kernel<32><<<(unsigned)tiles, FILL_THREADS, 0, st>>>(fp);
+    MKB_LAUNCHED(h);
+    if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));
+    return MKB_OK;
+}
+
+extern "C" int mkb_occupancy_points(mkb_handle_t h, void *stream, const double *centers, int64_t M,
+                                    const float *coords, const double *sigmas, int64_t n_atoms, int32_t C,
+                                    float *out, uint32_t flags) {
+    MKB_ENTER(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M < 0 || n_atoms < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
+    if (C < 1 || C > 32) return fail(h, MKB_ERR_BAD_ARG, "C=%d: 1..32 channels per call", C);
+    if (M == 0) return MKB_OK;
+    if (!centers || !out) return fail(h, MKB_ERR_BAD_ARG, "null centers/out");
+    if (n_atoms >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "n_atoms must be < 2^31");
+    if (n_atoms > 0 && (!coords || !sigmas)) return fail(h, MKB_ERR_BAD_ARG, "null coords/sigmas");
+
+    unsigned nb = 1024;
+    while ((long long)nb < 2 * n_atoms && nb < (1u << 22)) nb <<= 1;
+    const unsigned hmask = nb - 1;
+    int *item_bucket;
+    unsigned *item_slot, *bcount, *bstart, *order;
+    float *s2;
+    int rc;
+    const size_t na = (size_t)std::max<long long>(n_atoms, 1);
+    if ((rc = scratch_get(h, S_ITEM_CELL, na, &item_bucket))) return rc;
+    if ((rc = scratch_get(h, S_ITEM_SLOT, na, &item_slot))) return rc;
+    if ((rc = scratch_get(h, S_CELL_COUNT, (size_t)nb + 1, &bcount))) return rc;
+    if ((rc = scratch_get(h, S_PT_BUCKET, (size_t)nb + 1, &bstart))) return rc;
+    if ((rc = scratch_get(h, S_PT_ORDER, na, &order))) return rc;
+    if ((rc = scratch_get(h, S_PT_S2, na * (size_t)C, &s2))) return rc;
+    MKB_CUDA(h, cudaMemsetAsync(bcount, 0, sizeof(unsigned) * ((size_t)nb + 1), st));
+    if (n_atoms > 0) {
+        const int g1 = (int)cdiv(n_atoms, 256);
+        pt_bin_kernel<<<g1, 256, 0, st>>>(coords, n_atoms, hmask, item_bucket, item_slot, bcount);
+        MKB_LAUNCHED(h);
+        pt_sigma_kernel<<<(int)cdiv(n_atoms * C, 256), 256, 0, st>>>(sigmas, n_atoms * C, s2);
+        MKB_LAUNCHED(h);
+    }
+    if ((rc = scan_u32(h, st, bcount, bstart, (long long)nb + 1))) return rc;
+    if (n_atoms > 0) {
+        pt_order_kernel<<<(int)cdiv(n_atoms, 256), 256, 0, st>>>(n_atoms, item_bucket, item_slot, bstart, order);
+        MKB_LAUNCHED(h);
+    }
+    const unsigned g2 = (unsigned)cdiv(M, 128);
+    if (C <= 8) occ_points_kernel<8><<<g2, 128, 0, st>>>(centers, M, coords, s2, C, hmask, bstart, order, out, flags);
+    else if (C <= 16) occ_points_kernel<16><<<g2, 128, 0, st>>>(centers, M, coords, s2, C, hmask, bstart, order, out, flags);
+    else occ_points_kernel<32><<<g2, 128, 0, st>>>(centers, M, coords, s2, C, hmask, bstart, order, out, flags);
+    MKB_LAUNCHED(h);
+    return MKB_OK;
+}

@@ -1,0 +1,139 @@
+"""Host side of the occupancy kernels: mirror of ``moleculekit.occupancy_utils`` over libmkb200.
+
+``calculate_occupancy(centers, coords, sigmas, results)`` keeps the reference's signature and in-place
+max-accumulate contract (moleculekit/occupancy_utils/occupancy_utils.pyx:34-61); the batched regular-grid entry
+points are what ``tools.voxeldescriptors`` and the benchmark drive.  PyTorch is only the device container.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MAX_CHANNELS_PER_CALL = 32
+
+
+def _dev(device) -> torch.device:
+    if device is None:
+        if not torch.cuda.is_available():
+            raise _lib.MkbError("moleculekit_b200 needs a CUDA device (there is no CPU fallback)")
+        return torch.device("cuda", torch.cuda.current_device())
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise _lib.MkbError(f"moleculekit_b200 runs on CUDA devices only, got {d}")
+    return torch.device("cuda", d.index if d.index is not None else torch.cuda.current_device())
+
+
+def _stream_ptr(dev: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def make_grid_descs(origins, voxelsizes, dims, atom_offsets, out_offsets=None) -> tuple[np.ndarray, np.ndarray]:
+    """Pack per-grid descriptors (``mkb_grid_desc``) for a batch.
+
+    origins (B,3) f64: centre of voxel (0,0,0); voxelsizes (B,) or scalar; dims (B,3) int; atom_offsets (B+1,)
+    (grid b owns atom rows [off[b], off[b+1])) or a (B,2) array of explicit [begin, end) ranges.
+    Returns (descs, out_offsets (B+1,) in voxels)."""
+    origins = np.atleast_2d(np.asarray(origins, dtype=np.float64))
+    B = origins.shape[0]
+    dims = np.atleast_2d(np.asarray(dims)).astype(np.int64)
+    vs = np.broadcast_to(np.asarray(voxelsizes, dtype=np.float64), (B,))
+    ao = np.asarray(atom_offsets, dtype=np.int64)
+    if ao.ndim == 1:
+        begin, end = ao[:-1], ao[1:]
+    else:
+        begin, end = ao[:, 0], ao[:, 1]
+    nvox = dims.prod(axis=1)
+    if out_offsets is None:
+        out_offsets = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(nvox, out=out_offsets[1:])
+    out_offsets = np.asarray(out_offsets, dtype=np.int64)
+    d = np.zeros(B, dtype=_lib.GRID_DESC)
+    d["origin"] = origins
+    d["voxelsize"] = vs
+    d["dims"] = dims
+    d["atom_begin"] = begin
+    d["atom_end"] = end
+    d["out_offset"] = out_offsets[:B]
+    return d, out_offsets
+
+
+def occupancy_grid_batch(coords: torch.Tensor, sigmas: torch.Tensor, descs: np.ndarray, out: torch.Tensor,
+                         accumulate: bool = False) -> torch.Tensor:
+    """Launch K2+K1 for a batch of regular grids.  coords (N,3) f32 cuda, sigmas (N,C) f64 cuda,
+    out (sum M_b, C) f32 cuda (written in place).  Stream-ordered on torch's current stream."""
+    dev = out.device
+    assert coords.is_cuda and sigmas.is_cuda and out.is_cuda and coords.device == dev == sigmas.device
+    assert coords.dtype == torch.float32 and sigmas.dtype == torch.float64 and out.dtype == torch.float32
+    assert coords.is_contiguous() and sigmas.is_contiguous() and out.is_contiguous()
+    assert coords.ndim == 2 and coords.shape[1] == 3 and sigmas.ndim == 2 and sigmas.shape[0] == coords.shape[0]
+    descs = np.ascontiguousarray(descs, dtype=_lib.GRID_DESC)
+    Cn = int(sigmas.shape[1])
+    if Cn > MAX_CHANNELS_PER_CALL:
+        raise ValueError(f"at most {MAX_CHANNELS_PER_CALL} channels per call; split the channel set")
+    h = _lib.handle(dev.index)
+    with torch.cuda.device(dev):
+        rc = _lib.load().mkb_occupancy_grid_batch(
+            h, _stream_ptr(dev), C.c_void_p(coords.data_ptr()), C.c_void_p(sigmas.data_ptr()),
+            int(coords.shape[0]), Cn, descs.ctypes.data_as(C.c_void_p), int(descs.shape[0]),
+            C.c_void_p(out.data_ptr()), _lib.OCC_ACCUMULATE if accumulate else 0)
+    _lib.check(rc, h)
+    return out
+
+
+def occupancy_points(centers: torch.Tensor, coords: torch.Tensor, sigmas: torch.Tensor, out: torch.Tensor,
+                     accumulate: bool = False) -> torch.Tensor:
+    """K1b: arbitrary centres (M,3) f64 cuda -> out (M,C) f32 cuda."""
+    dev = out.device
+    assert centers.is_cuda and coords.is_cuda and sigmas.is_cuda and out.is_cuda
+    assert centers.dtype == torch.float64 and coords.dtype == torch.float32 and sigmas.dtype == torch.float64
+    assert out.dtype == torch.float32
+    assert centers.is_contiguous() and coords.is_contiguous() and sigmas.is_contiguous() and out.is_contiguous()
+    Cn = int(sigmas.shape[1])
+    if Cn > MAX_CHANNELS_PER_CALL:
+        raise ValueError(f"at most {MAX_CHANNELS_PER_CALL} channels per call; split the channel set")
+    h = _lib.handle(dev.index)
+    with torch.cuda.device(dev):
+        rc = _lib.load().mkb_occupancy_points(
+            h, _stream_ptr(dev), C.c_void_p(centers.data_ptr()), int(centers.shape[0]),
+            C.c_void_p(coords.data_ptr()), C.c_void_p(sigmas.data_ptr()), int(coords.shape[0]), Cn,
+            C.c_void_p(out.data_ptr()), _lib.OCC_ACCUMULATE if accumulate else 0)
+    _lib.check(rc, h)
+    return out
+
+
+def _channel_chunks(C_total: int):
+    for s in range(0, C_total, MAX_CHANNELS_PER_CALL):
+        yield s, min(C_total, s + MAX_CHANNELS_PER_CALL)
+
+
+def calculate_occupancy(centers, coords, sigmas, results, device=None) -> None:
+    """Drop-in for ``moleculekit.occupancy_utils.calculate_occupancy`` (occupancy_utils.pyx:34-61).
+
+    centers (M,3) f64, coords (N,3) f32, sigmas (N,C) f64, results (M,C) f64 **accumulated in place**
+    (results = max(results, value), NaN never stored) -- same dtype errors as the Cython memoryviews."""
+    for name, arr, dt, nd in (("centers", centers, np.float64, 2), ("coords", coords, np.float32, 2),
+                              ("sigmas", sigmas, np.float64, 2), ("results", results, np.float64, 2)):
+        if not isinstance(arr, np.ndarray) or arr.dtype != dt:
+            raise ValueError(f"Buffer dtype mismatch, expected '{np.dtype(dt).name}' for {name}")
+        if arr.ndim != nd:
+            raise ValueError(f"Buffer has wrong number of dimensions (expected {nd}, got {arr.ndim})")
+    M, N, Cn = centers.shape[0], coords.shape[0], sigmas.shape[1]
+    if results.shape[0] < M or results.shape[1] < Cn:
+        raise ValueError("results buffer too small")
+    if M == 0 or Cn == 0:
+        return
+    dev = _dev(device)
+    d_centers = torch.from_numpy(np.ascontiguousarray(centers)).to(dev)
+    d_coords = torch.from_numpy(np.ascontiguousarray(coords)).to(dev)
+    for c0, c1 in _channel_chunks(Cn):
+        d_sig = torch.from_numpy(np.ascontiguousarray(sigmas[:, c0:c1])).to(dev)
+        d_out = torch.empty((M, c1 - c0), dtype=torch.float32, device=dev)
+        occupancy_points(d_centers, d_coords, d_sig, d_out)
+        val = d_out.cpu().numpy().astype(np.float64)
+        old = results[:M, c0:c1]
+        # reference update rule `value > old ? value : old` (NaN in `old` sticks, never produced by us)
+        np.copyto(old, val, where=val > old)

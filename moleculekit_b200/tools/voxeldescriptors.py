@@ -1,0 +1,291 @@
+"""Drop-in for the voxelisation entry points of ``moleculekit.tools.voxeldescriptors``.
+
+``getCenters`` / ``getVoxelDescriptors`` keep the reference's signatures, defaults, return arity and error
+messages (moleculekit/tools/voxeldescriptors.py:197-203,251-264,345-360); the occupancy fill runs on the B200
+through libmkb200 (no CPU path).  ``getVoxelDescriptorsBatch`` is the batched form the hardware wants: many
+molecules / pockets per launch, optionally left on the device.
+
+Out of scope here (inputs to the hot path): atom typing (``getChannels`` needs RDKit /
+OpenBabel).  Pass ``userchannels`` (bool or float, (natoms, nchannels)); if the real ``moleculekit`` package is
+importable we defer to its ``getChannels`` for the default-channel case.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+
+from .. import occupancy_utils as _occ
+from ..elements import vdw_radii_of
+
+logger = logging.getLogger(__name__)
+
+_order = ("hydrophobic", "aromatic", "hbond_acceptor", "hbond_donor", "positive_ionizable",
+          "negative_ionizable", "metal", "occupancies")
+
+
+# ----------------------------------------------------------------------------------------------- host geometry
+def _mol_coords(mol):
+    """(natoms, 3[, 1]) coordinates of the molecule's current frame, like ``mol.get("coords")``."""
+    if hasattr(mol, "get"):
+        return mol.get("coords")
+    c = np.asarray(mol.coords)
+    if c.ndim == 3:
+        c = c[:, :, getattr(mol, "frame", 0)]
+    return c
+
+
+def _bounding_box(mol):
+    """moleculekit/util.py:376-379 (min / max over atoms, dtype of the coordinates, i.e. float32)."""
+    c = _mol_coords(mol)
+    return np.squeeze(np.min(c, axis=0)), np.squeeze(np.max(c, axis=0))
+
+
+def _grid_spec(mol, buffer, boxsize, center, voxelsize):
+    """(bb_min, nvoxels) with the reference's arithmetic (voxeldescriptors.py:229-243): float32 bounding box in
+    `buffer` mode, float64 ``center - boxsize/2`` in `boxsize` mode."""
+    if boxsize is None:
+        bb_min, bb_max = _bounding_box(mol)
+        bb_min = np.array(bb_min, copy=True)
+        bb_max = np.array(bb_max, copy=True)
+        bb_min -= buffer  # in place: stays in the coordinate dtype (float32), like the reference
+        bb_max += buffer
+        nvoxels = np.ceil((bb_max - bb_min) / voxelsize).astype(int) + 1
+    else:
+        boxsize = np.array(boxsize)
+        center = np.array(center)
+        nvoxels = np.ceil(boxsize / voxelsize).astype(int)
+        bb_min = center - (boxsize / 2)
+    return bb_min, nvoxels
+
+
+def _centers_from_spec(bb_min, nvoxels, voxelsize) -> np.ndarray:
+    """(prod(nvoxels), 3) float64 centres, bit-identical to voxeldescriptors.py:125-132,245-247:
+    c[ix,iy,iz,d] = float64(i_d * voxelsize) + bb_min[d], z fastest."""
+    nx, ny, nz = (int(v) for v in nvoxels)
+    out = np.empty((nx, ny, nz, 3), dtype=np.float64)
+    for d, n in enumerate((nx, ny, nz)):
+        axis = (np.arange(n) * voxelsize).astype(np.float64) + np.asarray(bb_min)[d]
+        shape = [1, 1, 1]
+        shape[d] = n
+        out[..., d] = axis.reshape(shape)
+    return out.reshape(nx * ny * nz, 3)
+
+
+def getCenters(mol=None, buffer: float = 0, boxsize: list | None = None, center: list | None = None,
+               voxelsize: float = 1):
+    """Get a set of centers for voxelization (reference: voxeldescriptors.py:197-248).
+
+    Returns ``(centers (nvoxels, 3) float64, nvoxels (3,) int)``; see the reference docstring for the arguments."""
+    bb_min, nvoxels = _grid_spec(mol, buffer, boxsize, center, voxelsize)
+    return _centers_from_spec(bb_min, nvoxels, voxelsize), nvoxels
+
+
+def _channels_to_sigmas(channels, elements):
+    """bool channels -> per-channel sigmas = vdW radius * mask (voxeldescriptors.py:117-121,332-335)."""
+    channels = np.asarray(channels)
+    if channels.dtype == bool:
+        sigmas = vdw_radii_of(elements)
+        channels = sigmas[:, np.newaxis] * channels.astype(float)
+    return channels
+
+
+def getChannels(mol, aromaticNitrogen: bool = False, version: int = 2, validitychecks: bool = True):
+    """Atom typing is an INPUT of the accelerated path (RDKit/OpenBabel chemistry).  Defer to the
+    real moleculekit when it is installed; otherwise ask for ``userchannels``."""
+    try:
+        from moleculekit.tools.voxeldescriptors import getChannels as _ref_getChannels  # type: ignore
+    except Exception as e:  # pragma: no cover - depends on the environment
+        raise RuntimeError(
+            "Default channels need moleculekit's atom typing (getChannels), which is outside the B200 hot path. "
+            "Pass userchannels=(natoms, nchannels) bool/float array.") from e
+    return _ref_getChannels(mol, aromaticNitrogen, version, validitychecks)
+
+
+# ----------------------------------------------------------------------------------------------- device drivers
+def _occupancy_grid(coords, sigmas, bb_min, nvoxels, voxelsize, device=None) -> np.ndarray:
+    """One regular grid -> (M, C) float64 numpy (the `_getOccupancyC` of the reference, :515-533)."""
+    coords = np.ascontiguousarray(np.asarray(coords).astype(np.float32))
+    sigmas = np.ascontiguousarray(np.asarray(sigmas).astype(np.float64))
+    dev = _occ._dev(device)
+    M = int(np.prod(nvoxels))
+    Cn = sigmas.shape[1]
+    feats = np.empty((M, Cn), dtype=np.float64)
+    if M == 0 or Cn == 0:
+        return feats
+    d_coords = torch.from_numpy(coords).to(dev)
+    for c0, c1 in _occ._channel_chunks(Cn):
+        d_sig = torch.from_numpy(np.ascontiguousarray(sigmas[:, c0:c1])).to(dev)
+        descs, _ = _occ.make_grid_descs(np.asarray(bb_min, dtype=np.float64)[None, :], float(voxelsize),
+                                        np.asarray(nvoxels)[None, :], np.array([0, coords.shape[0]]))
+        d_out = torch.empty((M, c1 - c0), dtype=torch.float32, device=dev)
+        _occ.occupancy_grid_batch(d_coords, d_sig, descs, d_out)
+        feats[:, c0:c1] = d_out.cpu().numpy()
+    return feats
+
+
+def _occupancy_points(coords, centers, sigmas, device=None) -> np.ndarray:
+    coords = np.ascontiguousarray(np.asarray(coords).astype(np.float32))
+    centers = np.ascontiguousarray(np.asarray(centers).astype(np.float64))
+    sigmas = np.ascontiguousarray(np.asarray(sigmas).astype(np.float64))
+    occus = np.zeros((centers.shape[0], sigmas.shape[1]))
+    _occ.calculate_occupancy(centers, coords, sigmas, occus, device=device)
+    return occus
+
+
+def getVoxelDescriptors(mol, boxsize: list | None = None, voxelsize: float = 1, buffer: float = 0,
+                        center: list | None = None, usercenters: np.ndarray | None = None,
+                        userchannels: np.ndarray | None = None, usercoords: np.ndarray | None = None,
+                        aromaticNitrogen: bool = False, method: str = "C", version: int = 2,
+                        validitychecks: bool = True, device=None):
+    """Calculate descriptors of atom properties for voxels in a grid bounding the molecule.
+
+    Same arguments, return arity and errors as moleculekit/tools/voxeldescriptors.py:251-365:
+    ``(features (M,C) f64, centers (M,3) f64[, nvoxels (3,)])`` -- nvoxels only when `usercenters` is None.
+    The only addition is the keyword ``device`` (default: current CUDA device)."""
+    channels = userchannels
+    if channels is None:
+        channels, mol = getChannels(mol, aromaticNitrogen, version, validitychecks)
+    channels = np.asarray(channels)
+    if channels.dtype == bool:
+        channels = _channels_to_sigmas(channels, mol.element)
+
+    nvoxels = None
+    centers = usercenters
+    spec = None
+    if centers is None:
+        bb_min, nvoxels = _grid_spec(mol, buffer, boxsize, center, voxelsize)
+        spec = (bb_min, nvoxels)
+        centers = _centers_from_spec(bb_min, nvoxels, voxelsize)
+
+    coords = usercoords
+    if coords is None:
+        coords = _mol_coords(mol)
+    coords = np.asarray(coords)
+    if coords.ndim == 3:
+        if coords.shape[2] != 1:
+            raise RuntimeError(
+                "Only a single set of coordinates should be passed for voxelixation. "
+                "Make sure your coordinates are either 3D with a last dim of 1 or 2D."
+            )
+        coords = coords[:, :, 0]
+
+    if method.upper() == "C":
+        if spec is not None:
+            features = _occupancy_grid(coords, channels, spec[0], spec[1], voxelsize, device=device)
+        else:
+            centers = np.asarray(centers)  # the reference docstring passes a list here
+            features = _occupancy_points(coords, centers, channels, device=device)
+    else:
+        raise RuntimeError("As of moleculekit 0.9.2 we only support C implementation of voxelization")
+
+    if nvoxels is None:
+        return features, centers
+    return features, centers, nvoxels
+
+
+# ----------------------------------------------------------------------------------------------- batched API
+class VoxelBatch:
+    """A batch of molecules / pockets voxelised in one launch sequence.
+
+    coords: list of (N_b, 3) arrays (or one concatenated (N, 3) array with `atom_offsets`)
+    channels: list of (N_b, C) float sigma arrays (bool masks need `elements`), same C for all.
+    Grids: either ``boxsize`` (+ per-item ``centers`` (B,3)) or ``buffer`` (bounding box of each item).
+    """
+
+    def __init__(self, coords, channels, *, boxsize=None, centers=None, buffer=0.0, voxelsize=1.0,
+                 atom_offsets=None, elements=None):
+        if atom_offsets is None:
+            counts = [len(c) for c in coords]
+            atom_offsets = np.zeros(len(coords) + 1, dtype=np.int64)
+            np.cumsum(counts, out=atom_offsets[1:])
+            coords_cat = np.concatenate([np.asarray(c, dtype=np.float32).reshape(-1, 3) for c in coords]) \
+                if len(coords) else np.zeros((0, 3), np.float32)
+            if elements is not None:
+                channels = [_channels_to_sigmas(ch, el) for ch, el in zip(channels, elements)]
+            chan_cat = np.concatenate([np.asarray(c, dtype=np.float64) for c in channels]) \
+                if len(channels) else np.zeros((0, 8), np.float64)
+        else:
+            atom_offsets = np.asarray(atom_offsets, dtype=np.int64)
+            coords_cat = np.asarray(coords, dtype=np.float32).reshape(-1, 3)
+            chan_cat = np.asarray(channels, dtype=np.float64)
+        B = len(atom_offsets) - 1
+        self.B = B
+        self.atom_offsets = atom_offsets
+        self.coords = np.ascontiguousarray(coords_cat)
+        self.sigmas = np.ascontiguousarray(chan_cat)
+        self.voxelsize = float(voxelsize)
+        origins = np.zeros((B, 3), dtype=np.float64)
+        dims = np.zeros((B, 3), dtype=np.int64)
+        if boxsize is not None:
+            bs = np.array(boxsize, dtype=np.float64)
+            ctr = np.asarray(centers, dtype=np.float64).reshape(B, 3)
+            dims[:] = np.ceil(bs / voxelsize).astype(int)
+            origins[:] = ctr - (bs / 2)
+        else:
+            for b in range(B):
+                c = self.coords[atom_offsets[b]:atom_offsets[b + 1]]
+                bb_min = np.min(c, axis=0) - np.float32(buffer)
+                bb_max = np.max(c, axis=0) + np.float32(buffer)
+                dims[b] = np.ceil((bb_max - bb_min) / voxelsize).astype(int) + 1
+                origins[b] = bb_min
+        self.origins, self.dims = origins, dims
+        self.descs, self.out_offsets = _occ.make_grid_descs(origins, self.voxelsize, dims, atom_offsets)
+        self.total_voxels = int(self.out_offsets[-1])
+        self.C = int(self.sigmas.shape[1])
+
+    def centers(self, b: int) -> np.ndarray:
+        return _centers_from_spec(self.origins[b], self.dims[b], self.voxelsize)
+
+    def to_device(self, device=None):
+        dev = _occ._dev(device)
+        return torch.from_numpy(self.coords).to(dev), torch.from_numpy(self.sigmas).to(dev)
+
+    def run(self, d_coords, d_sigmas, out: torch.Tensor | None = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty((self.total_voxels, self.C), dtype=torch.float32, device=d_coords.device)
+        return _occ.occupancy_grid_batch(d_coords, d_sigmas, self.descs, out)
+
+    def split(self, feats):
+        """(sum M_b, C) -> list of per-item (M_b, C) views."""
+        return [feats[self.out_offsets[b]:self.out_offsets[b + 1]] for b in range(self.B)]
+
+
+def pinned_array(shape, dtype=np.float32) -> np.ndarray:
+    """A numpy array backed by page-locked host memory (async H2D / D2H at full PCIe rate)."""
+    t = torch.empty(tuple(int(x) for x in np.atleast_1d(shape)), dtype=getattr(torch, np.dtype(dtype).name),
+                    pin_memory=True)
+    return t.numpy()
+
+
+def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, buffer=0.0, voxelsize=1.0,
+                             elements=None, atom_offsets=None, device=None, return_tensor: bool = False,
+                             dtype=np.float64, out: np.ndarray | None = None):
+    """Voxelise a batch of molecules / pockets in one launch sequence (HOST arrays in, HOST arrays out).
+
+    coords / channels: lists of per-item (N_b, 3) / (N_b, C) arrays, or concatenated arrays with ``atom_offsets``
+    (B+1,).  Grids: ``boxsize`` + per-item ``centers`` (B, 3), or ``buffer`` around each item's bounding box.
+    Returns ``(features, nvoxels)``: features is a list of (M_b, C) arrays -- float64 by default like the reference,
+    ``dtype=np.float32`` skips the upcast, ``out`` (float32 (sum M_b, C), ideally from :func:`pinned_array`) receives
+    the device result directly -- or, with ``return_tensor=True``, ``(tensor, nvoxels, voxel_offsets)`` with one
+    float32 CUDA tensor left on the device (the layout per-GPU consumers keep resident).  ``nvoxels`` is (B, 3)."""
+    batch = VoxelBatch(coords, channels, boxsize=boxsize, centers=centers, buffer=buffer, voxelsize=voxelsize,
+                       elements=elements, atom_offsets=atom_offsets)
+    dev = _occ._dev(device)
+    d_coords = torch.from_numpy(batch.coords).to(dev, non_blocking=True)
+    d_sig = torch.from_numpy(batch.sigmas).to(dev, non_blocking=True)
+    d_out = batch.run(d_coords, d_sig)
+    if return_tensor:
+        return d_out, batch.dims.copy(), batch.out_offsets.copy()
+    if out is not None:
+        if out.dtype != np.float32 or out.shape != (batch.total_voxels, batch.C) or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"out must be a C-contiguous float32 array of shape {(batch.total_voxels, batch.C)}")
+        torch.from_numpy(out).copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        host = out
+    else:
+        host = d_out.cpu().numpy()
+        if dtype is not None and np.dtype(dtype) != np.float32:
+            host = host.astype(dtype)
+    return batch.split(host), batch.dims.copy()
