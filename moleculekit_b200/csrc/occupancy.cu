@@ -192,30 +192,81 @@ __device__ __noinline__ bool exact_gate(const GridDev *g, const float *coords, u
     return d2 < CUTOFF_A * CUTOFF_A;
 }
 
+constexpr int MAX_ROWS = FILL_THREADS;  // cell rows feeding one tile: (R+1)^2, R = (TILE-1+2*cutv)/TILE
+
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// grid = (max tiles per grid, B): blockIdx.y is the grid (molecule / pocket), blockIdx.x its tile.
 template <int CP>
 __global__ void __launch_bounds__(FILL_THREADS, (CP <= 8 ? 2 : 1)) occ_fill_kernel(const FillParams p) {
-    __shared__ float4 s_ent[LIST_CAP];   // x, y, z relative to the tile corner (voxel units), w = sigma^2 (voxel units)
-    __shared__ unsigned s_mask[LIST_CAP];
-    __shared__ unsigned s_src[LIST_CAP];
+    __shared__ float4 s_ent[LIST_CAP];    // x, y, z relative to the tile corner (voxel units), w = sigma^2 (voxel units)
+    __shared__ unsigned s_mask[LIST_CAP]; // channel bits of the atom's single sigma; 0 = several sigmas (slow path)
+    __shared__ unsigned s_src[LIST_CAP];  // atom row (exact gate / multi-sigma path)
+    __shared__ unsigned s_rpos[MAX_ROWS]; // first sorted atom of each cell row
+    __shared__ unsigned s_rbase[MAX_ROWS + 1];  // exclusive prefix of the row lengths
+    __shared__ GridDev s_g;
     __shared__ int s_cnt;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long tile = blockIdx.x;
-    const GridDev *g = p.grids + find_grid_tile(p.grids, p.B, tile);
+    const GridDev *gg = p.grids + blockIdx.y;
+    {
+        const int ntiles = __ldg(&gg->tiles[0]) * __ldg(&gg->tiles[1]) * __ldg(&gg->tiles[2]);
+        if ((int)blockIdx.x >= ntiles) return;  // ragged batch: this grid has fewer tiles than the largest one
+    }
+    if (tid < (int)(sizeof(GridDev) / 4)) reinterpret_cast<unsigned *>(&s_g)[tid] = reinterpret_cast<const unsigned *>(gg)[tid];
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    const GridDev &g = s_g;
 
-    const int nx = g->dims[0], ny = g->dims[1], nz = g->dims[2];
-    const int local = (int)(tile - g->tile_base);
-    const int tzN = g->tiles[2], tyN = g->tiles[1];
-    const int tz = local % tzN, ty = (local / tzN) % tyN, tx = local / (tzN * tyN);
+    const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+    const int tzN = g.tiles[2], tyN = g.tiles[1];
+    const int local = blockIdx.x;
+    const int tz = local % tzN, txy = local / tzN, ty = txy % tyN, tx = txy / tyN;
+
+    // cell rows feeding this tile: cells [tx, tx+R] x [ty, ty+R], each a contiguous z-run [tz, tz+R]
+    const int R = g.rcells;
+    const int cN1 = g.cells[1], cN2 = g.cells[2];
+    const int cx1 = min(tx + R, g.cells[0] - 1), cy1 = min(ty + R, cN1 - 1), cz1 = min(tz + R, cN2 - 1);
+    const int ncy = cy1 - ty + 1;
+    const int nrows = (cx1 - tx + 1) * ncy;
+    if (tid < nrows) {
+        const int rx = tid / ncy, ry = tid - rx * ncy;
+        const long long cb = g.cell_base + ((long long)(tx + rx) * cN1 + (ty + ry)) * cN2;
+        const unsigned a = __ldg(p.cell_start + cb + tz), e = __ldg(p.cell_start + cb + cz1 + 1);
+        s_rpos[tid] = a;
+        s_rbase[tid + 1] = e - a;
+    }
+    if (tid == 0) s_rbase[0] = 0;
+    __syncthreads();
+    if (warp == 0) {  // inclusive scan of the row lengths (nrows <= 512: 16 chunks of 32 at most)
+        unsigned carry = 0;
+        for (int c0 = 0; c0 < nrows; c0 += 32) {
+            const int r = c0 + lane;
+            unsigned v = (r < nrows) ? s_rbase[r + 1] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (r < nrows) s_rbase[r + 1] = v + carry;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    const unsigned total = s_rbase[nrows];
 
     // warp -> 2x4x4 voxel block of the tile, lane -> voxel (z fastest so 4 lanes cover one 128-byte output line)
     const int bx = warp >> 2, by = (warp >> 1) & 1, bz = warp & 1;
     const int vx = bx * 2 + (lane >> 4), vy = by * 4 + ((lane >> 2) & 3), vz = bz * 4 + (lane & 3);
-    const float fvx = (float)vx, fvy = (float)vy, fvz = (float)vz;
-    const float bcx = (float)(bx * 2), bcy = (float)(by * 4), bcz = (float)(bz * 4);
-    const int ix = tx * TILE + vx, iy = ty * TILE + vy, iz = tz * TILE + vz;
-
-    const float cut2v = g->cut2v, cut_lo = g->cut2v_lo, cut_hi = g->cut2v_hi;
     const int C = p.C;
 
     float acc[CP];
@@ -223,119 +274,118 @@ __global__ void __launch_bounds__(FILL_THREADS, (CP <= 8 ? 2 : 1)) occ_fill_kern
     for (int h = 0; h < CP; ++h) acc[h] = 0.0f;
     bool touched = false;
 
-    // cell rows feeding this tile: cells [tx, tx+R] x [ty, ty+R], each a contiguous z-run [tz, tz+R]
-    const int R = g->rcells;
-    const int cN1 = g->cells[1], cN2 = g->cells[2];
-    const int cx1 = min(tx + R, g->cells[0] - 1), cy1 = min(ty + R, cN1 - 1), cz1 = min(tz + R, cN2 - 1);
-    const int ncy = cy1 - ty + 1;
-    const int nrows = (cx1 - tx + 1) * ncy;
-    const double tox = (double)(tx * TILE), toy = (double)(ty * TILE), toz = (double)(tz * TILE);
+    if (total != 0) {
+        const float fvx = (float)vx, fvy = (float)vy, fvz = (float)vz;
+        const float bcx = (float)(bx * 2), bcy = (float)(by * 4), bcz = (float)(bz * 4);
+        const float cut2v = g.cut2v, cut_hi = g.cut2v_hi, band = g.cut2v_hi - g.cut2v;
+        const double tox = (double)(tx * TILE), toy = (double)(ty * TILE), toz = (double)(tz * TILE);
+        // 32-bit shared-window addresses taken ONCE (volatile: ptxas otherwise rebuilds them from SR_CgaCtaId per use)
+        unsigned ent_sa, mask_sa;
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(ent_sa) : "l"(s_ent));
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(mask_sa) : "l"(s_mask));
 
-    int row = 0;
-    unsigned pos = 0, end = 0;
-    bool have_row = false, more = true;
-    while (more) {
-        if (tid == 0) s_cnt = 0;
-        __syncthreads();
-        int est = 0;
-        while (true) {
-            if (!have_row) {
-                if (row >= nrows) { more = false; break; }
-                const int rx = row / ncy, ry = row - rx * ncy;
-                const long long cb = g->cell_base + ((long long)(tx + rx) * cN1 + (ty + ry)) * cN2;
-                pos = __ldg(p.cell_start + cb + tz);
-                end = __ldg(p.cell_start + cb + cz1 + 1);
-                have_row = true;
+        for (unsigned c0 = 0; c0 < total; c0 += LIST_CAP) {  // one pass unless > LIST_CAP atoms sit in the halo
+            if (c0) {
+                __syncthreads();  // previous pass fully consumed
+                if (tid == 0) s_cnt = 0;
+                __syncthreads();
             }
-            if (pos >= end) { have_row = false; ++row; continue; }
-            const unsigned n_piece = min(end - pos, (unsigned)FILL_THREADS);
-            if (est + (int)n_piece > LIST_CAP) break;  // flush what we have, then resume from (row, pos)
-            bool pass = false;
-            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            unsigned m = 0, sr = 0;
-            if ((unsigned)tid < n_piece) {
-                const unsigned i = pos + tid;
-                e.x = (float)(p.px[i] - tox);
-                e.y = (float)(p.py[i] - toy);
-                e.z = (float)(p.pz[i] - toz);
-                e.w = p.s2[i];
-                m = p.mask[i];
-                sr = p.src[i];
-                const float ddx = fmaxf(fmaxf(-e.x, e.x - (float)(TILE - 1)), 0.f);
-                const float ddy = fmaxf(fmaxf(-e.y, e.y - (float)(TILE - 1)), 0.f);
-                const float ddz = fmaxf(fmaxf(-e.z, e.z - (float)(TILE - 1)), 0.f);
-                pass = (m != 0) && (ddx * ddx + ddy * ddy + ddz * ddz <= cut_hi);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_cnt, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) {
-                    const int slot = base + __popc(bal & ((1u << lane) - 1u));
-                    s_ent[slot] = e;
-                    s_mask[slot] = m;
-                    s_src[slot] = sr;
+            const unsigned c1 = min(total, c0 + (unsigned)LIST_CAP);
+            // ---- gather: every thread takes atoms k = c0 + tid, + 512, ... of the concatenated cell rows
+            for (unsigned k0 = c0; k0 < c1; k0 += FILL_THREADS) {
+                const unsigned k = k0 + tid;
+                bool pass = false;
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned m = 0, sr = 0;
+                if (k < c1) {
+                    int lo = 0, hi = nrows - 1;  // row with rbase[row] <= k < rbase[row + 1]
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (s_rbase[mid] <= k) lo = mid; else hi = mid - 1;
+                    }
+                    const unsigned i = s_rpos[lo] + (k - s_rbase[lo]);
+                    e.x = (float)(p.px[i] - tox);
+                    e.y = (float)(p.py[i] - toy);
+                    e.z = (float)(p.pz[i] - toz);
+                    e.w = p.s2[i];
+                    m = p.mask[i];
+                    sr = p.src[i];
+                    const float ddx = fmaxf(fmaxf(-e.x, e.x - (float)(TILE - 1)), 0.f);
+                    const float ddy = fmaxf(fmaxf(-e.y, e.y - (float)(TILE - 1)), 0.f);
+                    const float ddz = fmaxf(fmaxf(-e.z, e.z - (float)(TILE - 1)), 0.f);
+                    pass = (m != 0) && (ddx * ddx + ddy * ddy + ddz * ddz <= cut_hi);
+                    if (sr & 0x80000000u) m = 0;  // several distinct sigmas: per-channel path
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt, __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (pass) {
+                        const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                        s_ent[slot] = e;
+                        s_mask[slot] = m;
+                        s_src[slot] = sr & 0x7fffffffu;
+                    }
                 }
             }
-            pos += n_piece;
-            est += (int)n_piece;
-        }
-        __syncthreads();
-        const int n = s_cnt;
+            __syncthreads();
+            const int n = s_cnt;
 
-        // ---- consume: each warp culls the tile list against its 2x4x4 block, then all lanes evaluate the survivors
-        for (int c0 = 0; c0 < n; c0 += 32) {
-            const int j = c0 + lane;
-            bool hit = false;
-            if (j < n) {
-                const float4 e = s_ent[j];
-                const float rx = e.x - bcx, ry = e.y - bcy, rz = e.z - bcz;
-                const float ddx = fmaxf(fmaxf(-rx, rx - 1.f), 0.f);
-                const float ddy = fmaxf(fmaxf(-ry, ry - 3.f), 0.f);
-                const float ddz = fmaxf(fmaxf(-rz, rz - 3.f), 0.f);
-                hit = (ddx * ddx + ddy * ddy + ddz * ddz) <= cut_hi;
-            }
-            unsigned bal = __ballot_sync(0xffffffffu, hit);
-            touched = touched || (bal != 0);
-            while (bal) {
-                const int k = __ffs(bal) - 1;
-                bal &= bal - 1;
-                const int jj = c0 + k;
-                const float4 e = s_ent[jj];
-                const unsigned sr = s_src[jj];
-                const float dx = e.x - fvx, dy = e.y - fvy, dz = e.z - fvz;
-                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                bool in = d2 < cut2v;
-                if (d2 > cut_lo && d2 < cut_hi)  // within 4e-6 of the gate: decide exactly like the reference
-                    in = exact_gate(g, p.coords, sr & 0x7fffffffu, ix, iy, iz);
-                const float r = in ? rcp_approx(d2) : 0.0f;
-                if (!(sr & 0x80000000u)) {
-                    const unsigned cm = s_mask[jj];
-                    const float q = e.w * r;  // (sigma^2/d2); 0 outside the gate; +inf at d2 == 0 -> value 1
+            // ---- consume: each warp culls the list against its 2x4x4 block, then all lanes evaluate the survivors
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                bool hit = false;
+                if (j < n) {
+                    const float4 e = s_ent[j];
+                    const float rx = e.x - bcx, ry = e.y - bcy, rz = e.z - bcz;
+                    const float ddx = fmaxf(fmaxf(-rx, rx - 1.f), 0.f);
+                    const float ddy = fmaxf(fmaxf(-ry, ry - 3.f), 0.f);
+                    const float ddz = fmaxf(fmaxf(-rz, rz - 3.f), 0.f);
+                    hit = (ddx * ddx + ddy * ddy + ddz * ddz) <= cut_hi;
+                }
+                unsigned bal = __ballot_sync(0xffffffffu, hit);
+                touched = touched || (bal != 0);
+                while (bal) {
+                    const int jj = j0 + __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    const float4 e = lds_f4(ent_sa + jj * 16);
+                    const unsigned cm = lds_u32(mask_sa + jj * 4);
+                    const float dx = e.x - fvx, dy = e.y - fvy, dz = e.z - fvz;
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const float r = rcp_approx(d2);
+                    float gate = (d2 < cut2v) ? 1.0f : 0.0f;
+                    if (fabsf(d2 - cut2v) <= band)  // within 4e-6 of the gate: decide exactly like the reference
+                        gate = exact_gate(&g, p.coords, s_src[jj], tx * TILE + vx, ty * TILE + vy, tz * TILE + vz) ? 1.0f : 0.0f;
+                    const bool in = gate != 0.0f;
+                    const float q = in ? e.w * r : 0.0f;  // sigma^2/d2; +inf at d2 == 0 -> value 1
+                    if (cm != 0) {
 #pragma unroll
-                    for (int h = 0; h < CP; ++h)
-                        if (cm & (1u << h)) acc[h] = fmaxf(acc[h], q);
-                } else {
-                    // several distinct sigmas on this atom: per-channel q (user-supplied float channels)
-                    const double *sg = p.sigmas + (long long)(sr & 0x7fffffffu) * C;
-                    const double ivs = g->inv_vs;
+                        for (int h = 0; h < CP; ++h)
+                            if (cm & (1u << h)) acc[h] = fmaxf(acc[h], q);
+                    } else {
+                        // several distinct sigmas on this atom: per-channel q (user-supplied float channels)
+                        const double *sg = p.sigmas + (long long)s_src[jj] * C;
+                        const double ivs = g.inv_vs;
+                        const float rr = in ? r : 0.0f;
 #pragma unroll
-                    for (int h = 0; h < CP; ++h) {
-                        if (h < C) {
-                            const double s = sg[h] * ivs;
-                            const float sq = (s == 0.0 || s != s) ? 0.0f : fmaxf((float)(s * s), FLT_MIN);
-                            acc[h] = fmaxf(acc[h], sq * r);  // 0*inf = NaN is dropped by fmaxf
+                        for (int h = 0; h < CP; ++h) {
+                            if (h < C) {
+                                const double s = sg[h] * ivs;
+                                const float sq = (s == 0.0 || s != s) ? 0.0f : fmaxf((float)(s * s), FLT_MIN);
+                                acc[h] = fmaxf(acc[h], sq * rr);  // 0*inf = NaN is dropped by fmaxf
+                            }
                         }
                     }
                 }
             }
         }
-        if (more) __syncthreads();  // list is about to be overwritten
     }
 
     // ---- epilogue: one transcendental per voxel-channel, streaming 32-byte stores
+    const int ix = tx * TILE + vx, iy = ty * TILE + vy, iz = tz * TILE + vz;
     if (ix < nx && iy < ny && iz < nz) {
+        float *const o = p.out + (g.out_offset + ((long long)ix * ny + iy) * nz + iz) * C;
         float v[CP];
         if (touched) {
 #pragma unroll
@@ -344,7 +394,6 @@ __global__ void __launch_bounds__(FILL_THREADS, (CP <= 8 ? 2 : 1)) occ_fill_kern
 #pragma unroll
             for (int h = 0; h < CP; ++h) v[h] = 0.0f;
         }
-        float *o = p.out + (g->out_offset + ((long long)ix * ny + iy) * nz + iz) * C;
         if (p.flags & MKB_OCC_ACCUMULATE) {
 #pragma unroll
             for (int h = 0; h < CP; ++h)
@@ -492,6 +541,8 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
         g.inv_vs = 1.0 / s.voxelsize;
         g.cutv = (int)std::ceil(cut);
         g.rcells = (TILE - 1 + 2 * g.cutv) / TILE;
+        if ((g.rcells + 1) * (g.rcells + 1) > MAX_ROWS)
+            return fail(h, MKB_ERR_BAD_ARG, "grid %d: voxelsize %g too small for one call", b, s.voxelsize);
         g.cut2v = (float)(cut * cut);
         g.cut2v_lo = g.cut2v * (1.0f - GATE_BAND);
         g.cut2v_hi = g.cut2v * (1.0f + GATE_BAND);
@@ -561,10 +612,18 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     fp.cell_start = cell_start; fp.coords = coords; fp.sigmas = sigmas; fp.out = out; fp.flags = flags;
     fp.vec_ok = (C == 8 && ((uintptr_t)out % 16 == 0)) ? 1 : 0;
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
-    if (C <= 8) occ_fill_kernel<8><<<(unsigned)tiles, FILL_THREADS, 0, st>>>(fp);
-    else if (C <= 16) occ_fill_kernel<16><<<(unsigned)tiles, FILL_THREADS, 0, st>>>(fp);
-    else occ_fill_kernel<32><<<(unsigned)tiles, FILL_THREADS, 0, st>>>(fp);
-    MKB_LAUNCHED(h);
+    for (int b0 = 0; b0 < B; b0 += 65535) {  // blockIdx.y = grid of the batch
+        const int nb = std::min(65535, B - b0);
+        fp.grids = d_grids + b0;
+        fp.B = nb;
+        long long mt = 0;
+        for (int b = b0; b < b0 + nb; ++b) mt = std::max<long long>(mt, (long long)gd[b].tiles[0] * gd[b].tiles[1] * gd[b].tiles[2]);
+        const dim3 grid((unsigned)mt, (unsigned)nb);
+        if (C <= 8) occ_fill_kernel<8><<<grid, FILL_THREADS, 0, st>>>(fp);
+        else if (C <= 16) occ_fill_kernel<16><<<grid, FILL_THREADS, 0, st>>>(fp);
+        else occ_fill_kernel<32><<<grid, FILL_THREADS, 0, st>>>(fp);
+        MKB_LAUNCHED(h);
+    }
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));
     return MKB_OK;
 }

@@ -1,0 +1,328 @@
+"""GPU parity of the distance path (K3-K6) against the oracle, the reference's stored goldens and the frozen outputs of
+the reference's compiled kernels.  float32 / index outputs must be BIT-identical.  Mirrors the reference's
+tests/test_metricdistance.py, tests/test_distance.py and tests/test_interactions.py::test_metal_coordination."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    """Bit pattern with NaNs canonicalised: x86 SSE produces the 'default NaN' 0xFFC00000 (sign set), the GPU
+    0x7FFFFFFF; both are NaN, and no consumer can tell them apart except by reinterpreting the bits."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = a.view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
+
+
+def _groups(off, atoms):
+    return [atoms[off[i]:off[i + 1]].tolist() for i in range(len(off) - 1)]
+
+
+@pytest.fixture(scope="module")
+def du():
+    import torch
+
+    assert torch.cuda.is_available()
+    from moleculekit_b200 import distance_utils
+
+    return distance_utils
+
+
+@pytest.fixture(scope="module")
+def mol(g_traj):
+    from moleculekit_b200.molecule_lite import MolLite
+
+    g = g_traj
+    return MolLite(g["coords"], g["box"], element=g["element"], name=g["name"], resname=g["resname"], resid=g["resid"],
+                   chain=g["chain"], segid=g["segid"],
+                   named_selections={s: m for s, m in zip(g["sel_strings"].tolist(), g["sel_masks"])})
+
+
+# ------------------------------------------------------------------------------------------ raw kernels, bit exact
+def test_raw_dist_trajectory(du, g_raw):
+    g = g_raw
+    c, bx, ch, s1, s2 = g["coords"], g["box"], g["chains"], g["sel1"], g["sel2"]
+    for key, a, b, selfd, pbc in (("dist_pbc", s1, s2, False, True), ("dist_nopbc", s1, s2, False, False),
+                                  ("dist_self_pbc", s1, s1, True, True)):
+        r = np.zeros_like(g[key])
+        du.dist_trajectory(c, bx, a, b, ch, selfd, pbc, r)
+        assert np.array_equal(_bits(r), _bits(g[key])), key
+
+
+def test_raw_contacts(du, g_raw):
+    g = g_raw
+    c, bx, ch, s1, s2 = g["coords"], g["box"], g["chains"], g["sel1"], g["sel2"]
+    off, pairs = du.contacts_trajectory_arrays(c, bx, s1, s2, ch, False, True, 6.5)
+    assert np.diff(off).tolist() == g["ct_cnt"].tolist() and np.array_equal(pairs, g["ct_pairs"])
+    off, pairs = du.contacts_trajectory_arrays(c, bx, s1, s1, ch, True, True, 7.25)
+    assert np.diff(off).tolist() == g["ct_self_cnt"].tolist() and np.array_equal(pairs, g["ct_self_pairs"])
+    lst = du.contacts_trajectory(c, bx, s1, s2, ch, False, True, 6.5)
+    assert isinstance(lst, list) and len(lst) == c.shape[2] and lst[0] == g["ct_pairs"][:g["ct_cnt"][0]].reshape(-1).tolist()
+
+
+def test_raw_reductions(du, g_raw):
+    g = g_raw
+    c, bx, ch = g["coords"], g["box"], g["chains"]
+    F = c.shape[2]
+    g1, g2 = _groups(g["g1_off"], g["g1_atoms"]), _groups(g["g2_off"], g["g2_atoms"])
+    gc1 = np.array([ch[x[0]] for x in g1], np.uint32); gc2 = np.array([ch[x[0]] for x in g2], np.uint32)
+    for r1 in (0, 1):
+        for r2 in (0, 1):
+            r = np.zeros((F, len(g1) * len(g2)), np.float32)
+            du.dist_trajectory_reduction(c, bx, g1, g2, gc1, gc2, False, True, g["masses"], r1, r2, r)
+            assert np.array_equal(_bits(r), _bits(g[f"red_{r1}{r2}"])), (r1, r2)
+    r = np.zeros_like(g["red_self"])
+    du.dist_trajectory_reduction(c, bx, g1, g1, gc1, gc1, True, True, g["masses"], 0, 0, r)
+    assert np.array_equal(_bits(r), _bits(g["red_self"]))
+    r = np.zeros_like(g["red_pairs_01"])
+    du.dist_trajectory_reduction_pairs(c, bx, g1[:6], g2, gc1[:6], gc2, True, g["masses"], 0, 1, r)
+    assert np.array_equal(_bits(r), _bits(g["red_pairs_01"]))
+
+
+def test_raw_cdist_pdist_squareform_collisions(du, g_raw):
+    g = g_raw
+    for D in (1, 2, 3, 5):
+        a, b = g[f"cd{D}_a"], g[f"cd{D}_b"]
+        r = np.zeros((len(a), len(b)), np.float32); du.cdist(a, b, r)
+        assert np.array_equal(_bits(r), _bits(g[f"cd{D}_out"]))
+        p = np.zeros(len(a) * (len(a) - 1) // 2, np.float32); du.pdist(a, p)
+        assert np.array_equal(_bits(p), _bits(g[f"pd{D}_out"]))
+    assert np.array_equal(du.squareform(g["pd3_out"]), g["sq_out"])
+    coll = np.array(du.get_collisions(g["cd3_a"], g["cd3_b"], 6.0), np.uint32).reshape(-1, 2)
+    assert np.array_equal(coll, g["coll_out"])
+
+
+def test_reference_test_distance_py():
+    """tests/test_distance.py:1-28 of the reference, verbatim expectations."""
+    from moleculekit_b200.distance import cdist, pdist, squareform
+
+    x = np.array([0, 1, 2])[:, None]; y = np.array([3, 4, 5])[:, None]
+    assert np.allclose(cdist(x, y), [[3.0, 4.0, 5.0], [2.0, 3.0, 4.0], [1.0, 2.0, 3.0]])
+    d = cdist(np.array([[0, 1], [2, 3]]), np.array([[4, 5], [6, 7], [8, 9]]))
+    assert np.allclose(d, [[5.656854, 8.485281, 11.313708], [2.828427, 5.656854, 8.485281]])
+    p = pdist(np.array([[4, 5], [6, 7], [8, 9]]))
+    assert np.allclose(p, [2.828427, 5.656854, 2.828427]) and p.dtype == np.float32
+    sq = squareform(p)
+    assert sq.shape == (3, 3) and np.allclose(sq, sq.T) and np.allclose(np.diag(sq), 0) and sq[0, 2] == p[1]
+
+
+def test_random_vs_oracle_large_wraps_and_half_ties(du, oracle):
+    """Unwrapped walk with |n| up to ~6, integer lattice coordinates with d/box exactly k + 0.5 (roundf half away),
+    a zero box component (NaN distances) -- all must match the oracle bit for bit, including NaN patterns."""
+    rng = np.random.default_rng(11)
+    N, F = 160, 37
+    c = (rng.normal(size=(N, 3, F)) * 40).astype(np.float32)
+    c[:40] = np.round(c[:40])  # integers: with box = 2, 4, 6 many quotients are exact half-integers
+    bx = np.tile(np.array([[2.0], [4.0], [6.0]], np.float32), (1, F))
+    bx[:, F // 2:] = np.abs(rng.normal(size=(3, F - F // 2)) * 3 + 17).astype(np.float32)
+    bx[1, -1] = 0.0
+    ch = rng.integers(0, 3, N).astype(np.uint32)
+    s1 = np.sort(rng.choice(N, 70, replace=False)).astype(np.uint32)
+    s2 = np.sort(rng.choice(N, 90, replace=False)).astype(np.uint32)
+    for selfd, a, b in ((False, s1, s2), (True, s1, s1)):
+        P = du.n_columns(len(a), len(b), selfd)
+        want = np.zeros((F, P), np.float32); oracle.dist_trajectory(c, bx, a, b, ch, selfd, True, want)
+        got = np.zeros((F, P), np.float32); du.dist_trajectory(c, bx, a, b, ch, selfd, True, got)
+        assert np.isnan(want).any() and np.array_equal(_bits(got), _bits(want))
+        assert du.contacts_trajectory(c, bx, a, b, ch, selfd, True, 9.5) == oracle.contacts_trajectory(c, bx, a, b, ch, selfd, True, 9.5)
+
+
+def test_frame_shard_view_equals_full(du, g_raw):
+    """A frame slice of a resident device trajectory (what a GPU shard sees) gives the same rows."""
+    import torch
+
+    g = g_raw
+    dev = torch.device("cuda", 0)
+    c = torch.from_numpy(g["coords"]).to(dev); bx = torch.from_numpy(g["box"]).to(dev)
+    s1 = torch.from_numpy(g["sel1"].astype(np.int32)).to(dev); s2 = torch.from_numpy(g["sel2"].astype(np.int32)).to(dev)
+    ch = torch.from_numpy(g["chains"].view(np.int32)).to(dev)
+    full = du.dist_trajectory_device(c, bx, s1, s2, ch, False, True)
+    part = du.dist_trajectory_device(c[:, :, 2:6], bx[:, 2:6], s1, s2, ch, False, True)
+    assert torch.equal(full[2:6], part)
+    assert np.array_equal(_bits(full.cpu().numpy()), _bits(g["dist_pbc"]))
+
+
+# ------------------------------------------------------------------------------------------ MetricDistance API
+def test_distances_and_contacts(mol, g_traj):
+    """tests/test_metricdistance.py:37-51,182-193"""
+    from moleculekit_b200.projections.metricdistance import MetricDistance
+
+    data = MetricDistance("protein and name CA", "resname MOL and noh", metric="distances", periodic="selections").project(mol)
+    assert data.dtype == np.float32 and data.shape == (20, 2493)
+    assert np.allclose(data, g_traj["gold_distances"], atol=1e-3), "Distance calculation is broken"
+    assert np.array_equal(_bits(data), _bits(g_traj["ref_distances"]))
+    cont = MetricDistance("protein and name CA", "resname MOL and noh", periodic="selections", metric="contacts",
+                          threshold=8).project(mol)
+    assert cont.dtype == bool and np.allclose(cont, g_traj["gold_distances"] < 8, atol=1e-3)
+    assert np.array_equal(cont, g_traj["ref_distances"] <= np.float32(8))
+    trunc = MetricDistance("protein and name CA", "resname MOL and noh", periodic="selections", truncate=12.5).project(mol)
+    ref = g_traj["ref_distances"].copy(); ref[ref > 12.5] = 12.5
+    assert np.array_equal(_bits(trunc), _bits(ref))
+
+
+def test_mindistances(mol, g_traj):
+    """tests/test_metricdistance.py:196-228"""
+    from moleculekit_b200.projections.metricdistance import MetricDistance
+
+    kw = dict(periodic="selections", groupsel1="residue", groupsel2="all")
+    data = MetricDistance("protein and noh", "resname MOL and noh", **kw).project(mol)
+    assert data.shape == (20, 277) and np.allclose(data, g_traj["gold_mindistances"], atol=1e-3)
+    assert np.array_equal(_bits(data), _bits(g_traj["ref_mindistances"]))
+    data = MetricDistance("protein and noh", "resname MOL and noh", truncate=3, **kw).project(mol)
+    assert np.allclose(data, np.clip(g_traj["gold_mindistances"], 0, 3), atol=1e-3)
+
+
+def test_selfmindistance(mol, g_traj):
+    """tests/test_metricdistance.py:231-278 (manual == auto == golden[::10])"""
+    from moleculekit_b200.projections.metricdistance import MetricDistance, MetricSelfDistance
+
+    sel = "protein and resid 1 to 50 and noh"
+    manual = MetricDistance(sel, sel, periodic=None, groupsel1="residue", groupsel2="residue").project(mol)
+    auto = MetricSelfDistance(sel, groupsel="residue").project(mol)
+    assert manual.shape == (20, 1225) and np.array_equal(manual, auto)
+    assert np.allclose(auto, g_traj["gold_selfmindistance"], atol=1e-3)
+    assert np.array_equal(_bits(auto), _bits(g_traj["ref_selfmindistance"]))
+
+
+def test_periodicity_and_com(mol, g_traj):
+    """tests/test_metricdistance.py:329-352 + COM reductions frozen from the reference"""
+    from moleculekit_b200.projections.metricdistance import MetricDistance
+
+    a = "protein and resid 1 to 20 and noh"
+    d1 = MetricDistance(a, "resname MOL and noh", periodic="selections").project(mol)
+    d2 = MetricDistance(a, "resname MOL and noh", periodic="chains").project(mol)
+    assert np.allclose(d1, d2) and np.array_equal(_bits(d2), _bits(g_traj["ref_chains_distances"]))
+    m2 = mol.copy(); m2.chain[:] = ""
+    d3 = MetricDistance(a, "resname MOL and noh", periodic="chains").project(m2)
+    assert not np.allclose(d1, d3)
+    b = "protein and resid 1 to 50 and noh"
+    kw = dict(groupsel1="residue", groupsel2="all")
+    cc = MetricDistance(b, "resname MOL and noh", "selections", groupreduce1="com", groupreduce2="com", **kw).project(mol)
+    assert np.array_equal(_bits(cc), _bits(g_traj["ref_com_com"]))
+    cl = MetricDistance(b, "resname MOL and noh", "selections", groupreduce1="com", groupreduce2="closest", **kw).project(mol)
+    assert np.array_equal(_bits(cl), _bits(g_traj["ref_com_closest"]))
+
+
+def test_atomselect_forms_and_mapping(mol):
+    """tests/test_metricdistance.py:54-96: string / index / bool / manual groups, mapping shape"""
+    from moleculekit_b200.projections.metricdistance import MetricSelfDistance
+
+    data = MetricSelfDistance("protein and name CA", metric="contacts", threshold=8).project(mol)
+    assert data.shape == (20, 38226) and data.dtype == bool
+    ca = mol.atomselect("protein and name CA", indexes=True)
+    m = MetricSelfDistance(ca, metric="contacts", threshold=8)
+    assert np.array_equal(m.project(mol), data) and m.getMapping(mol).shape == (38226, 3)
+    assert np.array_equal(MetricSelfDistance(mol.atomselect("protein and name CA"), metric="contacts").project(mol), data)
+    m = MetricSelfDistance([ca[0::3], ca[1::3], ca[2::3]])
+    d3 = m.project(mol); mp = m.getMapping(mol)
+    assert d3.shape == (20, 3) and mp.shape == (3, 3)
+    masks = [np.isin(np.arange(mol.numAtoms), ca[k::3]) for k in range(3)]
+    assert np.array_equal(MetricSelfDistance(masks).project(mol), d3)
+
+
+def test_distances_trivial():
+    """tests/test_metricdistance.py:99-179 (analytic, incl. PBC wrap in a 2 A box and column ordering)"""
+    from moleculekit_b200.molecule_lite import MolLite
+    from moleculekit_b200.projections.metricdistance import MetricDistance
+
+    coords = np.zeros((3, 3, 2), dtype=np.float32)
+    coords[1, :, 0] = [3, 3, 3]; coords[2, :, 0] = [5, 5, 5]; coords[1, :, 1] = [7, 7, 7]; coords[2, :, 1] = [6, 6, 6]
+    mol = MolLite(coords, element=["C"] * 3, name=["C"] * 3, chain=list("012"))
+    i0, i12 = np.array([0]), np.array([1, 2])
+    real = np.linalg.norm(coords[[1, 2], :, :], axis=1).T
+    assert np.allclose(MetricDistance(i0, i12, metric="distances", periodic=None).project(mol), real)
+    wrapped = np.linalg.norm(np.mod(coords, 2)[[1, 2], :, :], axis=1).T
+    mol.box = np.full((3, 2), 2, dtype=np.float32)
+    assert np.allclose(MetricDistance(i0, i12, metric="distances", periodic="selections").project(mol), wrapped)
+    data = MetricDistance(i0, i12, metric="distances", periodic=None, groupsel1="all", groupsel2="all").project(mol)
+    assert np.allclose(data.flatten(), np.min(real, axis=1))
+    coords = np.zeros((4, 3, 2), dtype=np.float32)
+    coords[1, :, 0] = [1, 1, 1]; coords[2, :, 0] = [3, 3, 3]; coords[3, :, 0] = [5, 5, 5]
+    coords[1, :, 1] = [1, 1, 1]; coords[2, :, 1] = [7, 7, 7]; coords[3, :, 1] = [6, 6, 6]
+    mol = MolLite(coords, element=["C"] * 4, chain=list("0123"))
+    real = np.hstack((np.linalg.norm(coords[[2, 3]] - coords[0], axis=1).T, np.linalg.norm(coords[[2, 3]] - coords[1], axis=1).T))
+    assert np.allclose(MetricDistance(np.array([0, 1]), np.array([2, 3]), metric="distances", periodic=None).project(mol), real)
+
+
+def test_com_and_pair_distances(g_3ptb):
+    """tests/test_metricdistance.py:355-493 (analytic COM cases, 3ptb constants, pairs=True)"""
+    from moleculekit_b200.molecule_lite import MolLite
+    from moleculekit_b200.projections.metricdistance import MetricDistance
+
+    xyz = np.array([[0, 0, 0], [-1, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)[:, :, None]
+    mol = MolLite(xyz, element=["H"] * 4, resid=[0, 1, 1, 0])
+    fix = dict(periodic=None, groupsel1="all", groupsel2="all", groupreduce1="com", groupreduce2="com")
+    I = lambda *a: np.array(a)
+    assert abs(MetricDistance(I(0), I(1), **fix).project(mol)[0][0] - 1) < 1e-5
+    assert abs(MetricDistance(I(0, 1), I(2), **fix).project(mol)[0][0] - 1.5) < 1e-5
+    assert abs(MetricDistance(I(0, 1, 2), I(3), **fix).project(mol)[0][0] - 1) < 1e-5
+    fix["groupsel1"] = "residue"
+    assert np.allclose(MetricDistance(I(0, 1, 2), I(3), **fix).project(mol), [[1, 1]])
+    fix["groupsel1"], fix["groupreduce1"] = "all", "closest"
+    assert np.allclose(MetricDistance(I(0, 1, 2), I(3), **fix).project(mol), [[1]])
+    fix["groupsel1"] = "residue"
+    assert np.allclose(MetricDistance(I(0, 1, 2), I(3), **fix).project(mol), [[1, 1.4142135]])
+
+    g = g_3ptb
+    mol = MolLite(g["coords"], g["box"], element=g["element"], resid=g["resid"], resname=g["resname"], name=g["name"],
+                  chain=g["chain"], named_selections={"protein": g["sel_protein"], "resname BEN": g["sel_ben"]})
+    kw = dict(groupsel1="all", groupsel2="all")
+    for r1, r2, key, const in (("com", "com", "ref_com_com", None), ("com", "closest", "ref_com_closest", 8.978174),
+                               ("closest", "com", "ref_closest_com", 3.8286476),
+                               ("closest", "closest", "ref_closest_closest", 2.8153415)):
+        d = MetricDistance("protein", "resname BEN", None, groupreduce1=r1, groupreduce2=r2, **kw).project(mol)
+        assert np.array_equal(_bits(d), _bits(g[key])), key
+        if const is not None:
+            assert abs(d[0][0] - const) < 1e-5
+    sel1 = np.array([0, 1, 2]).reshape(-1, 1); sel2 = np.array([1, 2, 3]).reshape(-1, 1)
+    res = MetricDistance(sel1, sel2, None, pairs=True).project(mol)
+    ref = np.linalg.norm(g["coords"][sel1.flatten(), :, 0] - g["coords"][sel2.flatten(), :, 0], axis=1)
+    assert np.allclose(res, ref) and MetricDistance(sel1, sel2, None, pairs=True).getMapping(mol).shape == (3, 3)
+    res = MetricDistance([g["sel_residue_1"], g["sel_residue_2"]], [g["sel_residue_3"], g["sel_residue_4"]], None,
+                         pairs=True).project(mol)
+    assert np.array_equal(_bits(res), _bits(g["ref_pairs_residue"]))
+    with pytest.raises(RuntimeError, match="Pairs calculation not implemented without groups"):
+        MetricDistance(np.array([0, 1]), np.array([2, 3]), None, pairs=True).project(mol)
+
+
+def test_calculate_contacts_and_metal_coordination(mol, g_traj, g_3ptb, g_5vl5):
+    """ordered index pairs: tests/test_interactions.py:329-350 + frozen calculate_contacts outputs"""
+    from moleculekit_b200.distance import calculate_contacts
+    from moleculekit_b200.molecule_lite import MolLite
+
+    sel = {s: m for s, m in zip(g_traj["sel_strings"].tolist(), g_traj["sel_masks"])}
+    ca, lig, noh = sel["protein and name CA"], sel["resname MOL and noh"], sel["protein and noh"]
+    for key, a, b, per, thr in (("ct_ca_lig_sel8", ca, lig, "selections", 8), ("ct_ca_ca_none6", ca, ca, None, 6),
+                                ("ct_noh_lig_chains5", noh, lig, "chains", 5)):
+        res = calculate_contacts(mol, a, b, per, thr)
+        assert [len(r) for r in res] == g_traj[key + "_cnt"].tolist(), key
+        assert all(r.dtype == np.uint32 and r.shape[1:] == (2,) for r in res)
+        assert np.array_equal(np.vstack(res), g_traj[key + "_pairs"]), key
+    m3 = MolLite(g_3ptb["coords"], g_3ptb["box"], element=g_3ptb["element"])
+    res = calculate_contacts(m3, g_3ptb["mc_sel1"], g_3ptb["mc_sel2"], None, 3.5)
+    assert np.array_equal(res[0], g_3ptb["mc_expected"])
+    m5 = MolLite(g_5vl5["coords"], g_5vl5["box"], element=g_5vl5["element"])
+    per = None if np.all(g_5vl5["box"] == 0) else "selections"
+    r1 = calculate_contacts(m5, g_5vl5["mc_a_sel1"], g_5vl5["mc_a_sel2"], per, 3.5)
+    r2 = calculate_contacts(m5, g_5vl5["mc_b_sel1"], g_5vl5["mc_b_sel2"], per, 3.5)
+    assert np.array_equal(np.vstack((r1[0], r2[0])), g_5vl5["mc_expected"])
+
+
+def test_errors(mol):
+    from moleculekit_b200.molecule_lite import MolLite
+    from moleculekit_b200.projections.metricdistance import MetricDistance
+
+    with pytest.raises(RuntimeError, match="can only be None, 'chains' or 'selections'"):
+        MetricDistance("a", "b", periodic="everything")
+    nobox = MolLite(np.zeros((3, 3, 2), np.float32))
+    with pytest.raises(RuntimeError, match="No periodic box dimensions given"):
+        MetricDistance(np.array([0]), np.array([1, 2]), periodic="selections").project(nobox)
+    with pytest.raises(RuntimeError, match="Selection returned 0 atoms"):
+        MetricDistance(np.zeros(3, bool), np.array([1]), None).project(nobox)
+    with pytest.raises(RuntimeError, match="not supported"):
+        MetricDistance(np.array([0]), np.array([1]), None, metric="bananas").project(nobox)
+    bad = MolLite(np.zeros((3, 3, 2), np.float32), box=np.ones((3, 5), np.float32))
+    with pytest.raises(RuntimeError, match="Different number of frames"):
+        MetricDistance(np.array([0]), np.array([1]), "selections").project(bad)
