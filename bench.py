@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="items per GPU (0 = the config's size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (C2 ligands, C5 fine grids, C4 distances)")
     return ap.parse_args()
 
 
@@ -94,12 +95,9 @@ def cpu_kind():
     return "port"
 
 
-def cpu_sample(w, n_items: int, procs: int):
-    """Time the CPU kernel on the first n_items of the workload, one single-threaded process per item (the
-    reference kernel is single-threaded: OpenMP is commented out in its setup.py:48)."""
+def _cpu_sample_once(w, n_items: int, procs: int, kind: str):
     import multiprocessing as mp
 
-    kind = cpu_kind()
     jobs = [(kind, w["coords"][b], w["sigmas"][b], w["boxsize"], w["centers"][b], w["voxelsize"])
             for b in range(n_items)]
     ctx = mp.get_context("fork")
@@ -107,10 +105,23 @@ def cpu_sample(w, n_items: int, procs: int):
     with ctx.Pool(processes=procs) as pool:
         res = pool.map(_cpu_worker, jobs, chunksize=1)
     wall = time.perf_counter() - t0
-    vc = sum(r[1] for r in res)
-    return dict(value=vc / wall, unit=UNIT, cores=procs, kind=kind,
-                sample=f"{n_items} of the workload's items, kernel only (centres prebuilt), {procs} processes x 1 thread, "
-                       f"{sum(r[0] for r in res):.1f} core-seconds"), wall
+    return sum(r[1] for r in res) / wall, wall, sum(r[0] for r in res)
+
+
+def cpu_sample(w, n_items: int, procs: int):
+    """Time the CPU kernel on the first items of the workload, one single-threaded process per item (the reference
+    kernel is single-threaded: OpenMP is commented out in its setup.py:48).  The kernel streams a 6 MB centre array per
+    atom, so oversubscribing hyper-threads can LOWER throughput: two process counts are tried (all logical cores and a
+    quarter of them) and the better one is reported, with both in `sample`."""
+    kind = cpu_kind()
+    tried = []
+    for p in sorted({max(1, procs // 4), procs}):
+        n = min(n_items, p)
+        tried.append((p,) + _cpu_sample_once(w, n, p, kind))
+    best = max(tried, key=lambda t: t[1])
+    desc = "; ".join(f"{p} procs x 1 thread on {min(n_items, p)} items: {v:.3g} vc/s ({cs:.0f} core-s)" for p, v, _, cs in tried)
+    return dict(value=best[1], unit=UNIT, cores=best[0], kind=kind,
+                sample=f"kernel only (centres prebuilt), first items of the workload; {desc}"), best[2]
 
 
 def run_reference(a):
@@ -119,7 +130,7 @@ def run_reference(a):
         return
     procs = os.cpu_count() or 1
     w = make_workload(a.workload, a.batch, 0)
-    n_items = min(len(w["coords"]), max(1, min(procs, 64)))
+    n_items = min(len(w["coords"]), max(1, procs))
     for _ in range(a.warmup):
         cpu_sample(w, n_items, procs)
     walls, base = [], None
@@ -180,6 +191,65 @@ class ClockSampler:
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------- side measurements
+def _time_cuda(fn, warm=3, steps=10):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def extra_workloads(dev, peak):
+    """Other BASELINE configs on one GPU, device-resident, reported beside the headline (not part of `value`)."""
+    import torch
+
+    from moleculekit_b200 import _lib, distance_utils as du, workloads
+    from moleculekit_b200.tools import voxeldescriptors as vd
+
+    out = {}
+    for key, w in (("c2_ligand_poses", workloads.ligand_poses(B=1024)), ("c5_fine_grids", workloads.fine_grids(B=4))):
+        vb = vd.VoxelBatch(w["coords"], w["sigmas"], boxsize=w["boxsize"], centers=w["centers"], voxelsize=w["voxelsize"])
+        d_c, d_s = vb.to_device(dev)
+        o = torch.empty((vb.total_voxels, vb.C), dtype=torch.float32, device=dev)
+        ms = _time_cuda(lambda: vb.run(d_c, d_s, o))
+        vb.run(d_c, d_s, o)
+        _, fill = _lib.get_timing(dev.index)
+        nb = workloads.occupancy_algorithmic_bytes(vb.total_voxels, vb.coords.shape[0], vb.C)
+        out[key] = dict(workload=w["name"], voxel_channels_per_s=vb.total_voxels * vb.C / (ms * 1e-3), ms_per_step=ms,
+                        fill_kernel_ms=fill, fill_kernel_gbs=nb / (fill * 1e-3) / 1e9, frac_of_peak=nb / (fill * 1e-3) / 1e9 / peak)
+        del o, d_c, d_s
+    # C4a: dense periodic distances, 256 x 1024 atoms, 10k frames (only the selected atoms are materialised)
+    n1, n2, F = 256, 1024, 10000
+    rng = np.random.default_rng(7)
+    L = 36.84
+    start = rng.uniform(0, L, size=(n1 + n2, 3, 1)).astype(np.float32)
+    coords = start + np.cumsum(rng.normal(0, 0.3, size=(n1 + n2, 3, F)).astype(np.float32), axis=2)
+    box = np.repeat((L * (1 + 0.002 * rng.normal(size=F))).astype(np.float32)[None, :], 3, axis=0)
+    d_c = torch.from_numpy(np.ascontiguousarray(coords)).to(dev); d_b = torch.from_numpy(np.ascontiguousarray(box)).to(dev)
+    s1 = torch.arange(0, n1, dtype=torch.int32, device=dev); s2 = torch.arange(n1, n1 + n2, dtype=torch.int32, device=dev)
+    ch = torch.ones(n1 + n2, dtype=torch.int32, device=dev); ch[n1:] = 2
+    for metric, s in (("distances", 4), ("contacts", 1)):
+        o = torch.empty((F, n1 * n2), dtype=torch.float32 if s == 4 else torch.uint8, device=dev)
+        ms = _time_cuda(lambda: du.dist_trajectory_device(d_c, d_b, s1, s2, ch, False, True, metric=metric, threshold=12.0, out=o), steps=5)
+        du.dist_trajectory_device(d_c, d_b, s1, s2, ch, False, True, metric=metric, threshold=12.0, out=o)
+        prep, main = _lib.get_timing(dev.index)
+        nb = F * ((n1 + n2) * 12 + 12 + n1 * n2 * s)
+        out[f"c4a_{metric}"] = dict(workload=f"C4a: {F} frames x {n1}x{n2} periodic pairs ({metric})",
+                                    pair_frames_per_s=F * n1 * n2 / (ms * 1e-3), ms_per_step=ms, gather_ms=prep,
+                                    kernel_ms=main, kernel_gbs=nb / (main * 1e-3) / 1e9,
+                                    frac_of_peak=nb / (main * 1e-3) / 1e9 / peak)
+        del o
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
@@ -288,15 +358,21 @@ def run_ours(a):
     alg_bytes = workloads.occupancy_algorithmic_bytes(batch.total_voxels, n_atoms, batch.C)
     fill_mean = float(np.mean(fill_ms))
     achieved = alg_bytes / (fill_mean * 1e-3) / 1e9
-    roofline = dict(bound="hbm", kernel="occ_fill_kernel<8>", achieved=achieved, peak=peak, unit="GB/s",
+    roofline = dict(bound="hbm", kernel="occ_fill8_kernel", achieved=achieved, peak=peak, unit="GB/s",
                     frac=achieved / peak, traffic=None, peak_source=f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
                     algorithmic_bytes_per_launch=int(alg_bytes), kernel_ms_mean=fill_mean,
                     kernel_ms_min=float(np.min(fill_ms)), prep_ms_mean=float(np.mean(prep_ms)),
                     kernel_share_of_step=fill_mean / ms_step)
+    extra = None
+    if world == 1 and not a.no_extra:
+        try:
+            extra = extra_workloads(dev, peak)
+        except Exception as e:  # never let a side measurement break the headline line
+            extra = {"error": repr(e)}
     cpu = None
     if not a.no_cpu and world == 1:
         procs = os.cpu_count() or 1
-        n_items = min(batch.B, max(1, min(procs, 32)))
+        n_items = min(batch.B, max(1, procs))
         cpu, _ = cpu_sample(w, n_items, procs)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
@@ -305,7 +381,7 @@ def run_ours(a):
                             voxel_channels_per_gpu=int(n_vc),
                             l2="no flush needed: each step streams %.2f GB of grid output, >> 126 MB L2" % (n_vc * 4 / 1e9),
                             parallelism=f"batch sharded over {world} GPU(s), no collective"),
-                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk)
+                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk, extra=extra)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

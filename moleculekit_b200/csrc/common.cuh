@@ -24,6 +24,7 @@ enum ScratchSlot {
     S_PT_ORDER,     // points path: atom order
     S_ROWCNT,       // contacts: per-row counts
     S_COM,          // reductions: centres of mass
+    S_TILE_TOTAL,   // occupancy fast path: halo atom count per tile
     S_NSLOTS
 };
 

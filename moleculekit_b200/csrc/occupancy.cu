@@ -20,6 +20,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cfloat>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 
@@ -177,6 +178,7 @@ struct FillParams {
     float *out;
     unsigned flags;
     int vec_ok;
+    int txp_shift;  // fast path launch: blockIdx.z = (grid << txp_shift) | tile_x
 };
 
 // float64 re-evaluation of the gate with the reference's exact operations (pyx:49-53; centres as built by
@@ -411,6 +413,298 @@ __global__ void __launch_bounds__(FILL_THREADS, (CP <= 8 ? 2 : 1)) occ_fill_kern
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K1 fast path (C <= 8): quarter-warp candidate lists.
+//   The 2x4x4 block of a warp is split into four 2x2x2 sub-blocks, one per quarter-warp (8 lanes).  An atom within
+//   5 A of the 2x4x4 block is within 5 A of only ~66 % of the voxels of a 2x2x2 sub-block it touches (43 % for the
+//   whole block), so giving every quarter its OWN compacted candidate list removes a third of the wasted lane work.
+//   Lists hold 16-bit indices into the tile list; LDS.128 serves the four quarters' four different records in its four
+//   phases at no extra cost.  Shorter quarters are padded with a far-away sentinel so the loop stays branch-free.
+// ---------------------------------------------------------------------------------------------------------
+constexpr float GATE_SCALE = 1.2676506002282294e30f;  // 2^100
+constexpr int V3_CAP = 1024;   // tile list (halo atoms of one 8x8x8 tile) per pass
+constexpr int V3_PCAP = 160;   // parent (2x4x4 block) candidates per round
+constexpr int V3_QCAP = 96;    // sub-block (2x2x2) candidates per round
+
+__global__ void occ_tile_total_kernel(const GridDev *__restrict__ grids, const unsigned *__restrict__ cell_start,
+                                      unsigned *__restrict__ tile_total) {
+    const GridDev &g = grids[blockIdx.y];
+    const int ntiles = g.tiles[0] * g.tiles[1] * g.tiles[2];
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= ntiles) return;
+    const int tzN = g.tiles[2], tyN = g.tiles[1];
+    const int tz = local % tzN, txy = local / tzN, ty = txy % tyN, tx = txy / tyN;
+    const int R = g.rcells, cN1 = g.cells[1], cN2 = g.cells[2];
+    const int cx1 = min(tx + R, g.cells[0] - 1), cy1 = min(ty + R, cN1 - 1), cz1 = min(tz + R, cN2 - 1);
+    unsigned total = 0;
+    for (int cx = tx; cx <= cx1; ++cx)
+        for (int cy = ty; cy <= cy1; ++cy) {
+            const long long cb = g.cell_base + ((long long)cx * cN1 + cy) * cN2;
+            total += cell_start[cb + cz1 + 1] - cell_start[cb + tz];
+        }
+    tile_total[g.tile_base + local] = total;
+}
+
+__global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillParams p, const unsigned *__restrict__ tile_total) {
+    __shared__ float4 s_ent[V3_CAP + 1];  // +1: sentinel
+    __shared__ unsigned s_mask[V3_CAP + 1];
+    __shared__ unsigned s_src[V3_CAP];
+    __shared__ unsigned s_rpos[128];
+    __shared__ unsigned s_rbase[128 + 1];
+    __shared__ unsigned short s_pidx[FILL_THREADS / 32][V3_PCAP];
+    __shared__ unsigned short s_qidx[FILL_THREADS / 32][4][V3_QCAP];
+    __shared__ int s_cnt;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // grid = (tiles_z, tiles_y, grids << txp_shift | tiles_x): no integer division in the prologue
+    const int tz = blockIdx.x, ty = blockIdx.y, tx = blockIdx.z & ((1 << p.txp_shift) - 1);
+    const GridDev *gg = p.grids + (blockIdx.z >> p.txp_shift);
+    const int tzN = __ldg(&gg->tiles[2]), tyN = __ldg(&gg->tiles[1]);
+    if (tz >= tzN || ty >= tyN || tx >= __ldg(&gg->tiles[0])) return;  // ragged batch / power-of-two padding
+    const int local = (tx * tyN + ty) * tzN + tz;
+    const int nx = __ldg(&gg->dims[0]), ny = __ldg(&gg->dims[1]), nz = __ldg(&gg->dims[2]);
+
+    // lane -> voxel: quarter q = lane >> 3 owns the 2x2x2 sub-block (qy, qz) of the warp's 2x4x4 block
+    const int bx = warp >> 2, by = (warp >> 1) & 1, bz = warp & 1;
+    const int q = lane >> 3, sub = lane & 7;
+    const int vx = bx * 2 + (sub >> 2), vy = by * 4 + (q >> 1) * 2 + ((sub >> 1) & 1), vz = bz * 4 + (q & 1) * 2 + (sub & 1);
+    const int ix = tx * TILE + vx, iy = ty * TILE + vy, iz = tz * TILE + vz;
+    const bool inside = ix < nx && iy < ny && iz < nz;
+    float *const o = p.out + (__ldg(&gg->out_offset) + ((long long)ix * ny + iy) * nz + iz) * 8;
+
+    const unsigned total = __ldg(tile_total + __ldg(&gg->tile_base) + local);
+    float acc[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) acc[h] = 0.0f;
+    bool touched = false;
+
+    if (total != 0) {
+        // ---- cell rows feeding this tile (same scheme as the generic kernel)
+        const int R = __ldg(&gg->rcells);
+        const int cN1 = __ldg(&gg->cells[1]), cN2 = __ldg(&gg->cells[2]);
+        const int cx1 = min(tx + R, __ldg(&gg->cells[0]) - 1), cy1 = min(ty + R, cN1 - 1), cz1 = min(tz + R, cN2 - 1);
+        const int ncy = cy1 - ty + 1;
+        const int nrows = (cx1 - tx + 1) * ncy;  // <= 128 checked on the host
+        if (tid < nrows) {
+            const int rx = tid / ncy, ry = tid - rx * ncy;
+            const long long cb = __ldg(&gg->cell_base) + ((long long)(tx + rx) * cN1 + (ty + ry)) * cN2;
+            const unsigned a = __ldg(p.cell_start + cb + tz), e = __ldg(p.cell_start + cb + cz1 + 1);
+            s_rpos[tid] = a;
+            s_rbase[tid + 1] = e - a;
+        }
+        if (tid == 0) {
+            s_rbase[0] = 0;
+            s_cnt = 0;
+            s_ent[V3_CAP] = make_float4(1e18f, 1e18f, 1e18f, 0.0f);  // sentinel: never inside the gate
+            s_mask[V3_CAP] = 1u;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned carry = 0;
+            for (int c0 = 0; c0 < nrows; c0 += 32) {
+                const int r = c0 + lane;
+                unsigned v = (r < nrows) ? s_rbase[r + 1] : 0u;
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, v, s);
+                    if (lane >= s) v += t;
+                }
+                if (r < nrows) s_rbase[r + 1] = v + carry;
+                carry += __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        __syncthreads();
+
+        const float cut_lo = __ldg(&gg->cut2v_lo), cut_hi = __ldg(&gg->cut2v_hi);
+        const float gate_k = GATE_SCALE * cut_lo;  // exact: power-of-two scaling
+        const unsigned band_bits = __float_as_uint(cut_hi - cut_lo);
+        const float fvx = (float)vx, fvy = (float)vy, fvz = (float)vz;
+        const float bcx = (float)(bx * 2), bcy = (float)(by * 4), bcz = (float)(bz * 4);
+        unsigned short *const my_p = s_pidx[warp];
+        unsigned short *const my_q = s_qidx[warp][q];
+        unsigned ent_sa, mask_sa;  // taken once; volatile so ptxas does not rebuild them from SR_CgaCtaId per use
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(ent_sa) : "l"(s_ent));
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(mask_sa) : "l"(s_mask));
+
+        for (unsigned c0 = 0; c0 < total; c0 += V3_CAP) {  // one pass unless > V3_CAP atoms sit in the halo
+            if (c0) {
+                __syncthreads();
+                if (tid == 0) s_cnt = 0;
+                __syncthreads();
+            }
+            const unsigned c1 = min(total, c0 + (unsigned)V3_CAP);
+            {
+                const double tox = (double)(tx * TILE), toy = (double)(ty * TILE), toz = (double)(tz * TILE);
+                for (unsigned k0 = c0; k0 < c1; k0 += FILL_THREADS) {
+                    const unsigned k = k0 + tid;
+                    bool pass = false;
+                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                    unsigned m = 0, sr = 0;
+                    if (k < c1) {
+                        int lo = 0, hi = nrows - 1;
+                        while (lo < hi) {
+                            const int mid = (lo + hi + 1) >> 1;
+                            if (s_rbase[mid] <= k) lo = mid; else hi = mid - 1;
+                        }
+                        const unsigned i = s_rpos[lo] + (k - s_rbase[lo]);
+                        e.x = (float)(p.px[i] - tox);
+                        e.y = (float)(p.py[i] - toy);
+                        e.z = (float)(p.pz[i] - toz);
+                        e.w = p.s2[i];
+                        m = p.mask[i];
+                        sr = p.src[i];
+                        const float ddx = fmaxf(fmaxf(-e.x, e.x - (float)(TILE - 1)), 0.f);
+                        const float ddy = fmaxf(fmaxf(-e.y, e.y - (float)(TILE - 1)), 0.f);
+                        const float ddz = fmaxf(fmaxf(-e.z, e.z - (float)(TILE - 1)), 0.f);
+                        pass = (m != 0) && (ddx * ddx + ddy * ddy + ddz * ddz <= cut_hi);
+                        if (sr & 0x80000000u) m = 0;  // several distinct sigmas: per-channel path
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                    if (bal) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_cnt, __popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (pass) {
+                            const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                            s_ent[slot] = e;
+                            s_mask[slot] = m;
+                            s_src[slot] = sr & 0x7fffffffu;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            const int n = s_cnt;
+
+            int j0 = 0;
+            while (j0 < n) {
+                // ---- stage A: tile list -> indices of the atoms within reach of this warp's 2x4x4 block
+                int np = 0;
+                for (; j0 < n && np <= V3_PCAP - 32; j0 += 32) {
+                    const int j = j0 + lane;
+                    const float4 e = lds_f4(ent_sa + min(j, n - 1) * 16);
+                    const float rx = e.x - bcx, ry = e.y - bcy, rz = e.z - bcz;
+                    const float ddx = fmaxf(fmaxf(-rx, rx - 1.f), 0.f);
+                    const float ddy = fmaxf(fmaxf(-ry, ry - 3.f), 0.f);
+                    const float ddz = fmaxf(fmaxf(-rz, rz - 3.f), 0.f);
+                    const bool hit = (j < n) & (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= cut_hi);
+                    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                    if (hit) my_p[np + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)j;
+                    np += __popc(bal);
+                }
+                if (np == 0) continue;
+                touched = true;
+                __syncwarp();
+                // ---- stage B: parent list -> four sub-block lists; stage C: evaluate
+                int cq0 = 0, cq1 = 0, cq2 = 0, cq3 = 0;
+                for (int k0 = 0; k0 < np; k0 += 32) {
+                    const int k = k0 + lane;
+                    const bool live = k < np;
+                    const unsigned idx = my_p[min(k, np - 1)];
+                    bool h0, h1, h2, h3, multi;
+                    {
+                        const float4 e = lds_f4(ent_sa + idx * 16);
+                        const float rx = e.x - bcx, ry = e.y - bcy, rz = e.z - bcz;
+                        const float ddx = fmaxf(fmaxf(-rx, rx - 1.f), 0.f);
+                        const float y0 = fmaxf(fmaxf(-ry, ry - 1.f), 0.f), y1 = fmaxf(fmaxf(2.f - ry, ry - 3.f), 0.f);
+                        const float z0 = fmaxf(fmaxf(-rz, rz - 1.f), 0.f), z1 = fmaxf(fmaxf(2.f - rz, rz - 3.f), 0.f);
+                        const float xx = ddx * ddx;
+                        const float a0 = fmaf(y0, y0, xx), a1 = fmaf(y1, y1, xx);
+                        multi = live & (lds_u32(mask_sa + idx * 4) == 0);
+                        const bool ok = live & !multi;
+                        h0 = ok & (fmaf(z0, z0, a0) <= cut_hi);  // q = qy*2 + qz
+                        h1 = ok & (fmaf(z1, z1, a0) <= cut_hi);
+                        h2 = ok & (fmaf(z0, z0, a1) <= cut_hi);
+                        h3 = ok & (fmaf(z1, z1, a1) <= cut_hi);
+                    }
+                    // atoms carrying several distinct sigmas (user float channels): whole-warp per-channel path
+                    for (unsigned bm = __ballot_sync(0xffffffffu, multi); bm; bm &= bm - 1) {
+                        const int jj = my_p[k0 + __ffs(bm) - 1];
+                        const float4 e = s_ent[jj];
+                        const float dx = e.x - fvx, dy = e.y - fvy, dz = e.z - fvz;
+                        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        bool in = d2 < cut_lo;
+                        if (!in && d2 < cut_hi) in = exact_gate(gg, p.coords, s_src[jj], ix, iy, iz);
+                        const float rr = in ? rcp_approx(d2) : 0.0f;
+                        const double *sg = p.sigmas + (long long)s_src[jj] * p.C;
+                        const double ivs = __ldg(&gg->inv_vs);
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) {
+                            if (h < p.C) {
+                                const double sv = sg[h] * ivs;
+                                const float sq = (sv == 0.0 || sv != sv) ? 0.0f : fmaxf((float)(sv * sv), FLT_MIN);
+                                acc[h] = fmaxf(acc[h], sq * rr);  // 0*inf = NaN is dropped by fmaxf
+                            }
+                        }
+                    }
+                    const unsigned lt = (1u << lane) - 1u;
+                    const unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
+                    const unsigned b2 = __ballot_sync(0xffffffffu, h2), b3 = __ballot_sync(0xffffffffu, h3);
+                    unsigned short *const wq = s_qidx[warp][0];
+                    if (h0) wq[0 * V3_QCAP + cq0 + __popc(b0 & lt)] = (unsigned short)idx;
+                    if (h1) wq[1 * V3_QCAP + cq1 + __popc(b1 & lt)] = (unsigned short)idx;
+                    if (h2) wq[2 * V3_QCAP + cq2 + __popc(b2 & lt)] = (unsigned short)idx;
+                    if (h3) wq[3 * V3_QCAP + cq3 + __popc(b3 & lt)] = (unsigned short)idx;
+                    cq0 += __popc(b0); cq1 += __popc(b1); cq2 += __popc(b2); cq3 += __popc(b3);
+                    const int nmax = max(max(cq0, cq1), max(cq2, cq3));
+                    if (k0 + 32 < np && nmax <= V3_QCAP - 32) continue;
+                    // pad the shorter quarters with the sentinel, then run all four lists in lock-step
+                    const int mine = (q == 0) ? cq0 : (q == 1) ? cq1 : (q == 2) ? cq2 : cq3;
+                    for (int c = mine + sub; c < nmax; c += 8) my_q[c] = (unsigned short)V3_CAP;
+                    __syncwarp();
+                    for (int c = 0; c < nmax; ++c) {
+                        const unsigned jj = my_q[c];
+                        const float4 e = lds_f4(ent_sa + jj * 16);
+                        const unsigned cm = lds_u32(mask_sa + jj * 4);
+                        const float dx = e.x - fvx, dy = e.y - fvy, dz = e.z - fvz;
+                        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        const float qf = e.w * rcp_approx(d2);  // sigma^2/d2; +inf at d2 == 0 -> value 1
+                        // gate on the FMA pipe (the ALU pipe carries the 8 FMNMX and is the busiest unit):
+                        // g = sat(2^100 * (cut_lo - d2)) is exactly 1 for d2 < cut_lo and 0 otherwise (NaN -> 0)
+                        float qv = qf * __saturatef(fmaf(-GATE_SCALE, d2, gate_k));
+                        // d2 in [cut_lo, cut_hi): (d2 - cut_lo) as unsigned bits is < bits(band) only for 0 <= t < band
+                        if (__float_as_uint(d2 - cut_lo) < band_bits) {  // within 4e-6 of the gate: decide like the reference
+                            if (exact_gate(gg, p.coords, s_src[jj], ix, iy, iz)) qv = qf;
+                        }
+#pragma unroll
+                        for (int h = 0; h < 8; ++h)
+                            if (cm & (1u << h)) acc[h] = fmaxf(acc[h], qv);
+                    }
+                    __syncwarp();
+                    cq0 = cq1 = cq2 = cq3 = 0;
+                }
+            }
+        }
+    }
+
+    // ---- epilogue
+    if (inside) {
+        const int C = p.C;
+        float v[8];
+        if (touched) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) v[h] = occ_value(acc[h]);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) v[h] = 0.0f;
+        }
+        float *const oo = p.vec_ok ? o : p.out + (__ldg(&gg->out_offset) + ((long long)ix * ny + iy) * nz + iz) * C;
+        if (p.flags & MKB_OCC_ACCUMULATE) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h)
+                if (h < C) { const float old = oo[h]; v[h] = (v[h] > old) ? v[h] : old; }
+        }
+        if (p.vec_ok) {
+            __stcs(reinterpret_cast<float4 *>(oo), make_float4(v[0], v[1], v[2], v[3]));
+            __stcs(reinterpret_cast<float4 *>(oo) + 1, make_float4(v[4], v[5], v[6], v[7]));
+        } else {
+#pragma unroll
+            for (int h = 0; h < 8; ++h)
+                if (h < C) oo[h] = v[h];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K1b: arbitrary centres.  Atoms hashed into 5 A cells (count -> scan -> order); one thread per centre visits the
 // 27 neighbouring buckets.  Distances in float64 exactly as the reference (pyx:49-53), so the gate is exact.
 // ---------------------------------------------------------------------------------------------------------
@@ -611,7 +905,13 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     fp.px = px; fp.py = py; fp.pz = pz; fp.s2 = s2; fp.mask = mask; fp.src = src;
     fp.cell_start = cell_start; fp.coords = coords; fp.sigmas = sigmas; fp.out = out; fp.flags = flags;
     fp.vec_ok = (C == 8 && ((uintptr_t)out % 16 == 0)) ? 1 : 0;
+    fp.txp_shift = 0;
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
+    bool fast8 = (C <= 8);
+    for (int b = 0; b < B && fast8; ++b) fast8 = (gd[b].rcells + 1) * (gd[b].rcells + 1) <= 128;
+    if (getenv("MKB_OCC_GENERIC")) fast8 = false;  // debugging / A-B switch: force the generic kernel
+    unsigned *tile_total = nullptr;
+    if (fast8 && (rc = scratch_get(h, S_TILE_TOTAL, (size_t)tiles, &tile_total))) return rc;
     for (int b0 = 0; b0 < B; b0 += 65535) {  // blockIdx.y = grid of the batch
         const int nb = std::min(65535, B - b0);
         fp.grids = d_grids + b0;
@@ -619,7 +919,26 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
         long long mt = 0;
         for (int b = b0; b < b0 + nb; ++b) mt = std::max<long long>(mt, (long long)gd[b].tiles[0] * gd[b].tiles[1] * gd[b].tiles[2]);
         const dim3 grid((unsigned)mt, (unsigned)nb);
-        if (C <= 8) occ_fill_kernel<8><<<grid, FILL_THREADS, 0, st>>>(fp);
+        if (fast8) {
+            occ_tile_total_kernel<<<dim3((unsigned)cdiv(mt, 128), (unsigned)nb), 128, 0, st>>>(fp.grids, cell_start, tile_total);
+            MKB_LAUNCHED(h);
+            int mx = 1, my = 1, mz = 1;
+            for (int b = b0; b < b0 + nb; ++b) {
+                mx = std::max(mx, gd[b].tiles[0]); my = std::max(my, gd[b].tiles[1]); mz = std::max(mz, gd[b].tiles[2]);
+            }
+            int sh = 0;
+            while ((1 << sh) < mx) ++sh;
+            fp.txp_shift = sh;
+            const int per_launch = std::max(1, 65535 >> sh);  // gridDim.z <= 65535
+            if (my > 65535) return fail(h, MKB_ERR_BAD_ARG, "grid too large along y for one call");
+            for (int c0 = 0; c0 < nb; c0 += per_launch) {
+                const int cn = std::min(per_launch, nb - c0);
+                FillParams fq = fp;
+                fq.grids = fp.grids + c0;
+                occ_fill8_kernel<<<dim3((unsigned)mz, (unsigned)my, (unsigned)(cn << sh)), FILL_THREADS, 0, st>>>(fq, tile_total);
+                if (c0 + per_launch < nb) MKB_LAUNCHED(h);
+            }
+        } else if (C <= 8) occ_fill_kernel<8><<<grid, FILL_THREADS, 0, st>>>(fp);
         else if (C <= 16) occ_fill_kernel<16><<<grid, FILL_THREADS, 0, st>>>(fp);
         else occ_fill_kernel<32><<<grid, FILL_THREADS, 0, st>>>(fp);
         MKB_LAUNCHED(h);

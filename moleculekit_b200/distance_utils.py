@@ -20,17 +20,26 @@ _NAN = float("nan")
 
 
 def _traj(coords: torch.Tensor, box: torch.Tensor) -> _lib.Traj:
+    """`mkb_traj` view of a (N, 3, F) frame-minor trajectory (contiguous, or a frame slice of a contiguous one)."""
     assert coords.is_cuda and box.is_cuda and coords.dtype == torch.float32 and box.dtype == torch.float32
     assert coords.ndim == 3 and coords.shape[1] == 3 and box.ndim == 2 and box.shape[0] == 3
-    assert coords.stride(2) == 1 and coords.stride(1) == coords.stride(0) // 3 and box.stride(1) == 1, \
-        "coords must be (N, 3, F) frame-minor (a frame slice of a contiguous trajectory is fine)"
+    N, _, F = coords.shape
     t = _lib.Traj()
+    t.n_atoms, t.n_frames = N, F
+    if F <= 1 or N == 0:
+        # strides of size-1 / empty dimensions are meaningless (numpy views may carry 0): normalise
+        coords = coords.contiguous()
+        box = box.contiguous()
+        t.frame_stride = max(F, 1)
+        t.frame_stride_box = max(F, 1)
+    else:
+        assert coords.stride(2) == 1 and coords.stride(0) == 3 * coords.stride(1) and box.stride(1) == 1, \
+            "coords must be (N, 3, F) frame-minor (a frame slice of a contiguous trajectory is fine)"
+        t.frame_stride = coords.stride(1)
+        t.frame_stride_box = box.stride(0)
     t.coords = coords.data_ptr()
     t.box = box.data_ptr()
-    t.n_atoms = coords.shape[0]
-    t.n_frames = coords.shape[2]
-    t.frame_stride = coords.stride(1) if coords.shape[0] * coords.shape[2] else max(coords.shape[2], 1)
-    t.frame_stride_box = box.stride(0) if box.shape[1] else max(box.shape[1], 1)
+    t._keepalive = (coords, box)  # the normalised copies must outlive the launch
     return t
 
 
