@@ -179,6 +179,7 @@ struct FillParams {
     unsigned flags;
     int vec_ok;
     int txp_shift;  // fast path launch: blockIdx.z = (grid << txp_shift) | tile_x
+    int bulk_store; // fast path: stage the tile in smem and store rows with cp.async.bulk (TMA)
 };
 
 // float64 re-evaluation of the gate with the reference's exact operations (pyx:49-53; centres as built by
@@ -676,17 +677,43 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillPa
         }
     }
 
-    // ---- epilogue
+    // ---- epilogue: one transcendental per voxel-channel
+    float v[8];
+    if (touched) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) v[h] = occ_value(acc[h]);
+    } else {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) v[h] = 0.0f;
+    }
+    if (p.bulk_store) {
+        // TMA path: the tile is staged in shared memory as [x][y][z][channel] (the tile list's storage is dead by now)
+        // and leaves the SM as 64 bulk-async row copies (cp.async.bulk.global.shared::cta, SASS UBLKCP) of up to
+        // 256 contiguous bytes each: full-sector writes, no per-thread store instructions, clipping by row length.
+        __syncthreads();  // every warp is done reading the tile list
+        float4 *const stage = s_ent;
+        const int vt = (vx * TILE + vy) * TILE + vz;
+        stage[vt * 2 + 0] = make_float4(v[0], v[1], v[2], v[3]);
+        stage[vt * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid < TILE * TILE) {
+            const int rx = tid >> 3, ry = tid & 7;
+            const int ixr = tx * TILE + rx, iyr = ty * TILE + ry;
+            const int nzr = min(TILE, nz - tz * TILE);
+            if (ixr < nx && iyr < ny) {
+                float *const dst = p.out + (__ldg(&gg->out_offset) + ((long long)ixr * ny + iyr) * nz + tz * TILE) * 8;
+                const unsigned src = (unsigned)__cvta_generic_to_shared(stage + tid * (TILE * 2));
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(dst), "r"(src), "r"(nzr * 32) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the copy
+        }
+        return;
+    }
     if (inside) {
         const int C = p.C;
-        float v[8];
-        if (touched) {
-#pragma unroll
-            for (int h = 0; h < 8; ++h) v[h] = occ_value(acc[h]);
-        } else {
-#pragma unroll
-            for (int h = 0; h < 8; ++h) v[h] = 0.0f;
-        }
         float *const oo = p.vec_ok ? o : p.out + (__ldg(&gg->out_offset) + ((long long)ix * ny + iy) * nz + iz) * C;
         if (p.flags & MKB_OCC_ACCUMULATE) {
 #pragma unroll
@@ -906,6 +933,9 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     fp.cell_start = cell_start; fp.coords = coords; fp.sigmas = sigmas; fp.out = out; fp.flags = flags;
     fp.vec_ok = (C == 8 && ((uintptr_t)out % 16 == 0)) ? 1 : 0;
     fp.txp_shift = 0;
+    // opt-in (MKB_OCC_BULK_STORE=1): measured 21 % slower in this non-persistent kernel because the CTA has to wait for
+    // the asynchronous smem read before it may retire; kept for the persistent variant
+    fp.bulk_store = (fp.vec_ok && !(flags & MKB_OCC_ACCUMULATE) && getenv("MKB_OCC_BULK_STORE")) ? 1 : 0;
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
     bool fast8 = (C <= 8);
     for (int b = 0; b < B && fast8; ++b) fast8 = (gd[b].rcells + 1) * (gd[b].rcells + 1) <= 128;

@@ -189,3 +189,19 @@ def test_full_size_c3_properties(vd, oracle):
         centers, _ = vd.getCenters(boxsize=w["boxsize"], center=w["centers"][b], voxelsize=1.0)
         want = np.zeros((centers.shape[0], 8)); oracle.calculate_occupancy(centers, w["coords"][b], w["sigmas"][b], want)
         _assert_occ_close(out[offs[b]:offs[b + 1]].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("env", ["MKB_OCC_BULK_STORE", "MKB_OCC_GENERIC"])
+def test_alternative_kernel_paths_agree(vd, monkeypatch, env):
+    """The opt-in TMA bulk-store epilogue and the generic (non quarter-warp) kernel produce the same bits as the
+    default fast path (ragged grid: dims not multiples of the 8-voxel tile)."""
+    from moleculekit_b200 import workloads
+
+    w = workloads.protein_pockets(B=2, n_atoms=700, box=37.0, radius=12.0, seed=21)
+    kw = dict(boxsize=[37.0, 29.0, 22.0], centers=w["centers"], voxelsize=1.0)
+    ref, dims = vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], **kw)
+    monkeypatch.setenv(env, "1")
+    alt, _ = vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], **kw)
+    assert dims.tolist() == [[37, 29, 22]] * 2
+    for a, b in zip(ref, alt):
+        assert np.array_equal(a, b)
