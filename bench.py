@@ -358,7 +358,7 @@ def run_ours(a):
     alg_bytes = workloads.occupancy_algorithmic_bytes(batch.total_voxels, n_atoms, batch.C)
     fill_mean = float(np.mean(fill_ms))
     achieved = alg_bytes / (fill_mean * 1e-3) / 1e9
-    roofline = dict(bound="hbm", kernel="occ_fill8_kernel", achieved=achieved, peak=peak, unit="GB/s",
+    roofline = dict(bound="hbm", kernel=("occ_fill8w_kernel" if w["voxelsize"] >= 5.0 / 7 else "occ_fill8_kernel"), achieved=achieved, peak=peak, unit="GB/s",
                     frac=achieved / peak, traffic=None, peak_source=f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
                     algorithmic_bytes_per_launch=int(alg_bytes), kernel_ms_mean=fill_mean,
                     kernel_ms_min=float(np.min(fill_ms)), prep_ms_mean=float(np.mean(prep_ms)),

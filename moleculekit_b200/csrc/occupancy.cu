@@ -29,6 +29,7 @@
 namespace mkb {
 
 constexpr int TILE = 8;
+constexpr float TILE_C = 0.5f * (TILE - 1);  // tile-frame origin: centre of the 8-voxel tile
 constexpr int FILL_THREADS = 512;
 constexpr int LIST_CAP = 1536;
 constexpr double CUTOFF_A = 5.0;      // occupancy_utils.pyx:53: dist2 < 25
@@ -44,7 +45,7 @@ struct GridDev {
     int cutv;    // halo in voxels: ceil(5 / vs)
     int rcells;  // neighbour reach in cells: (TILE - 1 + 2 cutv) / TILE
     float cut2v, cut2v_lo, cut2v_hi;  // (5/vs)^2 in voxel units and the re-check band
-    float pad0;
+    int cell;    // cell edge in voxels (8 for the tile kernels, 4 for the warp-per-block kernel)
     long long atom_begin, atom_end, out_offset;
     long long item_base, tile_base, cell_base;
 };
@@ -112,7 +113,7 @@ __global__ void occ_bin_kernel(const float *__restrict__ coords, const GridDev *
         const double p = ((double)coords[3 * a + d] - g.origin[d]) * g.inv_vs;
         // atoms farther than the 5 A halo from the grid cannot touch any voxel (NaN fails both tests)
         live = live && (p >= -(double)g.cutv) && (p <= (double)(g.dims[d] - 1 + g.cutv));
-        int ci = live ? (int)floor((p + (double)g.cutv) * (1.0 / TILE)) : 0;
+        int ci = live ? (int)floor((p + (double)g.cutv) / (double)g.cell) : 0;
         c[d] = min(max(ci, 0), g.cells[d] - 1);
     }
     if (!live) {
@@ -132,9 +133,8 @@ __global__ void occ_bin_kernel(const float *__restrict__ coords, const GridDev *
 __global__ void occ_scatter_kernel(const float *__restrict__ coords, const double *__restrict__ sigmas, int C,
                                    const GridDev *__restrict__ grids, int B, long long n_items,
                                    const int *__restrict__ item_cell, const unsigned *__restrict__ item_slot,
-                                   const unsigned *__restrict__ cell_start, double *__restrict__ px,
-                                   double *__restrict__ py, double *__restrict__ pz, float *__restrict__ s2,
-                                   unsigned *__restrict__ mask, unsigned *__restrict__ src) {
+                                   const unsigned *__restrict__ cell_start, float4 *__restrict__ rec_pos,
+                                   uint4 *__restrict__ rec_tag) {
     const long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (it >= n_items) return;
     const int cid = item_cell[it];
@@ -143,9 +143,16 @@ __global__ void occ_scatter_kernel(const float *__restrict__ coords, const doubl
     const GridDev &g = grids[b];
     const long long a = g.atom_begin + (it - g.item_base);
     const unsigned dst = cell_start[g.cell_base + cid] + item_slot[it];
-    px[dst] = ((double)coords[3 * a + 0] - g.origin[0]) * g.inv_vs;
-    py[dst] = ((double)coords[3 * a + 1] - g.origin[1]) * g.inv_vs;
-    pz[dst] = ((double)coords[3 * a + 2] - g.origin[2]) * g.inv_vs;
+    // position relative to the atom's own cell origin (float64 subtraction, one rounding to float: |rel| < cell <= 8 voxels,
+    // absolute error <= 2.4e-7 voxel); the cell coordinates travel in the tag so a tile can rebase exactly.
+    const int cz = cid % g.cells[2], cxy = cid / g.cells[2], cy = cxy % g.cells[1], cx = cxy / g.cells[1];
+    const int cc[3] = {cx, cy, cz};
+    float rel[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double pv = ((double)coords[3 * a + d] - g.origin[d]) * g.inv_vs;
+        rel[d] = (float)(pv - (double)(cc[d] * g.cell - g.cutv));
+    }
     const double *sg = sigmas + a * C;
     double first = 0.0;
     unsigned m = 0;
@@ -158,9 +165,8 @@ __global__ void occ_scatter_kernel(const float *__restrict__ coords, const doubl
         else multi = true;
     }
     const double sv = first * g.inv_vs;  // sigma in voxel units
-    s2[dst] = m ? fmaxf((float)(sv * sv), FLT_MIN) : 0.0f;
-    mask[dst] = m;
-    src[dst] = (unsigned)a | (multi ? 0x80000000u : 0u);
+    rec_pos[dst] = make_float4(rel[0], rel[1], rel[2], m ? fmaxf((float)(sv * sv), FLT_MIN) : 0.0f);
+    rec_tag[dst] = make_uint4(m, (unsigned)a | (multi ? 0x80000000u : 0u), (unsigned)cx | ((unsigned)cy << 10) | ((unsigned)cz << 20), 0u);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -169,9 +175,8 @@ __global__ void occ_scatter_kernel(const float *__restrict__ coords, const doubl
 struct FillParams {
     const GridDev *grids;
     int B, C;
-    const double *px, *py, *pz;
-    const float *s2;
-    const unsigned *mask, *src;
+    const float4 *rec_pos;  // cell-sorted atoms: x, y, z relative to the cell origin (voxels), sigma^2 (voxels^2)
+    const uint4 *rec_tag;   // channel mask, atom row | multi-sigma flag << 31, packed cell coordinates
     const unsigned *cell_start;
     const float *coords;
     const double *sigmas;
@@ -278,10 +283,11 @@ __global__ void __launch_bounds__(FILL_THREADS, (CP <= 8 ? 2 : 1)) occ_fill_kern
     bool touched = false;
 
     if (total != 0) {
-        const float fvx = (float)vx, fvy = (float)vy, fvz = (float)vz;
-        const float bcx = (float)(bx * 2), bcy = (float)(by * 4), bcz = (float)(bz * 4);
+        // tile frame: origin at the tile CENTRE (voxel 3.5), so |coordinate| <= 3.5 + cutv and fp32 spacing is finest
+        const float fvx = (float)vx - TILE_C, fvy = (float)vy - TILE_C, fvz = (float)vz - TILE_C;
+        const float bcx = (float)(bx * 2) - TILE_C, bcy = (float)(by * 4) - TILE_C, bcz = (float)(bz * 4) - TILE_C;
         const float cut2v = g.cut2v, cut_hi = g.cut2v_hi, band = g.cut2v_hi - g.cut2v;
-        const double tox = (double)(tx * TILE), toy = (double)(ty * TILE), toz = (double)(tz * TILE);
+        const int cshift_x = tx * TILE + g.cutv, cshift_y = ty * TILE + g.cutv, cshift_z = tz * TILE + g.cutv;
         // 32-bit shared-window addresses taken ONCE (volatile: ptxas otherwise rebuilds them from SR_CgaCtaId per use)
         unsigned ent_sa, mask_sa;
         asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(ent_sa) : "l"(s_ent));
@@ -307,15 +313,16 @@ __global__ void __launch_bounds__(FILL_THREADS, (CP <= 8 ? 2 : 1)) occ_fill_kern
                         if (s_rbase[mid] <= k) lo = mid; else hi = mid - 1;
                     }
                     const unsigned i = s_rpos[lo] + (k - s_rbase[lo]);
-                    e.x = (float)(p.px[i] - tox);
-                    e.y = (float)(p.py[i] - toy);
-                    e.z = (float)(p.pz[i] - toz);
-                    e.w = p.s2[i];
-                    m = p.mask[i];
-                    sr = p.src[i];
-                    const float ddx = fmaxf(fmaxf(-e.x, e.x - (float)(TILE - 1)), 0.f);
-                    const float ddy = fmaxf(fmaxf(-e.y, e.y - (float)(TILE - 1)), 0.f);
-                    const float ddz = fmaxf(fmaxf(-e.z, e.z - (float)(TILE - 1)), 0.f);
+                    e = __ldg(p.rec_pos + i);
+                    const uint4 tg = __ldg(p.rec_tag + i);
+                    m = tg.x;
+                    sr = tg.y;
+                    e.x += (float)((int)(tg.z & 1023u) * TILE - cshift_x) - TILE_C;  // exact: small integers
+                    e.y += (float)((int)((tg.z >> 10) & 1023u) * TILE - cshift_y) - TILE_C;
+                    e.z += (float)((int)(tg.z >> 20) * TILE - cshift_z) - TILE_C;
+                    const float ddx = fmaxf(fabsf(e.x) - TILE_C, 0.f);
+                    const float ddy = fmaxf(fabsf(e.y) - TILE_C, 0.f);
+                    const float ddz = fmaxf(fabsf(e.z) - TILE_C, 0.f);
                     pass = (m != 0) && (ddx * ddx + ddy * ddy + ddz * ddz <= cut_hi);
                     if (sr & 0x80000000u) m = 0;  // several distinct sigmas: per-channel path
                 }
@@ -463,6 +470,20 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillPa
     if (tz >= tzN || ty >= tyN || tx >= __ldg(&gg->tiles[0])) return;  // ragged batch / power-of-two padding
     const int local = (tx * tyN + ty) * tzN + tz;
     const int nx = __ldg(&gg->dims[0]), ny = __ldg(&gg->dims[1]), nz = __ldg(&gg->dims[2]);
+    const unsigned total = __ldg(tile_total + __ldg(&gg->tile_base) + local);
+
+    // ---- empty tile (3 of 4 tiles in a typical pocket grid): stream the zeros with minimal index math and retire
+    if (total == 0 && p.vec_ok && !(p.flags & MKB_OCC_ACCUMULATE)) {
+        const int row = tid >> 3, izz = tz * TILE + (tid & 7);  // 8 consecutive threads = one 256-byte row
+        const int ixr = tx * TILE + (row >> 3), iyr = ty * TILE + (row & 7);
+        if (ixr < nx && iyr < ny && izz < nz) {
+            float4 *d = reinterpret_cast<float4 *>(p.out + (__ldg(&gg->out_offset) + ((long long)ixr * ny + iyr) * nz + izz) * 8);
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            __stcs(d, z4);
+            __stcs(d + 1, z4);
+        }
+        return;
+    }
 
     // lane -> voxel: quarter q = lane >> 3 owns the 2x2x2 sub-block (qy, qz) of the warp's 2x4x4 block
     const int bx = warp >> 2, by = (warp >> 1) & 1, bz = warp & 1;
@@ -472,7 +493,6 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillPa
     const bool inside = ix < nx && iy < ny && iz < nz;
     float *const o = p.out + (__ldg(&gg->out_offset) + ((long long)ix * ny + iy) * nz + iz) * 8;
 
-    const unsigned total = __ldg(tile_total + __ldg(&gg->tile_base) + local);
     float acc[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) acc[h] = 0.0f;
@@ -518,8 +538,9 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillPa
         const float cut_lo = __ldg(&gg->cut2v_lo), cut_hi = __ldg(&gg->cut2v_hi);
         const float gate_k = GATE_SCALE * cut_lo;  // exact: power-of-two scaling
         const unsigned band_bits = __float_as_uint(cut_hi - cut_lo);
-        const float fvx = (float)vx, fvy = (float)vy, fvz = (float)vz;
-        const float bcx = (float)(bx * 2), bcy = (float)(by * 4), bcz = (float)(bz * 4);
+        // tile frame: origin at the tile CENTRE (voxel 3.5), so |coordinate| <= 3.5 + cutv and fp32 spacing is finest
+        const float fvx = (float)vx - TILE_C, fvy = (float)vy - TILE_C, fvz = (float)vz - TILE_C;
+        const float bcx = (float)(bx * 2) - TILE_C, bcy = (float)(by * 4) - TILE_C, bcz = (float)(bz * 4) - TILE_C;
         unsigned short *const my_p = s_pidx[warp];
         unsigned short *const my_q = s_qidx[warp][q];
         unsigned ent_sa, mask_sa;  // taken once; volatile so ptxas does not rebuild them from SR_CgaCtaId per use
@@ -534,7 +555,8 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillPa
             }
             const unsigned c1 = min(total, c0 + (unsigned)V3_CAP);
             {
-                const double tox = (double)(tx * TILE), toy = (double)(ty * TILE), toz = (double)(tz * TILE);
+                const int cutv = __ldg(&gg->cutv);
+                const int cshift_x = tx * TILE + cutv, cshift_y = ty * TILE + cutv, cshift_z = tz * TILE + cutv;
                 for (unsigned k0 = c0; k0 < c1; k0 += FILL_THREADS) {
                     const unsigned k = k0 + tid;
                     bool pass = false;
@@ -547,15 +569,16 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillPa
                             if (s_rbase[mid] <= k) lo = mid; else hi = mid - 1;
                         }
                         const unsigned i = s_rpos[lo] + (k - s_rbase[lo]);
-                        e.x = (float)(p.px[i] - tox);
-                        e.y = (float)(p.py[i] - toy);
-                        e.z = (float)(p.pz[i] - toz);
-                        e.w = p.s2[i];
-                        m = p.mask[i];
-                        sr = p.src[i];
-                        const float ddx = fmaxf(fmaxf(-e.x, e.x - (float)(TILE - 1)), 0.f);
-                        const float ddy = fmaxf(fmaxf(-e.y, e.y - (float)(TILE - 1)), 0.f);
-                        const float ddz = fmaxf(fmaxf(-e.z, e.z - (float)(TILE - 1)), 0.f);
+                        e = __ldg(p.rec_pos + i);
+                        const uint4 tg = __ldg(p.rec_tag + i);
+                        m = tg.x;
+                        sr = tg.y;
+                        e.x += (float)((int)(tg.z & 1023u) * TILE - cshift_x) - TILE_C;  // exact: small integers
+                        e.y += (float)((int)((tg.z >> 10) & 1023u) * TILE - cshift_y) - TILE_C;
+                        e.z += (float)((int)(tg.z >> 20) * TILE - cshift_z) - TILE_C;
+                        const float ddx = fmaxf(fabsf(e.x) - TILE_C, 0.f);
+                        const float ddy = fmaxf(fabsf(e.y) - TILE_C, 0.f);
+                        const float ddz = fmaxf(fabsf(e.z) - TILE_C, 0.f);
                         pass = (m != 0) && (ddx * ddx + ddy * ddy + ddz * ddz <= cut_hi);
                         if (sr & 0x80000000u) m = 0;  // several distinct sigmas: per-channel path
                     }
@@ -732,6 +755,238 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillPa
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K1 warp-per-block path (C <= 8, default): no CTA-level synchronisation at all.
+//   Each WARP owns one 2x4x4 voxel block end to end: it gathers the block's own halo from 4-voxel cells (<= 128
+//   contiguous cell rows), keeps the survivors as records in its private shared-memory list, splits them into the four
+//   2x2x2 quarter lists and runs the lock-step candidate loop.  Compared with the tile kernel above this removes the
+//   three __syncthreads per tile, the intra-CTA load imbalance (a CTA lived as long as its busiest block) and the
+//   stage where all 16 warps re-scanned the whole tile list; empty blocks retire after one row scan.
+//   CTA = 4 warps = 4 z-consecutive blocks, purely a container.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int W_WARPS = 4;
+constexpr int W_CELL = 4;    // cell edge of the binning used with this kernel
+constexpr int W_ROWS = 128;   // cell rows per block: (Rx+1)(Ry+1)
+constexpr int W_PCAP = 192;   // block candidates per round
+constexpr int W_QCAP = 96;    // sub-block candidates per round
+
+__global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillParams p) {
+    __shared__ float4 s_pent[W_WARPS][W_PCAP + 1];    // block candidates: x, y, z in the block frame, sigma^2 (+ sentinel)
+    __shared__ unsigned s_pmask[W_WARPS][W_PCAP + 1];  // channel mask; 0 = several sigmas
+    __shared__ unsigned s_psrc[W_WARPS][W_PCAP];
+    __shared__ unsigned s_rpos[W_WARPS][W_ROWS];
+    __shared__ unsigned s_rbase[W_WARPS][W_ROWS + 1];
+    __shared__ unsigned short s_qidx[W_WARPS][4][W_QCAP];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bzi = blockIdx.x * W_WARPS + warp, byi = blockIdx.y, bxi = blockIdx.z & ((1 << p.txp_shift) - 1);
+    const GridDev *gg = p.grids + (blockIdx.z >> p.txp_shift);
+    const int nx = __ldg(&gg->dims[0]), ny = __ldg(&gg->dims[1]), nz = __ldg(&gg->dims[2]);
+    if (bxi * 2 >= nx || byi * 4 >= ny || bzi * 4 >= nz) return;  // padding of the launch grid / ragged batch
+
+    // ---- cell rows of this block's halo: shifted voxel range [lo, lo + ext - 1 + 2 cutv] per axis (W_CELL = 4)
+    const int cutv = __ldg(&gg->cutv);
+    const int cN1 = __ldg(&gg->cells[1]), cN2 = __ldg(&gg->cells[2]);
+    const int cx0 = (bxi * 2) / W_CELL, cx1 = min((bxi * 2 + 1 + 2 * cutv) / W_CELL, __ldg(&gg->cells[0]) - 1);
+    const int cy0 = byi, cy1 = min((byi * 4 + 3 + 2 * cutv) / W_CELL, cN1 - 1);
+    const int cz0 = bzi, cz1 = min((bzi * 4 + 3 + 2 * cutv) / W_CELL, cN2 - 1);
+    const int ncy = cy1 - cy0 + 1;
+    const int nrows = (cx1 - cx0 + 1) * ncy;  // <= W_ROWS checked on the host
+    unsigned *const rpos = s_rpos[warp], *const rbase = s_rbase[warp];
+    const long long cell_base = __ldg(&gg->cell_base);
+    const float inv_ncy = 1.0f / (float)ncy;
+    unsigned carry = 0;
+    for (int r0 = 0; r0 < nrows; r0 += 32) {  // row lengths + inclusive scan, 32 rows per step
+        const int r = r0 + lane;
+        unsigned v = 0;
+        if (r < nrows) {
+            const int rx = (int)(((float)r + 0.5f) * inv_ncy), ry = r - rx * ncy;  // exact for small r
+            const long long cb = cell_base + ((long long)(cx0 + rx) * cN1 + (cy0 + ry)) * cN2;
+            const unsigned a = __ldg(p.cell_start + cb + cz0);
+            v = __ldg(p.cell_start + cb + cz1 + 1) - a;
+            rpos[r] = a;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (r < nrows) rbase[r + 1] = v + carry;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+    const unsigned total = carry;
+
+    // lane -> voxel of the block (block frame: origin at the block centre)
+    const int q = lane >> 3, sub = lane & 7;
+    const int lx = sub >> 2, ly = (q >> 1) * 2 + ((sub >> 1) & 1), lz = (q & 1) * 2 + (sub & 1);
+    const int ix = bxi * 2 + lx, iy = byi * 4 + ly, iz = bzi * 4 + lz;
+    const bool inside = ix < nx && iy < ny && iz < nz;
+
+    float acc[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) acc[h] = 0.0f;
+    bool touched = false;
+
+    if (total != 0) {
+        if (lane == 0) {
+            rbase[0] = 0;
+            s_pent[warp][W_PCAP] = make_float4(1e18f, 1e18f, 1e18f, 0.0f);  // sentinel: never inside the gate
+            s_pmask[warp][W_PCAP] = 1u;
+        }
+        __syncwarp();
+        const float cut_lo = __ldg(&gg->cut2v_lo), cut_hi = __ldg(&gg->cut2v_hi);
+        const float gate_k = GATE_SCALE * cut_lo;
+        const unsigned band_bits = __float_as_uint(cut_hi - cut_lo);
+        const float fvx = (float)lx - 0.5f, fvy = (float)ly - 1.5f, fvz = (float)lz - 1.5f;
+        // cell origin -> block-centre frame: (c * cell - cutv) - (block corner + half extent)
+        const int sx = bxi * 2 + cutv, sy = byi * 4 + cutv, sz = bzi * 4 + cutv;
+        float4 *const pent = s_pent[warp];
+        unsigned *const pmask = s_pmask[warp], *const psrc = s_psrc[warp];
+        unsigned short *const my_q = s_qidx[warp][q];
+        unsigned ent_sa, mask_sa;
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(ent_sa) : "l"(pent));
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(mask_sa) : "l"(pmask));
+
+        int np = 0;
+        for (unsigned k0 = 0; k0 < total; k0 += 32) {
+            // ---- gather 32 atoms of the concatenated cell rows, keep those within reach of the block
+            {
+                const unsigned k = min(k0 + lane, total - 1);
+                int lo = 0, hi = nrows - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (rbase[mid] <= k) lo = mid; else hi = mid - 1;
+                }
+                const unsigned i = rpos[lo] + (k - rbase[lo]);
+                float4 e = __ldg(p.rec_pos + i);
+                const uint4 tg = __ldg(p.rec_tag + i);
+                e.x += (float)((int)(tg.z & 1023u) * W_CELL - sx) - 0.5f;  // exact: small integers and halves
+                e.y += (float)((int)((tg.z >> 10) & 1023u) * W_CELL - sy) - 1.5f;
+                e.z += (float)((int)(tg.z >> 20) * W_CELL - sz) - 1.5f;
+                const float ddx = fmaxf(fabsf(e.x) - 0.5f, 0.f);
+                const float ddy = fmaxf(fabsf(e.y) - 1.5f, 0.f);
+                const float ddz = fmaxf(fabsf(e.z) - 1.5f, 0.f);
+                const bool pass = (k0 + lane < total) & (tg.x != 0) & (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= cut_hi);
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) {
+                    const int slot = np + __popc(bal & ((1u << lane) - 1u));
+                    pent[slot] = e;
+                    pmask[slot] = (tg.y & 0x80000000u) ? 0u : tg.x;
+                    psrc[slot] = tg.y & 0x7fffffffu;
+                }
+                np += __popc(bal);
+            }
+            if (np <= W_PCAP - 32 && k0 + 32 < total) continue;
+            if (np == 0) continue;
+            touched = true;
+            __syncwarp();
+            // ---- block list -> four 2x2x2 sub-block lists, evaluated in lock-step
+            int cq0 = 0, cq1 = 0, cq2 = 0, cq3 = 0;
+            for (int j0 = 0; j0 < np; j0 += 32) {
+                const int j = j0 + lane;
+                const bool live = j < np;
+                const unsigned idx = min(j, np - 1);
+                bool h0, h1, h2, h3, multi;
+                {
+                    const float4 e = lds_f4(ent_sa + idx * 16);
+                    const float ddx = fmaxf(fabsf(e.x) - 0.5f, 0.f);
+                    const float y0 = fmaxf(fabsf(e.y + 1.f) - 0.5f, 0.f), y1 = fmaxf(fabsf(e.y - 1.f) - 0.5f, 0.f);
+                    const float z0 = fmaxf(fabsf(e.z + 1.f) - 0.5f, 0.f), z1 = fmaxf(fabsf(e.z - 1.f) - 0.5f, 0.f);
+                    const float xx = ddx * ddx;
+                    const float a0 = fmaf(y0, y0, xx), a1 = fmaf(y1, y1, xx);
+                    multi = live & (lds_u32(mask_sa + idx * 4) == 0);
+                    const bool ok = live & !multi;
+                    h0 = ok & (fmaf(z0, z0, a0) <= cut_hi);  // q = qy*2 + qz
+                    h1 = ok & (fmaf(z1, z1, a0) <= cut_hi);
+                    h2 = ok & (fmaf(z0, z0, a1) <= cut_hi);
+                    h3 = ok & (fmaf(z1, z1, a1) <= cut_hi);
+                }
+                // atoms carrying several distinct sigmas (user float channels): whole-warp per-channel path
+                for (unsigned bm = __ballot_sync(0xffffffffu, multi); bm; bm &= bm - 1) {
+                    const int jj = j0 + __ffs(bm) - 1;
+                    const float4 e = pent[jj];
+                    const float dx = e.x - fvx, dy = e.y - fvy, dz = e.z - fvz;
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    bool in = d2 < cut_lo;
+                    if (!in && d2 < cut_hi) in = exact_gate(gg, p.coords, psrc[jj], ix, iy, iz);
+                    const float rr = in ? rcp_approx(d2) : 0.0f;
+                    const double *sg = p.sigmas + (long long)psrc[jj] * p.C;
+                    const double ivs = __ldg(&gg->inv_vs);
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) {
+                        if (h < p.C) {
+                            const double sv = sg[h] * ivs;
+                            const float sq = (sv == 0.0 || sv != sv) ? 0.0f : fmaxf((float)(sv * sv), FLT_MIN);
+                            acc[h] = fmaxf(acc[h], sq * rr);  // 0*inf = NaN is dropped by fmaxf
+                        }
+                    }
+                }
+                const unsigned lt = (1u << lane) - 1u;
+                const unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
+                const unsigned b2 = __ballot_sync(0xffffffffu, h2), b3 = __ballot_sync(0xffffffffu, h3);
+                unsigned short *const wq = s_qidx[warp][0];
+                if (h0) wq[0 * W_QCAP + cq0 + __popc(b0 & lt)] = (unsigned short)idx;
+                if (h1) wq[1 * W_QCAP + cq1 + __popc(b1 & lt)] = (unsigned short)idx;
+                if (h2) wq[2 * W_QCAP + cq2 + __popc(b2 & lt)] = (unsigned short)idx;
+                if (h3) wq[3 * W_QCAP + cq3 + __popc(b3 & lt)] = (unsigned short)idx;
+                cq0 += __popc(b0); cq1 += __popc(b1); cq2 += __popc(b2); cq3 += __popc(b3);
+                const int nmax = max(max(cq0, cq1), max(cq2, cq3));
+                if (j0 + 32 < np && nmax <= W_QCAP - 32) continue;
+                // pad the shorter quarters with the sentinel, then run all four lists in lock-step
+                const int mine = (q == 0) ? cq0 : (q == 1) ? cq1 : (q == 2) ? cq2 : cq3;
+                for (int c = mine + sub; c < nmax; c += 8) my_q[c] = (unsigned short)W_PCAP;
+                __syncwarp();
+                for (int c = 0; c < nmax; ++c) {
+                    const unsigned jj = my_q[c];
+                    const float4 e = lds_f4(ent_sa + jj * 16);
+                    const unsigned cm = lds_u32(mask_sa + jj * 4);
+                    const float dx = e.x - fvx, dy = e.y - fvy, dz = e.z - fvz;
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const float qf = e.w * rcp_approx(d2);  // sigma^2/d2; +inf at d2 == 0 -> value 1
+                    float qv = qf * __saturatef(fmaf(-GATE_SCALE, d2, gate_k));  // exact 0/1 gate on the FMA pipe
+                    if (__float_as_uint(d2 - cut_lo) < band_bits) {  // within 4e-6 of the gate: decide like the reference
+                        if (exact_gate(gg, p.coords, psrc[jj], ix, iy, iz)) qv = qf;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 8; ++h)
+                        if (cm & (1u << h)) acc[h] = fmaxf(acc[h], qv);
+                }
+                __syncwarp();
+                cq0 = cq1 = cq2 = cq3 = 0;
+            }
+            np = 0;
+            __syncwarp();
+        }
+    }
+
+    // ---- epilogue: one transcendental per voxel-channel, 32-byte streaming stores (4 lanes = one 128-byte line)
+    if (inside) {
+        const int C = p.C;
+        float v[8];
+        if (touched) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) v[h] = occ_value(acc[h]);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) v[h] = 0.0f;
+        }
+        float *const oo = p.out + (__ldg(&gg->out_offset) + ((long long)ix * ny + iy) * nz + iz) * C;
+        if (p.flags & MKB_OCC_ACCUMULATE) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h)
+                if (h < C) { const float old = oo[h]; v[h] = (v[h] > old) ? v[h] : old; }
+        }
+        if (p.vec_ok) {
+            __stcs(reinterpret_cast<float4 *>(oo), make_float4(v[0], v[1], v[2], v[3]));
+            __stcs(reinterpret_cast<float4 *>(oo) + 1, make_float4(v[4], v[5], v[6], v[7]));
+        } else {
+#pragma unroll
+            for (int h = 0; h < 8; ++h)
+                if (h < C) oo[h] = v[h];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K1b: arbitrary centres.  Atoms hashed into 5 A cells (count -> scan -> order); one thread per centre visits the
 // 27 neighbouring buckets.  Distances in float64 exactly as the reference (pyx:49-53), so the gate is exact.
 // ---------------------------------------------------------------------------------------------------------
@@ -845,6 +1100,22 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     if (n_atoms >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "n_atoms must be < 2^31");
     if (n_atoms > 0 && (!coords || !sigmas)) return fail(h, MKB_ERR_BAD_ARG, "null coords/sigmas");
 
+    // kernel variant: 0 = warp-per-block (C <= 8, default), 1 = tile kernel with quarter lists (MKB_OCC_TILE=1),
+    // 2 = generic tile kernel (9..32 channels, very small voxels, or MKB_OCC_GENERIC=1).  It fixes the cell size.
+    int variant = (C <= 8) ? 0 : 2;
+    if (variant == 0 && getenv("MKB_OCC_TILE")) variant = 1;
+    const bool force_warp = getenv("MKB_OCC_WARP") != nullptr;
+    if (getenv("MKB_OCC_GENERIC")) variant = 2;
+    for (int b = 0; b < B && variant != 2; ++b) {
+        if (!(grids[b].voxelsize > 0.0)) break;  // reported below
+        const int cv = (int)std::ceil(CUTOFF_A / grids[b].voxelsize);
+        // fine grids (cutoff > 7 voxels): a 32-voxel block is small against its own halo, the 512-voxel tile kernel
+        // amortises the gather better (measured: 0.5 A grids 0.66 ms vs 0.86 ms; 1 A grids 2.54 ms vs 2.38 ms)
+        if (variant == 0 && ((cv > 7 && !force_warp) || ((1 + 2 * cv) / 4 + 1) * ((3 + 2 * cv) / 4 + 1) > W_ROWS)) variant = 1;
+        if (variant == 1 && ((TILE - 1 + 2 * cv) / TILE + 1) * ((TILE - 1 + 2 * cv) / TILE + 1) > 128) variant = 2;
+    }
+    const int cellsz = (variant == 0) ? W_CELL : TILE;
+
     std::vector<GridDev> gd((size_t)B);
     long long items = 0, tiles = 0, cells = 0;
     for (int b = 0; b < B; ++b) {
@@ -867,7 +1138,7 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
         g.cut2v = (float)(cut * cut);
         g.cut2v_lo = g.cut2v * (1.0f - GATE_BAND);
         g.cut2v_hi = g.cut2v * (1.0f + GATE_BAND);
-        g.pad0 = 0.f;
+        g.cell = cellsz;
         long long nt = 1, nc = 1;
         for (int d = 0; d < 3; ++d) {
             if (s.dims[d] <= 0) return fail(h, MKB_ERR_BAD_ARG, "grid %d: dims must be positive", b);
@@ -875,7 +1146,8 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
             g.origin[d] = s.origin[d];
             g.dims[d] = s.dims[d];
             g.tiles[d] = (s.dims[d] + TILE - 1) / TILE;
-            g.cells[d] = (s.dims[d] + 2 * g.cutv + TILE - 1) / TILE;
+            g.cells[d] = (s.dims[d] + 2 * g.cutv + cellsz - 1) / cellsz;
+            if (g.cells[d] > 1023) return fail(h, MKB_ERR_BAD_ARG, "grid %d: too many voxels along an axis for one call", b);
             nt *= g.tiles[d];
             nc *= g.cells[d];
         }
@@ -895,9 +1167,9 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
 
     GridDev *d_grids;
     int *item_cell;
-    unsigned *item_slot, *cell_count, *cell_start, *mask, *src;
-    double *px, *py, *pz;
-    float *s2;
+    unsigned *item_slot, *cell_count, *cell_start;
+    float4 *rec_pos;
+    uint4 *rec_tag;
     int rc;
     const size_t ni = (size_t)std::max<long long>(items, 1);
     if ((rc = scratch_get(h, S_DESC, (size_t)B, &d_grids))) return rc;
@@ -905,12 +1177,8 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     if ((rc = scratch_get(h, S_ITEM_SLOT, ni, &item_slot))) return rc;
     if ((rc = scratch_get(h, S_CELL_COUNT, (size_t)cells + 1, &cell_count))) return rc;
     if ((rc = scratch_get(h, S_CELL_START, (size_t)cells + 1, &cell_start))) return rc;
-    if ((rc = scratch_get(h, S_SORT_PX, ni, &px))) return rc;
-    if ((rc = scratch_get(h, S_SORT_PY, ni, &py))) return rc;
-    if ((rc = scratch_get(h, S_SORT_PZ, ni, &pz))) return rc;
-    if ((rc = scratch_get(h, S_SORT_S2, ni, &s2))) return rc;
-    if ((rc = scratch_get(h, S_SORT_MASK, ni, &mask))) return rc;
-    if ((rc = scratch_get(h, S_SORT_SRC, ni, &src))) return rc;
+    if ((rc = scratch_get(h, S_SORT_PX, ni, &rec_pos))) return rc;
+    if ((rc = scratch_get(h, S_SORT_PY, ni, &rec_tag))) return rc;
 
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[0], st));
     MKB_CUDA(h, cudaMemcpyAsync(d_grids, gd.data(), sizeof(GridDev) * (size_t)B, cudaMemcpyHostToDevice, st));
@@ -924,12 +1192,12 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     if (items > 0) {
         const int nb = (int)cdiv(items, 256);
         occ_scatter_kernel<<<nb, 256, 0, st>>>(coords, sigmas, C, d_grids, B, items, item_cell, item_slot, cell_start,
-                                               px, py, pz, s2, mask, src);
+                                               rec_pos, rec_tag);
         MKB_LAUNCHED(h);
     }
     FillParams fp;
     fp.grids = d_grids; fp.B = B; fp.C = C;
-    fp.px = px; fp.py = py; fp.pz = pz; fp.s2 = s2; fp.mask = mask; fp.src = src;
+    fp.rec_pos = rec_pos; fp.rec_tag = rec_tag;
     fp.cell_start = cell_start; fp.coords = coords; fp.sigmas = sigmas; fp.out = out; fp.flags = flags;
     fp.vec_ok = (C == 8 && ((uintptr_t)out % 16 == 0)) ? 1 : 0;
     fp.txp_shift = 0;
@@ -937,12 +1205,34 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     // the asynchronous smem read before it may retire; kept for the persistent variant
     fp.bulk_store = (fp.vec_ok && !(flags & MKB_OCC_ACCUMULATE) && getenv("MKB_OCC_BULK_STORE")) ? 1 : 0;
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
-    bool fast8 = (C <= 8);
-    for (int b = 0; b < B && fast8; ++b) fast8 = (gd[b].rcells + 1) * (gd[b].rcells + 1) <= 128;
-    if (getenv("MKB_OCC_GENERIC")) fast8 = false;  // debugging / A-B switch: force the generic kernel
+    const bool fast8 = (variant == 1);
     unsigned *tile_total = nullptr;
     if (fast8 && (rc = scratch_get(h, S_TILE_TOTAL, (size_t)tiles, &tile_total))) return rc;
-    for (int b0 = 0; b0 < B; b0 += 65535) {  // blockIdx.y = grid of the batch
+    if (variant == 0) {
+        // warp-per-block kernel: grid = (z-blocks / 4, y-blocks, grid << sh | x-block)
+        int b0 = 0;
+        while (b0 < B) {
+            int mx = 1, my = 1, mz = 1, sh = 0, nb = 0;
+            for (int b = b0; b < B; ++b) {  // extend the chunk while gridDim.z stays legal
+                const int ax = std::max(mx, (gd[b].dims[0] + 1) / 2);
+                int s2 = 0;
+                while ((1 << s2) < ax) ++s2;
+                if (((long long)(nb + 1) << s2) > 65535) break;
+                mx = ax; sh = s2; ++nb;
+                my = std::max(my, (gd[b].dims[1] + 3) / 4);
+                mz = std::max(mz, (gd[b].dims[2] + 3) / 4);
+            }
+            if (nb == 0 || my > 65535) return fail(h, MKB_ERR_BAD_ARG, "grid %d too large for one launch", b0);
+            FillParams fq = fp;
+            fq.grids = d_grids + b0;
+            fq.B = nb;
+            fq.txp_shift = sh;
+            occ_fill8w_kernel<<<dim3((unsigned)cdiv(mz, W_WARPS), (unsigned)my, (unsigned)(nb << sh)), W_WARPS * 32, 0, st>>>(fq);
+            MKB_LAUNCHED(h);
+            b0 += nb;
+        }
+    }
+    for (int b0 = 0; b0 < B && variant != 0; b0 += 65535) {  // tile kernels: blockIdx.y = grid of the batch
         const int nb = std::min(65535, B - b0);
         fp.grids = d_grids + b0;
         fp.B = nb;
