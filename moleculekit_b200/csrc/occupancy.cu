@@ -847,16 +847,13 @@ __global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillP
         asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(mask_sa) : "l"(pmask));
 
         int np = 0;
+        int row = 0;  // row of this lane's current atom: k only grows, so the row pointer only advances
         for (unsigned k0 = 0; k0 < total; k0 += 32) {
             // ---- gather 32 atoms of the concatenated cell rows, keep those within reach of the block
             {
                 const unsigned k = min(k0 + lane, total - 1);
-                int lo = 0, hi = nrows - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (rbase[mid] <= k) lo = mid; else hi = mid - 1;
-                }
-                const unsigned i = rpos[lo] + (k - rbase[lo]);
+                while (rbase[row + 1] <= k) ++row;  // rbase[nrows] == total > k: terminates
+                const unsigned i = rpos[row] + (k - rbase[row]);
                 float4 e = __ldg(p.rec_pos + i);
                 const uint4 tg = __ldg(p.rec_tag + i);
                 e.x += (float)((int)(tg.z & 1023u) * W_CELL - sx) - 0.5f;  // exact: small integers and halves
