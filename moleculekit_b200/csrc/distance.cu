@@ -121,6 +121,23 @@ static int launch_gather(mkb_ctx *h, cudaStream_t st, const mkb_traj *t, const I
 constexpr int K3_ROWS = 16;
 constexpr int K3_COLS = 256;
 
+// Branch-light form of wrap_axis for the dense kernel: the three axes take the fast path unconditionally and only OR
+// their "risky" flags; one rare branch per PAIR redoes the exact division for the flagged axes.
+struct Wrapped {
+    float d;      // d - b * n with the fast n
+    bool risky;   // the fast n may differ from roundf(fl(d / b))
+};
+__device__ __forceinline__ Wrapped wrap_fast(float d, float b, float rb) {
+    const float q = __fmul_rn(d, rb);
+    const float n = __fsub_rn(__fadd_rn(q, 12582912.0f), 12582912.0f);
+    const float fr = fabsf(__fsub_rn(q, n));
+    const float lim = fmaf(-6e-7f, fabsf(q), 0.5f);
+    Wrapped w;
+    w.d = __fsub_rn(d, __fmul_rn(b, n));
+    w.risky = !(fr < lim);
+    return w;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(K3_COLS) dist_kernel(const float4 *__restrict__ G1, const float4 *__restrict__ G2,
                                                         long long n1, long long n2, const float *__restrict__ box,
@@ -135,14 +152,31 @@ __global__ void __launch_bounds__(K3_COLS) dist_kernel(const float4 *__restrict_
     const float4 b = G2[f * n2 + j];
     const unsigned cb = __float_as_uint(b.w);
     const BoxF bx = load_box(box, box_stride, f);
-    const long long i1 = min(i0 + K3_ROWS, n1);
-    for (long long i = i0; i < i1; ++i) {
-        if (selfdist && j <= i) continue;
-        const float4 a = __ldg(G1 + f * n1 + i);
-        const bool wrap = pbc && (__float_as_uint(a.w) != cb);
-        const float d = __fsqrt_rn(pair_d2(a, b, bx, wrap));
-        const long long col = selfdist ? (i * n2 - (i * (i + 1)) / 2 + (j - i - 1)) : (i * n2 + j);
-        store_dist<MODE>(out, f * P + col, d, truncate, threshold);
+    const int rows = (int)(min(i0 + K3_ROWS, n1) - i0);
+    const float4 *__restrict__ arow = G1 + f * n1 + i0;
+    // running output index: non-self (i, j) -> i*n2 + j ; self -> i*n2 - i(i+1)/2 + (j - i - 1), step n2 - i - 2
+    long long idx = f * P + (selfdist ? (i0 * n2 - (i0 * (i0 + 1)) / 2 + (j - i0 - 1)) : (i0 * n2 + j));
+    long long step = selfdist ? (n2 - i0 - 2) : n2;
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {
+        const float4 a = __ldg(arow + r);
+        if (!selfdist || j > i0 + r) {
+            float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+            if (pbc && (__float_as_uint(a.w) != cb)) {
+                const Wrapped wx = wrap_fast(dx, bx.bx, bx.rx), wy = wrap_fast(dy, bx.by, bx.ry),
+                              wz = wrap_fast(dz, bx.bz, bx.rz);
+                if (wx.risky | wy.risky | wz.risky) {  // rare: a quotient within 6e-7|q| of a half-integer, or huge
+                    dx = wrap_axis(dx, bx.bx, bx.rx);
+                    dy = wrap_axis(dy, bx.by, bx.ry);
+                    dz = wrap_axis(dz, bx.bz, bx.rz);
+                } else {
+                    dx = wx.d; dy = wy.d; dz = wz.d;
+                }
+            }
+            store_dist<MODE>(out, idx, __fsqrt_rn(sq3(dx, dy, dz)), truncate, threshold);
+        }
+        idx += step;
+        if (selfdist) --step;
     }
 }
 
