@@ -24,7 +24,8 @@ enum ScratchSlot {
     S_PT_ORDER,     // points path: atom order
     S_ROWCNT,       // contacts: per-row counts
     S_COM,          // reductions: centres of mass
-    S_TILE_TOTAL,   // occupancy fast path: halo atom count per tile
+    S_TILE_TOTAL,   // occupancy fast paths: halo atom count per tile / per block
+    S_BLOCK_BASE,   // occupancy warp kernel: first block id of every grid
     S_NSLOTS
 };
 

@@ -769,7 +769,30 @@ constexpr int W_ROWS = 128;   // cell rows per block: (Rx+1)(Ry+1)
 constexpr int W_PCAP = 192;   // block candidates per round
 constexpr int W_QCAP = 96;    // sub-block candidates per round
 
-__global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillParams p) {
+// halo atom count of every 2x4x4 block (one THREAD per block: 32x cheaper than letting each warp find out that
+// its block is empty -- and 70 % of the blocks of a pocket grid are).  block id = ((grid, bx), by, bz) flattened.
+__global__ void occ_block_total_kernel(const GridDev *__restrict__ grids, const unsigned *__restrict__ cell_start,
+                                       const long long *__restrict__ block_base, unsigned *__restrict__ block_total) {
+    const GridDev &g = grids[blockIdx.y];
+    const int nbx = (g.dims[0] + 1) / 2, nby = (g.dims[1] + 3) / 4, nbz = (g.dims[2] + 3) / 4;
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= nbx * nby * nbz) return;
+    const int bzi = local % nbz, bxy = local / nbz, byi = bxy % nby, bxi = bxy / nby;
+    const int cutv = g.cutv, cN1 = g.cells[1], cN2 = g.cells[2];
+    const int cx0 = (bxi * 2) / W_CELL, cx1 = min((bxi * 2 + 1 + 2 * cutv) / W_CELL, g.cells[0] - 1);
+    const int cy0 = byi, cy1 = min((byi * 4 + 3 + 2 * cutv) / W_CELL, cN1 - 1);
+    const int cz0 = bzi, cz1 = min((bzi * 4 + 3 + 2 * cutv) / W_CELL, cN2 - 1);
+    unsigned total = 0;
+    for (int cx = cx0; cx <= cx1; ++cx)
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            const long long cb = g.cell_base + ((long long)cx * cN1 + cy) * cN2;
+            total += cell_start[cb + cz1 + 1] - cell_start[cb + cz0];
+        }
+    block_total[block_base[blockIdx.y] + local] = total;
+}
+
+__global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillParams p, const long long *__restrict__ block_base,
+                                                                     const unsigned *__restrict__ block_total) {
     __shared__ float4 s_pent[W_WARPS][W_PCAP + 1];    // block candidates: x, y, z in the block frame, sigma^2 (+ sentinel)
     __shared__ unsigned s_pmask[W_WARPS][W_PCAP + 1];  // channel mask; 0 = several sigmas
     __shared__ unsigned s_psrc[W_WARPS][W_PCAP];
@@ -782,6 +805,23 @@ __global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillP
     const GridDev *gg = p.grids + (blockIdx.z >> p.txp_shift);
     const int nx = __ldg(&gg->dims[0]), ny = __ldg(&gg->dims[1]), nz = __ldg(&gg->dims[2]);
     if (bxi * 2 >= nx || byi * 4 >= ny || bzi * 4 >= nz) return;  // padding of the launch grid / ragged batch
+
+    // ---- empty block (no atom within reach): stream 32 x 32 B of zeros and retire
+    {
+        const int nby = (ny + 3) >> 2, nbz = (nz + 3) >> 2;
+        const unsigned tot = __ldg(block_total + __ldg(block_base + (blockIdx.z >> p.txp_shift)) +
+                                   ((long long)bxi * nby + byi) * nbz + bzi);
+        if (tot == 0 && p.vec_ok && !(p.flags & MKB_OCC_ACCUMULATE)) {
+            const int ix = bxi * 2 + (lane >> 4), iy = byi * 4 + ((lane >> 2) & 3), iz = bzi * 4 + (lane & 3);
+            if (ix < nx && iy < ny && iz < nz) {
+                float4 *d = reinterpret_cast<float4 *>(p.out + (__ldg(&gg->out_offset) + ((long long)ix * ny + iy) * nz + iz) * 8);
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                __stcs(d, z4);
+                __stcs(d + 1, z4);
+            }
+            return;
+        }
+    }
 
     // ---- cell rows of this block's halo: shifted voxel range [lo, lo + ext - 1 + 2 cutv] per axis (W_CELL = 4)
     const int cutv = __ldg(&gg->cutv);
@@ -1206,7 +1246,25 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     unsigned *tile_total = nullptr;
     if (fast8 && (rc = scratch_get(h, S_TILE_TOTAL, (size_t)tiles, &tile_total))) return rc;
     if (variant == 0) {
-        // warp-per-block kernel: grid = (z-blocks / 4, y-blocks, grid << sh | x-block)
+        // per-block halo counts (thread per block), then the warp-per-block kernel:
+        // grid = (z-blocks / 4, y-blocks, grid << sh | x-block)
+        std::vector<long long> bbase((size_t)B + 1, 0);
+        long long maxblk = 0;
+        for (int b = 0; b < B; ++b) {
+            const long long nbk = (long long)((gd[b].dims[0] + 1) / 2) * ((gd[b].dims[1] + 3) / 4) * ((gd[b].dims[2] + 3) / 4);
+            bbase[b + 1] = bbase[b] + nbk;
+            maxblk = std::max(maxblk, nbk);
+        }
+        long long *d_bbase;
+        unsigned *d_btotal;
+        if ((rc = scratch_get(h, S_BLOCK_BASE, (size_t)B + 1, &d_bbase))) return rc;
+        if ((rc = scratch_get(h, S_TILE_TOTAL, (size_t)bbase[B], &d_btotal))) return rc;
+        MKB_CUDA(h, cudaMemcpyAsync(d_bbase, bbase.data(), sizeof(long long) * ((size_t)B + 1), cudaMemcpyHostToDevice, st));
+        for (int c0 = 0; c0 < B; c0 += 65535) {
+            const int cn = std::min(65535, B - c0);
+            occ_block_total_kernel<<<dim3((unsigned)cdiv(maxblk, 256), (unsigned)cn), 256, 0, st>>>(d_grids + c0, cell_start, d_bbase + c0, d_btotal);
+            MKB_LAUNCHED(h);
+        }
         int b0 = 0;
         while (b0 < B) {
             int mx = 1, my = 1, mz = 1, sh = 0, nb = 0;
@@ -1224,7 +1282,7 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
             fq.grids = d_grids + b0;
             fq.B = nb;
             fq.txp_shift = sh;
-            occ_fill8w_kernel<<<dim3((unsigned)cdiv(mz, W_WARPS), (unsigned)my, (unsigned)(nb << sh)), W_WARPS * 32, 0, st>>>(fq);
+            occ_fill8w_kernel<<<dim3((unsigned)cdiv(mz, W_WARPS), (unsigned)my, (unsigned)(nb << sh)), W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
             MKB_LAUNCHED(h);
             b0 += nb;
         }
