@@ -133,14 +133,12 @@ def run_reference(a):
     n_items = min(len(w["coords"]), max(1, procs))
     for _ in range(a.warmup):
         cpu_sample(w, n_items, procs)
-    walls, base = [], None
+    vals, walls, base = [], [], None
     for _ in range(a.steps):
-        base, wall = cpu_sample(w, n_items, procs)
-        walls.append(wall)
-    vc_step = n_items * int(np.prod(np.ceil(np.array(w["boxsize"]) / w["voxelsize"]))) * 8
-    base["value"] = vc_step * len(walls) / sum(walls)
-    best = (base, sum(walls) / len(walls))
-    vals = walls
+        base, wall = cpu_sample(w, n_items, procs)   # each step = one bounded sample (best of two process counts)
+        vals.append(base["value"]); walls.append(wall)
+    base["value"] = float(np.mean(vals))
+    best = (base, float(np.mean(walls)))
     line = dict(impl="reference", metric=METRIC, value=base["value"], unit=UNIT, n_gpus=a.gpus, steps=len(vals),
                 warmup=a.warmup, ms_per_step=best[1] * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
@@ -358,8 +356,19 @@ def run_ours(a):
     alg_bytes = workloads.occupancy_algorithmic_bytes(batch.total_voxels, n_atoms, batch.C)
     fill_mean = float(np.mean(fill_ms))
     achieved = alg_bytes / (fill_mean * 1e-3) / 1e9
+    traffic = None
+    try:  # dram bytes of one launch of the same command, from the committed `ncu --set full` capture
+        if a.workload == "c3" and not a.batch:
+            tr = 0.0
+            for ln in open(os.path.join(ROOT, "profiles", "r01_fill_final_metrics.txt")):
+                f = ln.split()
+                if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tr += float(f[1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
+            traffic = tr or None
+    except Exception:
+        traffic = None
     roofline = dict(bound="hbm", kernel=("occ_fill8w_kernel" if w["voxelsize"] >= 5.0 / 7 else "occ_fill8_kernel"), achieved=achieved, peak=peak, unit="GB/s",
-                    frac=achieved / peak, traffic=None, peak_source=f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
+                    frac=achieved / peak, traffic=traffic, peak_source=f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
                     algorithmic_bytes_per_launch=int(alg_bytes), kernel_ms_mean=fill_mean,
                     kernel_ms_min=float(np.min(fill_ms)), prep_ms_mean=float(np.mean(prep_ms)),
                     kernel_share_of_step=fill_mean / ms_step)

@@ -151,6 +151,16 @@ int mkb_collisions_count(mkb_handle_t h, void *stream, const float *c1, int64_t 
 int mkb_collisions_fill(mkb_handle_t h, void *stream, const float *c1, int64_t n1, const float *c2, int64_t n2,
                         float threshold, const int64_t *row_offsets, uint32_t *pairs);
 
+/* K7 (stretch row a13): bond perception, replaces bond_grid_search (moleculekit/bondguesser.py:259-392) +
+ * grid_bonds/_is_close (moleculekit/bondguesser_utils/bondguesser_utils.pyx:89-163).  coords [n,3] / radii [n] float32,
+ * is_hydrogen [n] uint32, device.  pairdist = final grid box edge (after the caller's max_boxes enlargement loop).
+ * Same two-call protocol as K4 with row_offsets [n + 1]; pairs come out as (i < j), unordered inside a row -- the SET
+ * equals the reference's (the host wrapper returns it in canonical sorted order). */
+int mkb_bonds_count(mkb_handle_t h, void *stream, const float *coords, const float *radii, const uint32_t *is_hydrogen,
+                    int64_t n, float pairdist, int64_t *row_offsets, int64_t *total_pairs);
+int mkb_bonds_fill(mkb_handle_t h, void *stream, const float *coords, const float *radii, const uint32_t *is_hydrogen,
+                   int64_t n, float pairdist, const int64_t *row_offsets, uint32_t *pairs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,7 @@ OUT = os.path.join(HERE, "_ref")
 MODULES = {
     "occupancy_utils": "moleculekit/occupancy_utils/occupancy_utils.pyx",
     "distance_utils": "moleculekit/distance_utils/distance_utils.pyx",
+    "bondguesser_utils": "moleculekit/bondguesser_utils/bondguesser_utils.pyx",
 }
 
 
@@ -74,7 +75,8 @@ def build(reference: str = "/root/reference", force: bool = False, verbose: bool
 
 
 def load():
-    """Import the two reference extension modules from oracle/_ref. Returns (occ, dist) or None."""
+    """Import the reference extension modules from oracle/_ref.  Returns (occupancy_utils, distance_utils,
+    bondguesser_utils) or None."""
     if not built():
         return None
     import importlib.util

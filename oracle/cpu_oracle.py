@@ -47,6 +47,7 @@ def lib():
         _lib.oracle_contacts_trajectory.restype = C.c_int64
         _lib.oracle_get_collisions.restype = C.c_int64
         _lib.oracle_squareform_dim.restype = C.c_int64
+        _lib.oracle_bond_grid_search.restype = C.c_int64
     return _lib
 
 
@@ -168,3 +169,27 @@ def squareform(distances):
     out = np.zeros((m, m), dtype=np.float32)
     lib().oracle_squareform(_p(d), C.c_int64(len(d)), _p(out))
     return out
+
+
+def bond_grid_search(coords, grid_cutoff, is_hydrogen, radii, max_boxes: float = 4e6, cutoff_incr: float = 1.26):
+    """moleculekit/bondguesser.py:259-392 (same arguments); returns (nbonds, 2) uint32 in the reference's order."""
+    coords = _f32(coords)
+    radii = _f32(radii)
+    ish = _u32(is_hydrogen)
+    n = coords.shape[0]
+    if n == 0:
+        return np.zeros((0, 2), np.uint32)
+    rng = coords.max(axis=0) - coords.min(axis=0)
+
+    def counts(pd):
+        ax = (np.floor(rng / pd).astype(np.int64) + 1).tolist()
+        return ax[0] * ax[1] * ax[2]
+
+    pairdist = float(grid_cutoff)
+    while counts(pairdist) > max_boxes:
+        pairdist *= cutoff_incr
+    args = (_p(coords), _p(radii), _p(ish), C.c_int64(n), C.c_double(pairdist))
+    total = lib().oracle_bond_grid_search(*args, None)
+    pairs = np.zeros((max(total, 1), 2), dtype=np.uint32)
+    lib().oracle_bond_grid_search(*args, _p(pairs))
+    return pairs[:total]

@@ -316,3 +316,108 @@ EXPORT void oracle_squareform(const float *d, int64_t n, float *out)
             ++k;
         }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Row a13 (stretch): bond guessing on a uniform non-periodic grid.
+ * bondguesser.py:259-392 (bond_grid_search: binning, traversal) +
+ * bondguesser_utils/bondguesser_utils.pyx:30-85 (14-entry half-shell neighbour table),
+ * :89-115 (_is_close), :119-163 (grid_bonds).
+ * coords (N,3) f32, radii (N) f32, is_hydrogen (N) u32, pairdist = final grid box edge (after the max_boxes
+ * enlargement loop, done by the caller).  pairs == NULL -> count only.  Output order = the reference's:
+ * boxes in order of first appearance (dict insertion order, :357-388), atoms of a box in index order,
+ * neighbour boxes in table order, (i, j) as emitted (not canonicalised).
+ * ------------------------------------------------------------------------------------------ */
+static int is_close(const float *c, const float *radii, const uint32_t *is_h, int64_t i, int64_t j, float cutoff2)
+{
+    if (is_h[i] && is_h[j]) return 0;
+    const float dx = c[3 * i + 0] - c[3 * j + 0];
+    const float dy = c[3 * i + 1] - c[3 * j + 1];
+    const float dz = c[3 * i + 2] - c[3 * j + 2];
+    float d2 = dx * dx;
+    d2 = d2 + dy * dy;
+    d2 = d2 + dz * dz;
+    if (d2 > cutoff2 || (double)d2 < 0.001) return 0;      /* pyx:106: float vs double literal */
+    const float cut = (float)(0.6 * (double)(radii[i] + radii[j]));   /* pyx:109: 0.6 is a double literal */
+    if (d2 > cut * cut) return 0;
+    return 1;
+}
+
+EXPORT int64_t oracle_bond_grid_search(const float *coords, const float *radii, const uint32_t *is_h,
+                                       int64_t n, double pairdist, uint32_t *pairs)
+{
+    if (n <= 0) return 0;
+    float mn[3], mx[3];
+    for (int d = 0; d < 3; ++d) { mn[d] = coords[d]; mx[d] = coords[d]; }
+    for (int64_t a = 1; a < n; ++a)
+        for (int d = 0; d < 3; ++d) {
+            const float v = coords[3 * a + d];
+            if (v < mn[d]) mn[d] = v;
+            if (v > mx[d]) mx[d] = v;
+        }
+    /* numpy: xyzrange f32; xyzrange / pairdist with a python float keeps f32 (weak scalar), floor, +1 */
+    const float pdf = (float)pairdist;
+    int64_t nb[3];
+    for (int d = 0; d < 3; ++d) nb[d] = (int64_t)floorf((mx[d] - mn[d]) / pdf) + 1;
+    const int64_t nboxes = nb[0] * nb[1] * nb[2], xy = nb[0] * nb[1];
+    int64_t *box = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    int64_t *cnt = (int64_t *)calloc((size_t)nboxes + 1, sizeof(int64_t));
+    int64_t *first = (int64_t *)malloc(sizeof(int64_t) * (size_t)nboxes);   /* first atom of each box */
+    for (int64_t b = 0; b < nboxes; ++b) first[b] = -1;
+    for (int64_t a = 0; a < n; ++a) {
+        int64_t bi[3];
+        for (int d = 0; d < 3; ++d) {
+            int64_t v = (int64_t)floorf((coords[3 * a + d] - mn[d]) / pdf);
+            if (v < 0) v = 0;
+            if (v > nb[d] - 1) v = nb[d] - 1;
+            bi[d] = v;
+        }
+        box[a] = bi[2] * xy + bi[1] * nb[0] + bi[0];
+        if (first[box[a]] < 0) first[box[a]] = a;
+        cnt[box[a] + 1]++;
+    }
+    for (int64_t b = 0; b < nboxes; ++b) cnt[b + 1] += cnt[b];          /* cnt = start offsets */
+    int64_t *members = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * (size_t)nboxes);
+    memcpy(cur, cnt, sizeof(int64_t) * (size_t)nboxes);
+    for (int64_t a = 0; a < n; ++a) members[cur[box[a]]++] = a;           /* index order inside a box */
+    const float cutoff2 = pdf * pdf;                                       /* pyx:136: float product */
+    int64_t total = 0;
+    /* boxes in order of first appearance == order of their first atom */
+    for (int64_t a0 = 0; a0 < n; ++a0) {
+        const int64_t b = box[a0];
+        if (first[b] != a0) continue;
+        const int64_t zi = b / xy, yi = (b % xy) / nb[0], xi = b % nb[0];
+        int64_t neigh[14];
+        int m = 0;
+        const int xr = xi < nb[0] - 1, yr = yi < nb[1] - 1, zr = zi < nb[2] - 1, xl = xi > 0, yl = yi > 0;
+        neigh[m++] = b;                                                   /* pyx:44-84, same order */
+        if (xr) neigh[m++] = b + 1;
+        if (yr) neigh[m++] = b + nb[0];
+        if (zr) neigh[m++] = b + xy;
+        if (xr && yr) neigh[m++] = b + nb[0] + 1;
+        if (xr && zr) neigh[m++] = b + xy + 1;
+        if (yr && zr) neigh[m++] = b + xy + nb[0];
+        if (xr && yl) neigh[m++] = b - nb[0] + 1;
+        if (xl && zr) neigh[m++] = b + xy - 1;
+        if (yl && zr) neigh[m++] = b + xy - nb[0];
+        if (xr && yr && zr) neigh[m++] = b + xy + nb[0] + 1;
+        if (xl && yr && zr) neigh[m++] = b + xy + nb[0] - 1;
+        if (xr && yl && zr) neigh[m++] = b + xy - nb[0] + 1;
+        if (xl && yl && zr) neigh[m++] = b + xy - nb[0] - 1;
+        for (int64_t ii = cnt[b]; ii < cnt[b + 1]; ++ii) {
+            const int64_t i = members[ii];
+            for (int k = 0; k < m; ++k) {
+                const int64_t nbx = neigh[k];
+                for (int64_t jj = (nbx == b) ? ii + 1 : cnt[nbx]; jj < cnt[nbx + 1]; ++jj) {
+                    const int64_t j = members[jj];
+                    if (is_close(coords, radii, is_h, i, j, cutoff2)) {
+                        if (pairs) { pairs[2 * total] = (uint32_t)i; pairs[2 * total + 1] = (uint32_t)j; }
+                        ++total;
+                    }
+                }
+            }
+        }
+    }
+    free(box); free(cnt); free(first); free(members); free(cur);
+    return total;
+}

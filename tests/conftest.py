@@ -55,6 +55,11 @@ def g_raw():
 
 
 @pytest.fixture(scope="session")
+def g_bonds():
+    return _npz("bonds.npz")
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import cpu_oracle
 

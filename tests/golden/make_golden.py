@@ -40,7 +40,7 @@ def main():
     from oracle import build_ref
 
     assert build_ref.build(), "oracle/_ref could not be built (is /root/reference present?)"
-    occ_ref, dist_ref = build_ref.load()
+    occ_ref, dist_ref = build_ref.load()[:2]
 
     from moleculekit.molecule import Molecule  # the reference (scratch build on PYTHONPATH)
     from moleculekit.tools.voxeldescriptors import getCenters
@@ -265,6 +265,27 @@ def main():
     rk["sq_out"] = np.array(dist_ref.squareform(rk["pd3_out"]))
     rk["coll_out"] = np.array(dist_ref.get_collisions(rk["cd3_a"], rk["cd3_b"], 6.0), dtype=np.uint32).reshape(-1, 2)
     np.savez_compressed(os.path.join(HERE, "rawkernels.npz"), **rk)
+
+    # ------------------------------------------------------------------ bond guessing (row a13): reference csv goldens
+    from moleculekit.bondguesser import guess_bonds, vdw_radii as ref_vdw
+    from moleculekit.molecule import calculateUniqueBonds
+
+    bg = {}
+    pdbids = ["3ptb", "3hyd", "6a5j", "5vbl", "7q5b", "1unc", "3zhi", "1a25", "1u5u", "1gzm", "6va1", "1bna", "3wbm",
+              "1awf", "5vav"]  # tests/test_bondguesser.py:10-26
+    for pid in pdbids:
+        m = Molecule(pid)
+        ref = np.loadtxt(os.path.join(REFT, "test_bondguesser", f"{pid}.csv"), delimiter=",").astype(np.uint32)
+        got, _ = calculateUniqueBonds(guess_bonds(m).astype(np.uint32), [])
+        assert np.array_equal(got, ref), pid  # the reference reproduces its own golden here
+        bg[f"{pid}_coords"] = m.coords[:, :, m.frame].copy()
+        bg[f"{pid}_element"] = strarr(m.element)
+        bg[f"{pid}_name"] = strarr(m.name)
+        bg[f"{pid}_bonds"] = ref
+    bg["pdbids"] = np.array(pdbids)
+    bg["vdw_keys"] = np.array(list(ref_vdw.keys()))
+    bg["vdw_vals"] = np.array([float(v) for v in ref_vdw.values()])
+    np.savez_compressed(os.path.join(HERE, "bonds.npz"), **bg)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
