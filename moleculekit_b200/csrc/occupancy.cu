@@ -185,6 +185,9 @@ struct FillParams {
     int vec_ok;
     int txp_shift;  // fast path launch: blockIdx.z = (grid << txp_shift) | tile_x
     int bulk_store; // fast path: stage the tile in smem and store rows with cp.async.bulk (TMA)
+    // warp kernel, uniform launches: descriptor of the chunk's first grid + per-grid strides
+    GridDev u;
+    long long u_out_stride, u_cell_stride, u_block_base, u_block_stride;
 };
 
 // float64 re-evaluation of the gate with the reference's exact operations (pyx:49-53; centres as built by
@@ -791,6 +794,11 @@ __global__ void occ_block_total_kernel(const GridDev *__restrict__ grids, const 
     block_total[block_base[blockIdx.y] + local] = total;
 }
 
+// UNIFORM: every grid of the launch has the same shape (the batched-pockets case): shape constants come from the
+// kernel parameters (constant bank) instead of a chain of dependent global loads -- an empty block then waits for ONE
+// load (its halo count) before it can retire.
+#define WG(field) (UNIFORM ? p.u.field : __ldg(&gg->field))
+template <bool UNIFORM>
 __global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillParams p, const long long *__restrict__ block_base,
                                                                      const unsigned *__restrict__ block_total) {
     __shared__ float4 s_pent[W_WARPS][W_PCAP + 1];    // block candidates: x, y, z in the block frame, sigma^2 (+ sentinel)
@@ -802,19 +810,21 @@ __global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillP
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bzi = blockIdx.x * W_WARPS + warp, byi = blockIdx.y, bxi = blockIdx.z & ((1 << p.txp_shift) - 1);
-    const GridDev *gg = p.grids + (blockIdx.z >> p.txp_shift);
-    const int nx = __ldg(&gg->dims[0]), ny = __ldg(&gg->dims[1]), nz = __ldg(&gg->dims[2]);
+    const int gi = blockIdx.z >> p.txp_shift;
+    const GridDev *gg = p.grids + gi;
+    const int nx = WG(dims[0]), ny = WG(dims[1]), nz = WG(dims[2]);
+    const long long out_offset = UNIFORM ? p.u.out_offset + (long long)gi * p.u_out_stride : __ldg(&gg->out_offset);
     if (bxi * 2 >= nx || byi * 4 >= ny || bzi * 4 >= nz) return;  // padding of the launch grid / ragged batch
 
     // ---- empty block (no atom within reach): stream 32 x 32 B of zeros and retire
     {
         const int nby = (ny + 3) >> 2, nbz = (nz + 3) >> 2;
-        const unsigned tot = __ldg(block_total + __ldg(block_base + (blockIdx.z >> p.txp_shift)) +
-                                   ((long long)bxi * nby + byi) * nbz + bzi);
+        const long long bb = UNIFORM ? p.u_block_base + (long long)gi * p.u_block_stride : __ldg(block_base + gi);
+        const unsigned tot = __ldg(block_total + bb + ((long long)bxi * nby + byi) * nbz + bzi);
         if (tot == 0 && p.vec_ok && !(p.flags & MKB_OCC_ACCUMULATE)) {
             const int ix = bxi * 2 + (lane >> 4), iy = byi * 4 + ((lane >> 2) & 3), iz = bzi * 4 + (lane & 3);
             if (ix < nx && iy < ny && iz < nz) {
-                float4 *d = reinterpret_cast<float4 *>(p.out + (__ldg(&gg->out_offset) + ((long long)ix * ny + iy) * nz + iz) * 8);
+                float4 *d = reinterpret_cast<float4 *>(p.out + (out_offset + ((long long)ix * ny + iy) * nz + iz) * 8);
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 __stcs(d, z4);
                 __stcs(d + 1, z4);
@@ -824,15 +834,15 @@ __global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillP
     }
 
     // ---- cell rows of this block's halo: shifted voxel range [lo, lo + ext - 1 + 2 cutv] per axis (W_CELL = 4)
-    const int cutv = __ldg(&gg->cutv);
-    const int cN1 = __ldg(&gg->cells[1]), cN2 = __ldg(&gg->cells[2]);
-    const int cx0 = (bxi * 2) / W_CELL, cx1 = min((bxi * 2 + 1 + 2 * cutv) / W_CELL, __ldg(&gg->cells[0]) - 1);
+    const int cutv = WG(cutv);
+    const int cN1 = WG(cells[1]), cN2 = WG(cells[2]);
+    const int cx0 = (bxi * 2) / W_CELL, cx1 = min((bxi * 2 + 1 + 2 * cutv) / W_CELL, WG(cells[0]) - 1);
     const int cy0 = byi, cy1 = min((byi * 4 + 3 + 2 * cutv) / W_CELL, cN1 - 1);
     const int cz0 = bzi, cz1 = min((bzi * 4 + 3 + 2 * cutv) / W_CELL, cN2 - 1);
     const int ncy = cy1 - cy0 + 1;
     const int nrows = (cx1 - cx0 + 1) * ncy;  // <= W_ROWS checked on the host
     unsigned *const rpos = s_rpos[warp], *const rbase = s_rbase[warp];
-    const long long cell_base = __ldg(&gg->cell_base);
+    const long long cell_base = UNIFORM ? p.u.cell_base + (long long)gi * p.u_cell_stride : __ldg(&gg->cell_base);
     const float inv_ncy = 1.0f / (float)ncy;
     unsigned carry = 0;
     for (int r0 = 0; r0 < nrows; r0 += 32) {  // row lengths + inclusive scan, 32 rows per step
@@ -873,7 +883,7 @@ __global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillP
             s_pmask[warp][W_PCAP] = 1u;
         }
         __syncwarp();
-        const float cut_lo = __ldg(&gg->cut2v_lo), cut_hi = __ldg(&gg->cut2v_hi);
+        const float cut_lo = WG(cut2v_lo), cut_hi = WG(cut2v_hi);
         const float gate_k = GATE_SCALE * cut_lo;
         const unsigned band_bits = __float_as_uint(cut_hi - cut_lo);
         const float fvx = (float)lx - 0.5f, fvy = (float)ly - 1.5f, fvz = (float)lz - 1.5f;
@@ -947,7 +957,7 @@ __global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillP
                     if (!in && d2 < cut_hi) in = exact_gate(gg, p.coords, psrc[jj], ix, iy, iz);
                     const float rr = in ? rcp_approx(d2) : 0.0f;
                     const double *sg = p.sigmas + (long long)psrc[jj] * p.C;
-                    const double ivs = __ldg(&gg->inv_vs);
+                    const double ivs = WG(inv_vs);
 #pragma unroll
                     for (int h = 0; h < 8; ++h) {
                         if (h < p.C) {
@@ -1006,7 +1016,7 @@ __global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillP
 #pragma unroll
             for (int h = 0; h < 8; ++h) v[h] = 0.0f;
         }
-        float *const oo = p.out + (__ldg(&gg->out_offset) + ((long long)ix * ny + iy) * nz + iz) * C;
+        float *const oo = p.out + (out_offset + ((long long)ix * ny + iy) * nz + iz) * C;
         if (p.flags & MKB_OCC_ACCUMULATE) {
 #pragma unroll
             for (int h = 0; h < 8; ++h)
@@ -1022,6 +1032,7 @@ __global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillP
         }
     }
 }
+#undef WG
 
 // ---------------------------------------------------------------------------------------------------------
 // K1b: arbitrary centres.  Atoms hashed into 5 A cells (count -> scan -> order); one thread per centre visits the
@@ -1282,7 +1293,24 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
             fq.grids = d_grids + b0;
             fq.B = nb;
             fq.txp_shift = sh;
-            occ_fill8w_kernel<<<dim3((unsigned)cdiv(mz, W_WARPS), (unsigned)my, (unsigned)(nb << sh)), W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
+            // uniform chunk: same shape everywhere and regularly spaced output / cells / blocks
+            bool uni = true;
+            const GridDev &g0 = gd[b0];
+            const long long nvox0 = (long long)g0.dims[0] * g0.dims[1] * g0.dims[2];
+            const long long ncell0 = (long long)g0.cells[0] * g0.cells[1] * g0.cells[2];
+            for (int b = b0; b < b0 + nb && uni; ++b) {
+                const GridDev &g = gd[b];
+                uni = g.dims[0] == g0.dims[0] && g.dims[1] == g0.dims[1] && g.dims[2] == g0.dims[2] && g.vs == g0.vs &&
+                      g.out_offset == g0.out_offset + (b - b0) * nvox0 && g.cell_base == g0.cell_base + (b - b0) * ncell0;
+            }
+            fq.u = g0;
+            fq.u_out_stride = nvox0;
+            fq.u_cell_stride = ncell0;
+            fq.u_block_base = bbase[b0];
+            fq.u_block_stride = bbase[b0 + 1] - bbase[b0];
+            const dim3 wgrid((unsigned)cdiv(mz, W_WARPS), (unsigned)my, (unsigned)(nb << sh));
+            if (uni) occ_fill8w_kernel<true><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
+            else occ_fill8w_kernel<false><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
             MKB_LAUNCHED(h);
             b0 += nb;
         }

@@ -210,3 +210,20 @@ def test_alternative_kernel_paths_agree(vd, monkeypatch, envs):
             # different kernels place atoms in different local frames: each within 1e-5 of the float64 oracle, zero pattern identical
             assert np.array_equal(a != 0, b != 0)
             assert np.allclose(a, b, rtol=1.5e-5, atol=0)
+
+
+def test_nonuniform_batch_buffer_mode(vd, oracle):
+    """Grids of different shapes in one batch (bounding-box mode): exercises the non-uniform launch path."""
+    rng = np.random.default_rng(17)
+    coords, sigmas = [], []
+    for n, spread in ((150, 3.0), (40, 1.5), (300, 5.0)):
+        coords.append((rng.normal(size=(n, 3)) * spread + rng.uniform(-30, 30, 3)).astype(np.float32))
+        sigmas.append(rng.choice([1.52, 1.7, 1.8], n)[:, None] * (rng.random((n, 8)) < 0.45))
+    feats, dims = vd.getVoxelDescriptorsBatch(coords, sigmas, buffer=4.0, voxelsize=1.0)
+    assert len({tuple(d) for d in dims.tolist()}) == 3
+    from moleculekit_b200.molecule_lite import MolLite
+    for b in range(3):
+        centers, nv = vd.getCenters(MolLite(coords[b]), buffer=4.0, voxelsize=1.0)
+        assert nv.tolist() == dims[b].tolist()
+        want = np.zeros((centers.shape[0], 8)); oracle.calculate_occupancy(centers, coords[b], sigmas[b], want)
+        _assert_occ_close(feats[b], want)
