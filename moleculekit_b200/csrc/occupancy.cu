@@ -767,9 +767,13 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillPa
 //   CTA = 4 warps = 4 z-consecutive blocks, purely a container.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int W_WARPS = 4;
+#ifndef MKB_W_MIN_CTAS
+#define MKB_W_MIN_CTAS 8
+#endif
+constexpr int W_MIN_CTAS = MKB_W_MIN_CTAS;  // resident CTAs per SM the register allocation must allow
 constexpr int W_CELL = 4;    // cell edge of the binning used with this kernel
-constexpr int W_ROWS = 128;   // cell rows per block: (Rx+1)(Ry+1)
-constexpr int W_PCAP = 192;   // block candidates per round
+constexpr int W_ROWS = 64;    // cell rows per block: (Rx+1)(Ry+1) (cutoff <= 7 voxels -> <= 20)
+constexpr int W_PCAP = 128;   // block candidates per round
 constexpr int W_QCAP = 96;    // sub-block candidates per round
 
 // halo atom count of every 2x4x4 block (one THREAD per block: 32x cheaper than letting each warp find out that
@@ -799,7 +803,7 @@ __global__ void occ_block_total_kernel(const GridDev *__restrict__ grids, const 
 // load (its halo count) before it can retire.
 #define WG(field) (UNIFORM ? p.u.field : __ldg(&gg->field))
 template <bool UNIFORM>
-__global__ void __launch_bounds__(W_WARPS * 32, 8) occ_fill8w_kernel(const FillParams p, const long long *__restrict__ block_base,
+__global__ void __launch_bounds__(W_WARPS * 32, W_MIN_CTAS) occ_fill8w_kernel(const FillParams p, const long long *__restrict__ block_base,
                                                                      const unsigned *__restrict__ block_total) {
     __shared__ float4 s_pent[W_WARPS][W_PCAP + 1];    // block candidates: x, y, z in the block frame, sigma^2 (+ sentinel)
     __shared__ unsigned s_pmask[W_WARPS][W_PCAP + 1];  // channel mask; 0 = several sigmas
