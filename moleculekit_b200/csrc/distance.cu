@@ -69,6 +69,8 @@ __device__ __forceinline__ float pair_d2(const float4 a, const float4 b, const B
 
 // store with the fused host post-ops of projections/util.py:74-84: results[results > truncate] = truncate, then
 // (contacts) results <= threshold.  NaN distances stay NaN / compare false exactly like numpy.
+constexpr int DIST_CONTACTS_D2 = 2;  // internal: contacts without truncate, decided on d2 <= T (no sqrt), see contact_d2_threshold
+
 template <int MODE>
 __device__ __forceinline__ void store_dist(void *out, long long idx, float d, float truncate, float threshold) {
     if (d > truncate) d = truncate;  // truncate = NaN disables (comparison false)
@@ -138,6 +140,29 @@ __device__ __forceinline__ Wrapped wrap_fast(float d, float b, float rb) {
     return w;
 }
 
+__device__ __forceinline__ float pair_d2_fastwrap(const float4 a, const float4 b, unsigned cb, const BoxF &bx, int pbc) {
+    float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+    if (pbc && (__float_as_uint(a.w) != cb)) {
+        const Wrapped wx = wrap_fast(dx, bx.bx, bx.rx), wy = wrap_fast(dy, bx.by, bx.ry), wz = wrap_fast(dz, bx.bz, bx.rz);
+        if (wx.risky | wy.risky | wz.risky) {  // rare: a quotient within 6e-7|q| of a half-integer, or huge
+            dx = wrap_axis(dx, bx.bx, bx.rx);
+            dy = wrap_axis(dy, bx.by, bx.ry);
+            dz = wrap_axis(dz, bx.bz, bx.rz);
+        } else {
+            dx = wx.d; dy = wy.d; dz = wz.d;
+        }
+    }
+    return sq3(dx, dy, dz);
+}
+
+template <int MODE>
+__device__ __forceinline__ void emit_dist(void *out, long long idx, float d2, float truncate, float threshold) {
+    if (MODE == DIST_CONTACTS_D2) reinterpret_cast<unsigned char *>(out)[idx] = (d2 <= threshold) ? 1 : 0;
+    else store_dist<MODE>(out, idx, __fsqrt_rn(d2), truncate, threshold);
+}
+
+// Each thread owns TWO sel2 columns (j and j + K3_COLS) so one broadcast load of the sel1 atom, the loop control and the
+// index arithmetic are shared by two pairs.
 template <int MODE>
 __global__ void __launch_bounds__(K3_COLS) dist_kernel(const float4 *__restrict__ G1, const float4 *__restrict__ G2,
                                                         long long n1, long long n2, const float *__restrict__ box,
@@ -145,36 +170,26 @@ __global__ void __launch_bounds__(K3_COLS) dist_kernel(const float4 *__restrict_
                                                         float threshold, long long P, void *__restrict__ out,
                                                         long long frame0) {
     const long long f = frame0 + blockIdx.z;
-    const long long j = (long long)blockIdx.x * K3_COLS + threadIdx.x;
+    const long long j0 = (long long)blockIdx.x * (2 * K3_COLS) + threadIdx.x, j1 = j0 + K3_COLS;
     const long long i0 = (long long)blockIdx.y * K3_ROWS;
-    if (selfdist && (long long)(blockIdx.x + 1) * K3_COLS <= i0 + 1) return;  // tile entirely below the diagonal
-    if (j >= n2) return;
-    const float4 b = G2[f * n2 + j];
-    const unsigned cb = __float_as_uint(b.w);
+    if (selfdist && (long long)(blockIdx.x + 1) * (2 * K3_COLS) <= i0 + 1) return;  // tile entirely below the diagonal
+    if (j0 >= n2) return;
+    const bool has1 = j1 < n2;
+    const float4 b0 = G2[f * n2 + j0];
+    const float4 b1 = has1 ? G2[f * n2 + j1] : b0;
+    const unsigned cb0 = __float_as_uint(b0.w), cb1 = __float_as_uint(b1.w);
     const BoxF bx = load_box(box, box_stride, f);
     const int rows = (int)(min(i0 + K3_ROWS, n1) - i0);
     const float4 *__restrict__ arow = G1 + f * n1 + i0;
     // running output index: non-self (i, j) -> i*n2 + j ; self -> i*n2 - i(i+1)/2 + (j - i - 1), step n2 - i - 2
-    long long idx = f * P + (selfdist ? (i0 * n2 - (i0 * (i0 + 1)) / 2 + (j - i0 - 1)) : (i0 * n2 + j));
+    long long idx = f * P + (selfdist ? (i0 * n2 - (i0 * (i0 + 1)) / 2 + (j0 - i0 - 1)) : (i0 * n2 + j0));
     long long step = selfdist ? (n2 - i0 - 2) : n2;
-#pragma unroll 4
+#pragma unroll 2
     for (int r = 0; r < rows; ++r) {
         const float4 a = __ldg(arow + r);
-        if (!selfdist || j > i0 + r) {
-            float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
-            if (pbc && (__float_as_uint(a.w) != cb)) {
-                const Wrapped wx = wrap_fast(dx, bx.bx, bx.rx), wy = wrap_fast(dy, bx.by, bx.ry),
-                              wz = wrap_fast(dz, bx.bz, bx.rz);
-                if (wx.risky | wy.risky | wz.risky) {  // rare: a quotient within 6e-7|q| of a half-integer, or huge
-                    dx = wrap_axis(dx, bx.bx, bx.rx);
-                    dy = wrap_axis(dy, bx.by, bx.ry);
-                    dz = wrap_axis(dz, bx.bz, bx.rz);
-                } else {
-                    dx = wx.d; dy = wy.d; dz = wz.d;
-                }
-            }
-            store_dist<MODE>(out, idx, __fsqrt_rn(sq3(dx, dy, dz)), truncate, threshold);
-        }
+        if (!selfdist || j0 > i0 + r) emit_dist<MODE>(out, idx, pair_d2_fastwrap(a, b0, cb0, bx, pbc), truncate, threshold);
+        if (has1 && (!selfdist || j1 > i0 + r))
+            emit_dist<MODE>(out, idx + K3_COLS, pair_d2_fastwrap(a, b1, cb1, bx, pbc), truncate, threshold);
         idx += step;
         if (selfdist) --step;
     }
@@ -423,17 +438,31 @@ extern "C" int mkb_dist_trajectory(mkb_handle_t h, void *stream, const mkb_traj 
     if ((rc = launch_gather<uint32_t>(h, st, t, sel1, n1, chains, G1))) return rc;
     if ((rc = launch_gather<uint32_t>(h, st, t, sel2, n2, chains, G2))) return rc;
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
-    const unsigned gx = (unsigned)cdiv(n2, K3_COLS), gy = (unsigned)cdiv(n1, K3_ROWS);
+    const unsigned gx = (unsigned)cdiv(n2, 2 * K3_COLS), gy = (unsigned)cdiv(n1, K3_ROWS);
     if (gy > 65535) return fail(h, MKB_ERR_BAD_ARG, "sel1 too large for one call (%lld)", (long long)n1);
+    // contacts without truncate: sqrtf(d2) <= thr  <=>  d2 <= T with T the largest float whose correctly rounded square
+    // root is <= thr -- the comparison moves to d2 and the square root disappears (NaN compares false either way)
+    int kmode = mode;
+    float kthr = threshold;
+    if (mode == MKB_DIST_CONTACTS && std::isnan(truncate) && threshold >= 0.0f && std::isfinite(threshold)) {
+        float T = threshold * threshold;
+        while (sqrtf(T) > threshold) T = nextafterf(T, -INFINITY);
+        while (sqrtf(nextafterf(T, INFINITY)) <= threshold) T = nextafterf(T, INFINITY);
+        kmode = DIST_CONTACTS_D2;
+        kthr = T;
+    }
     for (long long f0 = 0; f0 < F; f0 += 65535) {
         const unsigned gz = (unsigned)std::min<long long>(65535, F - f0);
         dim3 grid(gx, gy, gz);
-        if (mode == MKB_DIST_DISTANCES)
+        if (kmode == MKB_DIST_DISTANCES)
             dist_kernel<MKB_DIST_DISTANCES><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box,
-                                                                      selfdist, pbc, truncate, threshold, P, out, f0);
-        else
+                                                                      selfdist, pbc, truncate, kthr, P, out, f0);
+        else if (kmode == MKB_DIST_CONTACTS)
             dist_kernel<MKB_DIST_CONTACTS><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box,
-                                                                     selfdist, pbc, truncate, threshold, P, out, f0);
+                                                                     selfdist, pbc, truncate, kthr, P, out, f0);
+        else
+            dist_kernel<DIST_CONTACTS_D2><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box,
+                                                                    selfdist, pbc, truncate, kthr, P, out, f0);
         MKB_LAUNCHED(h);
     }
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));

@@ -129,6 +129,28 @@ def test_random_vs_oracle_large_wraps_and_half_ties(du, oracle):
         assert du.contacts_trajectory(c, bx, a, b, ch, selfd, True, 9.5) == oracle.contacts_trajectory(c, bx, a, b, ch, selfd, True, 9.5)
 
 
+def test_contact_threshold_ties(du, oracle):
+    """metric="contacts" is decided on d2 (no sqrt): must equal sqrtf(d2) <= threshold of the reference incl. exact
+    ties (3-4-5 triangles) and distances one ulp either side of the threshold."""
+    rng = np.random.default_rng(2)
+    n, F = 96, 3
+    base = rng.integers(-6, 7, size=(n, 3)).astype(np.float32)
+    c = np.repeat(base[:, :, None], F, axis=2)
+    c[:, :, 1] += (rng.integers(-2, 3, size=(n, 3)) * np.float32(2.0 ** -20)).astype(np.float32)  # +- a few ulp
+    c[:, :, 2] += rng.normal(0, 1e-3, size=(n, 3)).astype(np.float32)
+    bx = np.zeros((3, F), np.float32)
+    s1 = np.arange(0, 40, dtype=np.uint32); s2 = np.arange(40, n, dtype=np.uint32)
+    ch = np.zeros(n, np.uint32)
+    want_d = np.zeros((F, 40 * 56), np.float32); oracle.dist_trajectory(c, bx, s1, s2, ch, False, False, want_d)
+    for thr in (5.0, 3.0, 7.0710678, 1e-3):
+        got = du.dist_trajectory(c, bx, s1, s2, ch, False, False, None, metric="contacts", threshold=thr)
+        assert got.dtype == bool and np.array_equal(got, want_d <= np.float32(thr)), thr
+        assert (want_d == np.float32(thr)).any() or thr not in (5.0, 3.0)   # the tie cases really occur
+        gt = du.dist_trajectory(c, bx, s1, s2, ch, False, False, None, metric="contacts", threshold=thr, truncate=4.0)
+        wt = want_d.copy(); wt[wt > np.float32(4.0)] = np.float32(4.0)
+        assert np.array_equal(gt, wt <= np.float32(thr))
+
+
 def test_frame_shard_view_equals_full(du, g_raw):
     """A frame slice of a resident device trajectory (what a GPU shard sees) gives the same rows."""
     import torch
