@@ -247,6 +247,24 @@ def extra_workloads(dev, peak):
                                     kernel_ms=main, kernel_gbs=nb / (main * 1e-3) / 1e9,
                                     frac_of_peak=nb / (main * 1e-3) / 1e9 / peak)
         del o
+    # C4b: sparse ordered contacts (calculate_contacts), 1000 frames, 500 x 4500 atoms, <= 12 A
+    n1, n2, F = 500, 4500, 1000
+    start = rng.uniform(0, L, size=(n1 + n2, 3, 1)).astype(np.float32)
+    coords = start + np.cumsum(rng.normal(0, 0.3, size=(n1 + n2, 3, F)).astype(np.float32), axis=2)
+    box = np.repeat((L * (1 + 0.002 * rng.normal(size=F))).astype(np.float32)[None, :], 3, axis=0)
+    d_c = torch.from_numpy(np.ascontiguousarray(coords)).to(dev); d_b = torch.from_numpy(np.ascontiguousarray(box)).to(dev)
+    s1 = torch.arange(0, n1, dtype=torch.int32, device=dev); s2 = torch.arange(n1, n1 + n2, dtype=torch.int32, device=dev)
+    ch = torch.ones(n1 + n2, dtype=torch.int32, device=dev); ch[n1:] = 2
+    res = {}
+
+    def run_contacts():
+        res["off"], res["pairs"] = du.contacts_trajectory_device(d_c, d_b, s1, s2, ch, False, True, 12.0)
+
+    ms = _time_cuda(run_contacts, warm=2, steps=3)
+    npairs = int(res["pairs"].shape[0])
+    out["c4b_sparse_contacts"] = dict(workload=f"C4b: {F} frames x {n1}x{n2} periodic pair tests <= 12 A, ordered index pairs",
+                                      pair_tests_per_s=F * n1 * n2 / (ms * 1e-3), ms_per_step=ms, emitted_pairs=npairs,
+                                      output_gbs=(npairs * 8 + F * n1 * 8) / (ms * 1e-3) / 1e9)
     return out
 
 

@@ -213,7 +213,6 @@ __global__ void __launch_bounds__(256) contacts_kernel(const float4 *__restrict_
     if (row >= n_frames * n1) return;
     const long long f = row / n1, i = row - f * n1;
     const float4 a = G1[f * n1 + i];
-    const unsigned ca = __float_as_uint(a.w);
     const BoxF bx = load_box(box, box_stride, f);
     const unsigned s1 = FILL ? sel1[i] : 0u;
     long long pos = FILL ? row_offsets[row] : 0;
@@ -224,8 +223,7 @@ __global__ void __launch_bounds__(256) contacts_kernel(const float4 *__restrict_
         bool hit = false;
         if (j >= jstart && j < n2) {
             const float4 b = G2[f * n2 + j];
-            const bool wrap = pbc && (ca != __float_as_uint(b.w));
-            hit = pair_d2(a, b, bx, wrap) <= thr2;  // distance_utils.pyx:90
+            hit = pair_d2_fastwrap(a, b, __float_as_uint(b.w), bx, pbc) <= thr2;  // distance_utils.pyx:90
         }
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
         if (FILL) {
