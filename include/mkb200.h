@@ -151,6 +151,15 @@ int mkb_collisions_count(mkb_handle_t h, void *stream, const float *c1, int64_t 
 int mkb_collisions_fill(mkb_handle_t h, void *stream, const float *c1, int64_t n1, const float *c2, int64_t n2,
                         float threshold, const int64_t *row_offsets, uint32_t *pairs);
 
+/* K8: MetricShell radial histogram fused on the distance evaluation; replaces _shells
+ * (moleculekit/projections/metricshell.py:183-202) and the (F, P) matrix it consumed.  counts [n_frames, n1, numshells]
+ * uint32: partners j of centre sel1[c] with edges[e] < d <= edges[e+1] (edges [numshells+1] float64 device; d = the
+ * reference's float32 distance, truncated if truncate is not NaN, compared in float64).  selfdist: sel2 == sel1 and a
+ * centre is not its own partner.  1 <= numshells <= 32. */
+int mkb_shell_counts(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *sel1, int64_t n1,
+                     const uint32_t *sel2, int64_t n2, const uint32_t *chains, int32_t selfdist, int32_t pbc,
+                     float truncate, const double *edges, int32_t numshells, uint32_t *counts);
+
 /* K7 (stretch row a13): bond perception, replaces bond_grid_search (moleculekit/bondguesser.py:259-392) +
  * grid_bonds/_is_close (moleculekit/bondguesser_utils/bondguesser_utils.pyx:89-163).  coords [n,3] / radii [n] float32,
  * is_hydrogen [n] uint32, device.  pairdist = final grid box edge (after the caller's max_boxes enlargement loop).

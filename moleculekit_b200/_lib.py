@@ -34,7 +34,7 @@ EXPORTS = [
     "mkb_occupancy_grid_batch", "mkb_occupancy_points",
     "mkb_dist_trajectory", "mkb_contacts_count", "mkb_contacts_fill", "mkb_dist_reduction",
     "mkb_cdist", "mkb_pdist", "mkb_squareform", "mkb_collisions_count", "mkb_collisions_fill",
-    "mkb_bonds_count", "mkb_bonds_fill",
+    "mkb_bonds_count", "mkb_bonds_fill", "mkb_shell_counts",
 ]
 
 _lib = None
@@ -78,6 +78,7 @@ def load():
     lib.mkb_squareform.argtypes = [vp, vp, vp, i64, i64, vp]
     lib.mkb_collisions_count.argtypes = [vp, vp, vp, i64, vp, i64, f32, vp, C.POINTER(i64)]
     lib.mkb_collisions_fill.argtypes = [vp, vp, vp, i64, vp, i64, f32, vp, vp]
+    lib.mkb_shell_counts.argtypes = [vp, vp, tp, vp, i64, vp, i64, vp, i32, i32, f32, vp, i32, vp]
     lib.mkb_bonds_count.argtypes = [vp, vp, vp, vp, vp, i64, f32, vp, C.POINTER(i64)]
     lib.mkb_bonds_fill.argtypes = [vp, vp, vp, vp, vp, i64, f32, vp, vp]
     for name in EXPORTS:

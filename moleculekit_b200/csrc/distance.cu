@@ -272,6 +272,45 @@ __global__ void __launch_bounds__(256) collisions_kernel(const float *__restrict
     if (!FILL && lane == 0) row_counts[i] = cnt;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K8: MetricShell -- radial shell histogram fused onto the distance evaluation.
+// Replaces the O(F*P) numpy post-pass of moleculekit/projections/metricshell.py:183-202 (_shells) AND the (F, P)
+// distance matrix it needed: counts[f][c][e] = #partners j with edges[e] < d(c, j) <= edges[e+1], d = the reference's
+// truncated float32 distance compared in float64 like numpy does (float32 array vs float64 edges).
+// One warp per (frame, centre); lane e keeps the count of shell e (numshells <= 32).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shell_kernel(const float4 *__restrict__ G1, const float4 *__restrict__ G2,
+                                                    long long n1, long long n2, long long n_frames,
+                                                    const float *__restrict__ box, long long box_stride, int selfdist,
+                                                    int pbc, float truncate, const double *__restrict__ edges,
+                                                    int numshells, unsigned *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_frames * n1) return;
+    const long long f = row / n1, c = row - f * n1;
+    const float4 a = G1[f * n1 + c];
+    const BoxF bx = load_box(box, box_stride, f);
+    const double lo_mine = lane < numshells ? edges[lane] : 0.0, hi_mine = lane < numshells ? edges[lane + 1] : 0.0;
+    unsigned mine = 0;
+    for (long long jb = 0; jb < n2; jb += 32) {
+        const long long j = jb + lane;
+        const bool valid = j < n2 && !(selfdist && j == c);
+        double d = 0.0;
+        if (valid) {
+            const float4 b = G2[f * n2 + j];
+            float df = __fsqrt_rn(pair_d2_fastwrap(a, b, __float_as_uint(b.w), bx, pbc));
+            if (df > truncate) df = truncate;  // projections/util.py:74-75 before the histogram
+            d = (double)df;
+        }
+        for (int e = 0; e < numshells; ++e) {
+            const double lo = __shfl_sync(0xffffffffu, lo_mine, e), hi = __shfl_sync(0xffffffffu, hi_mine, e);
+            const unsigned bal = __ballot_sync(0xffffffffu, valid && d > lo && d <= hi);  // NaN: both false
+            if (lane == e) mine += __popc(bal);
+        }
+    }
+    if (lane < numshells) counts[row * numshells + lane] = mine;
+}
+
 __global__ void set_last_zero(long long *p, long long n) {
     if (threadIdx.x == 0 && blockIdx.x == 0) p[n] = 0;
 }
@@ -659,6 +698,27 @@ extern "C" int mkb_collisions_fill(mkb_handle_t h, void *stream, const float *c1
     const float thr2 = threshold * threshold;
     collisions_kernel<true><<<(unsigned)cdiv(n1 * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         c1, n1, c2, n2, thr2, nullptr, (const long long *)row_offsets, pairs);
+    MKB_LAUNCHED(h);
+    return MKB_OK;
+}
+
+extern "C" int mkb_shell_counts(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *sel1, int64_t n1,
+                                const uint32_t *sel2, int64_t n2, const uint32_t *chains, int32_t selfdist,
+                                int32_t pbc, float truncate, const double *edges, int32_t numshells,
+                                uint32_t *counts) {
+    MKB_ENTER(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (numshells < 1 || numshells > 32) return fail(h, MKB_ERR_BAD_ARG, "numshells=%d: 1..32 supported", numshells);
+    if (selfdist && n1 != n2) return fail(h, MKB_ERR_BAD_ARG, "selfdist needs sel1 == sel2");
+    float4 *G1, *G2;
+    int rc = contacts_common(h, st, t, sel1, n1, sel2, n2, chains, &G1, &G2);
+    if (rc) return rc;
+    const long long rows = t->n_frames * n1;
+    if (rows == 0) return MKB_OK;
+    if (!edges || !counts) return fail(h, MKB_ERR_BAD_ARG, "null edges/counts");
+    shell_kernel<<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(G1, G2, n1, n2, t->n_frames, t->box,
+                                                                 t->frame_stride_box, selfdist, pbc, truncate, edges,
+                                                                 numshells, counts);
     MKB_LAUNCHED(h);
     return MKB_OK;
 }

@@ -93,6 +93,39 @@ def contacts_trajectory_device(coords, box, sel1, sel2, chains, selfdist: bool, 
     return frame_off.contiguous(), pairs
 
 
+def shell_counts_device(coords, box, sel1, sel2, chains, selfdist: bool, pbc: bool, edges, truncate=None):
+    """K8 on CUDA tensors: (F, n1, numshells) int32 counts of sel2 partners per radial shell around each sel1 atom."""
+    dev = coords.device
+    F, n1 = coords.shape[2], len(sel1)
+    numshells = int(edges.shape[0]) - 1
+    counts = torch.zeros((F, n1, numshells), dtype=torch.int32, device=dev)
+    h = _lib.handle(dev.index)
+    tr = _traj(coords, box)
+    with torch.cuda.device(dev):
+        rc = _lib.load().mkb_shell_counts(
+            h, _stream_ptr(dev), C.byref(tr), _ptr(sel1), n1, _ptr(sel2), len(sel2), _ptr(chains),
+            int(bool(selfdist)), int(bool(pbc)), _NAN if truncate is None else float(truncate), _ptr(edges), numshells,
+            _ptr(counts))
+    _lib.check(rc, h)
+    return counts
+
+
+def shell_counts(coords, box, sel1, sel2, digitized_chains, selfdist, pbc, edges, truncate=None, device=None):
+    """Host form of K8: numpy in, (F, n1, numshells) int64 counts out."""
+    _check("coords", coords, np.float32, 3); _check("box", box, np.float32, 2)
+    _check("sel1", sel1, np.uint32, 1); _check("sel2", sel2, np.uint32, 1)
+    _check("digitized_chains", digitized_chains, np.uint32, 1)
+    edges = np.ascontiguousarray(edges, dtype=np.float64)
+    F = coords.shape[2]
+    if F == 0 or len(sel1) == 0:
+        return np.zeros((F, len(sel1), len(edges) - 1), dtype=np.int64)
+    d_coords, d_box, remap, d_ch, _ = upload_selected(coords, box, [sel1, sel2], digitized_chains, device=device)
+    dev = d_coords.device
+    out = shell_counts_device(d_coords, d_box, _sel_dev(sel1, remap, dev), _sel_dev(sel2, remap, dev), d_ch, selfdist,
+                              pbc, torch.from_numpy(edges).to(dev), truncate=truncate)
+    return out.cpu().numpy().astype(np.int64)
+
+
 def _groups_csr(groups, dev):
     off = np.zeros(len(groups) + 1, dtype=np.int64)
     if len(groups):

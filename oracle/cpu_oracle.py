@@ -193,3 +193,29 @@ def bond_grid_search(coords, grid_cutoff, is_hydrogen, radii, max_boxes: float =
     pairs = np.zeros((max(total, 1), 2), dtype=np.uint32)
     lib().oracle_bond_grid_search(*args, _p(pairs))
     return pairs[:total]
+
+
+def metric_shell(coords, box, sel1, sel2, digitized_chains, selfdist, pbc, numshells=4, shellwidth=3, truncate=None):
+    """moleculekit/projections/metricshell.py:183-202 (_shells) on top of dist_trajectory + the truncate post-op of
+    projections/util.py:74-75: (F, ncenters * numshells) float64 densities, centre-major."""
+    sel1, sel2 = _u32(sel1), _u32(sel2)
+    F = coords.shape[2]
+    n1, n2 = len(sel1), len(sel2)
+    P = (n1 * (n2 - 1)) // 2 if selfdist else n1 * n2
+    dist = np.zeros((F, P), dtype=np.float32)
+    dist_trajectory(coords, box, sel1, sel2, digitized_chains, selfdist, pbc, dist)
+    if truncate is not None:
+        dist[dist > truncate] = truncate
+    if selfdist:
+        ii, jj = np.triu_indices(n1, k=1)
+    else:
+        ii, jj = np.repeat(np.arange(n1), n2), np.tile(np.arange(n2), n1)
+    edges = np.arange(shellwidth * (numshells + 1), step=shellwidth)
+    vol = 4 / 3 * np.pi * (edges[1:] ** 3 - edges[:-1] ** 3)
+    out = np.ones((F, n1 * numshells)) * -1
+    for c in range(n1):
+        cols = ((ii == c) | (jj == c)) if selfdist else (ii == c)
+        for e in range(numshells):
+            inshell = (dist[:, cols] > edges[e]) & (dist[:, cols] <= edges[e + 1])
+            out[:, c * numshells + e] = np.sum(inshell, axis=1) / vol[e]
+    return out

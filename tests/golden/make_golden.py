@@ -165,6 +165,13 @@ def main():
     fx["ref_com_closest"] = MetricDistance("protein and resid 1 to 50 and noh", "resname MOL and noh", "selections",
                                            groupsel1="residue", groupsel2="all", groupreduce1="com",
                                            groupreduce2="closest").project(molskip)
+    # MetricShell (tests/test_metricshell.py:8-26): stored golden refdata.npy, frames ::10, + today's output
+    from moleculekit.projections.metricshell import MetricShell
+    fx["gold_shell"] = np.load(os.path.join(REFT, "test_projections", "metricshell", "refdata.npy"))[::10]
+    fx["ref_shell"] = MetricShell("protein and name CA", "resname MOL and noh", periodic="selections").project(molskip)
+    assert np.allclose(fx["ref_shell"], fx["gold_shell"])
+    fx["ref_shell_self"] = MetricShell("resname MOL and noh", "resname MOL and noh", periodic=None, numshells=6,
+                                       shellwidth=1.5, truncate=7.0).project(molskip)
     # ordered contact pairs from the reference's contacts_trajectory (bit-exact target)
     from moleculekit.distance import calculate_contacts
 

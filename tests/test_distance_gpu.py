@@ -348,3 +348,40 @@ def test_errors(mol):
     bad = MolLite(np.zeros((3, 3, 2), np.float32), box=np.ones((3, 5), np.float32))
     with pytest.raises(RuntimeError, match="Different number of frames"):
         MetricDistance(np.array([0]), np.array([1]), "selections").project(bad)
+
+
+def test_metricshell(mol, g_traj, oracle):
+    """tests/test_metricshell.py:8-56 -- stored golden (frames ::10), today's reference output (exact), the analytic
+    3-atom cases, a symmetric selection with truncate, and a random case against the oracle restatement."""
+    from moleculekit_b200.molecule_lite import MolLite
+    from moleculekit_b200.projections.metricshell import MetricShell
+
+    m = MetricShell("protein and name CA", "resname MOL and noh", periodic="selections")
+    data = m.project(mol)
+    assert data.shape == (20, 277 * 4) and data.dtype == np.float64
+    assert np.allclose(data, g_traj["gold_shell"]), "Shell density calculation is broken"
+    assert np.array_equal(data, g_traj["ref_shell"])
+    assert m.getMapping(mol).shape == (277 * 4, 3)
+    self_ = MetricShell("resname MOL and noh", "resname MOL and noh", periodic=None, numshells=6, shellwidth=1.5,
+                        truncate=7.0).project(mol)
+    assert np.array_equal(self_, g_traj["ref_shell_self"])
+
+    xyz = np.zeros((3, 3, 1), np.float32); xyz[1, :, 0] = [0.5, 0, 0]; xyz[2, :, 0] = [0, 1.5, 0]
+    tiny = MolLite(xyz, name=["CL"] * 3, resname=["CL"] * 3, element=["Cl"] * 3, resid=np.arange(3),
+                   named_selections={"name CL": np.ones(3, bool)})
+    d = MetricShell("name CL", "name CL", periodic=None).project(tiny)
+    assert np.allclose(d, [[0.01768388256576615, 0, 0, 0, 0.01768388256576615, 0, 0, 0, 0.01768388256576615, 0, 0, 0]])
+    d = MetricShell("name CL", "name CL", numshells=2, shellwidth=1, periodic=None).project(tiny)
+    assert np.allclose(d, [[0.23873241, 0.03410463, 0.23873241, 0.03410463, 0.0, 0.06820926]])
+
+    rng = np.random.default_rng(4)
+    c = (rng.normal(size=(70, 3, 5)) * 6).astype(np.float32)
+    c[:20] = np.round(c[:20])          # distances exactly on shell edges (3-4-5 ...) must fall in the lower shell
+    bx = np.full((3, 5), 21.0, np.float32)
+    rm = MolLite(c, bx, chain=["A"] * 30 + ["B"] * 40, name=["X"] * 70, resname=["R"] * 70)
+    s1 = np.arange(0, 30); s2 = np.arange(30, 70)
+    ch = np.ones(70, np.uint32); ch[s2] = 2
+    for ns, sw, tr in ((4, 3, None), (5, 2.5, 9.0), (3, 1, None)):
+        got = MetricShell(s1, s2, periodic="selections", numshells=ns, shellwidth=sw, truncate=tr).project(rm)
+        want = oracle.metric_shell(c, bx, s1.astype(np.uint32), s2.astype(np.uint32), ch, False, True, ns, sw, tr)
+        assert np.array_equal(got, want), (ns, sw, tr)
