@@ -265,6 +265,41 @@ def extra_workloads(dev, peak):
     out["c4b_sparse_contacts"] = dict(workload=f"C4b: {F} frames x {n1}x{n2} periodic pair tests <= 12 A, ordered index pairs",
                                       pair_tests_per_s=F * n1 * n2 / (ms * 1e-3), ms_per_step=ms, emitted_pairs=npairs,
                                       output_gbs=(npairs * 8 + F * n1 * 8) / (ms * 1e-3) / 1e9)
+    del d_c, d_b, res
+    # C6: orthorhombic wrapping (K9) of an unwrapped solvated system: 5k-atom solute + 18k waters, 512 frames
+    from moleculekit_b200 import wrapping as wr
+
+    n_prot, n_wat, F = 5000, 18000, 512
+    N = n_prot + 3 * n_wat
+    g = torch.Generator(device=dev).manual_seed(5)
+    L = 82.0
+    d_orig = torch.empty((N, 3, F), dtype=torch.float32, device=dev)
+    d_orig[:n_prot] = torch.randn((n_prot, 3, 1), generator=g, device=dev) * 9 + torch.randn((1, 3, F), generator=g, device=dev) * 25
+    wat_c = (torch.rand((n_wat, 1, 3, F), generator=g, device=dev) - 0.5) * (5 * L)
+    d_orig[n_prot:] = (wat_c + torch.randn((n_wat, 3, 3, 1), generator=g, device=dev) * 0.6).reshape(3 * n_wat, 3, F)
+    del wat_c
+    d_b = torch.full((3, F), L, dtype=torch.float32, device=dev)
+    groups = torch.cat([torch.zeros(1, dtype=torch.int32, device=dev),
+                        n_prot + 3 * torch.arange(n_wat + 1, dtype=torch.int32, device=dev)])
+    csel = torch.arange(0, n_prot, dtype=torch.int32, device=dev)
+    d_c = torch.empty_like(d_orig)
+    kms, cms, moved = [], [], 0
+    for it in range(6):
+        d_c.copy_(d_orig)                      # the wrap is in place and idempotent: restore the unwrapped input
+        wr.wrap_box_device(d_c, d_b, groups, csel)
+        prep, main = _lib.get_timing(dev.index)
+        if it:
+            kms.append(main); cms.append(prep)
+        else:
+            moved = int((d_c != d_orig).sum().item())
+    main, prep = float(np.mean(kms)), float(np.mean(cms))
+    nb = N * 3 * F * 4 + moved * 8 + 3 * F * 8
+    out["c6_wrap"] = dict(workload=f"C6: wrap_box, {N} atoms ({n_wat + 1} bonded groups) x {F} frames, centre = {n_prot} solute atoms",
+                          atom_frames_per_s=N * F / ((main + prep) * 1e-3), centre_kernel_ms=prep, group_kernel_ms=main,
+                          moved_fraction=moved / (N * 3 * F), kernel_gbs=nb / (main * 1e-3) / 1e9,
+                          frac_of_peak=nb / (main * 1e-3) / 1e9 / peak,
+                          whole_call_gbs=(nb + n_prot * 3 * F * 4) / ((main + prep) * 1e-3) / 1e9,
+                          whole_call_frac_of_peak=(nb + n_prot * 3 * F * 4) / ((main + prep) * 1e-3) / 1e9 / peak)
     return out
 
 

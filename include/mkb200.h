@@ -170,6 +170,17 @@ int mkb_bonds_count(mkb_handle_t h, void *stream, const float *coords, const flo
 int mkb_bonds_fill(mkb_handle_t h, void *stream, const float *coords, const float *radii, const uint32_t *is_hydrogen,
                    int64_t n, float pairdist, const int64_t *row_offsets, uint32_t *pairs);
 
+/* K9: orthorhombic wrapping of bonded groups, replaces wrap_box
+ * (moleculekit/wrapping/wrapping.pyx:91-144; called from Molecule.wrap, moleculekit/molecule.py:2077).  t->coords is
+ * MODIFIED IN PLACE like the reference's array.  groups [n_groups] uint32 device: ascending first-atom offsets of
+ * consecutive groups, group g = atoms [groups[g], groups[g+1]) -- so n_groups - 1 ranges, the last entry (n_atoms in
+ * Molecule.wrap) closes the last one.  centersel [n_centersel] uint32 device: atoms whose running-mean centre is the box
+ * centre of each frame; when n_centersel == 0 the fixed `center` (HOST float[3]) is used instead (pyx:106-108).
+ * float32 arithmetic with one rounding per operation and roundf half-away: bit-identical to the reference.  Index
+ * ranges are the caller's responsibility (the reference compiles with boundscheck off as well). */
+int mkb_wrap_box(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *groups, int64_t n_groups,
+                 const uint32_t *centersel, int64_t n_centersel, const float *center);
+
 #ifdef __cplusplus
 }
 #endif

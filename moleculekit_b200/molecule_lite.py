@@ -16,7 +16,7 @@ import numpy as np
 
 class MolLite:
     def __init__(self, coords, box=None, element=None, name=None, resname=None, resid=None, chain=None,
-                 segid=None, named_selections=None, frame: int = 0):
+                 segid=None, named_selections=None, frame: int = 0, bonds=None, boxangles=None):
         coords = np.asarray(coords, dtype=np.float32)
         if coords.ndim == 2:
             coords = coords[:, :, None]
@@ -37,6 +37,10 @@ class MolLite:
         self.resid = np.zeros(n, dtype=np.int64) if resid is None else np.asarray(resid, dtype=np.int64)
         self.named_selections = dict(named_selections or {})
         self.frame = frame
+        self.bonds = np.zeros((0, 2), dtype=np.uint32) if bonds is None else \
+            np.asarray(bonds, dtype=np.uint32).reshape(-1, 2)
+        self.boxangles = np.full((3, f), 90.0, dtype=np.float32) if boxangles is None else \
+            np.asarray(boxangles, dtype=np.float32)
 
     @property
     def numAtoms(self) -> int:

@@ -30,6 +30,7 @@ MODULES = {
     "occupancy_utils": "moleculekit/occupancy_utils/occupancy_utils.pyx",
     "distance_utils": "moleculekit/distance_utils/distance_utils.pyx",
     "bondguesser_utils": "moleculekit/bondguesser_utils/bondguesser_utils.pyx",
+    "wrapping": "moleculekit/wrapping/wrapping.pyx",
 }
 
 

@@ -219,3 +219,14 @@ def metric_shell(coords, box, sel1, sel2, digitized_chains, selfdist, pbc, numsh
             inshell = (dist[:, cols] > edges[e]) & (dist[:, cols] <= edges[e + 1])
             out[:, c * numshells + e] = np.sum(inshell, axis=1) / vol[e]
     return out
+
+
+def wrap_box(groups, coords, box, centersel, center):
+    """moleculekit/wrapping/wrapping.pyx:91-144 (same arguments); coords (N, 3, F) float32 C-contiguous, in place."""
+    assert coords.dtype == np.float32 and coords.flags["C_CONTIGUOUS"] and coords.ndim == 3 and coords.shape[1] == 3
+    groups, centersel = _u32(groups), _u32(centersel)
+    box, center = _f32(box), _f32(center)
+    F = coords.shape[2]
+    assert box.shape == (3, F)
+    lib().oracle_wrap_box(_p(groups), C.c_int64(len(groups)), _p(coords), _p(box), C.c_int64(F),
+                          _p(centersel), C.c_int64(len(centersel)), _p(center))

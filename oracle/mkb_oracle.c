@@ -421,3 +421,47 @@ EXPORT int64_t oracle_bond_grid_search(const float *coords, const float *radii, 
     free(box); free(cnt); free(first); free(members); free(cur);
     return total;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * wrap_box -- moleculekit/wrapping/wrapping.pyx:91-144 (orthorhombic wrapping).
+ * coords (n_atoms, 3, F) frame-minor float32, modified in place; box (3, F); groups [n_groups] are the
+ * first-atom offsets of consecutive bonded groups (group g = atoms [groups[g], groups[g+1])), the last
+ * entry closes the last group (pyx:123-125).  Centre of the box: running mean over centersel
+ * (pyx:113-118) or `center` when centersel is empty (pyx:106-108).  A group is translated along an
+ * axis by box*round(diff/box) when its running-mean centre is more than half a box from the box
+ * centre (pyx:137-142).  All arithmetic float32, one rounding per operation.
+ * ------------------------------------------------------------------------------------------------ */
+EXPORT void oracle_wrap_box(const uint32_t *groups, int64_t n_groups, float *coords, const float *box,
+                            int64_t F, const uint32_t *centersel, int64_t n_centersel, const float *center)
+{
+    float box_center[3] = {0.f, 0.f, 0.f}, half_box[3], grp_center[3];
+    if (n_centersel == 0)
+        for (int i = 0; i < 3; ++i) box_center[i] = center[i];
+    for (int64_t f = 0; f < F; ++f) {
+        if (n_centersel > 0) {
+            for (int i = 0; i < 3; ++i) box_center[i] = 0.f;
+            for (int64_t n = 0; n < n_centersel; ++n)
+                for (int i = 0; i < 3; ++i) {
+                    const float x = coords[((int64_t)centersel[n] * 3 + i) * F + f];
+                    box_center[i] = box_center[i] + (x - box_center[i]) / (float)(n + 1);
+                }
+        }
+        for (int i = 0; i < 3; ++i) half_box[i] = box[i * F + f] / 2.f;
+        for (int64_t g = 0; g + 1 < n_groups; ++g) {
+            const int64_t s = groups[g], e = groups[g + 1];
+            for (int i = 0; i < 3; ++i) grp_center[i] = 0.f;
+            int64_t n = 0;
+            for (int64_t k = s; k < e; ++k, ++n)
+                for (int i = 0; i < 3; ++i)
+                    grp_center[i] = grp_center[i] + (coords[(k * 3 + i) * F + f] - grp_center[i]) / (float)(n + 1);
+            for (int i = 0; i < 3; ++i) {
+                const float diff = grp_center[i] - box_center[i];
+                if (fabsf(diff) > half_box[i]) {
+                    const float b = box[i * F + f];
+                    const float translation = b * roundf(diff / b);
+                    for (int64_t a = s; a < e; ++a) coords[(a * 3 + i) * F + f] = coords[(a * 3 + i) * F + f] - translation;
+                }
+            }
+        }
+    }
+}

@@ -60,6 +60,11 @@ def g_bonds():
 
 
 @pytest.fixture(scope="session")
+def g_wrap():
+    return _npz("wrap.npz")
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import cpu_oracle
 

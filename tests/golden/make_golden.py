@@ -36,8 +36,75 @@ def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def wrapping_fixture():
+    """wrap.npz (K9, wrap_box): the reference's own orthorhombic test system (tests/test_wrapping.py:9-16), cut to the
+    protein + the first solvent groups and 3 frames, with (a) the output of the reference's compiled wrap_box on that cut
+    (bit-exact target), (b) the same atoms/frames of the reference's STORED golden output_wrapped.xtc (atol 1e-2, the
+    reference test's own tolerance) and (c) the bond list / bonded groups of the cut; plus seeded random cases."""
+    from oracle import build_ref
+
+    wref = build_ref.load()[3]
+    from moleculekit.molecule import Molecule, getBondedGroups
+
+    d = os.path.join(REFT, "test_wrapping")
+    mol = Molecule(os.path.join(d, "structure.prmtop"))
+    mol.read(os.path.join(d, "output.xtc"))
+    refmol = Molecule(os.path.join(d, "structure.prmtop"))
+    refmol.read(os.path.join(d, "output_wrapped.xtc"))
+    groups, _ = getBondedGroups(mol)
+    centersel = mol.atomselect("protein or resname ACE NME", indexes=True, guessBonds=False).astype(np.uint32)
+    ncut_groups = 900
+    K = int(groups[ncut_groups])
+    assert centersel.max() < K
+    frames = [0, 11, 29]
+    w = {}
+    w["coords"] = np.ascontiguousarray(mol.coords[:K][:, :, frames])
+    w["box"] = np.ascontiguousarray(mol.box[:, frames])
+    w["groups"] = groups[: ncut_groups + 1].copy()
+    w["centersel"] = centersel
+    w["bonds"] = mol.bonds[(mol.bonds < K).all(axis=1)].astype(np.uint32)
+    out = w["coords"].copy()
+    wref.wrap_box(w["groups"], out, w["box"], centersel, np.zeros(3, np.float32))
+    w["ref_wrapped"] = out
+    w["gold_wrapped_xtc"] = np.ascontiguousarray(refmol.coords[:K][:, :, frames])
+    assert np.allclose(out, w["gold_wrapped_xtc"], atol=1e-2)  # the reference reproduces its stored golden on the cut
+    assert not np.array_equal(out, w["coords"])
+    # fixed-centre variant (tests/test_wrapping.py:18-24 wraps 6X18 around a given point)
+    cen = np.array([94.64, 3.69, 1.11], dtype=np.float32)
+    out2 = w["coords"].copy()
+    wref.wrap_box(w["groups"], out2, w["box"], np.zeros(0, np.uint32), cen)
+    w["center_fixed"] = cen
+    w["ref_wrapped_fixed"] = out2
+    # seeded random cases incl. empty groups, single-atom groups, a zero box component (NaN translation)
+    rng = np.random.default_rng(99)
+    ncase = 6
+    for c in range(ncase):
+        N = int(rng.integers(5, 300)); F = int(rng.integers(1, 7))
+        cuts = np.unique(np.concatenate([[0], rng.integers(0, N, size=int(rng.integers(0, 40))), [N]])).astype(np.uint32)
+        if c == 1:
+            cuts = np.sort(np.concatenate([cuts, cuts[1:3]])).astype(np.uint32)  # repeated offsets = empty groups
+        box = rng.uniform(6, 25, size=(3, F)).astype(np.float32)
+        if c == 2:
+            box[1, 0] = 0.0
+        xyz = rng.normal(0, 35, size=(N, 3, F)).astype(np.float32)
+        cs = np.zeros(0, np.uint32) if c % 2 else np.sort(rng.choice(N, size=min(N, 17), replace=False)).astype(np.uint32)
+        cen = rng.normal(0, 4, 3).astype(np.float32)
+        o = xyz.copy()
+        with np.errstate(all="ignore"):
+            wref.wrap_box(cuts, o, box, cs, cen)
+        for k, v in (("groups", cuts), ("coords", xyz), ("box", box), ("centersel", cs), ("center", cen), ("ref", o)):
+            w[f"r{c}_{k}"] = v
+    w["ncase"] = np.array(ncase)
+    np.savez_compressed(os.path.join(HERE, "wrap.npz"), **w)
+
+
 def main():
     from oracle import build_ref
+
+    if "--only-wrapping" in sys.argv:
+        assert build_ref.build()
+        wrapping_fixture()
+        return
 
     assert build_ref.build(), "oracle/_ref could not be built (is /root/reference present?)"
     occ_ref, dist_ref = build_ref.load()[:2]
@@ -293,6 +360,8 @@ def main():
     bg["vdw_keys"] = np.array(list(ref_vdw.keys()))
     bg["vdw_vals"] = np.array([float(v) for v in ref_vdw.values()])
     np.savez_compressed(os.path.join(HERE, "bonds.npz"), **bg)
+
+    wrapping_fixture()
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

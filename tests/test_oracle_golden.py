@@ -187,3 +187,73 @@ def test_bond_kernel_vs_live_reference(oracle, refmods):
     want = np.array(bref.grid_bonds(coords, radii, ish, 4.0, 0, atoms_in_box, gridlist), dtype=np.uint32).reshape(-1, 2)
     got = oracle.bond_grid_search(coords, 4.0, ish, radii)           # range 3 < 4 -> a single box as well
     assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------ K9: wrap_box
+def _fbits(a):
+    """float32 bit patterns with NaNs canonicalised (x86 and the GPU produce different NaN payloads)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = a.view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
+
+
+def test_wrap_box_oracle_vs_golden(oracle, g_wrap):
+    """oracle_wrap_box against (a) the output of the reference's compiled wrap_box (bit-exact), (b) the reference's stored
+    golden trajectory output_wrapped.xtc at the reference test's tolerance (tests/test_wrapping.py:16) and (c) the seeded
+    reference outputs, incl. empty groups and a zero box component."""
+    g = g_wrap
+    zero = np.zeros(3, np.float32)
+    out = g["coords"].copy()
+    oracle.wrap_box(g["groups"], out, g["box"], g["centersel"], zero)
+    assert np.array_equal(_fbits(out), _fbits(g["ref_wrapped"]))
+    assert np.allclose(out, g["gold_wrapped_xtc"], atol=1e-2)
+    assert not np.array_equal(out, g["coords"])
+    out = g["coords"].copy()
+    oracle.wrap_box(g["groups"], out, g["box"], np.zeros(0, np.uint32), g["center_fixed"])
+    assert np.array_equal(_fbits(out), _fbits(g["ref_wrapped_fixed"]))
+    for c in range(int(g["ncase"])):
+        out = g[f"r{c}_coords"].copy()
+        oracle.wrap_box(g[f"r{c}_groups"], out, g[f"r{c}_box"], g[f"r{c}_centersel"], g[f"r{c}_center"])
+        assert np.array_equal(_fbits(out), _fbits(g[f"r{c}_ref"])), c
+
+
+def test_wrap_box_oracle_vs_live_reference(oracle, refmods):
+    if refmods is None or len(refmods) < 4:
+        pytest.skip("oracle/_ref not built")
+    wref = refmods[3]
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        N, F = int(rng.integers(1, 500)), int(rng.integers(1, 9))
+        cuts = np.unique(np.concatenate([[0], rng.integers(0, N, size=int(rng.integers(0, 80))), [N]])).astype(np.uint32)
+        box = rng.uniform(8, 30, size=(3, F)).astype(np.float32)
+        xyz = rng.normal(0, 40, size=(N, 3, F)).astype(np.float32)
+        cs = np.zeros(0, np.uint32) if trial % 3 == 0 else \
+            np.sort(rng.choice(N, size=min(N, 23), replace=False)).astype(np.uint32)
+        cen = rng.normal(0, 5, 3).astype(np.float32)
+        a, b = xyz.copy(), xyz.copy()
+        wref.wrap_box(cuts, a, box, cs, cen)
+        oracle.wrap_box(cuts, b, box, cs, cen)
+        assert np.array_equal(_fbits(a), _fbits(b)), trial
+
+
+def test_bonded_groups_host_mirror(g_wrap, refmods):
+    """getBondedGroups (host logic of the wrap path) reproduces the reference's group offsets on the cut of its own
+    test system, and the union-find keeps the reference's root identities on a scrambled bond list."""
+    from moleculekit_b200 import wrapping as wr
+    from moleculekit_b200.molecule_lite import MolLite
+
+    g = g_wrap
+    mol = MolLite(g["coords"], box=g["box"], bonds=g["bonds"])
+    groups, group = wr.getBondedGroups(mol)
+    assert groups.dtype == np.uint32 and np.array_equal(groups, g["groups"])
+    assert group.shape == (mol.numAtoms,) and group[0] == 0 and group[-1] == len(groups) - 2
+    if refmods is not None and len(refmods) >= 4:
+        rng = np.random.default_rng(11)
+        n = 400
+        bonds = rng.integers(0, n, size=(500, 2)).astype(np.uint32)
+        p1, s1 = np.arange(n, dtype=np.uint32), np.ones(n, np.uint32)
+        p2, s2 = p1.copy(), s1.copy()
+        refmods[3].get_bonded_groups(bonds, n, p1, s1)
+        wr.get_bonded_groups(bonds, n, p2, s2)
+        assert np.array_equal(p1, p2)

@@ -1,0 +1,184 @@
+"""GPU parity of K9 (orthorhombic wrap_box): bit-exact against the reference's compiled kernel outputs
+(tests/golden/wrap.npz), the reference's stored golden trajectory, and the oracle on seeded systems."""
+import logging
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _fbits(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = a.view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
+
+
+def test_reference_golden(g_wrap):
+    """tests/test_wrapping.py:9-16 on the committed cut of the reference's system: bit-identical to the reference kernel,
+    within the reference test's atol of its stored golden; plus the fixed-centre variant (test_wrapping.py:18-24)."""
+    from moleculekit_b200.wrapping import wrap_box
+
+    g = g_wrap
+    out = g["coords"].copy()
+    assert wrap_box(g["groups"], out, g["box"], g["centersel"], np.zeros(3, np.float32)) is None
+    assert np.array_equal(_fbits(out), _fbits(g["ref_wrapped"]))
+    assert np.allclose(out, g["gold_wrapped_xtc"], atol=1e-2)
+    out = g["coords"].copy()
+    wrap_box(g["groups"], out, g["box"], np.zeros(0, np.uint32), g["center_fixed"])
+    assert np.array_equal(_fbits(out), _fbits(g["ref_wrapped_fixed"]))
+
+
+def test_seeded_reference_cases(g_wrap):
+    """empty groups (repeated offsets), single-atom groups, a zero box component (NaN translation as in the reference)."""
+    from moleculekit_b200.wrapping import wrap_box
+
+    g = g_wrap
+    for c in range(int(g["ncase"])):
+        out = g[f"r{c}_coords"].copy()
+        wrap_box(g[f"r{c}_groups"], out, g[f"r{c}_box"], g[f"r{c}_centersel"], g[f"r{c}_center"])
+        assert np.array_equal(_fbits(out), _fbits(g[f"r{c}_ref"])), c
+
+
+def _solvated(rng, n_protein, n_water, F, box_edge=40.0):
+    """unwrapped-looking system: one big group + 3-atom groups that diffused several boxes away"""
+    N = n_protein + 3 * n_water
+    groups = np.concatenate([[0], n_protein + 3 * np.arange(n_water + 1)]).astype(np.uint32)
+    base = rng.normal(0, 8, size=(n_protein, 3, 1)).astype(np.float32) + rng.normal(0, 30, size=(1, 3, F)).astype(np.float32)
+    wat_c = rng.uniform(-3 * box_edge, 3 * box_edge, size=(n_water, 1, 3, F)).astype(np.float32)
+    wat = (wat_c + rng.normal(0, 0.6, size=(n_water, 3, 3, 1)).astype(np.float32)).reshape(3 * n_water, 3, F)
+    coords = np.ascontiguousarray(np.concatenate([base + rng.normal(0, 0.3, size=(n_protein, 3, F)).astype(np.float32), wat]))
+    box = (box_edge + rng.uniform(-1, 1, size=(3, F))).astype(np.float32)
+    assert coords.shape == (N, 3, F)
+    return groups, coords, box
+
+
+def test_large_vs_oracle_and_device_api(oracle):
+    """a solvated system over 64 frames vs the oracle; the device entry wraps the resident tensor in place; a frame shard
+    (slice of a resident trajectory, frame_stride > n_frames) wraps only its frames."""
+    import torch
+    from moleculekit_b200.wrapping import wrap_box, wrap_box_device
+
+    rng = np.random.default_rng(17)
+    groups, coords, box = _solvated(rng, 700, 2500, 64)
+    centersel = np.arange(0, 700, 3, dtype=np.uint32)
+    want = coords.copy()
+    oracle.wrap_box(groups, want, box, centersel, np.zeros(3, np.float32))
+    got = coords.copy()
+    wrap_box(groups, got, box, centersel, np.zeros(3, np.float32))
+    assert np.array_equal(_fbits(got), _fbits(want))
+    assert (got != coords).mean() > 0.3  # most waters really moved
+    # idempotence (size-independent property): wrapping a wrapped trajectory around the same centre moves nothing
+    again = got.copy()
+    wrap_box(groups, again, box, centersel, np.zeros(3, np.float32))
+    assert np.array_equal(_fbits(again), _fbits(got))
+
+    dev = torch.device("cuda:0")
+    d_coords = torch.from_numpy(coords).to(dev)
+    d_box = torch.from_numpy(box).to(dev)
+    d_groups = torch.from_numpy(groups.view(np.int32)).to(dev)
+    d_cs = torch.from_numpy(centersel.view(np.int32)).to(dev)
+    ret = wrap_box_device(d_coords[:, :, 16:48], d_box[:, 16:48], d_groups, d_cs)
+    assert ret.data_ptr() == d_coords[:, :, 16:48].data_ptr()
+    shard = d_coords.cpu().numpy()
+    assert np.array_equal(_fbits(shard[:, :, 16:48]), _fbits(want[:, :, 16:48]))
+    assert np.array_equal(shard[:, :, :16], coords[:, :, :16]) and np.array_equal(shard[:, :, 48:], coords[:, :, 48:])
+    # fixed centre on the device path
+    cen = np.array([3.5, -2.25, 10.0], np.float32)
+    d2 = torch.from_numpy(coords).to(dev)
+    wrap_box_device(d2, d_box, d_groups, None, cen)
+    want2 = coords.copy()
+    oracle.wrap_box(groups, want2, box, np.zeros(0, np.uint32), cen)
+    assert np.array_equal(_fbits(d2.cpu().numpy()), _fbits(want2))
+
+
+def test_single_frame_and_big_group(oracle):
+    """F = 1 (a structure) with a 20k-atom group: the sequential running mean of one long group, bit-exact."""
+    from moleculekit_b200.wrapping import wrap_box
+
+    rng = np.random.default_rng(23)
+    groups, coords, box = _solvated(rng, 20000, 300, 1, box_edge=25.0)
+    coords[:20000] += np.float32(60.0)                           # the big group sits several boxes away ...
+    centersel = np.arange(20000, 20000 + 90, dtype=np.uint32)    # ... from the centre, taken on some waters
+    want = coords.copy()
+    oracle.wrap_box(groups, want, box, centersel, np.zeros(3, np.float32))
+    got = coords.copy()
+    wrap_box(groups, got, box, centersel, np.zeros(3, np.float32))
+    assert np.array_equal(_fbits(got), _fbits(want))
+    assert not np.array_equal(got[:20000], coords[:20000])
+
+
+def test_molecule_wrap_mirror(g_wrap, oracle, caplog):
+    """Molecule.wrap mirror (molecule.py:1987-2090): bonds -> groups -> wrap_box; zero box is a logged no-op
+    (tests/test_wrapping.py:48-75); triclinic cells and bad unitcell names raise."""
+    from moleculekit_b200 import wrapping as wr
+    from moleculekit_b200.molecule_lite import MolLite
+
+    g = g_wrap
+    mask = np.zeros(g["coords"].shape[0], dtype=bool)
+    mask[g["centersel"]] = True
+    mol = MolLite(g["coords"].copy(), box=g["box"], bonds=g["bonds"], named_selections={"protein or resname ACE NME": mask})
+    wr.wrap(mol, "protein or resname ACE NME")
+    assert np.array_equal(_fbits(mol.coords), _fbits(g["ref_wrapped"]))
+    mol = MolLite(g["coords"].copy(), box=g["box"], bonds=g["bonds"])
+    wr.wrap(mol, wrapcenter=g["center_fixed"])
+    assert np.array_equal(_fbits(mol.coords), _fbits(g["ref_wrapped_fixed"]))
+    mol = MolLite(g["coords"].copy(), box=g["box"], bonds=g["bonds"])
+    wr.wrap(mol, wrapsel=mask)                                     # boolean mask selection
+    assert np.array_equal(_fbits(mol.coords), _fbits(g["ref_wrapped"]))
+
+    mol = MolLite(g["coords"].copy(), box=np.zeros_like(g["box"]), bonds=g["bonds"])
+    with caplog.at_level(logging.WARNING, logger="moleculekit_b200.wrapping"):
+        wr.wrap(mol, wrapsel=mask)
+    assert np.array_equal(mol.coords, g["coords"])
+    assert any("Zero box size" in r.getMessage() for r in caplog.records)
+
+    with pytest.raises(ValueError, match="Invalid unit cell type"):
+        wr.wrap(mol, unitcell="cubic")
+    mol = MolLite(g["coords"].copy(), box=g["box"][:, :2], bonds=g["bonds"])
+    with pytest.raises(RuntimeError, match="different number of simulation frames"):
+        wr.wrap(mol, wrapsel=mask)
+    tri = MolLite(g["coords"].copy(), box=g["box"], bonds=g["bonds"], boxangles=np.full((3, 3), 60.0, np.float32))
+    with pytest.raises(NotImplementedError):
+        wr.wrap(tri, wrapsel=mask)
+
+
+def test_argument_checks():
+    from moleculekit_b200.wrapping import wrap_box
+
+    c = np.zeros((4, 3, 2), np.float32)
+    b = np.ones((3, 2), np.float32)
+    g = np.array([0, 2, 4], np.uint32)
+    z = np.zeros(3, np.float32)
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        wrap_box(g.astype(np.int64), c, b, np.zeros(0, np.uint32), z)
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        wrap_box(g, c.astype(np.float64), b, np.zeros(0, np.uint32), z)
+    with pytest.raises(IndexError):
+        wrap_box(np.array([0, 9], np.uint32), c, b, np.zeros(0, np.uint32), z)
+    with pytest.raises(IndexError):
+        wrap_box(g, c, b, np.array([4], np.uint32), z)
+    # nothing to do: no groups / no atoms / no frames
+    wrap_box(np.array([0], np.uint32), c, b, np.zeros(0, np.uint32), z)
+    wrap_box(g, np.zeros((0, 3, 2), np.float32), b, np.zeros(0, np.uint32), z)
+    wrap_box(g, np.zeros((4, 3, 0), np.float32), np.zeros((3, 0), np.float32), np.zeros(0, np.uint32), z)
+
+
+def test_exact_division_sequence(tmp_path):
+    """csrc/exact_div.cuh (the reciprocal hoisted off the running-mean chain) against __fdiv_rn on ~1.2e9 operand pairs:
+    every divisor 1..2^17 plus large ones, numerators over the whole float range and at rounding boundaries."""
+    import os
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "divcheck")
+    subprocess.run([nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-I" + os.path.join(root, "moleculekit_b200", "csrc"),
+                    os.path.join(root, "tests", "cuda", "divcheck.cu"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mismatches=0" in r.stdout
