@@ -215,15 +215,18 @@ def extra_workloads(dev, peak):
     from moleculekit_b200.tools import voxeldescriptors as vd
 
     out = {}
-    for key, w in (("c2_ligand_poses", workloads.ligand_poses(B=1024)), ("c5_fine_grids", workloads.fine_grids(B=4))):
+    for key, w, layout in (("c2_ligand_poses", workloads.ligand_poses(B=1024), "xyzc"),
+                           ("c5_fine_grids", workloads.fine_grids(B=4), "xyzc"),
+                           ("c3_cxyz_layout", workloads.protein_pockets(B=128), "cxyz")):
         vb = vd.VoxelBatch(w["coords"], w["sigmas"], boxsize=w["boxsize"], centers=w["centers"], voxelsize=w["voxelsize"])
         d_c, d_s = vb.to_device(dev)
         o = torch.empty((vb.total_voxels, vb.C), dtype=torch.float32, device=dev)
-        ms = _time_cuda(lambda: vb.run(d_c, d_s, o))
-        vb.run(d_c, d_s, o)
+        ms = _time_cuda(lambda: vb.run(d_c, d_s, o, layout=layout))
+        vb.run(d_c, d_s, o, layout=layout)
         _, fill = _lib.get_timing(dev.index)
         nb = workloads.occupancy_algorithmic_bytes(vb.total_voxels, vb.coords.shape[0], vb.C)
-        out[key] = dict(workload=w["name"], voxel_channels_per_s=vb.total_voxels * vb.C / (ms * 1e-3), ms_per_step=ms,
+        out[key] = dict(workload=w["name"] + (" -> (B,C,X,Y,Z) channel-major output" if layout == "cxyz" else ""),
+                        voxel_channels_per_s=vb.total_voxels * vb.C / (ms * 1e-3), ms_per_step=ms,
                         fill_kernel_ms=fill, fill_kernel_gbs=nb / (fill * 1e-3) / 1e9, frac_of_peak=nb / (fill * 1e-3) / 1e9 / peak)
         del o, d_c, d_s
     # C4a: dense periodic distances, 256 x 1024 atoms, 10k frames (only the selected atoms are materialised)

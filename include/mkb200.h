@@ -43,6 +43,10 @@ typedef struct mkb_ctx *mkb_handle_t;
 #define MKB_OCC_ACCUMULATE 1u /* out = max(out, value): the reference accumulates into the caller's buffer
                                  (occupancy_utils.pyx:61); without it `out` is overwritten (caller passes zeros,
                                  voxeldescriptors.py:531, so both agree) */
+#define MKB_OCC_LAYOUT_CXYZ 2u /* grid b is written channel-major, out[b] = float32 [C][nx][ny][nz]
+                                 (the layout a Conv3d consumer wants, instead of the reference's [nx][ny][nz][C]
+                                 reshaped view, voxeldescriptors.py:298-299); grid b still starts at out + out_offset*C.
+                                 Same values bit for bit.  mkb_occupancy_grid_batch only. */
 
 /* output modes of the distance entry points (host post-ops of projections/util.py:74-84 fused in) */
 #define MKB_DIST_DISTANCES 0 /* float32 distances, optionally truncated */
@@ -84,6 +88,28 @@ typedef struct {
 int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
                              int64_t n_atoms, int32_t C, const mkb_grid_desc *grids, int32_t B,
                              float *out, uint32_t flags);
+
+/* K1 with device-side channel assembly: the reference builds sigmas = vdw_radius[:, None] *
+ * channels.astype(float) on the host (voxeldescriptors.py:332-335); here the (n_atoms,) float64 radii and a per-atom
+ * channel bit mask (bit c set = atom belongs to channel c) are the inputs and the (n_atoms, C) float64 matrix never
+ * exists -- 12 instead of 8*C bytes per atom over PCIe.  Bit-identical to mkb_occupancy_grid_batch on that matrix. */
+int mkb_occupancy_grid_batch_masked(mkb_handle_t h, void *stream, const float *coords, const double *radii,
+                                    const uint32_t *chanmask, int64_t n_atoms, int32_t C, const mkb_grid_desc *grids,
+                                    int32_t B, float *out, uint32_t flags);
+
+/* Voxel centres on the device, exactly getCenters (voxeldescriptors.py:116-123,243-247):
+ * centers[(out_offset_b + v) * 3 + d] = fl(fl(i_d * voxelsize) + origin[d]), v = (ix*ny + iy)*nz + iz; float64 device.
+ * K1 itself never needs this array. */
+int mkb_grid_centers(mkb_handle_t h, void *stream, const mkb_grid_desc *grids, int32_t B, double *centers);
+
+/* rotateCoordinates (voxeldescriptors.py:78-114), batched: molecule b = atoms [atom_offsets[b],
+ * atom_offsets[b+1]) (int64 device, [B+1]) is rotated three times in succession, new = (x - c_b) . R_{b,r}^T + c_b in
+ * float64 (row-major 3x3 matrices [B][3][3][3] and centres [B][3], float64 device; the host wrapper builds the matrices
+ * with the reference's rotationMatrix formula, util.py:101-117).  Result as float32 (what K1 consumes) and/or float64
+ * (what the reference returns); either output may be NULL.  Products and sums individually rounded, left to right
+ * (numpy's BLAS order is unspecified: parity is 1e-12 relative, not bitwise). */
+int mkb_rotate_coords(mkb_handle_t h, void *stream, const float *coords, int64_t n_atoms, const int64_t *atom_offsets,
+                      int32_t B, const double *matrices, const double *centers, float *out_f32, double *out_f64);
 
 /* K1b: occupancy at arbitrary centres (the `usercenters` branch, voxeldescriptors.py:338-340 ->
  * calculate_occupancy).  centers [M,3] float64 device; same arithmetic contract. */

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(PKG, "lib", "libmkb200.so")
 
 MKB_OK = 0
 OCC_ACCUMULATE = 1
+OCC_LAYOUT_CXYZ = 2
 DIST_DISTANCES = 0
 DIST_CONTACTS = 1
 
@@ -31,7 +32,8 @@ class Traj(C.Structure):
 EXPORTS = [
     "mkb_version", "mkb_create", "mkb_destroy", "mkb_last_error", "mkb_launch_count",
     "mkb_set_timing", "mkb_get_timing",
-    "mkb_occupancy_grid_batch", "mkb_occupancy_points",
+    "mkb_occupancy_grid_batch", "mkb_occupancy_grid_batch_masked", "mkb_occupancy_points",
+    "mkb_grid_centers", "mkb_rotate_coords",
     "mkb_dist_trajectory", "mkb_contacts_count", "mkb_contacts_fill", "mkb_dist_reduction",
     "mkb_cdist", "mkb_pdist", "mkb_squareform", "mkb_collisions_count", "mkb_collisions_fill",
     "mkb_bonds_count", "mkb_bonds_fill", "mkb_shell_counts", "mkb_wrap_box",
@@ -67,6 +69,9 @@ def load():
     lib.mkb_get_timing.argtypes = [vp, C.POINTER(f32), C.POINTER(f32)]
     lib.mkb_occupancy_grid_batch.argtypes = [vp, vp, vp, vp, i64, i32, vp, i32, vp, u32]
     lib.mkb_occupancy_points.argtypes = [vp, vp, vp, i64, vp, vp, i64, i32, vp, u32]
+    lib.mkb_occupancy_grid_batch_masked.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, i32, vp, u32]
+    lib.mkb_grid_centers.argtypes = [vp, vp, vp, i32, vp]
+    lib.mkb_rotate_coords.argtypes = [vp, vp, vp, i64, vp, i32, vp, vp, vp, vp]
     tp = C.POINTER(Traj)
     lib.mkb_dist_trajectory.argtypes = [vp, vp, tp, vp, i64, vp, i64, vp, i32, i32, i32, f32, f32, vp]
     lib.mkb_contacts_count.argtypes = [vp, vp, tp, vp, i64, vp, i64, vp, i32, i32, f32, vp, C.POINTER(i64)]

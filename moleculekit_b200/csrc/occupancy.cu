@@ -130,7 +130,8 @@ __global__ void occ_bin_kernel(const float *__restrict__ coords, const GridDev *
 // one vdW radius, voxeldescriptors.py:332-335) has ONE distinct non-zero sigma per atom -> one s2 and a channel
 // bit mask.  Atoms with several distinct sigmas are flagged (bit 31 of src) and take a per-channel path in K1.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void occ_scatter_kernel(const float *__restrict__ coords, const double *__restrict__ sigmas, int C,
+__global__ void occ_scatter_kernel(const float *__restrict__ coords, const double *__restrict__ sigmas,
+                                   const double *__restrict__ radii, const unsigned *__restrict__ chanmask, int C,
                                    const GridDev *__restrict__ grids, int B, long long n_items,
                                    const int *__restrict__ item_cell, const unsigned *__restrict__ item_slot,
                                    const unsigned *__restrict__ cell_start, float4 *__restrict__ rec_pos,
@@ -153,16 +154,24 @@ __global__ void occ_scatter_kernel(const float *__restrict__ coords, const doubl
         const double pv = ((double)coords[3 * a + d] - g.origin[d]) * g.inv_vs;
         rel[d] = (float)(pv - (double)(cc[d] * g.cell - g.cutv));
     }
-    const double *sg = sigmas + a * C;
     double first = 0.0;
     unsigned m = 0;
     bool multi = false;
-    for (int h = 0; h < C; ++h) {
-        const double s = sg[h];
-        if (s == 0.0 || s != s) continue;  // sigma == 0 skipped (pyx:56); NaN never wins the max (pyx:61)
-        if (m == 0) { first = s; m = 1u << h; }
-        else if (s == first) m |= 1u << h;
-        else multi = true;
+    if (sigmas) {
+        const double *sg = sigmas + a * C;
+        for (int h = 0; h < C; ++h) {
+            const double s = sg[h];
+            if (s == 0.0 || s != s) continue;  // sigma == 0 skipped (pyx:56); NaN never wins the max (pyx:61)
+            if (m == 0) { first = s; m = 1u << h; }
+            else if (s == first) m |= 1u << h;
+            else multi = true;
+        }
+    } else {
+        // device-side channel assembly (voxeldescriptors.py:332-335): sigmas[a, h] = radii[a] * float(mask bit h), i.e.
+        // one radius on the channels of the mask; a zero / NaN radius switches the atom off exactly as above
+        const double r = radii[a];
+        const unsigned mm = chanmask[a] & (C >= 32 ? 0xffffffffu : ((1u << C) - 1u));
+        if (mm && !(r == 0.0 || r != r)) { first = r; m = mm; }
     }
     const double sv = first * g.inv_vs;  // sigma in voxel units
     rec_pos[dst] = make_float4(rel[0], rel[1], rel[2], m ? fmaxf((float)(sv * sv), FLT_MIN) : 0.0f);
@@ -183,6 +192,7 @@ struct FillParams {
     float *out;
     unsigned flags;
     int vec_ok;
+    int cmajor;     // MKB_OCC_LAYOUT_CXYZ: grid b is stored [C][nx][ny][nz] (channel-major) instead of [nx][ny][nz][C]
     int txp_shift;  // fast path launch: blockIdx.z = (grid << txp_shift) | tile_x
     int bulk_store; // fast path: stage the tile in smem and store rows with cp.async.bulk (TMA)
     // warp kernel, uniform launches: descriptor of the chunk's first grid + per-grid strides
@@ -398,7 +408,9 @@ __global__ void __launch_bounds__(FILL_THREADS, (CP <= 8 ? 2 : 1)) occ_fill_kern
     // ---- epilogue: one transcendental per voxel-channel, streaming 32-byte stores
     const int ix = tx * TILE + vx, iy = ty * TILE + vy, iz = tz * TILE + vz;
     if (ix < nx && iy < ny && iz < nz) {
-        float *const o = p.out + (g.out_offset + ((long long)ix * ny + iy) * nz + iz) * C;
+        const long long vox = ((long long)ix * ny + iy) * nz + iz;
+        const long long cs = p.cmajor ? (long long)nx * ny * nz : 1;  // channel stride; voxel stride is C or 1
+        float *const o = p.out + g.out_offset * C + vox * (p.cmajor ? 1 : C);
         float v[CP];
         if (touched) {
 #pragma unroll
@@ -410,7 +422,7 @@ __global__ void __launch_bounds__(FILL_THREADS, (CP <= 8 ? 2 : 1)) occ_fill_kern
         if (p.flags & MKB_OCC_ACCUMULATE) {
 #pragma unroll
             for (int h = 0; h < CP; ++h)
-                if (h < C) { const float old = o[h]; v[h] = (v[h] > old) ? v[h] : old; }  // pyx:61 `value > old`
+                if (h < C) { const float old = o[h * cs]; v[h] = (v[h] > old) ? v[h] : old; }  // pyx:61 `value > old`
         }
         if (CP == 8 && p.vec_ok) {
             __stcs(reinterpret_cast<float4 *>(o), make_float4(v[0], v[1], v[2], v[3]));
@@ -418,7 +430,7 @@ __global__ void __launch_bounds__(FILL_THREADS, (CP <= 8 ? 2 : 1)) occ_fill_kern
         } else {
 #pragma unroll
             for (int h = 0; h < CP; ++h)
-                if (h < C) o[h] = v[h];
+                if (h < C) o[h * cs] = v[h];
         }
     }
 }
@@ -740,11 +752,13 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillPa
     }
     if (inside) {
         const int C = p.C;
-        float *const oo = p.vec_ok ? o : p.out + (__ldg(&gg->out_offset) + ((long long)ix * ny + iy) * nz + iz) * C;
+        const long long cs = p.cmajor ? (long long)nx * ny * nz : 1;
+        float *const oo = p.vec_ok ? o : p.out + __ldg(&gg->out_offset) * C +
+                                             (((long long)ix * ny + iy) * nz + iz) * (p.cmajor ? 1 : C);
         if (p.flags & MKB_OCC_ACCUMULATE) {
 #pragma unroll
             for (int h = 0; h < 8; ++h)
-                if (h < C) { const float old = oo[h]; v[h] = (v[h] > old) ? v[h] : old; }
+                if (h < C) { const float old = oo[h * cs]; v[h] = (v[h] > old) ? v[h] : old; }
         }
         if (p.vec_ok) {
             __stcs(reinterpret_cast<float4 *>(oo), make_float4(v[0], v[1], v[2], v[3]));
@@ -752,7 +766,7 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) occ_fill8_kernel(const FillPa
         } else {
 #pragma unroll
             for (int h = 0; h < 8; ++h)
-                if (h < C) oo[h] = v[h];
+                if (h < C) oo[h * cs] = v[h];
         }
     }
 }
@@ -832,6 +846,15 @@ __global__ void __launch_bounds__(W_WARPS * 32, W_MIN_CTAS) occ_fill8w_kernel(co
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 __stcs(d, z4);
                 __stcs(d + 1, z4);
+            }
+            return;
+        }
+        if (tot == 0 && p.cmajor && !(p.flags & MKB_OCC_ACCUMULATE)) {  // channel-major: 16-byte z-runs per channel
+            const int ix = bxi * 2 + (lane >> 4), iy = byi * 4 + ((lane >> 2) & 3), iz = bzi * 4 + (lane & 3);
+            if (ix < nx && iy < ny && iz < nz) {
+                const long long cs = (long long)nx * ny * nz;
+                float *d = p.out + out_offset * p.C + ((long long)ix * ny + iy) * nz + iz;
+                for (int h = 0; h < p.C; ++h) __stcs(d + h * cs, 0.f);
             }
             return;
         }
@@ -1020,15 +1043,20 @@ __global__ void __launch_bounds__(W_WARPS * 32, W_MIN_CTAS) occ_fill8w_kernel(co
 #pragma unroll
             for (int h = 0; h < 8; ++h) v[h] = 0.0f;
         }
-        float *const oo = p.out + (out_offset + ((long long)ix * ny + iy) * nz + iz) * C;
+        const long long cs = p.cmajor ? (long long)nx * ny * nz : 1;
+        float *const oo = p.out + out_offset * C + (((long long)ix * ny + iy) * nz + iz) * (p.cmajor ? 1 : C);
         if (p.flags & MKB_OCC_ACCUMULATE) {
 #pragma unroll
             for (int h = 0; h < 8; ++h)
-                if (h < C) { const float old = oo[h]; v[h] = (v[h] > old) ? v[h] : old; }
+                if (h < C) { const float old = oo[h * cs]; v[h] = (v[h] > old) ? v[h] : old; }
         }
         if (p.vec_ok) {
             __stcs(reinterpret_cast<float4 *>(oo), make_float4(v[0], v[1], v[2], v[3]));
             __stcs(reinterpret_cast<float4 *>(oo) + 1, make_float4(v[4], v[5], v[6], v[7]));
+        } else if (p.cmajor) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h)
+                if (h < C) __stcs(oo + h * cs, v[h]);
         } else {
 #pragma unroll
             for (int h = 0; h < 8; ++h)
@@ -1140,9 +1168,9 @@ static int scan_u32(mkb_ctx *h, cudaStream_t st, unsigned *in, unsigned *out, lo
 
 using namespace mkb;
 
-extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
-                                        int64_t n_atoms, int32_t C, const mkb_grid_desc *grids, int32_t B,
-                                        float *out, uint32_t flags) {
+static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
+                                     const double *radii, const uint32_t *chanmask, int64_t n_atoms, int32_t C,
+                                     const mkb_grid_desc *grids, int32_t B, float *out, uint32_t flags) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (B < 0 || n_atoms < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
@@ -1150,7 +1178,8 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     if (B == 0) return MKB_OK;
     if (!grids || !out) return fail(h, MKB_ERR_BAD_ARG, "null grids/out");
     if (n_atoms >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "n_atoms must be < 2^31");
-    if (n_atoms > 0 && (!coords || !sigmas)) return fail(h, MKB_ERR_BAD_ARG, "null coords/sigmas");
+    if (n_atoms > 0 && (!coords || (!sigmas && (!radii || !chanmask))))
+        return fail(h, MKB_ERR_BAD_ARG, "null coords/sigmas");
 
     // kernel variant: 0 = warp-per-block (C <= 8, default), 1 = tile kernel with quarter lists (MKB_OCC_TILE=1),
     // 2 = generic tile kernel (9..32 channels, very small voxels, or MKB_OCC_GENERIC=1).  It fixes the cell size.
@@ -1243,15 +1272,16 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     if ((rc = scan_u32(h, st, cell_count, cell_start, cells + 1))) return rc;
     if (items > 0) {
         const int nb = (int)cdiv(items, 256);
-        occ_scatter_kernel<<<nb, 256, 0, st>>>(coords, sigmas, C, d_grids, B, items, item_cell, item_slot, cell_start,
-                                               rec_pos, rec_tag);
+        occ_scatter_kernel<<<nb, 256, 0, st>>>(coords, sigmas, radii, chanmask, C, d_grids, B, items, item_cell, item_slot,
+                                               cell_start, rec_pos, rec_tag);
         MKB_LAUNCHED(h);
     }
     FillParams fp;
     fp.grids = d_grids; fp.B = B; fp.C = C;
     fp.rec_pos = rec_pos; fp.rec_tag = rec_tag;
     fp.cell_start = cell_start; fp.coords = coords; fp.sigmas = sigmas; fp.out = out; fp.flags = flags;
-    fp.vec_ok = (C == 8 && ((uintptr_t)out % 16 == 0)) ? 1 : 0;
+    fp.cmajor = (flags & MKB_OCC_LAYOUT_CXYZ) ? 1 : 0;
+    fp.vec_ok = (C == 8 && ((uintptr_t)out % 16 == 0) && !fp.cmajor) ? 1 : 0;
     fp.txp_shift = 0;
     // opt-in (MKB_OCC_BULK_STORE=1): measured 21 % slower in this non-persistent kernel because the CTA has to wait for
     // the asynchronous smem read before it may retire; kept for the persistent variant
@@ -1352,6 +1382,20 @@ extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const floa
     }
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));
     return MKB_OK;
+}
+
+extern "C" int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
+                                        int64_t n_atoms, int32_t C, const mkb_grid_desc *grids, int32_t B,
+                                        float *out, uint32_t flags) {
+    if (h && n_atoms > 0 && !sigmas) return fail(h, MKB_ERR_BAD_ARG, "null coords/sigmas");
+    return occupancy_grid_batch_impl(h, stream, coords, sigmas, nullptr, nullptr, n_atoms, C, grids, B, out, flags);
+}
+
+extern "C" int mkb_occupancy_grid_batch_masked(mkb_handle_t h, void *stream, const float *coords, const double *radii,
+                                               const uint32_t *chanmask, int64_t n_atoms, int32_t C,
+                                               const mkb_grid_desc *grids, int32_t B, float *out, uint32_t flags) {
+    if (h && n_atoms > 0 && (!radii || !chanmask)) return fail(h, MKB_ERR_BAD_ARG, "null radii/chanmask");
+    return occupancy_grid_batch_impl(h, stream, coords, nullptr, radii, chanmask, n_atoms, C, grids, B, out, flags);
 }
 
 extern "C" int mkb_occupancy_points(mkb_handle_t h, void *stream, const double *centers, int64_t M,

@@ -61,25 +61,87 @@ def make_grid_descs(origins, voxelsizes, dims, atom_offsets, out_offsets=None) -
     return d, out_offsets
 
 
-def occupancy_grid_batch(coords: torch.Tensor, sigmas: torch.Tensor, descs: np.ndarray, out: torch.Tensor,
-                         accumulate: bool = False) -> torch.Tensor:
-    """Launch K2+K1 for a batch of regular grids.  coords (N,3) f32 cuda, sigmas (N,C) f64 cuda,
-    out (sum M_b, C) f32 cuda (written in place).  Stream-ordered on torch's current stream."""
+def _layout_flag(layout: str) -> int:
+    if layout == "xyzc":
+        return 0
+    if layout == "cxyz":
+        return _lib.OCC_LAYOUT_CXYZ
+    raise ValueError("layout must be 'xyzc' (the reference's voxel-major order) or 'cxyz' (channel-major)")
+
+
+def occupancy_grid_batch(coords: torch.Tensor, sigmas: torch.Tensor | None, descs: np.ndarray, out: torch.Tensor,
+                         accumulate: bool = False, layout: str = "xyzc", radii: torch.Tensor | None = None,
+                         chanmask: torch.Tensor | None = None, n_channels: int | None = None) -> torch.Tensor:
+    """Launch K2+K1 for a batch of regular grids.  coords (N,3) f32 cuda, out (sum M_b * C) f32 cuda (written in place),
+    channels either as ``sigmas`` (N,C) f64 cuda -- the reference's matrix -- or, assembled on the device, as ``radii``
+    (N,) f64 + ``chanmask`` (N,) int32 bit masks with ``n_channels``.  ``layout="cxyz"`` stores every grid
+    channel-major, [C][nx][ny][nz].  Stream-ordered on torch's current stream."""
     dev = out.device
-    assert coords.is_cuda and sigmas.is_cuda and out.is_cuda and coords.device == dev == sigmas.device
-    assert coords.dtype == torch.float32 and sigmas.dtype == torch.float64 and out.dtype == torch.float32
-    assert coords.is_contiguous() and sigmas.is_contiguous() and out.is_contiguous()
-    assert coords.ndim == 2 and coords.shape[1] == 3 and sigmas.ndim == 2 and sigmas.shape[0] == coords.shape[0]
+    assert coords.is_cuda and out.is_cuda and coords.device == dev
+    assert coords.dtype == torch.float32 and out.dtype == torch.float32
+    assert coords.is_contiguous() and out.is_contiguous() and coords.ndim == 2 and coords.shape[1] == 3
     descs = np.ascontiguousarray(descs, dtype=_lib.GRID_DESC)
-    Cn = int(sigmas.shape[1])
+    flags = (_lib.OCC_ACCUMULATE if accumulate else 0) | _layout_flag(layout)
+    h = _lib.handle(dev.index)
+    if sigmas is not None:
+        assert sigmas.is_cuda and sigmas.device == dev and sigmas.dtype == torch.float64 and sigmas.is_contiguous()
+        assert sigmas.ndim == 2 and sigmas.shape[0] == coords.shape[0]
+        Cn = int(sigmas.shape[1])
+    else:
+        assert radii is not None and chanmask is not None and n_channels is not None
+        assert radii.is_cuda and chanmask.is_cuda and radii.dtype == torch.float64 and chanmask.dtype == torch.int32
+        assert radii.is_contiguous() and chanmask.is_contiguous()
+        assert radii.shape == (coords.shape[0],) and chanmask.shape == (coords.shape[0],)
+        Cn = int(n_channels)
     if Cn > MAX_CHANNELS_PER_CALL:
         raise ValueError(f"at most {MAX_CHANNELS_PER_CALL} channels per call; split the channel set")
+    with torch.cuda.device(dev):
+        if sigmas is not None:
+            rc = _lib.load().mkb_occupancy_grid_batch(
+                h, _stream_ptr(dev), C.c_void_p(coords.data_ptr()), C.c_void_p(sigmas.data_ptr()),
+                int(coords.shape[0]), Cn, descs.ctypes.data_as(C.c_void_p), int(descs.shape[0]),
+                C.c_void_p(out.data_ptr()), flags)
+        else:
+            rc = _lib.load().mkb_occupancy_grid_batch_masked(
+                h, _stream_ptr(dev), C.c_void_p(coords.data_ptr()), C.c_void_p(radii.data_ptr()),
+                C.c_void_p(chanmask.data_ptr()), int(coords.shape[0]), Cn, descs.ctypes.data_as(C.c_void_p),
+                int(descs.shape[0]), C.c_void_p(out.data_ptr()), flags)
+    _lib.check(rc, h)
+    return out
+
+
+def grid_centers(descs: np.ndarray, device=None) -> torch.Tensor:
+    """Voxel centres of a batch of grids on the device: (sum M_b, 3) float64 cuda, bit-identical to getCenters."""
+    dev = _dev(device)
+    descs = np.ascontiguousarray(descs, dtype=_lib.GRID_DESC)
+    total = int((descs["out_offset"] + descs["dims"].astype(np.int64).prod(axis=1)).max()) if len(descs) else 0
+    out = torch.empty((total, 3), dtype=torch.float64, device=dev)
     h = _lib.handle(dev.index)
     with torch.cuda.device(dev):
-        rc = _lib.load().mkb_occupancy_grid_batch(
-            h, _stream_ptr(dev), C.c_void_p(coords.data_ptr()), C.c_void_p(sigmas.data_ptr()),
-            int(coords.shape[0]), Cn, descs.ctypes.data_as(C.c_void_p), int(descs.shape[0]),
-            C.c_void_p(out.data_ptr()), _lib.OCC_ACCUMULATE if accumulate else 0)
+        rc = _lib.load().mkb_grid_centers(h, _stream_ptr(dev), descs.ctypes.data_as(C.c_void_p), int(descs.shape[0]),
+                                          C.c_void_p(out.data_ptr()))
+    _lib.check(rc, h)
+    return out
+
+
+def rotate_coords_device(coords: torch.Tensor, atom_offsets: torch.Tensor, matrices: torch.Tensor, centers: torch.Tensor,
+                         out_dtype=torch.float32) -> torch.Tensor:
+    """Batched rotateCoordinates on CUDA tensors: coords (N,3) f32, atom_offsets (B+1,) int64, matrices (B,3,3,3) f64
+    (x, y, z rotation of every molecule), centers (B,3) f64 -> rotated (N,3) float32 or float64."""
+    dev = coords.device
+    assert coords.is_cuda and coords.dtype == torch.float32 and coords.is_contiguous() and coords.shape[1] == 3
+    assert atom_offsets.dtype == torch.int64 and matrices.dtype == torch.float64 and centers.dtype == torch.float64
+    assert atom_offsets.is_contiguous() and matrices.is_contiguous() and centers.is_contiguous()
+    B = int(atom_offsets.numel()) - 1
+    assert matrices.shape == (B, 3, 3, 3) and centers.shape == (B, 3)
+    out = torch.empty(coords.shape, dtype=out_dtype, device=dev)
+    p32 = C.c_void_p(out.data_ptr()) if out_dtype == torch.float32 else C.c_void_p(0)
+    p64 = C.c_void_p(out.data_ptr()) if out_dtype == torch.float64 else C.c_void_p(0)
+    h = _lib.handle(dev.index)
+    with torch.cuda.device(dev):
+        rc = _lib.load().mkb_rotate_coords(h, _stream_ptr(dev), C.c_void_p(coords.data_ptr()), int(coords.shape[0]),
+                                           C.c_void_p(atom_offsets.data_ptr()), B, C.c_void_p(matrices.data_ptr()),
+                                           C.c_void_p(centers.data_ptr()), p32, p64)
     _lib.check(rc, h)
     return out
 

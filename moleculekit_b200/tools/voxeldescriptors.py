@@ -91,6 +91,52 @@ def _channels_to_sigmas(channels, elements):
     return channels
 
 
+def rotationMatrix(axis, theta: float) -> np.ndarray:
+    """Rotation by ``theta`` radians about ``axis`` from the unit quaternion (cos(t/2), -axis sin(t/2)) -- the formula of
+    moleculekit/util.py:101-117, evaluated with the same scalar operations so the matrices are bit-identical."""
+    from math import cos, sin, sqrt
+
+    axis = np.asarray(axis)
+    theta = np.asarray(theta)
+    axis = axis / sqrt(np.dot(axis, axis))
+    a = cos(theta / 2)
+    b, c, d = -axis * sin(theta / 2)
+    aa, bb, cc, dd = a * a, b * b, c * c, d * d
+    bc, ad, ac, ab, bd, cd = b * c, a * d, a * c, a * b, b * d, c * d
+    return np.array([[aa + bb - cc - dd, 2 * (bc + ad), 2 * (bd - ac)],
+                     [2 * (bc - ad), aa + cc - bb - dd, 2 * (cd + ab)],
+                     [2 * (bd + ac), 2 * (cd - ab), aa + dd - bb - cc]])
+
+
+def rotation_matrices(rotations) -> np.ndarray:
+    """(B, 3) angles [rx, ry, rz] -> (B, 3, 3, 3) float64: the x, y and z rotation matrices rotateCoordinates applies in
+    that order (voxeldescriptors.py:106-113)."""
+    rot = np.atleast_2d(np.asarray(rotations, dtype=np.float64))
+    out = np.zeros((rot.shape[0], 3, 3, 3), dtype=np.float64)
+    for b in range(rot.shape[0]):
+        out[b, 0] = rotationMatrix([1, 0, 0], rot[b, 0])
+        out[b, 1] = rotationMatrix([0, 1, 0], rot[b, 1])
+        out[b, 2] = rotationMatrix([0, 0, 1], rot[b, 2])
+    return out
+
+
+def rotateCoordinates(coords: np.ndarray, rotations: list, center: list, device=None) -> np.ndarray:
+    """Drop-in for voxeldescriptors.py:78-114: rotates (natoms, 3) coordinates about ``center`` by [rx, ry, rz] radians
+    around x, then y, then z; returns float64 like the reference (numpy promotes there).  Runs mkb_rotate_coords."""
+    c32 = np.ascontiguousarray(np.asarray(coords), dtype=np.float32)
+    if c32.ndim != 2 or c32.shape[1] != 3:
+        raise ValueError("coords must have shape (natoms, 3)")
+    if not np.array_equal(c32, np.asarray(coords)):
+        raise ValueError("rotateCoordinates on the GPU takes float32-representable coordinates (Molecule.coords)")
+    dev = _occ._dev(device)
+    d = _occ.rotate_coords_device(torch.from_numpy(c32).to(dev),
+                                  torch.tensor([0, c32.shape[0]], dtype=torch.int64, device=dev),
+                                  torch.from_numpy(rotation_matrices(list(rotations))).to(dev),
+                                  torch.from_numpy(np.asarray(center, dtype=np.float64).reshape(1, 3)).to(dev),
+                                  out_dtype=torch.float64)
+    return d.cpu().numpy()
+
+
 def getChannels(mol, aromaticNitrogen: bool = False, version: int = 2, validitychecks: bool = True):
     """Atom typing is an INPUT of the accelerated path (RDKit/OpenBabel chemistry).  Defer to the
     real moleculekit when it is installed; otherwise ask for ``userchannels``."""
@@ -195,26 +241,53 @@ class VoxelBatch:
     """
 
     def __init__(self, coords, channels, *, boxsize=None, centers=None, buffer=0.0, voxelsize=1.0,
-                 atom_offsets=None, elements=None):
+                 atom_offsets=None, elements=None, radii=None):
         if atom_offsets is None:
             counts = [len(c) for c in coords]
             atom_offsets = np.zeros(len(coords) + 1, dtype=np.int64)
             np.cumsum(counts, out=atom_offsets[1:])
             coords_cat = np.concatenate([np.asarray(c, dtype=np.float32).reshape(-1, 3) for c in coords]) \
                 if len(coords) else np.zeros((0, 3), np.float32)
-            if elements is not None:
-                channels = [_channels_to_sigmas(ch, el) for ch, el in zip(channels, elements)]
-            chan_cat = np.concatenate([np.asarray(c, dtype=np.float64) for c in channels]) \
-                if len(channels) else np.zeros((0, 8), np.float64)
+            masked = len(channels) > 0 and all(np.asarray(ch).dtype == bool for ch in channels) and \
+                (elements is not None or radii is not None)
+            if masked:
+                if radii is None:
+                    radii = [vdw_radii_of(el) for el in elements]
+                radii = np.concatenate([np.asarray(r, dtype=np.float64).reshape(-1) for r in radii])
+                chan_cat = np.concatenate([np.asarray(c, dtype=bool) for c in channels])
+            else:
+                if elements is not None:
+                    channels = [_channels_to_sigmas(ch, el) for ch, el in zip(channels, elements)]
+                chan_cat = np.concatenate([np.asarray(c, dtype=np.float64) for c in channels]) \
+                    if len(channels) else np.zeros((0, 8), np.float64)
         else:
             atom_offsets = np.asarray(atom_offsets, dtype=np.int64)
             coords_cat = np.asarray(coords, dtype=np.float32).reshape(-1, 3)
-            chan_cat = np.asarray(channels, dtype=np.float64)
+            masked = radii is not None and np.asarray(channels).dtype == bool
+            if masked:
+                radii = np.asarray(radii, dtype=np.float64).reshape(-1)
+                chan_cat = np.asarray(channels, dtype=bool)
+            else:
+                chan_cat = np.asarray(channels, dtype=np.float64)
         B = len(atom_offsets) - 1
         self.B = B
         self.atom_offsets = atom_offsets
         self.coords = np.ascontiguousarray(coords_cat)
-        self.sigmas = np.ascontiguousarray(chan_cat)
+        self.C = int(chan_cat.shape[1])
+        if masked:
+            # device-side channel assembly: sigma = radius on the channels of the mask; the (N, C) float64
+            # matrix of voxeldescriptors.py:332-335 is never built
+            if self.C > 32:
+                raise ValueError("bit-mask channels support at most 32 channels; pass float sigmas instead")
+            if radii.shape[0] != chan_cat.shape[0]:
+                raise ValueError("radii and channels must have one row per atom")
+            self.sigmas = None
+            self.radii = np.ascontiguousarray(radii)
+            bits = (chan_cat.astype(np.uint64) << np.arange(self.C, dtype=np.uint64)).sum(axis=1, dtype=np.uint64)
+            self.chanmask = np.ascontiguousarray(bits.astype(np.uint32).view(np.int32))
+        else:
+            self.sigmas = np.ascontiguousarray(chan_cat)
+            self.radii = self.chanmask = None
         self.voxelsize = float(voxelsize)
         origins = np.zeros((B, 3), dtype=np.float64)
         dims = np.zeros((B, 3), dtype=np.int64)
@@ -233,19 +306,51 @@ class VoxelBatch:
         self.origins, self.dims = origins, dims
         self.descs, self.out_offsets = _occ.make_grid_descs(origins, self.voxelsize, dims, atom_offsets)
         self.total_voxels = int(self.out_offsets[-1])
-        self.C = int(self.sigmas.shape[1])
 
     def centers(self, b: int) -> np.ndarray:
         return _centers_from_spec(self.origins[b], self.dims[b], self.voxelsize)
 
     def to_device(self, device=None):
+        """(coords, channels) on the device; channels = the sigma matrix, or the (radii, bit mask) pair."""
         dev = _occ._dev(device)
-        return torch.from_numpy(self.coords).to(dev), torch.from_numpy(self.sigmas).to(dev)
+        d_coords = torch.from_numpy(self.coords).to(dev, non_blocking=True)
+        if self.sigmas is not None:
+            return d_coords, torch.from_numpy(self.sigmas).to(dev, non_blocking=True)
+        return d_coords, (torch.from_numpy(self.radii).to(dev, non_blocking=True),
+                          torch.from_numpy(self.chanmask).to(dev, non_blocking=True))
 
-    def run(self, d_coords, d_sigmas, out: torch.Tensor | None = None) -> torch.Tensor:
+    def run(self, d_coords, d_channels, out: torch.Tensor | None = None, layout: str = "xyzc") -> torch.Tensor:
+        """K2+K1 on resident inputs.  ``out`` is (total_voxels, C) float32; with ``layout="cxyz"`` the memory of grid b
+        (rows [out_offsets[b], out_offsets[b+1])) holds that grid channel-major, see :meth:`as_cxyz`."""
         if out is None:
             out = torch.empty((self.total_voxels, self.C), dtype=torch.float32, device=d_coords.device)
-        return _occ.occupancy_grid_batch(d_coords, d_sigmas, self.descs, out)
+        if isinstance(d_channels, tuple):
+            return _occ.occupancy_grid_batch(d_coords, None, self.descs, out, layout=layout, radii=d_channels[0],
+                                             chanmask=d_channels[1], n_channels=self.C)
+        return _occ.occupancy_grid_batch(d_coords, d_channels, self.descs, out, layout=layout)
+
+    def rotate(self, d_coords, rotations, rot_centers) -> torch.Tensor:
+        """Random-rotation augmentation on the device: item b is rotated by rotations[b] = [rx, ry, rz] about
+        rot_centers[b] (batched rotateCoordinates); returns new float32 coords for :meth:`run`."""
+        dev = d_coords.device
+        mats = torch.from_numpy(rotation_matrices(np.asarray(rotations, dtype=np.float64).reshape(self.B, 3))).to(dev)
+        ctr = torch.from_numpy(np.ascontiguousarray(np.asarray(rot_centers, dtype=np.float64).reshape(self.B, 3))).to(dev)
+        off = torch.from_numpy(np.ascontiguousarray(self.atom_offsets)).to(dev)
+        return _occ.rotate_coords_device(d_coords, off, mats, ctr)
+
+    def centers_device(self, device=None) -> torch.Tensor:
+        """(total_voxels, 3) float64 voxel centres generated on the device (bit-identical to getCenters)."""
+        return _occ.grid_centers(self.descs, device=device)
+
+    def as_cxyz(self, feats, b: int | None = None):
+        """View a ``layout="cxyz"`` result as (C, X, Y, Z) for item b, or (B, C, X, Y, Z) for a uniform batch."""
+        if b is not None:
+            nx, ny, nz = (int(v) for v in self.dims[b])
+            return feats[self.out_offsets[b]:self.out_offsets[b + 1]].reshape(self.C, nx, ny, nz)
+        if not (self.dims == self.dims[0]).all():
+            raise ValueError("items have different grid sizes: ask for one item (b=...)")
+        nx, ny, nz = (int(v) for v in self.dims[0])
+        return feats.reshape(self.B, self.C, nx, ny, nz)
 
     def split(self, feats):
         """(sum M_b, C) -> list of per-item (M_b, C) views."""
@@ -260,23 +365,35 @@ def pinned_array(shape, dtype=np.float32) -> np.ndarray:
 
 
 def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, buffer=0.0, voxelsize=1.0,
-                             elements=None, atom_offsets=None, device=None, return_tensor: bool = False,
-                             dtype=np.float64, out: np.ndarray | None = None):
+                             elements=None, radii=None, atom_offsets=None, device=None, return_tensor: bool = False,
+                             dtype=np.float64, out: np.ndarray | None = None, layout: str = "xyzc",
+                             rotations=None, rotation_centers=None):
     """Voxelise a batch of molecules / pockets in one launch sequence (HOST arrays in, HOST arrays out).
 
     coords / channels: lists of per-item (N_b, 3) / (N_b, C) arrays, or concatenated arrays with ``atom_offsets``
     (B+1,).  Grids: ``boxsize`` + per-item ``centers`` (B, 3), or ``buffer`` around each item's bounding box.
+    Boolean ``channels`` with ``elements`` (vdW radii looked up) or explicit per-atom ``radii`` are assembled into
+    sigmas on the device.  ``rotations`` (B, 3) [rx, ry, rz] + ``rotation_centers`` (B, 3) rotate every item on the
+    device first (rotateCoordinates semantics; the grids stay where ``centers`` / the unrotated bounding boxes put them).
     Returns ``(features, nvoxels)``: features is a list of (M_b, C) arrays -- float64 by default like the reference,
     ``dtype=np.float32`` skips the upcast, ``out`` (float32 (sum M_b, C), ideally from :func:`pinned_array`) receives
     the device result directly -- or, with ``return_tensor=True``, ``(tensor, nvoxels, voxel_offsets)`` with one
-    float32 CUDA tensor left on the device (the layout per-GPU consumers keep resident).  ``nvoxels`` is (B, 3)."""
+    float32 CUDA tensor left on the device (the layout per-GPU consumers keep resident).  ``layout="cxyz"`` stores
+    each grid channel-major: the list entries / tensor slices are then (C, X, Y, Z) (tensor: (B, C, X, Y, Z) when all
+    grids have the same size).  ``nvoxels`` is (B, 3)."""
     batch = VoxelBatch(coords, channels, boxsize=boxsize, centers=centers, buffer=buffer, voxelsize=voxelsize,
-                       elements=elements, atom_offsets=atom_offsets)
+                       elements=elements, radii=radii, atom_offsets=atom_offsets)
     dev = _occ._dev(device)
-    d_coords = torch.from_numpy(batch.coords).to(dev, non_blocking=True)
-    d_sig = torch.from_numpy(batch.sigmas).to(dev, non_blocking=True)
-    d_out = batch.run(d_coords, d_sig)
+    d_coords, d_chan = batch.to_device(dev)
+    if rotations is not None:
+        if rotation_centers is None:
+            raise ValueError("rotation_centers is required with rotations")
+        d_coords = batch.rotate(d_coords, rotations, rotation_centers)
+    d_out = batch.run(d_coords, d_chan, layout=layout)
+    cx = layout == "cxyz"
     if return_tensor:
+        if cx and (batch.dims == batch.dims[0]).all():
+            d_out = batch.as_cxyz(d_out)
         return d_out, batch.dims.copy(), batch.out_offsets.copy()
     if out is not None:
         if out.dtype != np.float32 or out.shape != (batch.total_voxels, batch.C) or not out.flags["C_CONTIGUOUS"]:
@@ -288,4 +405,6 @@ def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, bu
         host = d_out.cpu().numpy()
         if dtype is not None and np.dtype(dtype) != np.float32:
             host = host.astype(dtype)
+    if cx:
+        return [batch.as_cxyz(host, b) for b in range(batch.B)], batch.dims.copy()
     return batch.split(host), batch.dims.copy()

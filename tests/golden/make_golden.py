@@ -98,9 +98,34 @@ def wrapping_fixture():
     np.savez_compressed(os.path.join(HERE, "wrap.npz"), **w)
 
 
+def rotation_fixture():
+    """rotate.npz: outputs of the reference's rotateCoordinates (tools/voxeldescriptors.py:78-114) and rotationMatrix
+    (util.py:70-117) on seeded inputs -- the float64 targets of mkb_rotate_coords."""
+    from moleculekit.tools.voxeldescriptors import rotateCoordinates
+    from moleculekit.util import rotationMatrix
+
+    rng = np.random.default_rng(314)
+    r = {}
+    n = 5
+    for c in range(n):
+        coords = (rng.normal(0, 20, size=(int(rng.integers(1, 400)), 3)) + rng.normal(0, 50, size=3)).astype(np.float32)
+        rot = rng.uniform(-2 * np.pi, 2 * np.pi, size=3)
+        cen = coords.mean(axis=0).astype(np.float64) if c % 2 else rng.normal(0, 30, size=3)
+        out = rotateCoordinates(coords, list(rot), list(cen))
+        assert out.dtype == np.float64
+        r[f"c{c}_coords"], r[f"c{c}_rot"], r[f"c{c}_center"], r[f"c{c}_out"] = coords, rot, cen, out
+        r[f"c{c}_mats"] = np.stack([rotationMatrix([1, 0, 0], rot[0]), rotationMatrix([0, 1, 0], rot[1]),
+                                    rotationMatrix([0, 0, 1], rot[2])])
+    r["ncase"] = np.array(n)
+    np.savez_compressed(os.path.join(HERE, "rotate.npz"), **r)
+
+
 def main():
     from oracle import build_ref
 
+    if "--only-rotation" in sys.argv:
+        rotation_fixture()
+        return
     if "--only-wrapping" in sys.argv:
         assert build_ref.build()
         wrapping_fixture()
@@ -362,6 +387,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "bonds.npz"), **bg)
 
     wrapping_fixture()
+    rotation_fixture()
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
