@@ -196,6 +196,15 @@ int mkb_bonds_count(mkb_handle_t h, void *stream, const float *coords, const flo
 int mkb_bonds_fill(mkb_handle_t h, void *stream, const float *coords, const float *radii, const uint32_t *is_hydrogen,
                    int64_t n, float pairdist, const int64_t *row_offsets, uint32_t *pairs);
 
+/* K10: the kernel of the `within` / `exwithin` atom selections, replaces within_distance
+ * (moleculekit/atomselect_utils/atomselect_utils.pyx:612-653; called from atomselect/atomselect.py:243-251).
+ * coords [n_atoms,3] float32 device (one frame, row-major); sel1 [n1] uint32 device = query atoms (NULL = all atoms,
+ * n1 == n_atoms); sel2 [n2] uint32 device = source atoms; results [n1] uint8 device: results[ii] is SET to 1 when some
+ * source atom lies at float32 squared distance < cutoff*cutoff of query ii and left untouched otherwise (the reference
+ * only ever writes True).  Cell list over the source atoms instead of the reference's n1 x n2 loop; identical output. */
+int mkb_within_distance(mkb_handle_t h, void *stream, const float *coords, int64_t n_atoms, const uint32_t *sel1,
+                        int64_t n1, const uint32_t *sel2, int64_t n2, float cutoff, uint8_t *results);
+
 /* K9: orthorhombic wrapping of bonded groups, replaces wrap_box
  * (moleculekit/wrapping/wrapping.pyx:91-144; called from Molecule.wrap, moleculekit/molecule.py:2077).  t->coords is
  * MODIFIED IN PLACE like the reference's array.  groups [n_groups] uint32 device: ascending first-atom offsets of

@@ -138,9 +138,78 @@ static int bond_args(mkb_ctx *h, const float *coords, const float *radii, const 
     return MKB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K10: `within` / `exwithin` selections.  Replaces within_distance
+// (moleculekit/atomselect_utils/atomselect_utils.pyx:612-653), a brute-force n1 x n2 loop with a TODO for a cell list.
+// The source atoms (sel2) are hashed into cells of edge cutoff(1+1e-5) with the K7 machinery; one thread per query atom
+// visits its 27 cells and stops at the first partner with ((dx*dx) + dy*dy) + dz*dz < cutoff*cutoff -- float32, each
+// operation rounded, strict '<' (pyx:628,647-650).  The answer is an OR, so the visiting order does not matter.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void within_gather_kernel(const float *__restrict__ coords, const unsigned *__restrict__ sel, long long n,
+                                     float *__restrict__ out) {
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long a = sel[k];
+    out[3 * k] = coords[3 * a]; out[3 * k + 1] = coords[3 * a + 1]; out[3 * k + 2] = coords[3 * a + 2];
+}
+
+__global__ void within_kernel(const float *__restrict__ coords, const unsigned *__restrict__ sel1, long long n1,
+                              const float *__restrict__ src, double inv_w, float sq_cutoff, unsigned hmask,
+                              const unsigned *__restrict__ bucket_start, const unsigned *__restrict__ order,
+                              unsigned char *__restrict__ results) {
+    const long long ii = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (ii >= n1) return;
+    const long long i = sel1 ? (long long)sel1[ii] : ii;
+    const float x = coords[3 * i], y = coords[3 * i + 1], z = coords[3 * i + 2];
+    if (!(x == x && y == y && z == z)) return;  // a NaN coordinate is never within anything (and has no cell)
+    const int cx = cell_of(x, inv_w), cy = cell_of(y, inv_w), cz = cell_of(z, inv_w);
+    for (int k = 0; k < 27; ++k) {
+        const int nx = cx + k / 9 - 1, ny = cy + (k / 3) % 3 - 1, nz = cz + k % 3 - 1;
+        const unsigned b = bond_hash(nx, ny, nz, hmask);
+        for (unsigned t = bucket_start[b]; t < bucket_start[b + 1]; ++t) {
+            const float *s = src + 3ll * order[t];
+            // atoms of other cells sharing the bucket are simply tested as well: any true hit is a valid answer
+            const float dx = __fsub_rn(x, s[0]), dy = __fsub_rn(y, s[1]), dz = __fsub_rn(z, s[2]);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d2 < sq_cutoff) { results[ii] = 1; return; }
+        }
+    }
+}
+
 }  // namespace mkb
 
 using namespace mkb;
+
+extern "C" int mkb_within_distance(mkb_handle_t h, void *stream, const float *coords, int64_t n_atoms,
+                                   const uint32_t *sel1, int64_t n1, const uint32_t *sel2, int64_t n2, float cutoff,
+                                   uint8_t *results) {
+    MKB_ENTER(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_atoms < 0 || n1 < 0 || n2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
+    if (n_atoms >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "n_atoms must be < 2^31");
+    if (cutoff != cutoff || std::isinf(cutoff)) return fail(h, MKB_ERR_BAD_ARG, "cutoff must be finite");
+    if (n1 == 0 || n2 == 0 || n_atoms == 0) return MKB_OK;
+    if (!coords || !sel2 || !results) return fail(h, MKB_ERR_BAD_ARG, "null argument");
+    if (!sel1 && n1 != n_atoms) return fail(h, MKB_ERR_BAD_ARG, "sel1 == NULL means all atoms: n1 must equal n_atoms");
+    // cutoff*cutoff is what the reference compares with (pyx:628), so a negative cutoff behaves like its magnitude;
+    // cutoff == 0 can match nothing (d2 < 0 is impossible)
+    const float sq = cutoff * cutoff;
+    if (!(sq > 0.f)) return MKB_OK;
+    float *src;
+    int rc;
+    if ((rc = scratch_get(h, S_SORT_PX, (size_t)n2 * 3, &src))) return rc;
+    if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[0], st));
+    within_gather_kernel<<<(unsigned)cdiv(n2, 256), 256, 0, st>>>(coords, sel2, n2, src);
+    MKB_LAUNCHED(h);
+    BondGrid g;
+    if ((rc = bond_build(h, st, src, n2, std::fabs(cutoff), &g))) return rc;
+    if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
+    within_kernel<<<(unsigned)cdiv(n1, 128), 128, 0, st>>>(coords, sel1, n1, src, g.inv_w, sq, g.hmask, g.bstart, g.order,
+                                                           results);
+    MKB_LAUNCHED(h);
+    if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));
+    return MKB_OK;
+}
 
 extern "C" int mkb_bonds_count(mkb_handle_t h, void *stream, const float *coords, const float *radii,
                                const uint32_t *is_hydrogen, int64_t n, float pairdist, int64_t *row_offsets,

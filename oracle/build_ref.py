@@ -31,6 +31,7 @@ MODULES = {
     "distance_utils": "moleculekit/distance_utils/distance_utils.pyx",
     "bondguesser_utils": "moleculekit/bondguesser_utils/bondguesser_utils.pyx",
     "wrapping": "moleculekit/wrapping/wrapping.pyx",
+    "atomselect_utils": "moleculekit/atomselect_utils/atomselect_utils.pyx",
 }
 
 

@@ -230,3 +230,13 @@ def wrap_box(groups, coords, box, centersel, center):
     assert box.shape == (3, F)
     lib().oracle_wrap_box(_p(groups), C.c_int64(len(groups)), _p(coords), _p(box), C.c_int64(F),
                           _p(centersel), C.c_int64(len(centersel)), _p(center))
+
+
+def within_distance(coords, cutoff, sel1, sel2, sel2_min_coords, sel2_max_coords, results):
+    """moleculekit/atomselect_utils/atomselect_utils.pyx:612-620 (same arguments); ``results`` (bool, len(sel1)) is
+    updated in place.  The min/max arguments only feed the reference's no-op pre-check."""
+    coords = _f32(coords)
+    sel1, sel2 = _u32(sel1), _u32(sel2)
+    assert results.dtype == np.bool_ and results.flags["C_CONTIGUOUS"] and results.shape == (len(sel1),)
+    lib().oracle_within_distance(_p(coords), C.c_float(cutoff), _p(sel1), C.c_int64(len(sel1)), _p(sel2),
+                                 C.c_int64(len(sel2)), _p(results.view(np.uint8)))

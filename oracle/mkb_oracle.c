@@ -465,3 +465,30 @@ EXPORT void oracle_wrap_box(const uint32_t *groups, int64_t n_groups, float *coo
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * within_distance -- moleculekit/atomselect_utils/atomselect_utils.pyx:612-653 (the kernel of the
+ * `within` / `exwithin` atom selections, atomselect/atomselect.py:231-254).
+ * results[ii] is SET (never cleared) when some sel2 atom j has
+ *   ((0 + dx*dx) + dy*dy) + dz*dz < cutoff*cutoff      -- all float32, strict '<'
+ * (the generated C calls powf(d, 2.0), which the compiler folds to d*d; pinned against the binary).
+ * The reference's bounding-box pre-check (pyx:632-643) passes for every finite coordinate and a NaN
+ * coordinate can never satisfy the distance test either, so it does not influence the result.
+ * ------------------------------------------------------------------------------------------------ */
+EXPORT void oracle_within_distance(const float *coords, float cutoff, const uint32_t *sel1, int64_t n1,
+                                   const uint32_t *sel2, int64_t n2, uint8_t *results)
+{
+    const float sq = cutoff * cutoff;
+    for (int64_t ii = 0; ii < n1; ++ii) {
+        const float *a = coords + 3 * (int64_t)sel1[ii];
+        for (int64_t jj = 0; jj < n2; ++jj) {
+            const float *b = coords + 3 * (int64_t)sel2[jj];
+            float diff = 0.f;
+            for (int k = 0; k < 3; ++k) {
+                const float d = a[k] - b[k];
+                diff = diff + d * d;
+            }
+            if (diff < sq) { results[ii] = 1; break; }
+        }
+    }
+}

@@ -60,6 +60,11 @@ def g_bonds():
 
 
 @pytest.fixture(scope="session")
+def g_within():
+    return _npz("within.npz")
+
+
+@pytest.fixture(scope="session")
 def g_rotate():
     return _npz("rotate.npz")
 

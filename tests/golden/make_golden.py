@@ -120,9 +120,56 @@ def rotation_fixture():
     np.savez_compressed(os.path.join(HERE, "rotate.npz"), **r)
 
 
+def within_fixture():
+    """within.npz (K10): `within` / `exwithin` selections of the reference on its own test structures.  Expected masks come
+    from the reference's STORED goldens tests/test_atomselect/selections.pickle where the selection string is stored
+    ('within 5 of nucleic', 'exwithin 5 of nucleic'), else from the live reference atomselect; the live result is
+    asserted equal to the stored golden wherever both exist (incl. the composite 'protein and within 8.3 of ...')."""
+    import pickle
+
+    from moleculekit.molecule import Molecule
+
+    with open(os.path.join(REFT, "test_atomselect", "selections.pickle"), "rb") as f:
+        stored = pickle.load(f)
+    w = {}
+    cases = []
+    for pid in ("3ptb", "1bna", "3wbm", "6a5j"):
+        mol = Molecule(pid)
+        mol.serial[10] = -88  # tests/test_atomselect.py:139-141 mutate the molecule before selecting
+        mol.beta[:] = 0
+        mol.beta[1000:] = -1
+        n = mol.numAtoms
+        w[f"{pid}_coords"] = np.ascontiguousarray(mol.coords[:, :, mol.frame])
+        for op, cutoff, src in (("within", 5, "nucleic"), ("exwithin", 5, "nucleic"), ("within", 8.3, "resname ALA"),
+                                ("exwithin", 4, "index 2"), ("within", 8, "resid 100"), ("exwithin", 3.05, "name CA")):
+            sel = f"{op} {cutoff} of {src}"
+            live = mol.atomselect(sel)
+            if (pid, sel) in stored:
+                ref = np.zeros(n, dtype=bool)
+                ref[np.asarray(stored[(pid, sel)], dtype=np.int64)] = True
+                assert np.array_equal(ref, live), (pid, sel)
+                origin = "stored"
+            else:
+                origin = "live"
+            key = f"{pid}_{len(cases)}"
+            w[key + "_source"] = mol.atomselect(src)
+            w[key + "_expected"] = live
+            cases.append((pid, op, str(cutoff), src, origin, key))
+        comp = "protein and within 8.3 of resname ALA"
+        ref = np.zeros(n, dtype=bool)
+        ref[np.asarray(stored[(pid, comp)], dtype=np.int64)] = True
+        assert np.array_equal(ref, mol.atomselect("protein") & mol.atomselect("within 8.3 of resname ALA")), pid
+    w["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "within.npz"), **w)
+    print("within cases:", len(cases), "stored-golden backed:", sum(c[4] == "stored" for c in cases))
+
+
 def main():
     from oracle import build_ref
 
+    if "--only-within" in sys.argv:
+        within_fixture()
+        return
     if "--only-rotation" in sys.argv:
         rotation_fixture()
         return
@@ -388,6 +435,7 @@ def main():
 
     wrapping_fixture()
     rotation_fixture()
+    within_fixture()
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -257,3 +257,52 @@ def test_bonded_groups_host_mirror(g_wrap, refmods):
         refmods[3].get_bonded_groups(bonds, n, p1, s1)
         wr.get_bonded_groups(bonds, n, p2, s2)
         assert np.array_equal(p1, p2)
+
+
+# ------------------------------------------------------------------------------------------------ K10: within_distance
+def _within_cases(g):
+    for pid, op, cutoff, src, origin, key in g["cases"].tolist():
+        yield pid, op, float(cutoff), origin, g[f"{pid}_coords"], g[key + "_source"], g[key + "_expected"]
+
+
+def test_within_oracle_vs_reference_goldens(oracle, g_within):
+    """`within` / `exwithin` masks of the reference (8 of the 24 cases are its stored selections.pickle goldens) from the
+    oracle's restatement of within_distance + the node logic of atomselect.py:231-254."""
+    n_stored = 0
+    for pid, op, cutoff, origin, coords, source, expected in _within_cases(g_within):
+        n = coords.shape[0]
+        mask = np.zeros(n, dtype=bool)
+        if source.any():
+            sc = coords[source]
+            oracle.within_distance(coords, cutoff, np.arange(n, dtype=np.uint32), np.where(source)[0].astype(np.uint32),
+                                   sc.min(axis=0), sc.max(axis=0), mask)
+            if op == "exwithin":
+                mask[source] = False
+        assert np.array_equal(mask, expected), (pid, op, cutoff)
+        n_stored += origin == "stored"
+    assert n_stored == 8
+
+
+def test_within_oracle_vs_live_reference(oracle, refmods):
+    if refmods is None or len(refmods) < 5:
+        pytest.skip("oracle/_ref not built")
+    ref = refmods[4]
+    rng = np.random.default_rng(21)
+    for t in range(12):
+        N = int(rng.integers(2, 500))
+        coords = rng.normal(0, 8, size=(N, 3)).astype(np.float32)
+        cutoff = np.float32(rng.uniform(1, 6))
+        if t % 3 == 0:  # atoms placed within a few ulps of the cutoff sphere of atom 0
+            dirs = rng.normal(size=(N - 1, 3))
+            dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+            coords[1:] = (coords[0] + dirs * (cutoff * (1 + rng.normal(0, 2e-7, size=(N - 1, 1))))).astype(np.float32)
+            sel2 = np.array([0], np.uint32)
+        else:
+            sel2 = np.sort(rng.choice(N, int(rng.integers(1, min(N, 60) + 1)), replace=False)).astype(np.uint32)
+        sel1 = np.sort(rng.choice(N, int(rng.integers(1, N + 1)), replace=False)).astype(np.uint32)
+        a, b = np.zeros(len(sel1), bool), np.zeros(len(sel1), bool)
+        a[0] = b[0] = True  # pre-set entries are never cleared
+        mn, mx = coords[sel2].min(axis=0), coords[sel2].max(axis=0)
+        ref.within_distance(coords, float(cutoff), sel1, sel2, mn, mx, a)
+        oracle.within_distance(coords, float(cutoff), sel1, sel2, mn, mx, b)
+        assert np.array_equal(a, b), t
