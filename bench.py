@@ -433,14 +433,14 @@ def run_ours(a):
     try:  # dram bytes of one launch of the same command, from the committed `ncu --set full` capture
         if a.workload == "c3" and not a.batch:
             tr = 0.0
-            for ln in open(os.path.join(ROOT, "profiles", "r01_fill_final_metrics.txt")):
+            for ln in open(os.path.join(ROOT, "profiles", "r01_fill_v6_2vox_metrics.txt")):
                 f = ln.split()
                 if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     tr += float(f[1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
             traffic = tr or None
     except Exception:
         traffic = None
-    roofline = dict(bound="hbm", kernel=("occ_fill8w_kernel" if w["voxelsize"] >= 5.0 / 7 else "occ_fill8_kernel"), achieved=achieved, peak=peak, unit="GB/s",
+    roofline = dict(bound="hbm", kernel=("occ_fill8v_kernel" if w["voxelsize"] >= 5.0 / 7 else "occ_fill8_kernel"), achieved=achieved, peak=peak, unit="GB/s",
                     frac=achieved / peak, traffic=traffic, peak_source=f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
                     algorithmic_bytes_per_launch=int(alg_bytes), kernel_ms_mean=fill_mean,
                     kernel_ms_min=float(np.min(fill_ms)), prep_ms_mean=float(np.mean(prep_ms)),

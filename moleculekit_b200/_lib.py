@@ -52,11 +52,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.isfile(LIB_PATH):
+    path = os.environ.get("MKB200_LIB", LIB_PATH)  # tuning hook: an alternative in-tree build of the same sources
+    if not os.path.isfile(path):
         raise ImportError(
-            f"{LIB_PATH} not found: build the CUDA extension first (python -m moleculekit_b200.build). "
+            f"{path} not found: build the CUDA extension first (python -m moleculekit_b200.build). "
             "moleculekit_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64, u32, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float
     lib.mkb_version.restype = C.c_int
     lib.mkb_create.argtypes = [C.c_int, C.POINTER(vp)]

@@ -44,7 +44,17 @@ def nvcc_path() -> str:
     return "nvcc"
 
 
-def build(force: bool = False, verbose: bool = True, extra: list[str] | None = None) -> str:
+def build(force: bool = False, verbose: bool = True, extra: list[str] | None = None, out: str | None = None) -> str:
+    """``out``: alternative output name inside lib/ (tuning experiments, selected at run time with MKB200_LIB)."""
+    if out is not None:
+        os.makedirs(LIBDIR, exist_ok=True)
+        target = os.path.join(LIBDIR, out)
+        env_extra = os.environ.get("MKB_NVCC_EXTRA", "").split()
+        cmd = [nvcc_path()] + NVCC_FLAGS + (extra or []) + env_extra + [f"-I{INCLUDE}", f"-I{CSRC}", "-o", target] + sources()
+        if verbose:
+            print("[mkb200 build]", " ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+        return target
     if not force and not _stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)

@@ -1064,6 +1064,347 @@ __global__ void __launch_bounds__(W_WARPS * 32, W_MIN_CTAS) occ_fill8w_kernel(co
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 v6 (default for C <= 8, cutoff <= 7 voxels): one warp = one 2x4x8 block, TWO voxels per lane.
+//   The block is eight 2x2x2 sub-blocks (sy in 0..1, sz in 0..3), four lanes each; a lane owns the x-pair of voxels
+//   (0, y, z) and (1, y, z).  Against the 2x4x4 kernel above:
+//     * one halo gather (cell rows are contiguous along z, so doubling the block along z adds ~20 % scanned atoms, not
+//       100 %), one row set-up, one prologue per 64 voxels instead of per 32;
+//     * a candidate is loaded once for two voxels that share dy, dz and the channel mask: 39 instructions per candidate
+//       for two pairs instead of 30 for one, while each 2x2x2 sub-block keeps its own list (same 47 % hit rate);
+//     * two independent dependency chains per lane (ILP) stand in for the halved number of resident warps.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int V_BZ = 8;       // block extent along z
+constexpr int V_PCAP = 160;   // block candidates per round
+constexpr int V_QCAP = 96;    // sub-block candidates per round
+constexpr int V_QSTRIDE = V_QCAP + 2;  // + one sentinel slot for the software-pipelined loop
+#ifndef MKB_V_PREFETCH
+#define MKB_V_PREFETCH 0  // software-pipelined candidate loads: no gain (2.32 vs 2.30 ms), costs registers
+#endif
+#ifndef MKB_V_MIN_CTAS
+#define MKB_V_MIN_CTAS 7  // 72 registers: measured 2.09 ms; 6 CTAs (80 regs) 2.30 ms, 8 CTAs (64 regs, spills) 2.40 ms
+#endif
+
+__global__ void occ_block_total_v_kernel(const GridDev *__restrict__ grids, const unsigned *__restrict__ cell_start,
+                                         const long long *__restrict__ block_base, unsigned *__restrict__ block_total) {
+    const GridDev &g = grids[blockIdx.y];
+    const int nbx = (g.dims[0] + 1) / 2, nby = (g.dims[1] + 3) / 4, nbz = (g.dims[2] + V_BZ - 1) / V_BZ;
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= nbx * nby * nbz) return;
+    const int bzi = local % nbz, bxy = local / nbz, byi = bxy % nby, bxi = bxy / nby;
+    const int cutv = g.cutv, cN1 = g.cells[1], cN2 = g.cells[2];
+    const int cx0 = (bxi * 2) / W_CELL, cx1 = min((bxi * 2 + 1 + 2 * cutv) / W_CELL, g.cells[0] - 1);
+    const int cy0 = byi, cy1 = min((byi * 4 + 3 + 2 * cutv) / W_CELL, cN1 - 1);
+    const int cz0 = bzi * (V_BZ / W_CELL), cz1 = min((bzi * V_BZ + V_BZ - 1 + 2 * cutv) / W_CELL, cN2 - 1);
+    unsigned total = 0;
+    for (int cx = cx0; cx <= cx1; ++cx)
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            const long long cb = g.cell_base + ((long long)cx * cN1 + cy) * cN2;
+            total += cell_start[cb + cz1 + 1] - cell_start[cb + cz0];
+        }
+    block_total[block_base[blockIdx.y] + local] = total;
+}
+
+template <bool UNIFORM>
+__global__ void __launch_bounds__(W_WARPS * 32, MKB_V_MIN_CTAS)
+occ_fill8v_kernel(const FillParams p, const long long *__restrict__ block_base, const unsigned *__restrict__ block_total) {
+    __shared__ float4 s_pent[W_WARPS][V_PCAP + 1];    // block candidates: x, y, z in the block frame, sigma^2 (+ sentinel)
+    __shared__ unsigned s_pmask[W_WARPS][V_PCAP + 1];  // channel mask; 0 = several sigmas
+    __shared__ unsigned s_psrc[W_WARPS][V_PCAP];
+    __shared__ unsigned s_rpos[W_WARPS][W_ROWS];
+    __shared__ unsigned s_rbase[W_WARPS][W_ROWS + 1];
+    __shared__ unsigned short s_qidx[W_WARPS][8][V_QSTRIDE];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bzi = blockIdx.x * W_WARPS + warp, byi = blockIdx.y, bxi = blockIdx.z & ((1 << p.txp_shift) - 1);
+    const int gi = blockIdx.z >> p.txp_shift;
+    const GridDev *gg = p.grids + gi;
+    const int nx = WG(dims[0]), ny = WG(dims[1]), nz = WG(dims[2]);
+    const long long out_offset = UNIFORM ? p.u.out_offset + (long long)gi * p.u_out_stride : __ldg(&gg->out_offset);
+    if (bxi * 2 >= nx || byi * 4 >= ny || bzi * V_BZ >= nz) return;  // padding of the launch grid / ragged batch
+    const int C = p.C;
+    const long long cs = p.cmajor ? (long long)nx * ny * nz : 1;  // channel stride; voxel stride is C or 1
+    const int vstride = p.cmajor ? 1 : C;
+
+    // ---- empty block (no atom within reach): stream 64 x 32 B of zeros and retire
+    {
+        const int nby = (ny + 3) >> 2, nbz = (nz + V_BZ - 1) / V_BZ;
+        const long long bb = UNIFORM ? p.u_block_base + (long long)gi * p.u_block_stride : __ldg(block_base + gi);
+        const unsigned tot = __ldg(block_total + bb + ((long long)bxi * nby + byi) * nbz + bzi);
+        if (tot == 0 && !(p.flags & MKB_OCC_ACCUMULATE)) {
+            const int iy = byi * 4 + (lane >> 3), iz = bzi * V_BZ + (lane & 7);  // 8 lanes = one 256-byte row
+            if (iy < ny && iz < nz) {
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const int ix = bxi * 2 + v;
+                    if (ix < nx) {
+                        float *d = p.out + out_offset * C + (((long long)ix * ny + iy) * nz + iz) * vstride;
+                        if (p.vec_ok) {
+                            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            __stcs(reinterpret_cast<float4 *>(d), z4);
+                            __stcs(reinterpret_cast<float4 *>(d) + 1, z4);
+                        } else {
+                            for (int h = 0; h < C; ++h) __stcs(d + h * cs, 0.f);
+                        }
+                    }
+                }
+            }
+            return;
+        }
+    }
+
+    // ---- cell rows of this block's halo (W_CELL = 4): rows run along z
+    const int cutv = WG(cutv);
+    const int cN1 = WG(cells[1]), cN2 = WG(cells[2]);
+    const int cx0 = (bxi * 2) / W_CELL, cx1 = min((bxi * 2 + 1 + 2 * cutv) / W_CELL, WG(cells[0]) - 1);
+    const int cy0 = byi, cy1 = min((byi * 4 + 3 + 2 * cutv) / W_CELL, cN1 - 1);
+    const int cz0 = bzi * (V_BZ / W_CELL), cz1 = min((bzi * V_BZ + V_BZ - 1 + 2 * cutv) / W_CELL, cN2 - 1);
+    const int ncy = cy1 - cy0 + 1;
+    const int nrows = (cx1 - cx0 + 1) * ncy;  // <= W_ROWS checked on the host
+    unsigned *const rpos = s_rpos[warp], *const rbase = s_rbase[warp];
+    const long long cell_base = UNIFORM ? p.u.cell_base + (long long)gi * p.u_cell_stride : __ldg(&gg->cell_base);
+    const float inv_ncy = 1.0f / (float)ncy;
+    const float cut_hi_row = WG(cut2v_hi);
+    unsigned carry = 0;
+    for (int r0 = 0; r0 < nrows; r0 += 32) {  // row lengths + inclusive scan, 32 rows per step
+        const int r = r0 + lane;
+        unsigned v = 0;
+        if (r < nrows) {
+            const int rx = (int)(((float)r + 0.5f) * inv_ncy), ry = r - rx * ncy;  // exact for small r
+            const long long cb = cell_base + ((long long)(cx0 + rx) * cN1 + (cy0 + ry)) * cN2;
+            const unsigned a = __ldg(p.cell_start + cb + cz0);
+            v = __ldg(p.cell_start + cb + cz1 + 1) - a;
+            rpos[r] = a;
+            // corner rows: the cell column [c*4 - cutv, c*4 + 4 - cutv) is further than the cutoff from the block's
+            // x/y extent -> none of its atoms can pass the cull below, skip the row
+            const int lox = (cx0 + rx) * W_CELL - cutv, loy = (cy0 + ry) * W_CELL - cutv;
+            const int gx = max(max(lox - (bxi * 2 + 1), bxi * 2 - (lox + W_CELL)), 0);
+            const int gy = max(max(loy - (byi * 4 + 3), byi * 4 - (loy + W_CELL)), 0);
+            if ((float)(gx * gx + gy * gy) > cut_hi_row) v = 0;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (r < nrows) rbase[r + 1] = v + carry;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+    const unsigned total = carry;
+
+    // lane -> sub-block s = (sy, sz) and position (ty, tz) in it; the lane's two voxels are x = 0 and x = 1
+    const int s = lane >> 2, t4 = lane & 3;
+    const int ly = (s >> 2) * 2 + (t4 >> 1), lz = (s & 3) * 2 + (t4 & 1);
+    const int ix0 = bxi * 2, iy = byi * 4 + ly, iz = bzi * V_BZ + lz;
+    const bool in_yz = iy < ny && iz < nz;
+    const bool inside0 = in_yz && ix0 < nx, inside1 = in_yz && ix0 + 1 < nx;
+
+    float acc0[8], acc1[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) acc0[h] = acc1[h] = 0.0f;
+    bool touched = false;
+
+    if (total != 0) {
+        if (lane == 0) {
+            rbase[0] = 0;
+            s_pent[warp][V_PCAP] = make_float4(1e18f, 1e18f, 1e18f, 0.0f);  // sentinel: never inside the gate
+            s_pmask[warp][V_PCAP] = 1u;
+        }
+        __syncwarp();
+        const float cut_lo = WG(cut2v_lo), cut_hi = WG(cut2v_hi);
+        const float gate_k = GATE_SCALE * cut_lo;
+        const unsigned band_bits = __float_as_uint(cut_hi - cut_lo);
+        const float fvy = (float)ly - 1.5f, fvz = (float)lz - 3.5f;  // block frame: origin at the block centre
+        const int sx = bxi * 2 + cutv, sy = byi * 4 + cutv, sz = bzi * V_BZ + cutv;
+        float4 *const pent = s_pent[warp];
+        unsigned *const pmask = s_pmask[warp], *const psrc = s_psrc[warp];
+        unsigned short *const wq = s_qidx[warp][0];
+        unsigned short *const my_q = s_qidx[warp][s];
+        unsigned ent_sa, mask_sa;
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(ent_sa) : "l"(pent));
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(mask_sa) : "l"(pmask));
+
+        int np = 0;
+        int row = 0;  // row of this lane's current atom: k only grows, so the row pointer only advances
+        for (unsigned k0 = 0; k0 < total; k0 += 32) {
+            // ---- gather 32 atoms of the concatenated cell rows, keep those within reach of the block
+            {
+                const unsigned k = min(k0 + lane, total - 1);
+                while (rbase[row + 1] <= k) ++row;  // rbase[nrows] == total > k: terminates
+                const unsigned i = rpos[row] + (k - rbase[row]);
+                float4 e = __ldg(p.rec_pos + i);
+                const uint4 tg = __ldg(p.rec_tag + i);
+                e.x += (float)((int)(tg.z & 1023u) * W_CELL - sx) - 0.5f;  // exact: small integers and halves
+                e.y += (float)((int)((tg.z >> 10) & 1023u) * W_CELL - sy) - 1.5f;
+                e.z += (float)((int)(tg.z >> 20) * W_CELL - sz) - 3.5f;
+                const float ddx = fmaxf(fabsf(e.x) - 0.5f, 0.f);
+                const float ddy = fmaxf(fabsf(e.y) - 1.5f, 0.f);
+                const float ddz = fmaxf(fabsf(e.z) - 3.5f, 0.f);
+                const bool pass = (k0 + lane < total) & (tg.x != 0) & (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= cut_hi);
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) {
+                    const int slot = np + __popc(bal & ((1u << lane) - 1u));
+                    pent[slot] = e;
+                    pmask[slot] = (tg.y & 0x80000000u) ? 0u : tg.x;
+                    psrc[slot] = tg.y & 0x7fffffffu;
+                }
+                np += __popc(bal);
+            }
+            if (np <= V_PCAP - 32 && k0 + 32 < total) continue;
+            if (np == 0) continue;
+            touched = true;
+            __syncwarp();
+            // ---- block list -> eight 2x2x2 sub-block lists, evaluated in lock-step
+            int cq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cq[u] = 0;
+            for (int j0 = 0; j0 < np; j0 += 32) {
+                const int j = j0 + lane;
+                const bool live = j < np;
+                const unsigned idx = min(j, np - 1);
+                bool hit[8], multi;
+                {
+                    const float4 e = lds_f4(ent_sa + idx * 16);
+                    const float ddx = fmaxf(fabsf(e.x) - 0.5f, 0.f);
+                    const float y0 = fmaxf(fabsf(e.y + 1.f) - 0.5f, 0.f), y1 = fmaxf(fabsf(e.y - 1.f) - 0.5f, 0.f);
+                    const float xx = ddx * ddx;
+                    const float a0 = fmaf(y0, y0, xx), a1 = fmaf(y1, y1, xx);
+                    multi = live & (lds_u32(mask_sa + idx * 4) == 0);
+                    const bool ok = live & !multi;
+#pragma unroll
+                    for (int zz = 0; zz < 4; ++zz) {  // sub-block centres along z: -3, -1, +1, +3
+                        const float zd = fmaxf(fabsf(e.z - (float)(2 * zz - 3)) - 0.5f, 0.f);
+                        const float z2 = zd * zd;
+                        hit[zz] = ok & (a0 + z2 <= cut_hi);      // s = sy*4 + sz
+                        hit[4 + zz] = ok & (a1 + z2 <= cut_hi);
+                    }
+                }
+                // atoms carrying several distinct sigmas (user float channels): whole-warp per-channel path
+                for (unsigned bm = __ballot_sync(0xffffffffu, multi); bm; bm &= bm - 1) {
+                    const int jj = j0 + __ffs(bm) - 1;
+                    const float4 e = pent[jj];
+                    const float dy = e.y - fvy, dz = e.z - fvz;
+                    const float s2 = fmaf(dz, dz, dy * dy);
+                    const double *sg = p.sigmas + (long long)psrc[jj] * C;
+                    const double ivs = WG(inv_vs);
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const float dx = e.x - ((float)v - 0.5f);
+                        const float d2 = fmaf(dx, dx, s2);
+                        bool in = d2 < cut_lo;
+                        if (!in && d2 < cut_hi) in = exact_gate(gg, p.coords, psrc[jj], ix0 + v, iy, iz);
+                        const float rr = in ? rcp_approx(d2) : 0.0f;
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) {
+                            if (h < C) {
+                                const double sv = sg[h] * ivs;
+                                const float sq = (sv == 0.0 || sv != sv) ? 0.0f : fmaxf((float)(sv * sv), FLT_MIN);
+                                if (v == 0) acc0[h] = fmaxf(acc0[h], sq * rr);  // 0*inf = NaN is dropped by fmaxf
+                                else acc1[h] = fmaxf(acc1[h], sq * rr);
+                            }
+                        }
+                    }
+                }
+                const unsigned lt = (1u << lane) - 1u;
+                int nmax = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned b = __ballot_sync(0xffffffffu, hit[u]);
+                    if (hit[u]) wq[u * V_QSTRIDE + cq[u] + __popc(b & lt)] = (unsigned short)idx;
+                    cq[u] += __popc(b);
+                    nmax = max(nmax, cq[u]);
+                }
+                if (j0 + 32 < np && nmax <= V_QCAP - 32) continue;
+                // pad the shorter lists with the sentinel, then run all eight in lock-step
+                int mine = cq[0];
+#pragma unroll
+                for (int u = 1; u < 8; ++u) mine = (s == u) ? cq[u] : mine;
+                for (int c = mine + t4; c <= nmax; c += 4) my_q[c] = (unsigned short)V_PCAP;  // incl. slot nmax (prefetch)
+                __syncwarp();
+#if MKB_V_PREFETCH
+                unsigned jj = my_q[0];
+                float4 e = lds_f4(ent_sa + jj * 16);
+                unsigned cm = lds_u32(mask_sa + jj * 4);
+#endif
+                for (int c = 0; c < nmax; ++c) {
+#if MKB_V_PREFETCH
+                    // software pipeline: the next candidate's index -> record loads are issued before this one's math
+                    const unsigned jn = my_q[c + 1];
+                    const float4 en = lds_f4(ent_sa + jn * 16);
+                    const unsigned cmn = lds_u32(mask_sa + jn * 4);
+#else
+                    const unsigned jj = my_q[c];
+                    const float4 e = lds_f4(ent_sa + jj * 16);
+                    const unsigned cm = lds_u32(mask_sa + jj * 4);
+#endif
+                    const float dy = e.y - fvy, dz = e.z - fvz;
+                    const float s2 = fmaf(dz, dz, dy * dy);
+                    const float dx0 = e.x + 0.5f, dx1 = e.x - 0.5f;
+                    const float d20 = fmaf(dx0, dx0, s2), d21 = fmaf(dx1, dx1, s2);
+                    const float qf0 = e.w * rcp_approx(d20), qf1 = e.w * rcp_approx(d21);  // +inf at d2 == 0 -> value 1
+                    float qv0 = qf0 * __saturatef(fmaf(-GATE_SCALE, d20, gate_k));  // exact 0/1 gate on the FMA pipe
+                    float qv1 = qf1 * __saturatef(fmaf(-GATE_SCALE, d21, gate_k));
+                    // within 4e-6 of the gate: decide like the reference (float64, its operation order)
+                    const bool n0 = __float_as_uint(d20 - cut_lo) < band_bits, n1 = __float_as_uint(d21 - cut_lo) < band_bits;
+                    if (n0 | n1) {
+                        if (n0 && exact_gate(gg, p.coords, psrc[jj], ix0, iy, iz)) qv0 = qf0;
+                        if (n1 && exact_gate(gg, p.coords, psrc[jj], ix0 + 1, iy, iz)) qv1 = qf1;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 8; ++h)
+                        if (cm & (1u << h)) { acc0[h] = fmaxf(acc0[h], qv0); acc1[h] = fmaxf(acc1[h], qv1); }
+#if MKB_V_PREFETCH
+                    jj = jn; e = en; cm = cmn;
+#endif
+                }
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) cq[u] = 0;
+            }
+            np = 0;
+            __syncwarp();
+        }
+    }
+
+    // ---- epilogue: one transcendental per non-zero voxel-channel (a channel that is zero across the warp -- metals,
+    // charged groups -- skips it), 32-byte streaming stores (8 lanes = one 256-byte row)
+    float val0[8], val1[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        val0[h] = val1[h] = 0.0f;
+        if (touched && __any_sync(0xffffffffu, (acc0[h] != 0.0f) | (acc1[h] != 0.0f))) {
+            val0[h] = occ_value(acc0[h]);
+            val1[h] = occ_value(acc1[h]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        if (v == 0 ? inside0 : inside1) {
+            float val[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) val[h] = v == 0 ? val0[h] : val1[h];
+            float *const oo = p.out + out_offset * C + (((long long)(ix0 + v) * ny + iy) * nz + iz) * vstride;
+            if (p.flags & MKB_OCC_ACCUMULATE) {
+#pragma unroll
+                for (int h = 0; h < 8; ++h)
+                    if (h < C) { const float old = oo[h * cs]; val[h] = (val[h] > old) ? val[h] : old; }
+            }
+            if (p.vec_ok) {
+                __stcs(reinterpret_cast<float4 *>(oo), make_float4(val[0], val[1], val[2], val[3]));
+                __stcs(reinterpret_cast<float4 *>(oo) + 1, make_float4(val[4], val[5], val[6], val[7]));
+            } else if (p.cmajor) {
+#pragma unroll
+                for (int h = 0; h < 8; ++h)
+                    if (h < C) __stcs(oo + h * cs, val[h]);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 8; ++h)
+                    if (h < C) oo[h] = val[h];
+            }
+        }
+    }
+}
 #undef WG
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1293,10 +1634,13 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
     if (variant == 0) {
         // per-block halo counts (thread per block), then the warp-per-block kernel:
         // grid = (z-blocks / 4, y-blocks, grid << sh | x-block)
+        // block = 2x4xBZ voxels per warp: BZ = 8 with two voxels per lane (default), 4 with MKB_OCC_WARP32=1 (A/B)
+        const bool v64 = getenv("MKB_OCC_WARP32") == nullptr;
+        const int BZ = v64 ? V_BZ : 4;
         std::vector<long long> bbase((size_t)B + 1, 0);
         long long maxblk = 0;
         for (int b = 0; b < B; ++b) {
-            const long long nbk = (long long)((gd[b].dims[0] + 1) / 2) * ((gd[b].dims[1] + 3) / 4) * ((gd[b].dims[2] + 3) / 4);
+            const long long nbk = (long long)((gd[b].dims[0] + 1) / 2) * ((gd[b].dims[1] + 3) / 4) * ((gd[b].dims[2] + BZ - 1) / BZ);
             bbase[b + 1] = bbase[b] + nbk;
             maxblk = std::max(maxblk, nbk);
         }
@@ -1307,7 +1651,8 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
         MKB_CUDA(h, cudaMemcpyAsync(d_bbase, bbase.data(), sizeof(long long) * ((size_t)B + 1), cudaMemcpyHostToDevice, st));
         for (int c0 = 0; c0 < B; c0 += 65535) {
             const int cn = std::min(65535, B - c0);
-            occ_block_total_kernel<<<dim3((unsigned)cdiv(maxblk, 256), (unsigned)cn), 256, 0, st>>>(d_grids + c0, cell_start, d_bbase + c0, d_btotal);
+            if (v64) occ_block_total_v_kernel<<<dim3((unsigned)cdiv(maxblk, 256), (unsigned)cn), 256, 0, st>>>(d_grids + c0, cell_start, d_bbase + c0, d_btotal);
+            else occ_block_total_kernel<<<dim3((unsigned)cdiv(maxblk, 256), (unsigned)cn), 256, 0, st>>>(d_grids + c0, cell_start, d_bbase + c0, d_btotal);
             MKB_LAUNCHED(h);
         }
         int b0 = 0;
@@ -1320,7 +1665,7 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
                 if (((long long)(nb + 1) << s2) > 65535) break;
                 mx = ax; sh = s2; ++nb;
                 my = std::max(my, (gd[b].dims[1] + 3) / 4);
-                mz = std::max(mz, (gd[b].dims[2] + 3) / 4);
+                mz = std::max(mz, (gd[b].dims[2] + BZ - 1) / BZ);
             }
             if (nb == 0 || my > 65535) return fail(h, MKB_ERR_BAD_ARG, "grid %d too large for one launch", b0);
             FillParams fq = fp;
@@ -1343,7 +1688,10 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             fq.u_block_base = bbase[b0];
             fq.u_block_stride = bbase[b0 + 1] - bbase[b0];
             const dim3 wgrid((unsigned)cdiv(mz, W_WARPS), (unsigned)my, (unsigned)(nb << sh));
-            if (uni) occ_fill8w_kernel<true><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
+            if (v64) {
+                if (uni) occ_fill8v_kernel<true><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
+                else occ_fill8v_kernel<false><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
+            } else if (uni) occ_fill8w_kernel<true><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
             else occ_fill8w_kernel<false><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
             MKB_LAUNCHED(h);
             b0 += nb;

@@ -191,10 +191,12 @@ def test_full_size_c3_properties(vd, oracle):
         _assert_occ_close(out[offs[b]:offs[b + 1]].cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("envs", [("MKB_OCC_TILE",), ("MKB_OCC_TILE", "MKB_OCC_BULK_STORE"), ("MKB_OCC_GENERIC",), ("MKB_OCC_WARP",)])
+@pytest.mark.parametrize("envs", [("MKB_OCC_TILE",), ("MKB_OCC_TILE", "MKB_OCC_BULK_STORE"), ("MKB_OCC_GENERIC",), ("MKB_OCC_WARP",),
+                                  ("MKB_OCC_WARP32",)])
 def test_alternative_kernel_paths_agree(vd, monkeypatch, envs):
-    """The tile kernel (quarter lists), its opt-in TMA bulk-store epilogue and the generic tile kernel produce the same
-    bits as the default warp-per-block kernel (ragged grid: dims not multiples of the block / tile sizes)."""
+    """The tile kernel (quarter lists), its opt-in TMA bulk-store epilogue, the generic tile kernel and the one-voxel-per-lane
+    warp kernel (2x4x4 blocks) agree with the default two-voxels-per-lane warp kernel (ragged grid: dims not multiples of
+    the block / tile sizes)."""
     from moleculekit_b200 import workloads
 
     w = workloads.protein_pockets(B=2, n_atoms=700, box=37.0, radius=12.0, seed=21)
