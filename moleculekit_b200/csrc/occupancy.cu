@@ -22,6 +22,7 @@
 #include <cfloat>
 #include <cstdlib>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -198,6 +199,8 @@ struct FillParams {
     // warp kernel, uniform launches: descriptor of the chunk's first grid + per-grid strides
     GridDev u;
     long long u_out_stride, u_cell_stride, u_block_base, u_block_stride;
+    float u_gate_k;        // 2^100 * cut2v_lo and the width of the re-check band, precomputed for uniform launches so the
+    unsigned u_band_bits;  // inner loop takes them straight from the constant bank
 };
 
 // float64 re-evaluation of the gate with the reference's exact operations (pyx:49-53; centres as built by
@@ -218,6 +221,11 @@ constexpr int MAX_ROWS = FILL_THREADS;  // cell rows feeding one tile: (R+1)^2, 
 __device__ __forceinline__ float4 lds_f4(unsigned addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ unsigned lds_u32(unsigned addr) {
@@ -1079,9 +1087,14 @@ constexpr int V_BZ = 8;       // block extent along z
 constexpr int V_PCAP = 160;   // block candidates per round
 constexpr int V_QCAP = 96;    // sub-block candidates per round
 constexpr int V_QSTRIDE = V_QCAP + 2;  // + one sentinel slot for the software-pipelined loop
-#ifndef MKB_V_PREFETCH
-#define MKB_V_PREFETCH 0  // software-pipelined candidate loads: no gain (2.32 vs 2.30 ms), costs registers
+#ifndef MKB_V_UNROLL2
+#define MKB_V_UNROLL2 0  // two candidates per trip: 2.19 vs 2.03 ms (spills at 72 registers)
 #endif
+#ifndef MKB_V_WARPS
+#define MKB_V_WARPS 1    // warps (= blocks) per CTA. A CTA holds its registers until its slowest warp retires: 4 -> 2.03 ms, 2 -> 1.87, 1 -> 1.85
+#endif
+constexpr int V_WARPS = MKB_V_WARPS;
+// (a software-pipelined variant that loaded the next candidate ahead of the math gave 2.32 vs 2.30 ms and cost registers)
 #ifndef MKB_V_MIN_CTAS
 #define MKB_V_MIN_CTAS 7  // 72 registers: measured 2.09 ms; 6 CTAs (80 regs) 2.30 ms, 8 CTAs (64 regs, spills) 2.40 ms
 #endif
@@ -1107,17 +1120,17 @@ __global__ void occ_block_total_v_kernel(const GridDev *__restrict__ grids, cons
 }
 
 template <bool UNIFORM>
-__global__ void __launch_bounds__(W_WARPS * 32, MKB_V_MIN_CTAS)
+__global__ void __launch_bounds__(V_WARPS * 32, MKB_V_MIN_CTAS * 4 / V_WARPS)
 occ_fill8v_kernel(const FillParams p, const long long *__restrict__ block_base, const unsigned *__restrict__ block_total) {
-    __shared__ float4 s_pent[W_WARPS][V_PCAP + 1];    // block candidates: x, y, z in the block frame, sigma^2 (+ sentinel)
-    __shared__ unsigned s_pmask[W_WARPS][V_PCAP + 1];  // channel mask; 0 = several sigmas
-    __shared__ unsigned s_psrc[W_WARPS][V_PCAP];
-    __shared__ unsigned s_rpos[W_WARPS][W_ROWS];
-    __shared__ unsigned s_rbase[W_WARPS][W_ROWS + 1];
-    __shared__ unsigned short s_qidx[W_WARPS][8][V_QSTRIDE];
+    __shared__ float4 s_pent[V_WARPS][V_PCAP + 1];    // block candidates: x, y, z in the block frame, sigma^2 (+ sentinel)
+    __shared__ unsigned s_pmask[V_WARPS][V_PCAP + 1];  // channel mask; 0 = several sigmas
+    __shared__ unsigned s_psrc[V_WARPS][V_PCAP];
+    __shared__ unsigned s_rpos[V_WARPS][W_ROWS];
+    __shared__ unsigned s_rbase[V_WARPS][W_ROWS + 1];
+    __shared__ unsigned short s_qidx[V_WARPS][8][V_QSTRIDE];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int bzi = blockIdx.x * W_WARPS + warp, byi = blockIdx.y, bxi = blockIdx.z & ((1 << p.txp_shift) - 1);
+    const int bzi = blockIdx.x * V_WARPS + warp, byi = blockIdx.y, bxi = blockIdx.z & ((1 << p.txp_shift) - 1);
     const int gi = blockIdx.z >> p.txp_shift;
     const GridDev *gg = p.grids + gi;
     const int nx = WG(dims[0]), ny = WG(dims[1]), nz = WG(dims[2]);
@@ -1213,17 +1226,18 @@ occ_fill8v_kernel(const FillParams p, const long long *__restrict__ block_base, 
         }
         __syncwarp();
         const float cut_lo = WG(cut2v_lo), cut_hi = WG(cut2v_hi);
-        const float gate_k = GATE_SCALE * cut_lo;
-        const unsigned band_bits = __float_as_uint(cut_hi - cut_lo);
+        const float gate_k = UNIFORM ? p.u_gate_k : GATE_SCALE * cut_lo;
+        const unsigned band_bits = UNIFORM ? p.u_band_bits : __float_as_uint(cut_hi - cut_lo);
         const float fvy = (float)ly - 1.5f, fvz = (float)lz - 3.5f;  // block frame: origin at the block centre
         const int sx = bxi * 2 + cutv, sy = byi * 4 + cutv, sz = bzi * V_BZ + cutv;
         float4 *const pent = s_pent[warp];
         unsigned *const pmask = s_pmask[warp], *const psrc = s_psrc[warp];
         unsigned short *const wq = s_qidx[warp][0];
         unsigned short *const my_q = s_qidx[warp][s];
-        unsigned ent_sa, mask_sa;
+        unsigned ent_sa, mask_sa, q_sa;
         asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(ent_sa) : "l"(pent));
         asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(mask_sa) : "l"(pmask));
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(q_sa) : "l"(my_q));
 
         int np = 0;
         int row = 0;  // row of this lane's current atom: k only grows, so the row pointer only advances
@@ -1322,31 +1336,21 @@ occ_fill8v_kernel(const FillParams p, const long long *__restrict__ block_base, 
                 for (int u = 1; u < 8; ++u) mine = (s == u) ? cq[u] : mine;
                 for (int c = mine + t4; c <= nmax; c += 4) my_q[c] = (unsigned short)V_PCAP;  // incl. slot nmax (prefetch)
                 __syncwarp();
-#if MKB_V_PREFETCH
-                unsigned jj = my_q[0];
-                float4 e = lds_f4(ent_sa + jj * 16);
-                unsigned cm = lds_u32(mask_sa + jj * 4);
-#endif
-                for (int c = 0; c < nmax; ++c) {
-#if MKB_V_PREFETCH
-                    // software pipeline: the next candidate's index -> record loads are issued before this one's math
-                    const unsigned jn = my_q[c + 1];
-                    const float4 en = lds_f4(ent_sa + jn * 16);
-                    const unsigned cmn = lds_u32(mask_sa + jn * 4);
-#else
-                    const unsigned jj = my_q[c];
+                auto candidate = [&](unsigned q_addr) {
+                    const unsigned jj = lds_u16(q_addr);
                     const float4 e = lds_f4(ent_sa + jj * 16);
                     const unsigned cm = lds_u32(mask_sa + jj * 4);
-#endif
                     const float dy = e.y - fvy, dz = e.z - fvz;
                     const float s2 = fmaf(dz, dz, dy * dy);
                     const float dx0 = e.x + 0.5f, dx1 = e.x - 0.5f;
                     const float d20 = fmaf(dx0, dx0, s2), d21 = fmaf(dx1, dx1, s2);
                     const float qf0 = e.w * rcp_approx(d20), qf1 = e.w * rcp_approx(d21);  // +inf at d2 == 0 -> value 1
-                    float qv0 = qf0 * __saturatef(fmaf(-GATE_SCALE, d20, gate_k));  // exact 0/1 gate on the FMA pipe
-                    float qv1 = qf1 * __saturatef(fmaf(-GATE_SCALE, d21, gate_k));
+                    // exact 0/1 gate on the FMA pipe: sat(2^100 (cut_lo - d2)) -- the difference is shared with the band test
+                    const float t0 = d20 - cut_lo, t1 = d21 - cut_lo;
+                    float qv0 = qf0 * __saturatef(t0 * -GATE_SCALE);
+                    float qv1 = qf1 * __saturatef(t1 * -GATE_SCALE);
                     // within 4e-6 of the gate: decide like the reference (float64, its operation order)
-                    const bool n0 = __float_as_uint(d20 - cut_lo) < band_bits, n1 = __float_as_uint(d21 - cut_lo) < band_bits;
+                    const bool n0 = __float_as_uint(t0) < band_bits, n1 = __float_as_uint(t1) < band_bits;
                     if (n0 | n1) {
                         if (n0 && exact_gate(gg, p.coords, psrc[jj], ix0, iy, iz)) qv0 = qf0;
                         if (n1 && exact_gate(gg, p.coords, psrc[jj], ix0 + 1, iy, iz)) qv1 = qf1;
@@ -1354,10 +1358,16 @@ occ_fill8v_kernel(const FillParams p, const long long *__restrict__ block_base, 
 #pragma unroll
                     for (int h = 0; h < 8; ++h)
                         if (cm & (1u << h)) { acc0[h] = fmaxf(acc0[h], qv0); acc1[h] = fmaxf(acc1[h], qv1); }
-#if MKB_V_PREFETCH
-                    jj = jn; e = en; cm = cmn;
-#endif
+                };
+#if MKB_V_UNROLL2
+                // two candidates per trip; slot nmax holds a sentinel, so an odd list simply evaluates it once
+                for (unsigned qa = q_sa, qe = q_sa + 2 * nmax; qa < qe; qa += 4) {
+                    candidate(qa);
+                    candidate(qa + 2);
                 }
+#else
+                for (unsigned qa = q_sa, qe = q_sa + 2 * nmax; qa < qe; qa += 2) candidate(qa);
+#endif
                 __syncwarp();
 #pragma unroll
                 for (int u = 0; u < 8; ++u) cq[u] = 0;
@@ -1531,9 +1541,11 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
     for (int b = 0; b < B && variant != 2; ++b) {
         if (!(grids[b].voxelsize > 0.0)) break;  // reported below
         const int cv = (int)std::ceil(CUTOFF_A / grids[b].voxelsize);
-        // fine grids (cutoff > 7 voxels): a 32-voxel block is small against its own halo, the 512-voxel tile kernel
-        // amortises the gather better (measured: 0.5 A grids 0.66 ms vs 0.86 ms; 1 A grids 2.54 ms vs 2.38 ms)
-        if (variant == 0 && ((cv > 7 && !force_warp) || ((1 + 2 * cv) / 4 + 1) * ((3 + 2 * cv) / 4 + 1) > W_ROWS)) variant = 1;
+        // very fine grids: the halo of a block spans more cell rows than a warp keeps (cutoff > 11 voxels) -> tile kernel.
+        // (Up to v5 the tile kernel also took every cutoff > 7 voxels: 0.66 ms vs 0.86 ms on 0.5 A grids; the 64-voxel
+        // block kernel now does those in 0.63 ms.  MKB_OCC_WARP32=1 restores the old rule together with the old kernel.)
+        const bool old_rule = getenv("MKB_OCC_WARP32") != nullptr && cv > 7 && !force_warp;
+        if (variant == 0 && (old_rule || ((1 + 2 * cv) / 4 + 1) * ((3 + 2 * cv) / 4 + 1) > W_ROWS)) variant = 1;
         if (variant == 1 && ((TILE - 1 + 2 * cv) / TILE + 1) * ((TILE - 1 + 2 * cv) / TILE + 1) > 128) variant = 2;
     }
     const int cellsz = (variant == 0) ? W_CELL : TILE;
@@ -1687,10 +1699,16 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             fq.u_cell_stride = ncell0;
             fq.u_block_base = bbase[b0];
             fq.u_block_stride = bbase[b0 + 1] - bbase[b0];
+            fq.u_gate_k = GATE_SCALE * g0.cut2v_lo;
+            {
+                const float band = g0.cut2v_hi - g0.cut2v_lo;
+                memcpy(&fq.u_band_bits, &band, sizeof(float));
+            }
             const dim3 wgrid((unsigned)cdiv(mz, W_WARPS), (unsigned)my, (unsigned)(nb << sh));
             if (v64) {
-                if (uni) occ_fill8v_kernel<true><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
-                else occ_fill8v_kernel<false><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
+                const dim3 vgrid((unsigned)cdiv(mz, V_WARPS), (unsigned)my, (unsigned)(nb << sh));
+                if (uni) occ_fill8v_kernel<true><<<vgrid, V_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
+                else occ_fill8v_kernel<false><<<vgrid, V_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
             } else if (uni) occ_fill8w_kernel<true><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
             else occ_fill8w_kernel<false><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
             MKB_LAUNCHED(h);
