@@ -1094,6 +1094,10 @@ constexpr int V_QSTRIDE = V_QCAP + 2;  // + one sentinel slot for the software-p
 #define MKB_V_WARPS 1    // warps (= blocks) per CTA. A CTA holds its registers until its slowest warp retires: 4 -> 2.03 ms, 2 -> 1.87, 1 -> 1.85
 #endif
 constexpr int V_WARPS = MKB_V_WARPS;
+#ifndef MKB_V_ZPER
+#define MKB_V_ZPER 1     // consecutive z blocks walked by one warp: 1 -> 1.86 ms, 2 -> 2.08, 4 -> 1.93, 8 -> 1.99 (longer-lived CTAs balance worse)
+#endif
+constexpr int V_ZPER = MKB_V_ZPER;
 // (a software-pipelined variant that loaded the next candidate ahead of the math gave 2.32 vs 2.30 ms and cost registers)
 #ifndef MKB_V_MIN_CTAS
 #define MKB_V_MIN_CTAS 7  // 72 registers: measured 2.09 ms; 6 CTAs (80 regs) 2.30 ms, 8 CTAs (64 regs, spills) 2.40 ms
@@ -1130,15 +1134,20 @@ occ_fill8v_kernel(const FillParams p, const long long *__restrict__ block_base, 
     __shared__ unsigned short s_qidx[V_WARPS][8][V_QSTRIDE];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int bzi = blockIdx.x * V_WARPS + warp, byi = blockIdx.y, bxi = blockIdx.z & ((1 << p.txp_shift) - 1);
+    const int byi = blockIdx.y, bxi = blockIdx.z & ((1 << p.txp_shift) - 1);
     const int gi = blockIdx.z >> p.txp_shift;
     const GridDev *gg = p.grids + gi;
     const int nx = WG(dims[0]), ny = WG(dims[1]), nz = WG(dims[2]);
     const long long out_offset = UNIFORM ? p.u.out_offset + (long long)gi * p.u_out_stride : __ldg(&gg->out_offset);
-    if (bxi * 2 >= nx || byi * 4 >= ny || bzi * V_BZ >= nz) return;  // padding of the launch grid / ragged batch
+    if (bxi * 2 >= nx || byi * 4 >= ny) return;  // padding of the launch grid / ragged batch
     const int C = p.C;
     const long long cs = p.cmajor ? (long long)nx * ny * nz : 1;  // channel stride; voxel stride is C or 1
     const int vstride = p.cmajor ? 1 : C;
+    // a warp walks V_ZPER consecutive blocks of its (x, y) column: fewer, longer-lived CTAs (the 70 % empty blocks no
+    // longer cost a CTA launch each) while the work per CTA stays small against the number of CTAs
+    for (int zi = 0; zi < V_ZPER; ++zi) {
+    const int bzi = (blockIdx.x * V_ZPER + zi) * V_WARPS + warp;
+    if (bzi * V_BZ >= nz) break;
 
     // ---- empty block (no atom within reach): stream 64 x 32 B of zeros and retire
     {
@@ -1163,7 +1172,7 @@ occ_fill8v_kernel(const FillParams p, const long long *__restrict__ block_base, 
                     }
                 }
             }
-            return;
+            continue;
         }
     }
 
@@ -1413,6 +1422,8 @@ occ_fill8v_kernel(const FillParams p, const long long *__restrict__ block_base, 
                     if (h < C) oo[h] = val[h];
             }
         }
+    }
+    __syncwarp();  // the lists are reused by the next block
     }
 }
 #undef WG
@@ -1706,7 +1717,7 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             }
             const dim3 wgrid((unsigned)cdiv(mz, W_WARPS), (unsigned)my, (unsigned)(nb << sh));
             if (v64) {
-                const dim3 vgrid((unsigned)cdiv(mz, V_WARPS), (unsigned)my, (unsigned)(nb << sh));
+                const dim3 vgrid((unsigned)cdiv(mz, V_WARPS * V_ZPER), (unsigned)my, (unsigned)(nb << sh));
                 if (uni) occ_fill8v_kernel<true><<<vgrid, V_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
                 else occ_fill8v_kernel<false><<<vgrid, V_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
             } else if (uni) occ_fill8w_kernel<true><<<wgrid, W_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
