@@ -60,6 +60,11 @@ def g_bonds():
 
 
 @pytest.fixture(scope="session")
+def g_interactions():
+    return _npz("interactions.npz")
+
+
+@pytest.fixture(scope="session")
 def g_within():
     return _npz("within.npz")
 

@@ -32,6 +32,11 @@ sys.path.insert(0, ROOT)
 REFT = "/root/reference/tests"
 
 
+def strarr(a):
+    """object string array -> fixed-width unicode (npz without pickle)"""
+    return np.array([str(x) for x in a])
+
+
 def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -164,9 +169,57 @@ def within_fixture():
     print("within cases:", len(cases), "stored-golden backed:", sum(c[4] == "stored" for c in cases))
 
 
+def interactions_fixture():
+    """interactions.npz: the reference's contact-type detectors on its own test structures (tests/test_interactions.py:
+    117-161 salt bridges on 5ME6_prepared with its inline expected pairs; :329-351 metal coordination on 5vl5 / 3ptb) plus
+    hydrophobic contacts and a two-frame periodic salt-bridge case from the live reference."""
+    from moleculekit.interactions.interactions import (get_protein_charged, hydrophobic_calculate,
+                                                       metal_coordination_calculate, saltbridge_calculate)
+    from moleculekit.molecule import Molecule
+
+    w = {}
+    mol = Molecule(os.path.join(REFT, "test_interactions", "5ME6_prepared.pdb"))
+    pos, neg = get_protein_charged(mol)
+    br = saltbridge_calculate(mol, pos, neg, "protein", "protein")
+    expected = np.array([[694, 725], [2146, 2183], [2158, 2346]])  # tests/test_interactions.py:158
+    assert np.array_equal(expected, br[0])
+    for k, v in (("coords", mol.coords), ("box", mol.box), ("resname", strarr(mol.resname)), ("name", strarr(mol.name)),
+                 ("element", strarr(mol.element)), ("protein", mol.atomselect("protein")), ("pos", pos), ("neg", neg),
+                 ("bridges", br[0])):
+        w["me6_" + k] = v
+    s1 = mol.atomselect("protein and resid 100 to 125")
+    hy = hydrophobic_calculate(mol, s1, "protein", 4.0)
+    w["me6_hyd_sel1"] = s1
+    w["me6_hyd"] = hy[0]
+    # two frames in a periodic box: the second frame is shifted by one box length along x for half of the atoms
+    m2 = mol.copy()
+    m2.coords = np.tile(m2.coords, (1, 1, 2)).copy()
+    L = np.float32(150.0)
+    m2.box = np.full((3, 2), L, dtype=np.float32)
+    m2.coords[::2, 0, 1] += L
+    half = np.zeros(m2.numAtoms, dtype=bool)
+    half[::2] = True
+    br2 = saltbridge_calculate(m2, pos, neg, half & m2.atomselect("protein"), ~half & m2.atomselect("protein"))
+    assert len(br2) == 2 and len(br2[0]) > 0 and np.array_equal(br2[0], br2[1])  # images are found across the box
+    w["me6_coords2"], w["me6_box2"], w["me6_half"], w["me6_bridges2"] = m2.coords, m2.box, half, br2[1]
+    for pid, a, b, ref in (("5vl5", "all", "resname S31 and not element Cu",
+                            [[933, 922], [933, 932], [933, 934], [933, 935], [933, 937], [933, 944]]),
+                           ("3ptb", "not protein", "protein", [[1629, 383], [1629, 396], [1629, 420], [1629, 460]])):
+        m = Molecule(pid)
+        res = metal_coordination_calculate(m, a, b)
+        assert np.array_equal(res[0], np.array(ref, dtype=np.uint32))  # tests/test_interactions.py:338-351
+        w[pid + "_coords"], w[pid + "_box"], w[pid + "_element"] = m.coords, m.box, strarr(m.element)
+        w[pid + "_sel1"], w[pid + "_sel2"], w[pid + "_metal"] = m.atomselect(a), m.atomselect(b), res[0]
+    np.savez_compressed(os.path.join(HERE, "interactions.npz"), **w)
+    print("interactions: hydrophobic pairs", len(hy[0]))
+
+
 def main():
     from oracle import build_ref
 
+    if "--only-interactions" in sys.argv:
+        interactions_fixture()
+        return
     if "--only-within" in sys.argv:
         within_fixture()
         return
@@ -436,6 +489,7 @@ def main():
     wrapping_fixture()
     rotation_fixture()
     within_fixture()
+    interactions_fixture()
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
