@@ -43,6 +43,7 @@ __device__ __forceinline__ float sq3(float dx, float dy, float dz) {
 
 struct BoxF {
     float bx, by, bz, rx, ry, rz;
+    float hx, hy, hz;  // b / 2
 };
 
 __device__ __forceinline__ BoxF load_box(const float *box, long long stride, long long f) {
@@ -53,6 +54,7 @@ __device__ __forceinline__ BoxF load_box(const float *box, long long stride, lon
     b.rx = __frcp_rn(b.bx);
     b.ry = __frcp_rn(b.by);
     b.rz = __frcp_rn(b.bz);
+    b.hx = __fmul_rn(b.bx, 0.5f); b.hy = __fmul_rn(b.by, 0.5f); b.hz = __fmul_rn(b.bz, 0.5f);
     return b;
 }
 
@@ -123,33 +125,32 @@ static int launch_gather(mkb_ctx *h, cudaStream_t st, const mkb_traj *t, const I
 constexpr int K3_ROWS = 16;
 constexpr int K3_COLS = 256;
 
-// Branch-light form of wrap_axis for the dense kernel: the three axes take the fast path unconditionally and only OR
-// their "risky" flags; one rare branch per PAIR redoes the exact division for the flagged axes.
-struct Wrapped {
-    float d;      // d - b * n with the fast n
-    bool risky;   // the fast n may differ from roundf(fl(d / b))
-};
-__device__ __forceinline__ Wrapped wrap_fast(float d, float b, float rb) {
+// Minimum-image step of the dense kernels: n = rint(d * fl(1/b)) by the magic-number trick, w = d - fl(b n) exactly as
+// the reference rounds it (pyx:41-49), and ONE test that n is the reference's roundf(fl(d / b)):  |w| < b/2 - 1e-6 |d|.
+// If the two integers differed, d/b would lie within 2e-7 |d/b| of a half-integer, hence |w| >= b/2 - 3e-7 |d| and the
+// test fails; exact ties (|w| == b/2: half-away vs half-even), |d/b| >= 2^22 (magic rounding invalid), NaN and boxes
+// that are zero / negative / non-finite fail it as well.  One rare branch per PAIR then redoes the flagged pair with the
+// general wrap_axis (exact division).  7 instructions per axis instead of 9 for the former quotient-distance test.
+__device__ __forceinline__ float wrap_fast(float d, float b, float rb, float hb, bool &risky) {
     const float q = __fmul_rn(d, rb);
     const float n = __fsub_rn(__fadd_rn(q, 12582912.0f), 12582912.0f);
-    const float fr = fabsf(__fsub_rn(q, n));
-    const float lim = fmaf(-6e-7f, fabsf(q), 0.5f);
-    Wrapped w;
-    w.d = __fsub_rn(d, __fmul_rn(b, n));
-    w.risky = !(fr < lim);
+    const float w = __fsub_rn(d, __fmul_rn(b, n));
+    risky = risky | !(fabsf(w) < fmaf(-1e-6f, fabsf(d), hb));
     return w;
 }
 
 __device__ __forceinline__ float pair_d2_fastwrap(const float4 a, const float4 b, unsigned cb, const BoxF &bx, int pbc) {
     float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
     if (pbc && (__float_as_uint(a.w) != cb)) {
-        const Wrapped wx = wrap_fast(dx, bx.bx, bx.rx), wy = wrap_fast(dy, bx.by, bx.ry), wz = wrap_fast(dz, bx.bz, bx.rz);
-        if (wx.risky | wy.risky | wz.risky) {  // rare: a quotient within 6e-7|q| of a half-integer, or huge
+        bool risky = false;
+        const float wx = wrap_fast(dx, bx.bx, bx.rx, bx.hx, risky), wy = wrap_fast(dy, bx.by, bx.ry, bx.hy, risky),
+                    wz = wrap_fast(dz, bx.bz, bx.rz, bx.hz, risky);
+        if (risky) {
             dx = wrap_axis(dx, bx.bx, bx.rx);
             dy = wrap_axis(dy, bx.by, bx.ry);
             dz = wrap_axis(dz, bx.bz, bx.rz);
         } else {
-            dx = wx.d; dy = wy.d; dz = wz.d;
+            dx = wx; dy = wy; dz = wz;
         }
     }
     return sq3(dx, dy, dz);

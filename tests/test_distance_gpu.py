@@ -129,6 +129,47 @@ def test_random_vs_oracle_large_wraps_and_half_ties(du, oracle):
         assert du.contacts_trajectory(c, bx, a, b, ch, selfd, True, 9.5) == oracle.contacts_trajectory(c, bx, a, b, ch, selfd, True, 9.5)
 
 
+def test_minimum_image_boundaries(du, oracle):
+    """The dense kernels take n = rint(d * (1/b)) and verify it with |d - b n| < b/2 - 1e-6 |d|: differences placed
+    within a few ulps of b/2, 1.4999 b, 1.5 b, 2.5 b (both signs), boxes that are powers of two / arbitrary / tiny / huge /
+    zero / negative / NaN / Inf, and NaN coordinates must all reproduce the reference bits."""
+    boxes = np.array([10.0, 7.3, 33.333, 8.0, 1e-3, 3e4, 0.0, -5.0, np.nan, np.inf, 1e-35, 1e32], np.float32)
+    F = len(boxes)
+    mults = [0.0, 0.25, 0.5, 0.75, 1.0, 1.4998, 1.4999, 1.49995, 1.5, 2.0, 2.5, 3.5, 100.5]
+    cols = []
+    for f in range(F):
+        b = boxes[f] if np.isfinite(boxes[f]) and boxes[f] != 0 else np.float32(6.0)
+        vals = []
+        for m in mults:
+            v = np.float32(np.float32(m) * np.abs(b))
+            for k in range(-3, 4):
+                w = v
+                for _ in range(abs(k)):
+                    w = np.nextafter(w, np.float32(np.inf if k > 0 else -np.inf), dtype=np.float32)
+                vals += [w, -w]
+        cols.append(np.array(vals, np.float32))
+    n2 = len(cols[0])
+    c = np.zeros((1 + n2, 3, F), np.float32)
+    for f in range(F):
+        c[1:, 0, f] = cols[f]
+        c[1:, 1, f] = cols[f][::-1]
+        c[1:, 2, f] = np.roll(cols[f], 5)
+    c[7, 2, 0] = np.nan
+    bx = np.repeat(boxes[None, :], 3, axis=0).copy()
+    bx[1] = np.roll(boxes, 1)
+    s1 = np.array([0], np.uint32); s2 = np.arange(1, 1 + n2, dtype=np.uint32)
+    ch = np.zeros(1 + n2, np.uint32); ch[1:] = 1
+    want = np.zeros((F, n2), np.float32)
+    with np.errstate(all="ignore"):
+        oracle.dist_trajectory(c, bx, s1, s2, ch, False, True, want)
+    got = np.zeros((F, n2), np.float32); du.dist_trajectory(c, bx, s1, s2, ch, False, True, got)
+    assert np.isnan(want).any() and np.isfinite(want).any()
+    bad = np.where(_bits(got) != _bits(want))
+    assert bad[0].size == 0, (bad[0][:5], bad[1][:5], got[bad][:5], want[bad][:5])
+    for thr in (3.0, 5.5):
+        assert du.contacts_trajectory(c, bx, s1, s2, ch, False, True, thr) == oracle.contacts_trajectory(c, bx, s1, s2, ch, False, True, thr)
+
+
 def test_contact_threshold_ties(du, oracle):
     """metric="contacts" is decided on d2 (no sqrt): must equal sqrtf(d2) <= threshold of the reference incl. exact
     ties (3-4-5 triangles) and distances one ulp either side of the threshold."""
