@@ -163,17 +163,18 @@ __device__ __forceinline__ void emit_dist(void *out, long long idx, float d2, fl
 }
 
 // Each thread owns TWO sel2 columns (j and j + K3_COLS) so one broadcast load of the sel1 atom, the loop control and the
-// index arithmetic are shared by two pairs.
-template <int MODE>
+// index arithmetic are shared by two pairs.  SELF / PBC are compile-time: the rectangular non-periodic-free inner loop
+// carries no per-row diagonal tests.
+template <int MODE, bool SELF>
 __global__ void __launch_bounds__(K3_COLS) dist_kernel(const float4 *__restrict__ G1, const float4 *__restrict__ G2,
                                                         long long n1, long long n2, const float *__restrict__ box,
-                                                        long long box_stride, int selfdist, int pbc, float truncate,
+                                                        long long box_stride, int pbc, float truncate,
                                                         float threshold, long long P, void *__restrict__ out,
                                                         long long frame0) {
     const long long f = frame0 + blockIdx.z;
     const long long j0 = (long long)blockIdx.x * (2 * K3_COLS) + threadIdx.x, j1 = j0 + K3_COLS;
     const long long i0 = (long long)blockIdx.y * K3_ROWS;
-    if (selfdist && (long long)(blockIdx.x + 1) * (2 * K3_COLS) <= i0 + 1) return;  // tile entirely below the diagonal
+    if (SELF && (long long)(blockIdx.x + 1) * (2 * K3_COLS) <= i0 + 1) return;  // tile entirely below the diagonal
     if (j0 >= n2) return;
     const bool has1 = j1 < n2;
     const float4 b0 = G2[f * n2 + j0];
@@ -183,16 +184,31 @@ __global__ void __launch_bounds__(K3_COLS) dist_kernel(const float4 *__restrict_
     const int rows = (int)(min(i0 + K3_ROWS, n1) - i0);
     const float4 *__restrict__ arow = G1 + f * n1 + i0;
     // running output index: non-self (i, j) -> i*n2 + j ; self -> i*n2 - i(i+1)/2 + (j - i - 1), step n2 - i - 2
-    long long idx = f * P + (selfdist ? (i0 * n2 - (i0 * (i0 + 1)) / 2 + (j0 - i0 - 1)) : (i0 * n2 + j0));
-    long long step = selfdist ? (n2 - i0 - 2) : n2;
+    long long idx = f * P + (SELF ? (i0 * n2 - (i0 * (i0 + 1)) / 2 + (j0 - i0 - 1)) : (i0 * n2 + j0));
+    if (SELF) {
+        long long step = n2 - i0 - 2;
 #pragma unroll 2
-    for (int r = 0; r < rows; ++r) {
-        const float4 a = __ldg(arow + r);
-        if (!selfdist || j0 > i0 + r) emit_dist<MODE>(out, idx, pair_d2_fastwrap(a, b0, cb0, bx, pbc), truncate, threshold);
-        if (has1 && (!selfdist || j1 > i0 + r))
+        for (int r = 0; r < rows; ++r) {
+            const float4 a = __ldg(arow + r);
+            if (j0 > i0 + r) emit_dist<MODE>(out, idx, pair_d2_fastwrap(a, b0, cb0, bx, pbc), truncate, threshold);
+            if (has1 && j1 > i0 + r)
+                emit_dist<MODE>(out, idx + K3_COLS, pair_d2_fastwrap(a, b1, cb1, bx, pbc), truncate, threshold);
+            idx += step;
+            --step;
+        }
+    } else if (has1) {
+#pragma unroll 2
+        for (int r = 0; r < rows; ++r) {
+            const float4 a = __ldg(arow + r);
+            emit_dist<MODE>(out, idx, pair_d2_fastwrap(a, b0, cb0, bx, pbc), truncate, threshold);
             emit_dist<MODE>(out, idx + K3_COLS, pair_d2_fastwrap(a, b1, cb1, bx, pbc), truncate, threshold);
-        idx += step;
-        if (selfdist) --step;
+            idx += n2;
+        }
+    } else {
+        for (int r = 0; r < rows; ++r) {
+            emit_dist<MODE>(out, idx, pair_d2_fastwrap(__ldg(arow + r), b0, cb0, bx, pbc), truncate, threshold);
+            idx += n2;
+        }
     }
 }
 
@@ -492,15 +508,16 @@ extern "C" int mkb_dist_trajectory(mkb_handle_t h, void *stream, const mkb_traj 
     for (long long f0 = 0; f0 < F; f0 += 65535) {
         const unsigned gz = (unsigned)std::min<long long>(65535, F - f0);
         dim3 grid(gx, gy, gz);
-        if (kmode == MKB_DIST_DISTANCES)
-            dist_kernel<MKB_DIST_DISTANCES><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box,
-                                                                      selfdist, pbc, truncate, kthr, P, out, f0);
-        else if (kmode == MKB_DIST_CONTACTS)
-            dist_kernel<MKB_DIST_CONTACTS><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box,
-                                                                     selfdist, pbc, truncate, kthr, P, out, f0);
-        else
-            dist_kernel<DIST_CONTACTS_D2><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box,
-                                                                    selfdist, pbc, truncate, kthr, P, out, f0);
+#define MKB_K3_LAUNCH(M, S)                                                                                       \
+    dist_kernel<M, S><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box, pbc, truncate, kthr, P, out, f0)
+        if (kmode == MKB_DIST_DISTANCES) {
+            if (selfdist) MKB_K3_LAUNCH(MKB_DIST_DISTANCES, true); else MKB_K3_LAUNCH(MKB_DIST_DISTANCES, false);
+        } else if (kmode == MKB_DIST_CONTACTS) {
+            if (selfdist) MKB_K3_LAUNCH(MKB_DIST_CONTACTS, true); else MKB_K3_LAUNCH(MKB_DIST_CONTACTS, false);
+        } else {
+            if (selfdist) MKB_K3_LAUNCH(DIST_CONTACTS_D2, true); else MKB_K3_LAUNCH(DIST_CONTACTS_D2, false);
+        }
+#undef MKB_K3_LAUNCH
         MKB_LAUNCHED(h);
     }
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));

@@ -199,8 +199,7 @@ struct FillParams {
     // warp kernel, uniform launches: descriptor of the chunk's first grid + per-grid strides
     GridDev u;
     long long u_out_stride, u_cell_stride, u_block_base, u_block_stride;
-    float u_gate_k;        // 2^100 * cut2v_lo and the width of the re-check band, precomputed for uniform launches so the
-    unsigned u_band_bits;  // inner loop takes them straight from the constant bank
+    unsigned u_band_bits;  // width of the gate re-check band, precomputed for uniform launches (constant bank operand)
 };
 
 // float64 re-evaluation of the gate with the reference's exact operations (pyx:49-53; centres as built by
@@ -1235,7 +1234,6 @@ occ_fill8v_kernel(const FillParams p, const long long *__restrict__ block_base, 
         }
         __syncwarp();
         const float cut_lo = WG(cut2v_lo), cut_hi = WG(cut2v_hi);
-        const float gate_k = UNIFORM ? p.u_gate_k : GATE_SCALE * cut_lo;
         const unsigned band_bits = UNIFORM ? p.u_band_bits : __float_as_uint(cut_hi - cut_lo);
         const float fvy = (float)ly - 1.5f, fvz = (float)lz - 3.5f;  // block frame: origin at the block centre
         const int sx = bxi * 2 + cutv, sy = byi * 4 + cutv, sz = bzi * V_BZ + cutv;
@@ -1710,7 +1708,6 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             fq.u_cell_stride = ncell0;
             fq.u_block_base = bbase[b0];
             fq.u_block_stride = bbase[b0 + 1] - bbase[b0];
-            fq.u_gate_k = GATE_SCALE * g0.cut2v_lo;
             {
                 const float band = g0.cut2v_hi - g0.cut2v_lo;
                 memcpy(&fq.u_band_bits, &band, sizeof(float));
