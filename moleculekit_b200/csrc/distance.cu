@@ -55,6 +55,9 @@ __device__ __forceinline__ BoxF load_box(const float *box, long long stride, lon
     b.ry = __frcp_rn(b.by);
     b.rz = __frcp_rn(b.bz);
     b.hx = __fmul_rn(b.bx, 0.5f); b.hy = __fmul_rn(b.by, 0.5f); b.hz = __fmul_rn(b.bz, 0.5f);
+#ifdef MKB_K3_PIN_HALF
+    asm volatile("" : "+f"(b.hx), "+f"(b.hy), "+f"(b.hz));  // keep the halves in registers (else recomputed per pair)
+#endif
     return b;
 }
 
@@ -165,8 +168,15 @@ __device__ __forceinline__ void emit_dist(void *out, long long idx, float d2, fl
 // Each thread owns TWO sel2 columns (j and j + K3_COLS) so one broadcast load of the sel1 atom, the loop control and the
 // index arithmetic are shared by two pairs.  SELF / PBC are compile-time: the rectangular non-periodic-free inner loop
 // carries no per-row diagonal tests.
+// (register sweep, C4a: compiler default 4.85 / 4.32 ms distances / contacts; forced 32 regs 5.10 / 4.89; 40 regs with the
+// box halves pinned 4.79 / 4.62; 48 regs 4.81 / 4.62; 61 regs 5.07 / 4.27 -- within noise of the default, which stays)
+#ifdef MKB_K3_MIN_CTAS
+#define MKB_K3_BOUNDS __launch_bounds__(K3_COLS, MKB_K3_MIN_CTAS)
+#else
+#define MKB_K3_BOUNDS __launch_bounds__(K3_COLS)
+#endif
 template <int MODE, bool SELF>
-__global__ void __launch_bounds__(K3_COLS) dist_kernel(const float4 *__restrict__ G1, const float4 *__restrict__ G2,
+__global__ void MKB_K3_BOUNDS dist_kernel(const float4 *__restrict__ G1, const float4 *__restrict__ G2,
                                                         long long n1, long long n2, const float *__restrict__ box,
                                                         long long box_stride, int pbc, float truncate,
                                                         float threshold, long long P, void *__restrict__ out,
