@@ -45,7 +45,6 @@ struct mkb_ctx {
     // optional per-kernel timing (bench.py roofline): events recorded on the launch stream
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before prep, before main kernel, after main kernel
-    bool wrap_smem_opt_in = false;  // K9: dynamic shared memory attribute set on this device
 };
 
 namespace mkb {

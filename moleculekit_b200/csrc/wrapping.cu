@@ -36,17 +36,13 @@ constexpr int WRAP_THREADS = 256;
 constexpr int WRAP_WARPS = WRAP_THREADS / 32;
 constexpr int WRAP_ROWS = WRAP_STAGE * 3;
 
-template <int NST>
-struct alignas(16) ChainSmemT {
-    float v[NST][WRAP_ROWS][32];  // [stage][atom*3 + axis][frame lane]
-    float rb[NST][WRAP_STAGE];    // (float)(n + 1)
-    float rr[NST][WRAP_STAGE];    // refined reciprocal of it
+struct alignas(16) ChainSmem {
+    float v[WRAP_NSTAGE][WRAP_ROWS][32];  // [stage][atom*3 + axis][frame lane]
+    float rb[WRAP_NSTAGE][WRAP_STAGE];    // (float)(n + 1)
+    float rr[WRAP_NSTAGE][WRAP_STAGE];    // refined reciprocal of it
     float tr[3][32];                      // translation per (axis, frame lane)
     int mv[3][32];                        // the group moves along this axis in this frame
 };
-using ChainSmem = ChainSmemT<WRAP_NSTAGE>;
-constexpr int WRAP_NSTAGE_CENTRE = 8;  // the centre kernel has the SM to itself: a deeper ring (97 KB, dynamic) hides DRAM latency
-using ChainSmemCentre = ChainSmemT<WRAP_NSTAGE_CENTRE>;
 
 __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -65,8 +61,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // is index[n] (INDIRECT: centersel, pyx:113-118) or first_atom + n (a group, pyx:127-134).  Warps 3..7 are the loaders
 // (cp.async rows of 32 frames into the ring, plus the (n + 1, reciprocal) tables), warps 0..2 walk the chain of axis =
 // warp and return its mean for frame lane (other warps return 0).
-template <bool INDIRECT, int NST>
-__device__ __forceinline__ float chain_32frames(ChainSmemT<NST> &sm, const float *coords, long long fs, long long f0, int nf,
+template <bool INDIRECT>
+__device__ __forceinline__ float chain_32frames(ChainSmem &sm, const float *coords, long long fs, long long f0, int nf,
                                                 const unsigned *__restrict__ index, long long first_atom,
                                                 long long count) {
     constexpr int LOADERS = WRAP_WARPS - 3;
@@ -77,7 +73,7 @@ __device__ __forceinline__ float chain_32frames(ChainSmemT<NST> &sm, const float
     const bool aligned16 = ((reinterpret_cast<unsigned long long>(coords) | (unsigned long long)(fs * 4)) & 15ull) == 0;
     auto issue = [&](long long s) {
         if (w >= 3 && s < nst) {
-            const int buf = (int)(s % NST), lw = w - 3;
+            const int buf = (int)(s % WRAP_NSTAGE), lw = w - 3;
             const long long n0 = s * WRAP_STAGE;
             const long long left = count - n0;
             const int rows = left < WRAP_STAGE ? 3 * (int)left : WRAP_ROWS;  // row = atom_in_stage*3 + axis
@@ -122,14 +118,14 @@ __device__ __forceinline__ float chain_32frames(ChainSmemT<NST> &sm, const float
         cp_async_commit();  // one group per stage, empty past the end: keeps the wait distance uniform
     };
 #pragma unroll
-    for (int s = 0; s < NST - 1; ++s) issue(s);
+    for (int s = 0; s < WRAP_NSTAGE - 1; ++s) issue(s);
     float c = 0.f;
     for (long long s = 0; s < nst; ++s) {
-        cp_async_wait<NST - 2>();  // this thread's copies of stage s have landed (only stage s + 1 may be pending)
+        cp_async_wait<WRAP_NSTAGE - 2>();  // this thread's copies of stage s have landed (only stage s + 1 may be pending)
         __syncthreads();                   // ... and everyone's; the chain warps are also done with stage s - 1,
-        issue(s + NST - 1);        // whose buffer the loaders refill while the chain walks stage s
+        issue(s + WRAP_NSTAGE - 1);        // whose buffer the loaders refill while the chain walks stage s
         if (w < 3) {
-            const int buf = (int)(s % NST);
+            const int buf = (int)(s % WRAP_NSTAGE);
             const long long left = count - s * WRAP_STAGE;
             const int m = left < WRAP_STAGE ? (int)left : WRAP_STAGE;
             // 8 atoms at a time: operands first (independent shared loads), then the dependent chain on the branch-free
@@ -173,8 +169,7 @@ __device__ __forceinline__ float chain_32frames(ChainSmemT<NST> &sm, const float
 __global__ void __launch_bounds__(WRAP_THREADS)
 wrap_center_kernel(const float *__restrict__ coords, long long F, long long fs, const unsigned *__restrict__ centersel,
                    long long n_centersel, float *__restrict__ centre) {
-    extern __shared__ __align__(16) unsigned char wrap_dyn_smem[];
-    ChainSmemCentre &sm = *reinterpret_cast<ChainSmemCentre *>(wrap_dyn_smem);
+    __shared__ ChainSmem sm;
     const long long f0 = 32ll * blockIdx.x;
     const int nf = (int)(F - f0 < 32 ? F - f0 : 32);
     const float c = chain_32frames<true>(sm, coords, fs, f0, nf, centersel, 0, n_centersel);
@@ -341,13 +336,8 @@ extern "C" int mkb_wrap_box(mkb_handle_t h, void *stream, const mkb_traj *t, con
     wrap_classify_kernel<<<(unsigned)cdiv(n_ranges, 256), 256, 0, st>>>(groups, n_ranges, long_list, n_long);
     MKB_LAUNCHED(h);
     if (n_centersel > 0) {
-        if (!h->wrap_smem_opt_in) {
-            MKB_CUDA(h, cudaFuncSetAttribute(wrap_center_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(ChainSmemCentre)));
-            h->wrap_smem_opt_in = true;
-        }
-        wrap_center_kernel<<<(unsigned)nchunks, WRAP_THREADS, sizeof(ChainSmemCentre), st>>>(t->coords, F, t->frame_stride,
-                                                                                            centersel, n_centersel, centre);
+        wrap_center_kernel<<<(unsigned)nchunks, WRAP_THREADS, 0, st>>>(t->coords, F, t->frame_stride, centersel,
+                                                                      n_centersel, centre);
         MKB_LAUNCHED(h);
     }
     WrapArgs A;
