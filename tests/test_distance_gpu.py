@@ -207,6 +207,40 @@ def test_frame_shard_view_equals_full(du, g_raw):
     assert np.array_equal(_bits(full.cpu().numpy()), _bits(g["dist_pbc"]))
 
 
+def test_full_size_c4a_properties(du, oracle):
+    """BASELINE config 4a at full size (10 000 frames x 256 x 1024 periodic pairs, 10.5 GB of float32 output) through
+    size-independent properties: swapping the selections gives the transposed matrix bit for bit (the minimum image is
+    symmetric), the fused contact map equals distances <= threshold, a frame shard equals the same rows, and ten full
+    frames equal the oracle."""
+    import torch
+
+    n1, n2, F, L = 256, 1024, 10000, 36.84
+    rng = np.random.default_rng(7)
+    start = rng.uniform(0, L, size=(n1 + n2, 3, 1)).astype(np.float32)
+    coords = start + np.cumsum(rng.normal(0, 0.3, size=(n1 + n2, 3, F)).astype(np.float32), axis=2)
+    box = np.repeat((L * (1 + 0.002 * rng.normal(size=F))).astype(np.float32)[None, :], 3, axis=0)
+    dev = torch.device("cuda", 0)
+    d_c = torch.from_numpy(np.ascontiguousarray(coords)).to(dev); d_b = torch.from_numpy(np.ascontiguousarray(box)).to(dev)
+    s1 = torch.arange(0, n1, dtype=torch.int32, device=dev); s2 = torch.arange(n1, n1 + n2, dtype=torch.int32, device=dev)
+    ch = torch.ones(n1 + n2, dtype=torch.int32, device=dev); ch[n1:] = 2
+    dist = du.dist_trajectory_device(d_c, d_b, s1, s2, ch, False, True)
+    assert dist.shape == (F, n1 * n2) and bool(torch.isfinite(dist).all()) and float(dist.max()) <= L * 0.5 * 3 ** 0.5 * 1.01
+    for f0 in range(0, F, 2500):  # swapped selections, in frame shards to bound memory
+        sw = du.dist_trajectory_device(d_c[:, :, f0:f0 + 2500], d_b[:, f0:f0 + 2500], s2, s1, ch, False, True)
+        assert torch.equal(sw.view(-1, n2, n1).transpose(1, 2).reshape(-1, n1 * n2), dist[f0:f0 + 2500])
+        del sw
+    con = du.dist_trajectory_device(d_c, d_b, s1, s2, ch, False, True, metric="contacts", threshold=12.0)
+    assert con.dtype == torch.bool and torch.equal(con, dist <= 12.0) and 0.05 < float(con.float().mean()) < 0.5
+    del con
+    frames = [0, 1, 777, 2499, 2500, 4999, 5000, 7501, 9998, 9999]
+    ch_h = np.ones(n1 + n2, np.uint32); ch_h[n1:] = 2
+    sub = np.ascontiguousarray(coords[:, :, frames]); subb = np.ascontiguousarray(box[:, frames])
+    want = np.zeros((len(frames), n1 * n2), np.float32)
+    oracle.dist_trajectory(sub, subb, np.arange(n1, dtype=np.uint32), np.arange(n1, n1 + n2, dtype=np.uint32), ch_h, False,
+                           True, want)
+    assert np.array_equal(dist[frames].cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
 # ------------------------------------------------------------------------------------------ MetricDistance API
 def test_distances_and_contacts(mol, g_traj):
     """tests/test_metricdistance.py:37-51,182-193"""
