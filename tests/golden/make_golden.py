@@ -32,6 +32,18 @@ sys.path.insert(0, ROOT)
 REFT = "/root/reference/tests"
 
 
+def scratch_copy(path: str) -> str:
+    """The reference's XTC reader drops index-cache files (.name, .name.numframes) next to the trajectory it reads;
+    /root/reference must not be written to, so trajectories are read from a scratch copy."""
+    import shutil
+    import tempfile
+
+    d = tempfile.mkdtemp(prefix="mkb_golden_")
+    dst = os.path.join(d, os.path.basename(path))
+    shutil.copyfile(path, dst)
+    return dst
+
+
 def strarr(a):
     """object string array -> fixed-width unicode (npz without pickle)"""
     return np.array([str(x) for x in a])
@@ -53,9 +65,9 @@ def wrapping_fixture():
 
     d = os.path.join(REFT, "test_wrapping")
     mol = Molecule(os.path.join(d, "structure.prmtop"))
-    mol.read(os.path.join(d, "output.xtc"))
+    mol.read(scratch_copy(os.path.join(d, "output.xtc")))
     refmol = Molecule(os.path.join(d, "structure.prmtop"))
-    refmol.read(os.path.join(d, "output_wrapped.xtc"))
+    refmol.read(scratch_copy(os.path.join(d, "output_wrapped.xtc")))
     groups, _ = getBondedGroups(mol)
     centersel = mol.atomselect("protein or resname ACE NME", indexes=True, guessBonds=False).astype(np.uint32)
     ncut_groups = 900
@@ -321,9 +333,9 @@ def main():
     tr = os.path.join(REFT, "test_projections", "trajectory")
     md = os.path.join(REFT, "test_projections", "metricdistance")
     mol = Molecule(os.path.join(tr, "filtered.pdb"))
-    mol.read(os.path.join(tr, "traj.xtc"))
+    mol.read(scratch_copy(os.path.join(tr, "traj.xtc")))
     molskip = Molecule(os.path.join(tr, "filtered.pdb"))
-    molskip.read(os.path.join(tr, "traj.xtc"), skip=10)
+    molskip.read(scratch_copy(os.path.join(tr, "traj.xtc")), skip=10)
     assert np.array_equal(molskip.coords, mol.coords[:, :, ::10])
     sels = ["protein and name CA", "resname MOL and noh", "protein and noh",
             "protein and resid 1 to 50 and noh", "protein and resid 1 to 20 and noh", "protein"]
