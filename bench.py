@@ -320,6 +320,22 @@ def extra_workloads(dev, peak):
     out["c7_within"] = dict(workload=f"C7: within 5 A of {n2} source atoms, {N} query atoms (cell list; reference = brute force)",
                             ms_per_call=ms, selected=int(res["m"].sum().item()), pair_tests_avoided=float(N) * n2,
                             equivalent_pair_tests_per_s=float(N) * n2 / (ms * 1e-3))
+    # C8: XTC decode on the device (K11): the 3 frames of tests/golden/xtc/real3.xtc (4507 atoms, re-encoded frames of the
+    # reference's test trajectory) repeated to a 3000-frame file
+    from moleculekit_b200 import xtc as px
+
+    raw3 = open(os.path.join(ROOT, "tests", "golden", "xtc", "real3.xtc"), "rb").read()
+    raw = raw3 * 1000
+    idx = px.index_xtc(raw)
+    d_bytes = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+    nat, Fx = idx["natoms"], len(idx["frames"])
+    d_xyz = torch.empty((nat, 3, Fx), dtype=torch.float32, device=dev)
+    ms = _time_cuda(lambda: px.decode_xtc_device(d_bytes, idx["frames"], nat, scale=10.0, out=d_xyz), warm=1, steps=3)
+    _, kms = _lib.get_timing(dev.index)
+    out["c8_xtc_decode"] = dict(workload=f"C8: XTC decode, {Fx} frames x {nat} atoms ({len(raw) / 1e6:.0f} MB compressed -> "
+                                         f"{nat * 3 * Fx * 4 / 1e6:.0f} MB frame-minor float32 on the device)",
+                                ms_per_call=ms, kernel_ms=kms, frames_per_s=Fx / (ms * 1e-3),
+                                atom_frames_per_s=nat * Fx / (ms * 1e-3), output_gbs=nat * 3 * Fx * 4 / (kms * 1e-3) / 1e9)
     return out
 
 

@@ -196,6 +196,26 @@ int mkb_bonds_count(mkb_handle_t h, void *stream, const float *coords, const flo
 int mkb_bonds_fill(mkb_handle_t h, void *stream, const float *coords, const float *radii, const uint32_t *is_hydrogen,
                    int64_t n, float pairdist, const int64_t *row_offsets, uint32_t *pairs);
 
+/* K11 (second half): XTC compressed coordinates decoded on the device; replaces the frame loop of
+ * xtc_read_new / xtc_read_frame (moleculekit/fileformats/xtc/src/xtc_src.cpp:195-258) around xdrfile_decompress_coord_float
+ * (src/xdrfile.cpp:750-982) and its host-side scatter into the frame-minor array.  file_bytes = the XTC file on the device;
+ * frames[f] (HOST) = one coordinate block as found by walking the XDR frame headers: byte offset and length of the bit stream,
+ * precision, minint/maxint, initial smallidx (smallidx < 0: natoms <= 9, the block is 3*natoms big-endian floats).
+ * coords (natoms, 3, n_frames) float32 device, element (a, d, f) at coords[(a*3 + d)*frame_stride + f], in nm, or multiplied
+ * by `scale` as a second float32 operation (10 = the reference's `coords *= 10`, readers.py:1846).  status [n_frames] int32
+ * device: 0 = ok, negative = corrupt block.  Bit-identical to the reference reader. */
+typedef struct {
+    int64_t data_offset;
+    int32_t nbytes;
+    int32_t natoms;
+    float precision;
+    int32_t minint[3];
+    int32_t maxint[3];
+    int32_t smallidx;
+} mkb_xtc_frame;
+int mkb_xtc_decode(mkb_handle_t h, void *stream, const uint8_t *file_bytes, int64_t file_size, const mkb_xtc_frame *frames,
+                   int64_t n_frames, int64_t natoms, float *coords, int64_t frame_stride, float scale, int32_t *status);
+
 /* K10: the kernel of the `within` / `exwithin` atom selections, replaces within_distance
  * (moleculekit/atomselect_utils/atomselect_utils.pyx:612-653; called from atomselect/atomselect.py:243-251).
  * coords [n_atoms,3] float32 device (one frame, row-major); sel1 [n1] uint32 device = query atoms (NULL = all atoms,

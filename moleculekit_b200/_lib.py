@@ -36,7 +36,7 @@ EXPORTS = [
     "mkb_grid_centers", "mkb_rotate_coords",
     "mkb_dist_trajectory", "mkb_contacts_count", "mkb_contacts_fill", "mkb_dist_reduction",
     "mkb_cdist", "mkb_pdist", "mkb_squareform", "mkb_collisions_count", "mkb_collisions_fill",
-    "mkb_bonds_count", "mkb_bonds_fill", "mkb_shell_counts", "mkb_wrap_box", "mkb_within_distance",
+    "mkb_bonds_count", "mkb_bonds_fill", "mkb_shell_counts", "mkb_wrap_box", "mkb_within_distance", "mkb_xtc_decode",
 ]
 
 _lib = None
@@ -88,6 +88,7 @@ def load():
     lib.mkb_bonds_count.argtypes = [vp, vp, vp, vp, vp, i64, f32, vp, C.POINTER(i64)]
     lib.mkb_bonds_fill.argtypes = [vp, vp, vp, vp, vp, i64, f32, vp, vp]
     lib.mkb_within_distance.argtypes = [vp, vp, vp, i64, vp, i64, vp, i64, f32, vp]
+    lib.mkb_xtc_decode.argtypes = [vp, vp, vp, i64, vp, i64, i64, vp, i64, f32, vp]
     lib.mkb_wrap_box.argtypes = [vp, vp, tp, vp, i64, vp, i64, C.POINTER(C.c_float)]
     for name in EXPORTS:
         if name in ("mkb_last_error", "mkb_launch_count", "mkb_version"):

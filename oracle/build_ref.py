@@ -32,6 +32,16 @@ MODULES = {
     "bondguesser_utils": "moleculekit/bondguesser_utils/bondguesser_utils.pyx",
     "wrapping": "moleculekit/wrapping/wrapping.pyx",
     "atomselect_utils": "moleculekit/atomselect_utils/atomselect_utils.pyx",
+    "xtc": "moleculekit/fileformats/xtc/xtc.pyx",
+}
+
+# extra C++ sources / include directories of a module (the reference's setup.py:55-66 lists the same files)
+EXTRA_SOURCES = {
+    "xtc": ["moleculekit/fileformats/xtc/src/xdrfile_xtc.cpp", "moleculekit/fileformats/xtc/src/xdrfile.cpp",
+            "moleculekit/fileformats/xtc/src/xtc_src.cpp"],
+}
+EXTRA_INCLUDES = {
+    "xtc": ["moleculekit/fileformats/xtc/include", "moleculekit/fileformats/xtc"],
 }
 
 
@@ -60,13 +70,14 @@ def build(reference: str = "/root/reference", force: bool = False, verbose: bool
             src = os.path.join(reference, rel)
             cpp = os.path.join(tmp, f"{mod}.cpp")
             so = os.path.join(OUT, f"{mod}.so")
-            cmd1 = [sys.executable, "-m", "cython", "--cplus", src, "-o", cpp]
+            incs = [os.path.join(reference, d) for d in EXTRA_INCLUDES.get(mod, [])]
+            extra = [os.path.join(reference, f) for f in EXTRA_SOURCES.get(mod, [])]
+            cmd1 = [sys.executable, "-m", "cython", "--cplus"] + [f"-I{d}" for d in incs] + [src, "-o", cpp]
             cmd2 = [
                 "g++", "-O3", "-shared", "-fPIC", "-w",
                 "-DPy_LIMITED_API=0x030B0000",
                 "-DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION",
-                f"-I{pyinc}", f"-I{npinc}", cpp, "-o", so,
-            ]
+                f"-I{pyinc}", f"-I{npinc}"] + [f"-I{d}" for d in incs] + [cpp] + extra + ["-o", so]
             for cmd in (cmd1, cmd2):
                 if verbose:
                     print("[oracle/_ref]", " ".join(cmd), flush=True)

@@ -240,3 +240,40 @@ def within_distance(coords, cutoff, sel1, sel2, sel2_min_coords, sel2_max_coords
     assert results.dtype == np.bool_ and results.flags["C_CONTIGUOUS"] and results.shape == (len(sel1),)
     lib().oracle_within_distance(_p(coords), C.c_float(cutoff), _p(sel1), C.c_int64(len(sel1)), _p(sel2),
                                  C.c_int64(len(sel2)), _p(results.view(np.uint8)))
+
+
+def read_xtc(raw: bytes):
+    """moleculekit/fileformats/xtc/xtc.pyx:34-55 (read_xtc) on a byte string: (coords (natoms,3,F) f32 [nm], box (3,3,F), time,
+    step).  Own header walk (xdrfile_xtc.cpp:29-67) + oracle_xtc_decode_block per frame."""
+    import struct
+
+    lib().oracle_xtc_decode_block.restype = C.c_int
+    pos, frames = 0, []
+    while pos + 16 <= len(raw):
+        magic, natoms, step = struct.unpack_from(">iii", raw, pos)
+        assert magic == 1995
+        (time,) = struct.unpack_from(">f", raw, pos + 12)
+        box = np.array(struct.unpack_from(">9f", raw, pos + 16), dtype=np.float32).reshape(3, 3)
+        (lsize,) = struct.unpack_from(">i", raw, pos + 52)
+        pos += 56
+        xyz = np.zeros((lsize, 3), dtype=np.float32)
+        if lsize <= 9:
+            xyz[:] = np.array(struct.unpack_from(f">{3 * lsize}f", raw, pos), dtype=np.float32).reshape(lsize, 3)
+            pos += 12 * lsize
+        else:
+            (prec,) = struct.unpack_from(">f", raw, pos)
+            ints = struct.unpack_from(">8i", raw, pos + 4)
+            nbytes = ints[7]
+            data = np.frombuffer(raw, dtype=np.uint8, count=nbytes, offset=pos + 36)
+            mn, mx = np.array(ints[0:3], np.int32), np.array(ints[3:6], np.int32)
+            rc = lib().oracle_xtc_decode_block(_p(data), C.c_int64(nbytes), C.c_int64(lsize), C.c_float(prec), _p(mn), _p(mx),
+                                               C.c_int32(ints[6]), _p(xyz))
+            assert rc == 0, rc
+            pos += 36 + ((nbytes + 3) // 4) * 4
+        frames.append((xyz, box, time, step))
+    F = len(frames)
+    n = frames[0][0].shape[0] if F else 0
+    coords = np.zeros((n, 3, F), np.float32); bx = np.zeros((3, 3, F), np.float32)
+    for f, (xyz, box, _, _) in enumerate(frames):
+        coords[:, :, f] = xyz; bx[:, :, f] = box
+    return coords, bx, np.array([t for _, _, t, _ in frames], np.float32), np.array([s for _, _, _, s in frames], np.int32)

@@ -492,3 +492,144 @@ EXPORT void oracle_within_distance(const float *coords, float cutoff, const uint
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * XTC compressed-coordinate decoding (second half) -- the algorithm of
+ * xdrfile_decompress_coord_float, moleculekit/fileformats/xtc/src/xdrfile.cpp:750-982 (the xdrfile / GROMACS "xdr3dfcoord"
+ * format), restated on a big-integer type instead of the reference's byte arrays:
+ *   bit stream, most significant bit first (decodebits, :637-670);
+ *   a group of 3 small integers is one mixed-radix number stored in 8-bit chunks, least significant chunk first
+ *   (decodeints, :681-729): value = sum_j chunk_j * 256^j, nums[2] = value % sizes[2], nums[1] = (value / sizes[2]) % sizes[1],
+ *   nums[0] = value / (sizes[1] sizes[2]);
+ *   per atom: full-range triple (+ minint), 1 flag bit, optional 5-bit run/adapt code, then run/3 atoms coded relative to the
+ *   previous one with the current small size magicints[smallidx]; the first atom of a run is swapped with its predecessor
+ *   (:906-925: water oxygen/hydrogen order); output = (float)int * inv_precision with inv_precision = (float)(1.0 / precision).
+ * One frame's coordinate block (after the `lsize` word) is decoded; returns 0 or a negative error.
+ * ------------------------------------------------------------------------------------------------ */
+static const int xtc_magic[] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322,
+    406, 512, 645, 812, 1024, 1290, 1625, 2048, 2580, 3250, 4096, 5060, 6501, 8192, 10321, 13003, 16384, 20642, 26007, 32768, 41285,
+    52015, 65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127, 524287, 660561, 832255, 1048576, 1321122, 1664510,
+    2097152, 2642245, 3329021, 4194304, 5284491, 6658042, 8388607, 10568983, 13316085, 16777216};
+#define XTC_FIRSTIDX 9
+#define XTC_LASTIDX ((int)(sizeof(xtc_magic) / sizeof(xtc_magic[0])))
+
+typedef struct { const uint8_t *p; int64_t nbytes; int64_t pos; /* bit position */ } xtc_bits;
+
+static uint32_t xtc_take(xtc_bits *b, int n)  /* n <= 32 bits, MSB first; bits past the end read as 0 */
+{
+    uint64_t v = 0;
+    for (int k = 0; k < n; ++k) {
+        const int64_t byte = b->pos >> 3;
+        const int bit = byte < b->nbytes ? (b->p[byte] >> (7 - (b->pos & 7))) & 1 : 0;
+        v = (v << 1) | (uint64_t)bit;
+        ++b->pos;
+    }
+    return (uint32_t)v;
+}
+
+static void xtc_take3(xtc_bits *b, int nbits, const uint32_t sizes[3], int32_t nums[3])
+{
+    unsigned __int128 v = 0;
+    int shift = 0;
+    while (nbits > 8) { v |= (unsigned __int128)xtc_take(b, 8) << shift; shift += 8; nbits -= 8; }
+    if (nbits > 0) v |= (unsigned __int128)xtc_take(b, nbits) << shift;
+    nums[2] = (int32_t)(v % sizes[2]); v /= sizes[2];
+    nums[1] = (int32_t)(v % sizes[1]); v /= sizes[1];
+    nums[0] = (int32_t)(uint32_t)v;
+}
+
+static int xtc_bits_of(uint32_t size)  /* xdrfile.cpp:455-465 */
+{
+    int n = 0;
+    uint64_t num = 1;
+    while (size >= num && n < 32) { ++n; num <<= 1; }
+    return n;
+}
+
+static int xtc_bits_of3(const uint32_t sizes[3])  /* xdrfile.cpp:480-510: bits of sizes[0]*sizes[1]*sizes[2] */
+{
+    unsigned __int128 prod = (unsigned __int128)sizes[0] * sizes[1] * sizes[2];
+    /* the reference counts whole low bytes plus the bits of the top byte (value >= num loop, so an exact power of two
+       gets one extra bit) */
+    int nbytes = 0;
+    unsigned __int128 t = prod;
+    while (t > 0xff) { t >>= 8; ++nbytes; }
+    int nb = 0;
+    unsigned num = 1;
+    while ((unsigned)t >= num) { ++nb; num *= 2; }
+    return nb + nbytes * 8;
+}
+
+EXPORT int oracle_xtc_decode_block(const uint8_t *data, int64_t nbytes, int64_t natoms, float precision, const int32_t minint[3],
+                                   const int32_t maxint[3], int32_t smallidx, float *out /* [natoms*3] */)
+{
+    uint32_t sizeint[3], bitsizeint[3] = {0, 0, 0};
+    for (int d = 0; d < 3; ++d) {
+        sizeint[d] = (uint32_t)(maxint[d] - minint[d] + 1);
+        if (!sizeint[d]) return -2;
+    }
+    int bitsize;
+    if ((sizeint[0] | sizeint[1] | sizeint[2]) > 0xffffff) {
+        for (int d = 0; d < 3; ++d) bitsizeint[d] = (uint32_t)xtc_bits_of(sizeint[d]);
+        bitsize = 0;
+    } else {
+        bitsize = xtc_bits_of3(sizeint);
+    }
+    if (smallidx < XTC_FIRSTIDX || smallidx >= XTC_LASTIDX) return -3;
+    int tmp = smallidx - 1;
+    if (tmp < XTC_FIRSTIDX) tmp = XTC_FIRSTIDX;
+    int smaller = xtc_magic[tmp] / 2, smallnum = xtc_magic[smallidx] / 2;
+    uint32_t sizesmall[3] = {(uint32_t)xtc_magic[smallidx], (uint32_t)xtc_magic[smallidx], (uint32_t)xtc_magic[smallidx]};
+    const float inv_precision = (float)(1.0 / precision);
+    xtc_bits b = {data, nbytes, 0};
+    int64_t i = 0, w = 0;
+    int run = 0;
+    while (i < natoms) {
+        int32_t cur[3], prev[3];
+        if (bitsize == 0) {
+            for (int d = 0; d < 3; ++d) cur[d] = (int32_t)xtc_take(&b, (int)bitsizeint[d]);
+        } else {
+            xtc_take3(&b, bitsize, sizeint, cur);
+        }
+        ++i;
+        for (int d = 0; d < 3; ++d) { cur[d] += minint[d]; prev[d] = cur[d]; }
+        int is_smaller = 0;
+        if (xtc_take(&b, 1)) {
+            run = (int)xtc_take(&b, 5);
+            is_smaller = run % 3;
+            run -= is_smaller;
+            --is_smaller;
+        }
+        if (run > 0) {
+            for (int k = 0; k < run; k += 3) {
+                int32_t s[3];
+                xtc_take3(&b, smallidx, sizesmall, s);
+                ++i;
+                for (int d = 0; d < 3; ++d) s[d] += prev[d] - smallnum;
+                if (k == 0) {  /* the first atom of the run goes BEFORE the atom it was coded against */
+                    if (w + 3 > natoms * 3) return -4;
+                    for (int d = 0; d < 3; ++d) { out[w++] = (float)s[d] * inv_precision; prev[d] = s[d]; }
+                    for (int d = 0; d < 3; ++d) s[d] = cur[d];
+                } else {
+                    for (int d = 0; d < 3; ++d) prev[d] = s[d];
+                }
+                if (w + 3 > natoms * 3) return -4;
+                for (int d = 0; d < 3; ++d) out[w++] = (float)s[d] * inv_precision;
+            }
+        } else {
+            if (w + 3 > natoms * 3) return -4;
+            for (int d = 0; d < 3; ++d) out[w++] = (float)cur[d] * inv_precision;
+        }
+        smallidx += is_smaller;
+        if (is_smaller < 0) {
+            smallnum = smaller;
+            smaller = smallidx > XTC_FIRSTIDX ? xtc_magic[smallidx - 1] / 2 : 0;
+        } else if (is_smaller > 0) {
+            smaller = smallnum;
+            smallnum = xtc_magic[smallidx] / 2;
+        }
+        if (smallidx < 0 || smallidx >= XTC_LASTIDX || !xtc_magic[smallidx]) return -3;
+        sizesmall[0] = sizesmall[1] = sizesmall[2] = (uint32_t)xtc_magic[smallidx];
+    }
+    return 0;
+}

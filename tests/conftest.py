@@ -60,6 +60,13 @@ def g_bonds():
 
 
 @pytest.fixture(scope="session")
+def g_xtc():
+    g = _npz("xtc.npz")
+    g["_dir"] = os.path.join(GOLDEN, "xtc")
+    return g
+
+
+@pytest.fixture(scope="session")
 def g_interactions():
     return _npz("interactions.npz")
 

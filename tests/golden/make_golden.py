@@ -226,9 +226,76 @@ def interactions_fixture():
     print("interactions: hydrophobic pairs", len(hy[0]))
 
 
+def xtc_fixture():
+    """tests/golden/xtc/*.xtc + xtc.npz (K11): XTC files written by the reference's own writer (xtc.pyx:91-104 write_xtc)
+    from seeded coordinates -- water-like triples (runs + the first-atom swap), a globular cloud, tightly clustered atoms
+    (small-range adaptation), ranges above 2^24 (the plain bit-field branch), 3 / 9 / 10 atoms (the uncompressed branch
+    and its boundary) and three re-encoded frames of the reference's real test trajectory -- with the arrays the
+    reference's read_xtc returns for them.  The reference reader is also run on its full real trajectories (scratch
+    copies) and must agree with the oracle frame for frame."""
+    from oracle import build_ref, cpu_oracle
+
+    xr = build_ref.load()[5]
+    out_dir = os.path.join(HERE, "xtc")
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(2024)
+
+    def water(nw, F, L):
+        o = rng.uniform(0, L, size=(nw, 1, 3, 1))
+        h = o + rng.normal(0, 0.06, size=(nw, 2, 3, 1))
+        return (np.concatenate([o, h], axis=1).reshape(nw * 3, 3, 1) +
+                np.cumsum(rng.normal(0, 0.05, size=(nw * 3, 3, F)), axis=2)).astype(np.float32)
+
+    real_src = scratch_copy(os.path.join(REFT, "test_projections", "trajectory", "traj.xtc"))
+    real = xr.read_xtc(real_src.encode())
+    cases = {
+        "water": water(120, 6, 3.0),
+        "globule": rng.normal(0, 1.5, size=(257, 3, 5)).astype(np.float32),
+        "clustered": (rng.normal(0, 0.02, size=(500, 3, 3)) + 5).astype(np.float32),
+        "wide_x": np.stack([np.linspace(-8500, 8500, 60), rng.normal(0, 1, 60), rng.normal(0, 1, 60)], 1)[:, :, None]
+        .repeat(2, 2).astype(np.float32),
+        "wide_xyz": (np.linspace(-9000, 9000, 50)[:, None, None] * np.ones((1, 3, 2))).astype(np.float32),
+        "atoms3": rng.normal(0, 1, size=(3, 3, 4)).astype(np.float32),
+        "atoms9": rng.normal(0, 1, size=(9, 3, 2)).astype(np.float32),
+        "atoms10": rng.normal(0, 1, size=(10, 3, 2)).astype(np.float32),
+        "real3": np.ascontiguousarray(real[0][:, :, [0, 100, 199]]),
+    }
+    w = {"names": np.array(list(cases))}
+    for name, xyz in cases.items():
+        F = xyz.shape[2]
+        box = np.zeros((3, 3, F), np.float32)
+        box[0, 0] = 3.1; box[1, 1] = 3.2; box[2, 2] = 3.3; box[1, 0] = 0.25
+        time = (np.arange(F) * 0.5 + 1).astype(np.float32)
+        step = (np.arange(F) * 10 + 5).astype(np.uint32)
+        fn = os.path.join(out_dir, name + ".xtc")
+        xr.write_xtc(fn.encode(), np.ascontiguousarray(xyz), box, time, step)
+        ref = xr.read_xtc(fn.encode())
+        got = cpu_oracle.read_xtc(open(fn, "rb").read())
+        for a, b in zip(ref, got):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), name
+        assert np.abs(ref[0] - xyz).max() < 2e-3, name  # the reference round-trips within its precision
+        for k, v in zip(("coords", "box", "time", "step"), ref):
+            w[f"{name}_{k}"] = np.asarray(v)
+    # full real trajectories: the oracle agrees with the reference on every frame (not committed: megabytes)
+    for rel in (("test_projections", "trajectory", "traj.xtc"), ("test_wrapping", "6X18.xtc")):
+        src = scratch_copy(os.path.join(REFT, *rel))
+        ref = xr.read_xtc(src.encode())
+        got = cpu_oracle.read_xtc(open(src, "rb").read())
+        assert all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(ref, got)), rel
+        print("real trajectory", rel[-1], ref[0].shape, "oracle == reference")
+    np.savez_compressed(os.path.join(HERE, "xtc.npz"), **w)
+    for fcache in os.listdir(out_dir):  # index caches the reference reader leaves next to every file it opens
+        if fcache.startswith("."):
+            os.remove(os.path.join(out_dir, fcache))
+
+
 def main():
     from oracle import build_ref
 
+    if "--only-xtc" in sys.argv:
+        assert build_ref.build()
+        xtc_fixture()
+        return
     if "--only-interactions" in sys.argv:
         interactions_fixture()
         return
@@ -502,6 +569,7 @@ def main():
     rotation_fixture()
     within_fixture()
     interactions_fixture()
+    xtc_fixture()
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

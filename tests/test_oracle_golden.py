@@ -306,3 +306,43 @@ def test_within_oracle_vs_live_reference(oracle, refmods):
         ref.within_distance(coords, float(cutoff), sel1, sel2, mn, mx, a)
         oracle.within_distance(coords, float(cutoff), sel1, sel2, mn, mx, b)
         assert np.array_equal(a, b), t
+
+
+# ------------------------------------------------------------------------------------------------ K11: XTC decoding
+def test_xtc_oracle_and_header_walk_vs_reference_goldens(oracle, g_xtc):
+    """The oracle's restatement of the XTC decompression and the product's header walk against arrays the reference's
+    read_xtc returned for files written by the reference's write_xtc (tests/golden/xtc/)."""
+    import os
+
+    from moleculekit_b200 import xtc as px  # host-only use: the header walk
+
+    g = g_xtc
+    for name in g["names"].tolist():
+        raw = open(os.path.join(g["_dir"], name + ".xtc"), "rb").read()
+        coords, box, time, step = oracle.read_xtc(raw)
+        assert np.array_equal(coords.view(np.uint32), g[f"{name}_coords"].view(np.uint32)), name
+        assert np.array_equal(box, g[f"{name}_box"]) and np.array_equal(time, g[f"{name}_time"])
+        assert np.array_equal(step, g[f"{name}_step"])
+        idx = px.index_xtc(raw)
+        assert idx["natoms"] == coords.shape[0] and len(idx["frames"]) == coords.shape[2]
+        assert np.array_equal(idx["box"], g[f"{name}_box"]) and np.array_equal(idx["time"], g[f"{name}_time"])
+        assert np.array_equal(idx["step"], g[f"{name}_step"])
+        assert (idx["frames"]["smallidx"] < 0).all() == (coords.shape[0] <= 9)
+    with pytest.raises(RuntimeError, match="bad magic"):
+        px.index_xtc(b"\\x00" * 64)
+
+
+def test_xtc_oracle_vs_live_reference(oracle, refmods, tmp_path):
+    if refmods is None or len(refmods) < 6:
+        pytest.skip("oracle/_ref not built")
+    xr = refmods[5]
+    rng = np.random.default_rng(77)
+    for t in range(6):
+        N, F = int(rng.integers(10, 400)), int(rng.integers(1, 5))
+        xyz = (rng.normal(0, [0.05, 1.0, 30.0][t % 3], size=(N, 3, F)) + rng.normal(0, 3, 3)[None, :, None]).astype(np.float32)
+        box = np.zeros((3, 3, F), np.float32)
+        fn = str(tmp_path / f"t{t}.xtc")
+        xr.write_xtc(fn.encode(), np.ascontiguousarray(xyz), box, np.zeros(F, np.float32), np.zeros(F, np.uint32))
+        ref = xr.read_xtc(fn.encode())
+        got = oracle.read_xtc(open(fn, "rb").read())
+        assert np.array_equal(np.asarray(ref[0]).view(np.uint32), got[0].view(np.uint32)), t
