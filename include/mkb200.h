@@ -203,7 +203,9 @@ int mkb_bonds_fill(mkb_handle_t h, void *stream, const float *coords, const floa
  * precision, minint/maxint, initial smallidx (smallidx < 0: natoms <= 9, the block is 3*natoms big-endian floats).
  * coords (natoms, 3, n_frames) float32 device, element (a, d, f) at coords[(a*3 + d)*frame_stride + f], in nm, or multiplied
  * by `scale` as a second float32 operation (10 = the reference's `coords *= 10`, readers.py:1846).  status [n_frames] int32
- * device: 0 = ok, negative = corrupt block.  Bit-identical to the reference reader. */
+ * device: 0 = ok, negative = corrupt block.  Blocks are read as big-endian 32-bit words: file_bytes + data_offset must be
+ * 4-byte aligned (XDR guarantees it for a buffer that starts on a word) and readable up to the next multiple of 4 bytes.
+ * Bit-identical to the reference reader. */
 typedef struct {
     int64_t data_offset;
     int32_t nbytes;

@@ -28,28 +28,49 @@ __constant__ int c_xtc_magic[73] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20
 constexpr int XTC_FIRSTIDX = 9, XTC_LASTIDX = 73;
 
 struct XtcBits {
-    const unsigned char *p;
-    long long nbytes;
-    long long pos;  // bit position
-    // n <= 32 bits, most significant first; bits past the end of the block read as zero
+    const unsigned *p32;   // the block as big-endian 32-bit words (XDR pads every block to 4 bytes and starts it on a word)
+    long long nwords;      // words that may be read (bits past the block read as zero)
+    long long word;        // next word to fetch
+    unsigned long long buf;  // upcoming bits, left-aligned
+    int avail;               // valid bits in buf
+
+    __device__ __forceinline__ void init(const unsigned char *data, long long nbytes) {
+        p32 = reinterpret_cast<const unsigned *>(data);
+        nwords = (nbytes + 3) >> 2;
+        word = 0; buf = 0; avail = 0;
+    }
+    // n <= 32 bits, most significant first
     __device__ __forceinline__ unsigned take(int n) {
-        if (n == 0) return 0u;
-        const long long byte = pos >> 3;
-        const int off = (int)(pos & 7);
-        unsigned long long w = 0;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) w = (w << 8) | (byte + j < nbytes ? (unsigned long long)p[byte + j] : 0ull);
-        pos += n;
-        return (unsigned)((w >> (40 - off - n)) & ((1ull << n) - 1ull));
+        if (avail < n) {  // avail <= 31 here: room for one more word
+            const unsigned v = word < nwords ? __byte_perm(__ldg(p32 + word), 0, 0x0123) : 0u;
+            ++word;
+            buf |= (unsigned long long)v << (32 - avail);
+            avail += 32;
+        }
+        const unsigned r = n ? (unsigned)(buf >> (64 - n)) : 0u;
+        buf <<= n;
+        avail -= n;
+        return r;
+    }
+    // an nbits-bit field as stored (MSB first), nbits <= 64
+    __device__ __forceinline__ unsigned long long take64(int nbits) {
+        if (nbits <= 32) return take(nbits);
+        const unsigned long long hi = take(nbits - 32);
+        return (hi << 32) | take(32);
     }
     // three integers packed as one mixed-radix number of nbits bits, stored in 8-bit chunks with the LEAST significant
-    // chunk first in the stream
+    // chunk first in the stream: k full chunks then r = nbits - 8k remaining bits (the most significant ones)
     __device__ __forceinline__ void take3(int nbits, unsigned s1, unsigned s2, int out[3]) {
         if (nbits <= 64) {
-            unsigned long long v = 0;
-            int shift = 0, left = nbits;
-            while (left > 8) { v |= (unsigned long long)take(8) << shift; shift += 8; left -= 8; }
-            if (left > 0) v |= (unsigned long long)take(left) << shift;
+            const unsigned long long V = take64(nbits);
+            const int k = (nbits - 1) >> 3, r = nbits - 8 * k;
+            unsigned long long v = V;
+            if (k > 0) {
+                const unsigned long long W = V >> r;  // the k chunks, first chunk most significant
+                const unsigned lo = (unsigned)W, hi = (unsigned)(W >> 32);
+                const unsigned long long rev = ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+                v = ((V & ((1ull << r) - 1ull)) << (8 * k)) | (rev >> (64 - 8 * k));
+            }
             if (v <= 0xffffffffull) {  // the common small-offset case: 32-bit divisions
                 unsigned u = (unsigned)v;
                 out[2] = (int)(u % s2); u /= s2;
@@ -107,7 +128,8 @@ __global__ void xtc_decode_kernel(const unsigned char *__restrict__ file, long l
     float *col = out + f;  // element (a, d) of this frame: col[(a*3 + d) * fs]
     const bool rescale = scale != 1.0f;
     auto emit = [&](long long w, float v) { col[w * fs] = rescale ? __fmul_rn(v, scale) : v; };
-    if (fr.natoms != natoms || fr.data_offset < 0 || fr.nbytes < 0 || fr.data_offset + fr.nbytes > file_size) {
+    if (fr.natoms != natoms || fr.data_offset < 0 || fr.nbytes < 0 || fr.data_offset + fr.nbytes > file_size ||
+        ((reinterpret_cast<unsigned long long>(file) + (unsigned long long)fr.data_offset) & 3ull)) {  // XDR: word aligned
         status[f] = -1;
         return;
     }
@@ -136,7 +158,8 @@ __global__ void xtc_decode_kernel(const unsigned char *__restrict__ file, long l
     int smallnum = c_xtc_magic[smallidx] / 2;
     unsigned sizesmall = (unsigned)c_xtc_magic[smallidx];
     const float inv_precision = (float)(1.0 / (double)fr.precision);
-    XtcBits b{data, (long long)fr.nbytes, 0};
+    XtcBits b;
+    b.init(data, (long long)fr.nbytes);
     long long i = 0, w = 0;
     const long long wmax = 3 * natoms;
     int run = 0;

@@ -107,7 +107,8 @@ def read_xtc_device(filename, frames=None, scale: float = 1.0, device=None):
     idx = index_xtc(raw)
     sel = slice(None) if frames is None else np.asarray(frames, dtype=np.int64)
     dev = _dev(device)
-    d_bytes = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev) if len(raw) else torch.zeros(0, dtype=torch.uint8, device=dev)
+    # (+4 zero bytes: the kernel reads whole 32-bit words, and a file cut right after its last block has no XDR padding)
+    d_bytes = torch.frombuffer(bytearray(raw) + bytearray(4), dtype=torch.uint8).to(dev)
     coords = decode_xtc_device(d_bytes, idx["frames"][sel], idx["natoms"], scale=scale)
     return coords, idx["box"][:, :, sel], idx["time"][sel], idx["step"][sel]
 
