@@ -336,6 +336,32 @@ def extra_workloads(dev, peak):
                                          f"{nat * 3 * Fx * 4 / 1e6:.0f} MB frame-minor float32 on the device)",
                                 ms_per_call=ms, kernel_ms=kms, frames_per_s=Fx / (ms * 1e-3),
                                 atom_frames_per_s=nat * Fx / (ms * 1e-3), output_gbs=nat * 3 * Fx * 4 / (kms * 1e-3) / 1e9)
+    # C9: the trajectory pipeline end to end without a host round trip: XTC bytes in pinned host memory -> H2D -> decode
+    # (K11) -> wrap around the first 100 atoms (K9, 3-atom groups) -> fused periodic contact map 256 x 1024 (K3) -> per-frame
+    # contact counts -> D2H of the counts
+    pinned = torch.frombuffer(bytearray(raw) + bytearray(4), dtype=torch.uint8).pin_memory()
+    groups = torch.arange(0, nat + 1, 3, dtype=torch.int32, device=dev)
+    if int(groups[-1]) != nat:
+        groups = torch.cat([groups, torch.tensor([nat], dtype=torch.int32, device=dev)])
+    csel = torch.arange(0, 100, dtype=torch.int32, device=dev)
+    bx9 = torch.from_numpy(np.ascontiguousarray(idx["box"][[0, 1, 2], [0, 1, 2], :] * np.float32(10.0))).to(dev)
+    s1 = torch.arange(0, 256, dtype=torch.int32, device=dev); s2 = torch.arange(256, 1280, dtype=torch.int32, device=dev)
+    ch = torch.ones(nat, dtype=torch.int32, device=dev); ch[256:] = 2
+    cmap = torch.empty((Fx, 256 * 1024), dtype=torch.uint8, device=dev)
+    res = {}
+
+    def pipeline():
+        d_b = pinned.to(dev, non_blocking=True)
+        xyz = px.decode_xtc_device(d_b, idx["frames"], nat, scale=10.0, out=d_xyz)
+        wr.wrap_box_device(xyz, bx9, groups, csel)
+        c = du.dist_trajectory_device(xyz, bx9, s1, s2, ch, False, True, metric="contacts", threshold=8.0, out=cmap)
+        res["counts"] = c.sum(dim=1, dtype=torch.int32).cpu()
+
+    ms = _time_cuda(pipeline, warm=1, steps=3)
+    out["c9_trajectory_pipeline"] = dict(
+        workload=f"C9: XTC file ({len(raw) / 1e6:.0f} MB, pinned host) -> H2D -> decode -> wrap -> 256x1024 periodic contact map "
+                 f"-> per-frame counts -> D2H; {Fx} frames x {nat} atoms, nothing but the file and the counts crosses PCIe",
+        ms_per_call=ms, frames_per_s=Fx / (ms * 1e-3), mean_contacts_per_frame=float(res["counts"].float().mean()))
     return out
 
 
