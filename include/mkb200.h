@@ -145,7 +145,10 @@ int mkb_dist_trajectory(mkb_handle_t h, void *stream, const mkb_traj *t, const u
  *        counts; *total_pairs (HOST) receives the grand total (this call synchronises the stream).
  * fill : pairs [total_pairs, 2] uint32 device receives (sel1[i], sel2[j]) in the reference's order: frame-major,
  *        then i ascending, then j ascending -- bit-exact index output.  thr2 = threshold*threshold in float
- *        (pyx:77), compare `<=`. */
+ *        (pyx:77), compare `<=`.
+ * The count call keeps one hit mask per (row, 32 columns) in the handle; a fill call with the SAME arguments (pointers,
+ * sizes, flags, threshold) emits the pairs from those masks instead of evaluating the distances again, any other fill call
+ * recomputes them.  Either way the pairs are consistent with the row_offsets of the count call. */
 int mkb_contacts_count(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *sel1, int64_t n1,
                        const uint32_t *sel2, int64_t n2, const uint32_t *chains, int32_t selfdist, int32_t pbc,
                        float threshold, int64_t *row_offsets, int64_t *total_pairs);

@@ -26,6 +26,7 @@ enum ScratchSlot {
     S_COM,          // reductions: centres of mass
     S_TILE_TOTAL,   // occupancy fast paths: halo atom count per tile / per block
     S_BLOCK_BASE,   // occupancy warp kernel: first block id of every grid
+    S_K4_BALLOTS,   // contacts: hit masks of the count pass, reused by the fill pass
     S_NSLOTS
 };
 
@@ -45,6 +46,20 @@ struct mkb_ctx {
     // optional per-kernel timing (bench.py roofline): events recorded on the launch stream
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before prep, before main kernel, after main kernel
+    // K4: the count call leaves one ballot word per (row, 32 columns); the fill call that follows with the SAME arguments
+    // reads them instead of evaluating every distance a second time
+    struct K4Key {
+        const void *coords = nullptr, *box = nullptr, *sel1 = nullptr, *sel2 = nullptr, *chains = nullptr;
+        long long F = 0, n1 = 0, n2 = 0, fs = 0, fsb = 0;
+        int selfdist = 0, pbc = 0;
+        unsigned thr_bits = 0;
+        bool valid = false;
+        bool same(const K4Key &o) const {
+            return valid && o.valid && coords == o.coords && box == o.box && sel1 == o.sel1 && sel2 == o.sel2 &&
+                   chains == o.chains && F == o.F && n1 == o.n1 && n2 == o.n2 && fs == o.fs && fsb == o.fsb &&
+                   selfdist == o.selfdist && pbc == o.pbc && thr_bits == o.thr_bits;
+        }
+    } k4_key;
 };
 
 namespace mkb {

@@ -19,6 +19,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cmath>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -225,7 +226,9 @@ __global__ void MKB_K3_BOUNDS dist_kernel(const float4 *__restrict__ G1, const f
 // ---------------------------------------------------------------------------------------------------------
 // K4: ordered contacts.  One warp per (frame, i) row.  FILL = false: counts; FILL = true: ordered write.
 // ---------------------------------------------------------------------------------------------------------
-template <bool FILL>
+// BAL: 0 = no ballot buffer; 1 = count pass that also SAVES one ballot word per (row, 32-column chunk); 2 = fill pass that
+// READS those words instead of evaluating the distances again.
+template <bool FILL, int BAL>
 __global__ void __launch_bounds__(256) contacts_kernel(const float4 *__restrict__ G1, const float4 *__restrict__ G2,
                                                        long long n1, long long n2, long long n_frames,
                                                        const float *__restrict__ box, long long box_stride,
@@ -234,17 +237,37 @@ __global__ void __launch_bounds__(256) contacts_kernel(const float4 *__restrict_
                                                        const unsigned *__restrict__ sel2,
                                                        long long *__restrict__ row_counts,
                                                        const long long *__restrict__ row_offsets,
-                                                       unsigned *__restrict__ pairs) {
+                                                       unsigned *__restrict__ pairs, unsigned *__restrict__ ballots) {
     const int lane = threadIdx.x & 31;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n_frames * n1) return;
     const long long f = row / n1, i = row - f * n1;
-    const float4 a = G1[f * n1 + i];
-    const BoxF bx = load_box(box, box_stride, f);
+    const long long chunks = (n2 + 31) >> 5;
     const unsigned s1 = FILL ? sel1[i] : 0u;
     long long pos = FILL ? row_offsets[row] : 0;
     long long cnt = 0;
     const long long jstart = selfdist ? i + 1 : 0;
+    if (BAL == 2) {
+        const unsigned *rb = ballots + row * chunks;
+        for (long long c0 = jstart >> 5; c0 < chunks; c0 += 32) {  // 32 chunk words per coalesced load
+            const unsigned mine = c0 + lane < chunks ? rb[c0 + lane] : 0u;
+            unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
+            while (nz) {
+                const int k = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const unsigned bal = __shfl_sync(0xffffffffu, mine, k);
+                if ((bal >> lane) & 1u) {
+                    const long long p = pos + __popc(bal & ((1u << lane) - 1u));
+                    pairs[2 * p + 0] = s1;
+                    pairs[2 * p + 1] = sel2[((c0 + k) << 5) + lane];
+                }
+                pos += __popc(bal);
+            }
+        }
+        return;
+    }
+    const float4 a = G1[f * n1 + i];
+    const BoxF bx = load_box(box, box_stride, f);
     for (long long jb = jstart - (jstart & 31); jb < n2; jb += 32) {  // aligned chunks keep loads coalesced
         const long long j = jb + lane;
         bool hit = false;
@@ -253,6 +276,7 @@ __global__ void __launch_bounds__(256) contacts_kernel(const float4 *__restrict_
             hit = pair_d2_fastwrap(a, b, __float_as_uint(b.w), bx, pbc) <= thr2;  // distance_utils.pyx:90
         }
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (BAL == 1 && lane == 0) ballots[row * chunks + (jb >> 5)] = bal;
         if (FILL) {
             if (hit) {
                 const long long p = pos + __popc(bal & ((1u << lane) - 1u));
@@ -563,10 +587,30 @@ extern "C" int mkb_contacts_count(mkb_handle_t h, void *stream, const mkb_traj *
     long long *counts;
     if ((rc = scratch_get(h, S_ROWCNT, (size_t)rows + 1, &counts))) return rc;
     const float thr2 = threshold * threshold;  // float product, distance_utils.pyx:77
+    h->k4_key.valid = false;
     if (rows > 0) {
-        contacts_kernel<false><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(
-            G1, G2, n1, n2, t->n_frames, t->box, t->frame_stride_box, selfdist, pbc, thr2, sel1, sel2, counts,
-            nullptr, nullptr);
+        // one ballot word per (row, 32 columns) for the fill call that follows -- unless that would be excessive
+        const long long chunks = (n2 + 31) / 32;
+        const long long words = rows * chunks;
+        unsigned *ballots = nullptr;
+        if (words > 0 && words <= (1ll << 29) && !getenv("MKB_K4_NO_BALLOTS")) {
+            if ((rc = scratch_get(h, S_K4_BALLOTS, (size_t)words, &ballots))) return rc;
+        }
+        if (ballots) {
+            contacts_kernel<false, 1><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(
+                G1, G2, n1, n2, t->n_frames, t->box, t->frame_stride_box, selfdist, pbc, thr2, sel1, sel2, counts,
+                nullptr, nullptr, ballots);
+            mkb_ctx::K4Key &k = h->k4_key;
+            k.coords = t->coords; k.box = t->box; k.sel1 = sel1; k.sel2 = sel2; k.chains = chains;
+            k.F = t->n_frames; k.n1 = n1; k.n2 = n2; k.fs = t->frame_stride; k.fsb = t->frame_stride_box;
+            k.selfdist = selfdist; k.pbc = pbc;
+            memcpy(&k.thr_bits, &threshold, sizeof(float));
+            k.valid = true;
+        } else {
+            contacts_kernel<false, 0><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(
+                G1, G2, n1, n2, t->n_frames, t->box, t->frame_stride_box, selfdist, pbc, thr2, sel1, sel2, counts,
+                nullptr, nullptr, nullptr);
+        }
         MKB_LAUNCHED(h);
     }
     set_last_zero<<<1, 32, 0, st>>>(counts, rows);
@@ -585,16 +629,35 @@ extern "C" int mkb_contacts_fill(mkb_handle_t h, void *stream, const mkb_traj *t
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (!row_offsets) return fail(h, MKB_ERR_BAD_ARG, "null row_offsets");
-    float4 *G1, *G2;
-    int rc = contacts_common(h, st, t, sel1, n1, sel2, n2, chains, &G1, &G2);
+    int rc = check_traj(h, t);
     if (rc) return rc;
+    if (n1 < 0 || n2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative selection size");
     const long long rows = t->n_frames * n1;
     if (rows == 0) return MKB_OK;
     if (!pairs) return fail(h, MKB_ERR_BAD_ARG, "null pairs");
     const float thr2 = threshold * threshold;
-    contacts_kernel<true><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(
+    // the count call with exactly these arguments left its hit masks behind: emit the pairs from them (row_offsets were
+    // computed from the same masks, so the two stay consistent whatever happened to the coordinates in between)
+    mkb_ctx::K4Key now;
+    now.coords = t->coords; now.box = t->box; now.sel1 = sel1; now.sel2 = sel2; now.chains = chains;
+    now.F = t->n_frames; now.n1 = n1; now.n2 = n2; now.fs = t->frame_stride; now.fsb = t->frame_stride_box;
+    now.selfdist = selfdist; now.pbc = pbc;
+    memcpy(&now.thr_bits, &threshold, sizeof(float));
+    now.valid = true;
+    if (h->k4_key.same(now) && h->scratch[S_K4_BALLOTS].ptr) {
+        if (!sel1 || !sel2) return fail(h, MKB_ERR_BAD_ARG, "null argument");
+        contacts_kernel<true, 2><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(
+            nullptr, nullptr, n1, n2, t->n_frames, nullptr, 0, selfdist, pbc, thr2, sel1, sel2, nullptr,
+            (const long long *)row_offsets, pairs, static_cast<unsigned *>(h->scratch[S_K4_BALLOTS].ptr));
+        MKB_LAUNCHED(h);
+        h->k4_key.valid = false;  // one fill per count
+        return MKB_OK;
+    }
+    float4 *G1, *G2;
+    if ((rc = contacts_common(h, st, t, sel1, n1, sel2, n2, chains, &G1, &G2))) return rc;
+    contacts_kernel<true, 0><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(
         G1, G2, n1, n2, t->n_frames, t->box, t->frame_stride_box, selfdist, pbc, thr2, sel1, sel2, nullptr,
-        (const long long *)row_offsets, pairs);
+        (const long long *)row_offsets, pairs, nullptr);
     MKB_LAUNCHED(h);
     return MKB_OK;
 }

@@ -170,6 +170,25 @@ def test_minimum_image_boundaries(du, oracle):
         assert du.contacts_trajectory(c, bx, s1, s2, ch, False, True, thr) == oracle.contacts_trajectory(c, bx, s1, s2, ch, False, True, thr)
 
 
+def test_contacts_fill_from_cached_masks_equals_recomputation(du, oracle, monkeypatch):
+    """mkb_contacts_fill normally emits the pairs from the hit masks its count call left behind; with MKB_K4_NO_BALLOTS the
+    distances are evaluated a second time.  Same ordered pairs either way (self and non-self, ragged column counts)."""
+    rng = np.random.default_rng(19)
+    N, F = 333, 9
+    c = (rng.normal(size=(N, 3, F)) * 9).astype(np.float32)
+    bx = np.abs(rng.normal(size=(3, F)) * 2 + 21).astype(np.float32)
+    ch = rng.integers(0, 2, N).astype(np.uint32)
+    s1 = np.sort(rng.choice(N, 77, replace=False)).astype(np.uint32)
+    s2 = np.sort(rng.choice(N, 131, replace=False)).astype(np.uint32)
+    for selfd, a, b in ((False, s1, s2), (True, s2, s2)):
+        want = oracle.contacts_trajectory(c, bx, a, b, ch, selfd, True, 7.5)
+        cached = du.contacts_trajectory(c, bx, a, b, ch, selfd, True, 7.5)
+        with monkeypatch.context() as m:
+            m.setenv("MKB_K4_NO_BALLOTS", "1")
+            recomputed = du.contacts_trajectory(c, bx, a, b, ch, selfd, True, 7.5)
+        assert cached == want and recomputed == want and sum(len(x) for x in want) > 100
+
+
 def test_contact_threshold_ties(du, oracle):
     """metric="contacts" is decided on d2 (no sqrt): must equal sqrtf(d2) <= threshold of the reference incl. exact
     ties (3-4-5 triangles) and distances one ulp either side of the threshold."""
