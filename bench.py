@@ -268,6 +268,17 @@ def extra_workloads(dev, peak):
     out["c4b_sparse_contacts"] = dict(workload=f"C4b: {F} frames x {n1}x{n2} periodic pair tests <= 12 A, ordered index pairs",
                                       pair_tests_per_s=F * n1 * n2 / (ms * 1e-3), ms_per_step=ms, emitted_pairs=npairs,
                                       output_gbs=(npairs * 8 + F * n1 * 8) / (ms * 1e-3) / 1e9)
+    # C4c: residue-level minimum distances (K5, MetricSelfDistance groupsel="residue"): 300 groups of 10 atoms, self
+    n_res, per, Fc = 300, 10, 1000
+    groups = [list(range(r * per, (r + 1) * per)) for r in range(n_res)]
+    gch = torch.arange(n_res, dtype=torch.int32, device=dev) % 2
+    masses = torch.ones(n_res * per, dtype=torch.float32, device=dev)
+    d_cc = d_c[: n_res * per, :, :Fc].contiguous(); d_bc = d_b[:, :Fc].contiguous()
+    ms = _time_cuda(lambda: du.dist_reduction_device(d_cc, d_bc, groups, groups, gch, gch, True, True, masses, 0, 0), warm=1, steps=3)
+    npairs = n_res * (n_res - 1) // 2
+    out["c4c_residue_mindist"] = dict(workload=f"C4c: {Fc} frames x {npairs} residue pairs ({per}x{per} atoms each), periodic, closest",
+                                      ms_per_step=ms, group_pairs_per_s=Fc * npairs / (ms * 1e-3),
+                                      atom_pair_tests_per_s=Fc * npairs * per * per / (ms * 1e-3))
     del d_c, d_b, res
     # C6: orthorhombic wrapping (K9) of an unwrapped solvated system: 5k-atom solute + 18k waters, 512 frames
     from moleculekit_b200 import wrapping as wr

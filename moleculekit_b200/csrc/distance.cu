@@ -160,6 +160,24 @@ __device__ __forceinline__ float pair_d2_fastwrap(const float4 a, const float4 b
     return sq3(dx, dy, dz);
 }
 
+// same with the wrap decision made by the caller (group chains, K5)
+__device__ __forceinline__ float pair_d2_fastwrap_flag(const float4 a, const float4 b, const BoxF &bx, bool wrap) {
+    float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+    if (wrap) {
+        bool risky = false;
+        const float wx = wrap_fast(dx, bx.bx, bx.rx, bx.hx, risky), wy = wrap_fast(dy, bx.by, bx.ry, bx.hy, risky),
+                    wz = wrap_fast(dz, bx.bz, bx.rz, bx.hz, risky);
+        if (risky) {
+            dx = wrap_axis(dx, bx.bx, bx.rx);
+            dy = wrap_axis(dy, bx.by, bx.ry);
+            dz = wrap_axis(dz, bx.bz, bx.rz);
+        } else {
+            dx = wx; dy = wy; dz = wz;
+        }
+    }
+    return sq3(dx, dy, dz);
+}
+
 template <int MODE>
 __device__ __forceinline__ void emit_dist(void *out, long long idx, float d2, float truncate, float threshold) {
     if (MODE == DIST_CONTACTS_D2) reinterpret_cast<unsigned char *>(out)[idx] = (d2 <= threshold) ? 1 : 0;
@@ -452,6 +470,55 @@ __global__ void __launch_bounds__(256) reduction_kernel(const float4 *__restrict
     }
 }
 
+// Small groups (residue - residue minimum distances: ~100 atom pairs per group pair): ONE THREAD per (frame, group pair)
+// walks the m1 x m2 atom pairs itself -- every lane busy, no shuffle reduction, no index divisions in the loop.  Threads of
+// a warp share group a (broadcast loads) and take consecutive groups b.  Same semantics as reduction_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(128) reduction_thread_kernel(const float4 *__restrict__ G1, long long nflat1,
+                                                                const float4 *__restrict__ G2, long long nflat2,
+                                                                const float4 *__restrict__ com1,
+                                                                const float4 *__restrict__ com2,
+                                                                const long long *__restrict__ off1, long long NG1,
+                                                                const long long *__restrict__ off2, long long NG2,
+                                                                const unsigned *__restrict__ gch1,
+                                                                const unsigned *__restrict__ gch2, long long n_frames,
+                                                                const float *__restrict__ box, long long box_stride,
+                                                                int selfdist, int pbc, int red1, int red2, int pairs,
+                                                                float truncate, float threshold, long long P,
+                                                                void *__restrict__ out) {
+    const long long per_frame = pairs ? NG1 : NG1 * NG2;
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f = blockIdx.y;
+    if (r >= per_frame) return;
+    long long a, b, col;
+    if (pairs) { a = r; b = r; col = r; }
+    else {
+        a = r / NG2; b = r - a * NG2;
+        if (selfdist) { if (b <= a) return; col = a * NG2 - (a * (a + 1)) / 2 + (b - a - 1); }
+        else col = r;
+    }
+    const bool wrap = pbc && (gch1[a] != gch2[b]);
+    const BoxF bx = load_box(box, box_stride, f);
+    const long long s1 = off1[a], s2 = off2[b];
+    const int m1 = red1 ? 1 : (int)(off1[a + 1] - s1), m2 = red2 ? 1 : (int)(off2[b + 1] - s2);
+    const float4 *pa0 = red1 ? com1 + f * NG1 + a : G1 + f * nflat1 + s1;
+    const float4 *pb0 = red2 ? com2 + f * NG2 + b : G2 + f * nflat2 + s2;
+    float best = INFINITY, first = 0.f;
+    for (int ia = 0; ia < m1; ++ia) {
+        const float4 pa = __ldg(pa0 + ia);
+        for (int ib = 0; ib < m2; ++ib) {
+            const float d2 = pair_d2_fastwrap_flag(pa, __ldg(pb0 + ib), bx, wrap);
+            if ((ia | ib) == 0) first = d2;
+            if (d2 < best) best = d2;
+        }
+    }
+    float m;
+    if (m1 <= 0 || m2 <= 0) m = -1.f;     // empty group: sqrt(-1) = NaN like the reference
+    else if (first != first) m = first;   // a NaN first element sticks (all later `<` comparisons are false)
+    else m = best;
+    store_dist<MODE>(out, f * P + col, __fsqrt_rn(m), truncate, threshold);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K6: cdist / pdist / squareform
 // ---------------------------------------------------------------------------------------------------------
@@ -705,6 +772,23 @@ extern "C" int mkb_dist_reduction(mkb_handle_t h, void *stream, const mkb_traj *
     }
     const long long per_frame = pairs ? NG1 : NG1 * NG2;
     const long long warps = F * per_frame;
+    // average atom pairs per group pair decides the work decomposition: small groups -> one thread per group pair
+    const double avg_pairs = (double)(red1 ? NG1 : nf1) / (double)std::max<long long>(NG1, 1) *
+                             (double)(red2 ? NG2 : nf2) / (double)std::max<long long>(NG2, 1);
+    const bool thread_per_pair = avg_pairs <= 512.0 && per_frame >= 4096 && F <= 65535 && !getenv("MKB_K5_WARP");
+    if (thread_per_pair) {
+        const dim3 grid((unsigned)cdiv(per_frame, 128), (unsigned)F);
+        if (mode == MKB_DIST_DISTANCES)
+            reduction_thread_kernel<MKB_DIST_DISTANCES><<<grid, 128, 0, st>>>(
+                G1, nf1, G2, nf2, com1, com2, (const long long *)g1_off, NG1, (const long long *)g2_off, NG2, gchains1,
+                gchains2, F, t->box, t->frame_stride_box, selfdist, pbc, red1, red2, pairs, truncate, threshold, P, out);
+        else
+            reduction_thread_kernel<MKB_DIST_CONTACTS><<<grid, 128, 0, st>>>(
+                G1, nf1, G2, nf2, com1, com2, (const long long *)g1_off, NG1, (const long long *)g2_off, NG2, gchains1,
+                gchains2, F, t->box, t->frame_stride_box, selfdist, pbc, red1, red2, pairs, truncate, threshold, P, out);
+        MKB_LAUNCHED(h);
+        return MKB_OK;
+    }
     if (warps * 32 / 256 >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "too many group pairs for one call");
     const unsigned nb = (unsigned)cdiv(warps * 32, 256);
     if (mode == MKB_DIST_DISTANCES)

@@ -81,6 +81,39 @@ def test_raw_reductions(du, g_raw):
     assert np.array_equal(_bits(r), _bits(g["red_pairs_01"]))
 
 
+def test_reductions_many_small_groups_thread_kernel(du, oracle, monkeypatch):
+    """Many small groups (residue-level minimum distances) take the one-thread-per-group-pair kernel; it must give the bits
+    of the oracle and of the warp-per-pair kernel (MKB_K5_WARP=1): closest / COM combinations, self distances, a NaN first
+    atom (sticks, pyx:260-275), an unusable box component."""
+    rng = np.random.default_rng(23)
+    N, F, NG = 420, 5, 90
+    c = (rng.normal(size=(N, 3, F)) * 11).astype(np.float32)
+    bx = np.abs(rng.normal(size=(3, F)) * 2 + 19).astype(np.float32)
+    bx[2, 3] = 0.0
+    cuts = np.sort(rng.choice(np.arange(1, N), NG - 1, replace=False))
+    groups = [list(range(a, b)) for a, b in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [N]]))]
+    c[groups[7][0], 1, 2] = np.nan  # first atom of group 7 in frame 2
+    gch = rng.integers(0, 3, NG).astype(np.uint32)
+    masses = rng.uniform(1, 16, N).astype(np.float32)
+    g2 = groups[:70]
+    for selfd, ga, gb, ca, cb in ((False, groups, g2, gch, gch[:70]), (True, groups, groups, gch, gch)):
+        P = du.n_columns(len(ga), len(gb), selfd)
+        for r1, r2 in ((0, 0), (1, 0), (1, 1)):
+            if selfd and (r1, r2) != (0, 0):
+                continue
+            want = np.zeros((F, P), np.float32)
+            with np.errstate(all="ignore"):
+                oracle.dist_trajectory_reduction(c, bx, ga, gb, ca, cb, selfd, True, masses, r1, r2, want)
+            got = np.zeros((F, P), np.float32)
+            du.dist_trajectory_reduction(c, bx, ga, gb, ca, cb, selfd, True, masses, r1, r2, got)
+            with monkeypatch.context() as m:
+                m.setenv("MKB_K5_WARP", "1")
+                warp = np.zeros((F, P), np.float32)
+                du.dist_trajectory_reduction(c, bx, ga, gb, ca, cb, selfd, True, masses, r1, r2, warp)
+            assert np.isnan(want).any() and np.array_equal(_bits(got), _bits(want)), (selfd, r1, r2)
+            assert np.array_equal(_bits(warp), _bits(want)), (selfd, r1, r2)
+
+
 def test_raw_cdist_pdist_squareform_collisions(du, g_raw):
     g = g_raw
     for D in (1, 2, 3, 5):
