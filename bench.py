@@ -263,6 +263,7 @@ def extra_workloads(dev, peak):
     def run_contacts():
         res["off"], res["pairs"] = du.contacts_trajectory_device(d_c, d_b, s1, s2, ch, False, True, 12.0)
 
+    n1c, n2c, Fsh = n1, n2, 1000
     ms = _time_cuda(run_contacts, warm=2, steps=3)
     npairs = int(res["pairs"].shape[0])
     out["c4b_sparse_contacts"] = dict(workload=f"C4b: {F} frames x {n1}x{n2} periodic pair tests <= 12 A, ordered index pairs",
@@ -331,6 +332,42 @@ def extra_workloads(dev, peak):
     out["c7_within"] = dict(workload=f"C7: within 5 A of {n2} source atoms, {N} query atoms (cell list; reference = brute force)",
                             ms_per_call=ms, selected=int(res["m"].sum().item()), pair_tests_avoided=float(N) * n2,
                             equivalent_pair_tests_per_s=float(N) * n2 / (ms * 1e-3))
+    # C4d: MetricShell radial histograms (K8): 500 centres x 4500 partners, 4 shells, 1000 frames of the C4b trajectory
+    edges = torch.tensor([0.0, 3.0, 6.0, 9.0, 12.0], dtype=torch.float64, device=dev)
+    c4 = start + np.cumsum(rng.normal(0, 0.3, size=(n1c + n2c, 3, Fsh)).astype(np.float32), axis=2)
+    d_c4 = torch.from_numpy(np.ascontiguousarray(c4)).to(dev); d_b4 = torch.from_numpy(np.ascontiguousarray(box[:, :Fsh])).to(dev)
+    ms = _time_cuda(lambda: du.shell_counts_device(d_c4, d_b4, s1, s2, ch, False, True, edges), warm=1, steps=3)
+    out["c4d_metricshell"] = dict(workload=f"C4d: MetricShell, {Fsh} frames x {n1c} centres x {n2c} partners, 4 shells, periodic",
+                                  ms_per_step=ms, pair_tests_per_s=Fsh * n1c * n2c / (ms * 1e-3))
+    del d_c4, d_b4
+    # C1: one getVoxelDescriptors call, host arrays in and out (latency of the drop-in API on a 3PTB-sized molecule)
+    import time as _time
+
+    from moleculekit_b200.molecule_lite import MolLite
+
+    w1 = workloads.protein_pockets(B=1, n_atoms=1639, box=60.0, radius=17.0, seed=5)
+    mol1 = MolLite(w1["coords"][0])
+    vd.getVoxelDescriptors(mol1, userchannels=w1["sigmas"][0], buffer=8, voxelsize=1)
+    torch.cuda.synchronize(dev)
+    t0 = _time.perf_counter()
+    for _ in range(5):
+        f1, c1, n1v = vd.getVoxelDescriptors(mol1, userchannels=w1["sigmas"][0], buffer=8, voxelsize=1)
+    dt = (_time.perf_counter() - t0) / 5
+    out["c1_single_call"] = dict(workload=f"C1-like: one getVoxelDescriptors call, 1639 atoms, grid {list(map(int, n1v))}, host float64 in/out",
+                                 ms_per_call=dt * 1e3, voxel_channels_per_s=f1.size / dt)
+    # C7b: bond perception (K7) on a 100k-atom solvated system
+    from moleculekit_b200.bondguesser import bond_grid_search
+
+    nb_at = 100_000
+    xyzb = (rng.uniform(0, 100, size=(nb_at // 3, 1, 3)) + rng.normal(0, 0.6, size=(nb_at // 3, 3, 3))).reshape(-1, 3).astype(np.float32)
+    radb = np.tile(np.array([1.52, 1.0, 1.0], np.float32), nb_at // 3)
+    ishb = (radb == 1.0).astype(np.uint32)
+    bond_grid_search(xyzb, 1.9 * 1.2, ishb, radb)
+    t0 = _time.perf_counter()
+    bonds = bond_grid_search(xyzb, 1.9 * 1.2, ishb, radb)
+    dt = _time.perf_counter() - t0
+    out["c7b_bond_search"] = dict(workload=f"K7: bond_grid_search, {len(xyzb)} atoms (host arrays in, sorted pairs out)", ms_per_call=dt * 1e3,
+                                  bonds=int(len(bonds)))
     # C8: XTC decode on the device (K11): the 3 frames of tests/golden/xtc/real3.xtc (4507 atoms, re-encoded frames of the
     # reference's test trajectory) repeated to a 3000-frame file
     from moleculekit_b200 import xtc as px
