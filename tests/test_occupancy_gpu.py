@@ -120,7 +120,7 @@ def test_channel_counts_and_multisigma(vd, oracle, C):
     _assert_occ_close(feats, want)
 
 
-@pytest.mark.parametrize("vs", [0.5, 0.7, 1.0, 1.9])
+@pytest.mark.parametrize("vs", [0.3, 0.4, 0.5, 0.7, 1.0, 1.9, 2.6])  # 0.3: tile kernel (halo rows exceed a warp), 0.4-1.0: 2x4x8 block kernel
 def test_voxel_sizes_buffer_mode(vd, oracle, vs):
     from moleculekit_b200.molecule_lite import MolLite
 
