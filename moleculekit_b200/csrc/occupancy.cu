@@ -1083,8 +1083,14 @@ __global__ void __launch_bounds__(W_WARPS * 32, W_MIN_CTAS) occ_fill8w_kernel(co
 //     * two independent dependency chains per lane (ILP) stand in for the halved number of resident warps.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int V_BZ = 8;       // block extent along z
-constexpr int V_PCAP = 160;   // block candidates per round
-constexpr int V_QCAP = 96;    // sub-block candidates per round
+#ifndef MKB_V_PCAP
+#define MKB_V_PCAP 192  // capacity sweep (ms per 256 pockets): 128/96 1.864, 160/96 1.858, 224/96 1.841, 192/128 1.814, 224/128 1.825, 256/128 1.850
+#endif
+#ifndef MKB_V_QCAP
+#define MKB_V_QCAP 128
+#endif
+constexpr int V_PCAP = MKB_V_PCAP;   // block candidates per round
+constexpr int V_QCAP = MKB_V_QCAP;   // sub-block candidates per round
 constexpr int V_QSTRIDE = V_QCAP + 2;  // + one sentinel slot for the software-pipelined loop
 #ifndef MKB_V_UNROLL2
 #define MKB_V_UNROLL2 0  // two candidates per trip: 2.19 vs 2.03 ms (spills at 72 registers)
