@@ -11,6 +11,7 @@ importable we defer to its ``getChannels`` for the default-channel case.
 """
 from __future__ import annotations
 
+import functools
 import logging
 
 import numpy as np
@@ -60,17 +61,24 @@ def _grid_spec(mol, buffer, boxsize, center, voxelsize):
     return bb_min, nvoxels
 
 
+@functools.lru_cache(maxsize=10)
+def _grid_offsets(nx: int, ny: int, nz: int, voxelsize: float) -> np.ndarray:
+    """(nx, ny, nz, 3) float64 float64(i_d * voxelsize), cached per grid shape like the reference's _getGridCenters
+    (voxeldescriptors.py:116-123, lru_cache(10))."""
+    out = np.empty((nx, ny, nz, 3), dtype=np.float64)
+    for d, n in enumerate((nx, ny, nz)):
+        shape = [1, 1, 1]
+        shape[d] = n
+        out[..., d] = (np.arange(n) * voxelsize).astype(np.float64).reshape(shape)
+    out.setflags(write=False)
+    return out
+
+
 def _centers_from_spec(bb_min, nvoxels, voxelsize) -> np.ndarray:
     """(prod(nvoxels), 3) float64 centres, bit-identical to voxeldescriptors.py:125-132,245-247:
     c[ix,iy,iz,d] = float64(i_d * voxelsize) + bb_min[d], z fastest."""
     nx, ny, nz = (int(v) for v in nvoxels)
-    out = np.empty((nx, ny, nz, 3), dtype=np.float64)
-    for d, n in enumerate((nx, ny, nz)):
-        axis = (np.arange(n) * voxelsize).astype(np.float64) + np.asarray(bb_min)[d]
-        shape = [1, 1, 1]
-        shape[d] = n
-        out[..., d] = axis.reshape(shape)
-    return out.reshape(nx * ny * nz, 3)
+    return (_grid_offsets(nx, ny, nz, float(voxelsize)) + np.asarray(bb_min, dtype=np.float64)).reshape(nx * ny * nz, 3)
 
 
 def getCenters(mol=None, buffer: float = 0, boxsize: list | None = None, center: list | None = None,
@@ -150,6 +158,17 @@ def getChannels(mol, aromaticNitrogen: bool = False, version: int = 2, validityc
 
 
 # ----------------------------------------------------------------------------------------------- device drivers
+_stage_buf: torch.Tensor | None = None
+
+
+def _staging(n: int) -> torch.Tensor:
+    """Grow-only page-locked float32 staging buffer for the single-call path (drop-in calls return pageable numpy)."""
+    global _stage_buf
+    if _stage_buf is None or _stage_buf.numel() < n:
+        _stage_buf = torch.empty(max(n, 1 << 20), dtype=torch.float32, pin_memory=True)
+    return _stage_buf[:n]
+
+
 def _occupancy_grid(coords, sigmas, bb_min, nvoxels, voxelsize, device=None) -> np.ndarray:
     """One regular grid -> (M, C) float64 numpy (the `_getOccupancyC` of the reference, :515-533)."""
     coords = np.ascontiguousarray(np.asarray(coords).astype(np.float32))
@@ -167,7 +186,10 @@ def _occupancy_grid(coords, sigmas, bb_min, nvoxels, voxelsize, device=None) -> 
                                         np.asarray(nvoxels)[None, :], np.array([0, coords.shape[0]]))
         d_out = torch.empty((M, c1 - c0), dtype=torch.float32, device=dev)
         _occ.occupancy_grid_batch(d_coords, d_sig, descs, d_out)
-        feats[:, c0:c1] = d_out.cpu().numpy()
+        stage = _staging(M * (c1 - c0)).view(M, c1 - c0)  # page-locked: the D2H runs at PCIe rate, then one upcast pass
+        stage.copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        feats[:, c0:c1] = stage.numpy()
     return feats
 
 
