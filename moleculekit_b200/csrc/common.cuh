@@ -27,6 +27,9 @@ enum ScratchSlot {
     S_TILE_TOTAL,   // occupancy fast paths: halo atom count per tile / per block
     S_BLOCK_BASE,   // occupancy warp kernel: first block id of every grid
     S_K4_BALLOTS,   // contacts: hit masks of the count pass, reused by the fill pass
+    S_BAND_BITMAP,  // occupancy run kernel: one bit per voxel whose gate decision is re-done in float64
+    S_QUEUE,        // occupancy run kernel: block queue counter
+    S_FIX_LIST,     // occupancy run kernel: voxels re-evaluated in float64 (count + list)
     S_NSLOTS
 };
 

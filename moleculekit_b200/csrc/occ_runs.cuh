@@ -1,0 +1,683 @@
+// occ_runs.cuh -- K1 v7, the default 8-channel fill: persistent "mask-run" kernel with TMA (cp.async.bulk) stores.
+// Included by occupancy.cu (after GridDev / exact_gate / occ_value).
+//
+// Replaces the inner loop of moleculekit/occupancy_utils/occupancy_utils.pyx:46-61.  What changed against v6
+// (occ_fill8v_kernel, 111 lane-instructions per in-gate (atom, voxel) pair, 16 predicated FMNMX per candidate):
+//
+//   * The hot loop tracks  r = d2 / sigma^2  (a MIN; q = 1/r) instead of max q = sigma^2 / d2: no reciprocal per pair.
+//     The record of a candidate is pre-scaled by 1/sigma -- (x, y, z)/sigma in the block-centre frame plus 1/sigma --
+//     so r of a voxel is two FFMAs:  dxs = fma(x_k, 1/sigma, -x_a/sigma);  r = fma(dxs, dxs, dys^2 + dzs^2).
+//   * One warp owns a 4x4x8 voxel block; a lane owns the 4 voxels of one x-row (they share dys, dzs).  The candidate
+//     is WARP-UNIFORM (one LDS.128 broadcast), so its channel mask is uniform too: candidates are counting-sorted by
+//     mask into runs (lane-parallel, shared-memory histogram), a run keeps ONE scalar running minimum per voxel
+//     (FSETP gate + predicated FMNMX), and the 8-channel update happens once per run, not once per pair.
+//   * The 5 A gate is a plain float compare in the loop.  Pairs whose d2 lies within 4e-6 (relative) of the gate
+//     -- where float32 could decide differently from the reference's float64 -- are found by a per-atom pre-pass
+//     (occ_band_kernel: the two lattice crossings of every (y, z) row of the cutoff sphere) and their voxels are
+//     recomputed in float64 with the reference's operation order by occ_fix_kernel after the fill.
+//   * Persistent CTAs (7 x 148 x 4 warps) pull blocks from an atomic queue; results are staged in shared memory in
+//     the output layout and leave the SM as cp.async.bulk.global.shared::cta row copies (SASS UBLKCP); the ~70 % of
+//     blocks without any atom in reach are 16 bulk copies from a zeroed shared-memory line, no CTA launch, no math.
+#pragma once
+
+namespace mkb {
+
+constexpr int R_BZ = 8;          // block = 4 x 4 x 8 voxels
+#ifndef MKB_R_CAP
+#define MKB_R_CAP 256            // candidates per round
+#endif
+constexpr int R_CAP = MKB_R_CAP;
+constexpr int R_ROWS = 64;       // cell rows (x, y) feeding one block: cutoff <= 14 voxels
+#ifndef MKB_R_WARPS
+#define MKB_R_WARPS 4
+#endif
+constexpr int R_WARPS = MKB_R_WARPS;
+#ifndef MKB_R_MIN_CTAS
+#define MKB_R_MIN_CTAS 7
+#endif
+#ifndef MKB_R_ZC
+#define MKB_R_ZC 4               // consecutive z blocks per queue item (they share the x/y set-up of the halo rows)
+#endif
+constexpr int R_ZC = MKB_R_ZC;
+constexpr int R_WARP_BYTES = ((R_CAP * 26 + 512 + R_ROWS * 4 + (R_ROWS + 4) * 4) + 127) / 128 * 128;
+static_assert(R_CAP * 16 >= 4096, "the 4 KB output stage aliases the candidate records (and only those)");
+static_assert(R_CAP <= 256 && R_CAP % 32 == 0, "ranks are bytes");
+#ifndef MKB_R_FMA_GATE
+#define MKB_R_FMA_GATE 0
+#endif
+constexpr float R_GATE_BIG = 1099511627776.0f;       // 2^40
+constexpr float R_GATE_HUGE = 8.507059173023462e37f;  // 2^126: what an out-of-range pair adds to r
+constexpr float R_BAND = 4e-6f;  // relative half-width of the band the float64 fix-up covers
+
+struct RunParams {
+    const GridDev *grids;
+    int B;
+    const float4 *rec_pos;
+    const uint4 *rec_tag;
+    const unsigned *cell_start;
+    const double *sigmas;        // multi-sigma atoms only
+    float *out;
+    const long long *item_base;  // [B + 1]: first queue item of every grid (item = 4 x 4 voxels in x, y and R_ZC blocks in z)
+    unsigned *queue;
+    unsigned total_items;
+    int cmajor;                  // MKB_OCC_LAYOUT_CXYZ: grid stored [C][nx][ny][nz]; plain 32-byte-segment stores instead of TMA rows
+    // uniform batches: descriptor of the first grid + strides (constant-bank operands)
+    GridDev u;
+    long long u_out_stride, u_cell_stride;
+    unsigned u_ipg, u_nby, u_nzc;  // items per grid, y blocks, z chunks
+};
+
+__device__ __forceinline__ void bulk_store_row(float *dst, unsigned src_smem, int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void store_cmajor_zero(float *grid, int nx, int ny, int nz, int x0, int iy, int iz) {
+    if (iy >= ny || iz >= nz) return;
+    const long long cs = (long long)nx * ny * nz;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (x0 + k < nx) {
+            float *const o = grid + ((long long)(x0 + k) * ny + iy) * nz + iz;
+#pragma unroll
+            for (int h = 0; h < 8; ++h) __stcs(o + h * cs, 0.0f);
+        }
+}
+// gate + running minimum: FSETP + predicated FMNMX (both on the ALU pipe), nothing else
+__device__ __forceinline__ void gated_min(float &m, float r, float cw) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p min.f32 %0, %0, %1;\n\t}" : "+f"(m) : "f"(r), "f"(cw));
+}
+// run end: the run's four minima go into the channels of its mask.  One real (warp-uniform) branch per channel: a dead
+// channel costs a test and a jump, not four FMNMX issue slots (nvcc if-converts the C++ form into 32 predicated FMNMX),
+// and the code stays 50 instructions long (a jump table per mask nibble thrashed the instruction cache).
+// run end: the run's four minima go into the channels of its mask.  MKB_R_FLUSH 0: 32 predicated FMNMX (compact, but every
+// one issues whether its channel is live or not); 1: one jump per mask nibble into code with only the live channels.
+#ifndef MKB_R_FLUSH
+#define MKB_R_FLUSH 1
+#endif
+template <int M, int BASE>
+__device__ __forceinline__ void apply_nibble(float (&acc)[8][4], float m0, float m1, float m2, float m3) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        if (M & (1 << b)) {
+            acc[BASE + b][0] = fminf(acc[BASE + b][0], m0); acc[BASE + b][1] = fminf(acc[BASE + b][1], m1);
+            acc[BASE + b][2] = fminf(acc[BASE + b][2], m2); acc[BASE + b][3] = fminf(acc[BASE + b][3], m3);
+        }
+}
+#define MKB_NIB_CASE(M, BASE) case M: apply_nibble<M, BASE>(acc, m0, m1, m2, m3); break;
+#define MKB_NIB_SWITCH(sel, BASE)                                                                          \
+    switch (sel) {                                                                                         \
+        MKB_NIB_CASE(1, BASE) MKB_NIB_CASE(2, BASE) MKB_NIB_CASE(3, BASE) MKB_NIB_CASE(4, BASE) MKB_NIB_CASE(5, BASE)       \
+        MKB_NIB_CASE(6, BASE) MKB_NIB_CASE(7, BASE) MKB_NIB_CASE(8, BASE) MKB_NIB_CASE(9, BASE) MKB_NIB_CASE(10, BASE)      \
+        MKB_NIB_CASE(11, BASE) MKB_NIB_CASE(12, BASE) MKB_NIB_CASE(13, BASE) MKB_NIB_CASE(14, BASE) MKB_NIB_CASE(15, BASE)  \
+        default: break;                                                                                    \
+    }
+
+#define RG(field) (UNIFORM ? p.u.field : __ldg(&gg->field))
+template <bool UNIFORM>
+__global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_kernel(const RunParams p) {
+    __shared__ __align__(128) unsigned char s_raw[R_WARPS][R_WARP_BYTES];
+    __shared__ __align__(128) float s_zero[64];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *const wb = s_raw[warp];
+    float4 *const rec = reinterpret_cast<float4 *>(wb);                         // sorted candidates: (x, y, z)/sigma, 1/sigma
+    float *const cwv = reinterpret_cast<float *>(wb + R_CAP * 16);              // gate in r units: cut2 / sigma^2
+    unsigned *const tmp = reinterpret_cast<unsigned *>(wb + R_CAP * 20);        // survivors (record index); then the run table
+    unsigned char *const key = wb + R_CAP * 24;
+    unsigned char *const rnk = wb + R_CAP * 25;
+    unsigned *const hist = reinterpret_cast<unsigned *>(wb + R_CAP * 26);       // 256 x 16-bit bins in 128 words
+    unsigned *const rpos = hist + 128;
+    unsigned *const rbase = rpos + R_ROWS;
+    const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(wb);
+    const unsigned zero_sa = (unsigned)__cvta_generic_to_shared(s_zero);
+
+    if (threadIdx.x < 64) s_zero[threadIdx.x] = 0.0f;
+    for (int i = lane; i < 128; i += 32) hist[i] = 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const int ly = lane >> 3, lz = lane & 7;
+    const float fy = (float)ly - 1.5f, fz = (float)lz - 3.5f;  // block frame: origin at the block centre
+    const unsigned lt = (1u << lane) - 1u;
+    const float INF = __int_as_float(0x7f800000);
+    bool pending = false;  // lanes 0..15: bulk copies still reading the stage
+
+    for (;;) {
+        unsigned id = 0;
+        if (lane == 0) id = atomicAdd(p.queue, 1u);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= p.total_items) break;
+        // ---- decode the item: grid, (x, y) block column, chunk of R_ZC z blocks.  Everything that depends on x, y only
+        // (cell rows of the halo, output row pointers) is set up once for the R_ZC blocks.
+        int gi;
+        unsigned local;
+        if (UNIFORM) {
+            gi = (int)(id / p.u_ipg);
+            local = id - (unsigned)gi * p.u_ipg;
+        } else {
+            int lo = 0, hi = p.B - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (__ldg(p.item_base + mid) <= (long long)id) lo = mid; else hi = mid - 1;
+            }
+            gi = lo;
+            local = id - (unsigned)__ldg(p.item_base + gi);
+        }
+        const GridDev *gg = p.grids + gi;
+        const int nx = RG(dims[0]), ny = RG(dims[1]), nz = RG(dims[2]);
+        const int nbz = (nz + R_BZ - 1) / R_BZ;
+        const unsigned nby = UNIFORM ? p.u_nby : (unsigned)(ny + 3) >> 2, nzc = UNIFORM ? p.u_nzc : (unsigned)(nbz + R_ZC - 1) / R_ZC;
+        const int zc = (int)(local % nzc);
+        const unsigned bxy = local / nzc;
+        const int byi = (int)(bxy % nby), bxi = (int)(bxy / nby);
+        const int x0 = bxi * 4, y0 = byi * 4;
+        const long long out_offset = UNIFORM ? p.u.out_offset + (long long)gi * p.u_out_stride : __ldg(&gg->out_offset);
+        // output rows of a block: lane (< 16) -> (x = lane >> 2, y = lane & 3), 8 voxels x 8 channels = 256 B each
+        const int rix = x0 + (lane >> 2), riy = y0 + (lane & 3);
+        const bool row_ok = lane < 16 && rix < nx && riy < ny;
+        float *const row_base = p.out + (out_offset + ((long long)rix * ny + riy) * nz) * 8;
+        // cell rows of the halo (cells of 4 voxels, rows run along z): lane -> rows lane and lane + 32
+        const int cutv = RG(cutv);
+        const int cN1 = RG(cells[1]), cN2 = RG(cells[2]);
+        const int cx0 = bxi, cx1 = min((x0 + 3 + 2 * cutv) >> 2, RG(cells[0]) - 1);
+        const int cy0 = byi, cy1 = min((y0 + 3 + 2 * cutv) >> 2, cN1 - 1);
+        const int ncy = cy1 - cy0 + 1;
+        const int nrows = (cx1 - cx0 + 1) * ncy;  // <= R_ROWS (host)
+        const float cut2 = RG(cut2v);
+        const float cut_cull = cut2 * (1.0f + 1e-5f);
+        const unsigned *const cstart = p.cell_start + (UNIFORM ? p.u.cell_base + (long long)gi * p.u_cell_stride : __ldg(&gg->cell_base));
+        unsigned rowc[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int r = lane + 32 * q;
+            rowc[q] = 0xffffffffu;
+            if (r < nrows) {
+                const int rx = (int)(((float)r + 0.5f) / (float)ncy), ry = r - rx * ncy;
+                // corner rows further than the cutoff from the block's x/y extent cannot contribute
+                const int lox = (cx0 + rx) * 4 - cutv, loy = (cy0 + ry) * 4 - cutv;
+                const int gx = max(max(lox - (x0 + 3), x0 - (lox + 4)), 0);
+                const int gy = max(max(loy - (y0 + 3), y0 - (loy + 4)), 0);
+                if ((float)(gx * gx + gy * gy) <= cut_cull) rowc[q] = (unsigned)(((cx0 + rx) * cN1 + (cy0 + ry)) * cN2);
+            }
+        }
+        const int sx = x0 + cutv, sy = y0 + cutv;
+
+        const int bz_end = min(nbz, (zc + 1) * R_ZC);
+        for (int bzi = zc * R_ZC; bzi < bz_end; ++bzi) {
+            const int z0 = bzi * R_BZ;
+            const int row_bytes = min(R_BZ, nz - z0) * 32;
+            float *const row_dst = row_base + z0 * 8;
+
+            // ---- row lengths of this block's z range + scan
+            const int cz0 = bzi * 2, cz1 = min((z0 + R_BZ - 1 + 2 * cutv) >> 2, cN2 - 1);
+            unsigned total = 0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (q * 32 < nrows) {  // warp-uniform
+                    unsigned v = 0, a = 0;
+                    if (rowc[q] != 0xffffffffu) {
+                        a = __ldg(cstart + rowc[q] + cz0);
+                        v = __ldg(cstart + rowc[q] + cz1 + 1) - a;
+                    }
+                    const unsigned len = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+                        if (lane >= o) v += t;
+                    }
+                    rpos[lane + 32 * q] = a;
+                    rbase[lane + 32 * q + 1] = v + total;  // rows past nrows repeat the total
+                    (void)len;
+                    total += __shfl_sync(0xffffffffu, v, 31);
+                }
+            }
+            if (total == 0) {
+                // no atom in reach: 16 rows of zeros straight from the zero line (TMA, nothing to wait for)
+                if (p.cmajor) {
+                    store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, z0 + lz);
+                } else {
+                    if (row_ok) bulk_store_row(row_dst, zero_sa, row_bytes);
+                    if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                continue;
+            }
+            if (lane == 0) rbase[0] = 0;
+            __syncwarp();
+
+            float acc[8][4];
+#pragma unroll
+            for (int h = 0; h < 8; ++h)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[h][k] = INF;
+            bool touched = false;
+            const int sz = z0 + cutv;
+            int np = 0, row = 0;
+            for (unsigned k0 = 0; k0 < total; k0 += 32) {
+                // ---- gather 32 atoms of the concatenated rows; keep those within reach of the block
+                {
+                    const unsigned k = min(k0 + lane, total - 1);
+                    while (rbase[row + 1] <= k) ++row;
+                    const unsigned i = rpos[row] + (k - rbase[row]);
+                    const float4 e = __ldg(p.rec_pos + i);
+                    const uint4 tg = __ldg(p.rec_tag + i);
+                    const float ex = e.x + ((float)((int)(tg.z & 1023u) * 4 - sx) - 1.5f);
+                    const float ey = e.y + ((float)((int)((tg.z >> 10) & 1023u) * 4 - sy) - 1.5f);
+                    const float ez = e.z + ((float)((int)(tg.z >> 20) * 4 - sz) - 3.5f);
+                    const float ddx = fmaxf(fabsf(ex) - 1.5f, 0.f);
+                    const float ddy = fmaxf(fabsf(ey) - 1.5f, 0.f);
+                    const float ddz = fmaxf(fabsf(ez) - 3.5f, 0.f);
+                    const bool pass = (k0 + lane < total) & (tg.x != 0) & (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= cut_cull);
+                    const bool multi = pass & ((tg.y >> 31) != 0);
+                    const bool single = pass & !multi;
+                    // atoms with several distinct sigmas (user float channels): whole-warp per-channel path
+                    for (unsigned bm = __ballot_sync(0xffffffffu, multi); bm; bm &= bm - 1) {
+                        const int sl = __ffs(bm) - 1;
+                        const float ax = __shfl_sync(0xffffffffu, ex, sl), ay = __shfl_sync(0xffffffffu, ey, sl),
+                                    az = __shfl_sync(0xffffffffu, ez, sl);
+                        const unsigned src = __shfl_sync(0xffffffffu, tg.y, sl) & 0x7fffffffu;
+                        const float dy = ay - fy, dz = az - fz;
+                        const float s2 = fmaf(dz, dz, dy * dy);
+                        const double ivs = RG(inv_vs);
+                        float d2[4];
+#pragma unroll
+                        for (int k2 = 0; k2 < 4; ++k2) {
+                            const float dx = ax - ((float)k2 - 1.5f);
+                            d2[k2] = fmaf(dx, dx, s2);
+                        }
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) {
+                            const double sv = __ldg(p.sigmas + (long long)src * 8 + h) * ivs;
+                            if (sv == 0.0 || sv != sv) continue;
+                            const float w = (float)(1.0 / (sv * sv));
+#pragma unroll
+                            for (int k2 = 0; k2 < 4; ++k2)
+                                if (d2[k2] < cut2) acc[h][k2] = fminf(acc[h][k2], d2[k2] * w);
+                        }
+                        touched = true;
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, single);
+                    if (single) {
+                        const int slot = np + __popc(bal & lt);
+                        const unsigned m = tg.x & 255u, sh = (m & 1u) * 16u;
+                        tmp[slot] = i;
+                        key[slot] = (unsigned char)m;
+                        const unsigned old = atomicAdd(&hist[m >> 1], 1u << sh);
+                        rnk[slot] = (unsigned char)((old >> sh) & 0xffffu);
+                    }
+                    np += __popc(bal);
+                }
+                if (np <= R_CAP - 32 && k0 + 32 < total) continue;
+                if (np == 0) continue;
+                touched = true;
+                __syncwarp();
+
+                // ---- counting sort by channel mask: END offsets of the 256 bins (8 per lane); a survivor of rank r in its bin
+                // goes to end - 1 - r, so the rank-0 survivor closes the run
+                unsigned cnt[8], off[8];
+                unsigned ridx;
+                {
+                    const uint4 hw = *reinterpret_cast<const uint4 *>(hist + 4 * lane);
+                    cnt[0] = hw.x & 0xffffu; cnt[1] = hw.x >> 16; cnt[2] = hw.y & 0xffffu; cnt[3] = hw.y >> 16;
+                    cnt[4] = hw.z & 0xffffu; cnt[5] = hw.z >> 16; cnt[6] = hw.w & 0xffffu; cnt[7] = hw.w >> 16;
+                    unsigned sum = 0, nzc2 = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { sum += cnt[j]; off[j] = sum; nzc2 += cnt[j] ? 1u : 0u; }
+                    unsigned v = sum | (nzc2 << 16);
+                    const unsigned mine = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+                        if (lane >= o) v += t;
+                    }
+                    const unsigned excl = v - mine;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) off[j] += excl & 0xffffu;
+                    ridx = excl >> 16;
+                    *reinterpret_cast<uint4 *>(hist + 4 * lane) =
+                        make_uint4(off[0] | (off[1] << 16), off[2] | (off[3] << 16), off[4] | (off[5] << 16), off[6] | (off[7] << 16));
+                }
+                // the stage of the previous block aliases the records: its bulk copies must have read it
+                if (pending) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    pending = false;
+                }
+                __syncwarp();
+                // ---- pass 2: records in run order, pre-scaled by 1/sigma (float64 rebase: one rounding per coordinate).
+                // The record that closes a run is stored NEGATED: every term of r is a square of a difference of record
+                // fields, so r is unchanged and the sign of .w is a free end-of-run flag.
+                for (int j = lane; j < np; j += 32) {
+                    const unsigned i = tmp[j];
+                    const unsigned m = key[j];
+                    const unsigned rk = rnk[j];
+                    const unsigned pos = ((hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu) - 1u - rk;
+                    const float4 e = __ldg(p.rec_pos + i);
+                    const uint4 tg = __ldg(p.rec_tag + i);
+                    const float sw = __uint_as_float(tg.w);
+                    const double dsw = rk == 0 ? -(double)sw : (double)sw;
+                    const double ex = (double)e.x + ((double)((int)(tg.z & 1023u) * 4 - sx) - 1.5);
+                    const double ey = (double)e.y + ((double)((int)((tg.z >> 10) & 1023u) * 4 - sy) - 1.5);
+                    const double ez = (double)e.z + ((double)((int)(tg.z >> 20) * 4 - sz) - 3.5);
+                    rec[pos] = make_float4((float)(ex * dsw), (float)(ey * dsw), (float)(ez * dsw), (float)dsw);
+#if MKB_R_FMA_GATE
+                    cwv[pos] = -(cut2 * (sw * sw)) * R_GATE_BIG;  // gate on the FMA pipe: sat((r - cw) 2^40) is 0 inside, 1 outside
+#else
+                    cwv[pos] = cut2 * (sw * sw);
+#endif
+                }
+                __syncwarp();
+                // run table (tmp is free now): the masks of the non-empty bins in order; clear the histogram
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (cnt[j]) tmp[ridx++] = (unsigned)(lane * 8 + j);
+                *reinterpret_cast<uint4 *>(hist + 4 * lane) = make_uint4(0u, 0u, 0u, 0u);
+                __syncwarp();
+
+                // ---- the hot loop: one warp-uniform candidate per half trip, 4 voxels per lane; two records in flight
+                // (a / b ping-pong, the next one is loaded before the current one is evaluated)
+                {
+#if MKB_R_FMA_GATE
+#define MKB_GATED_MIN(M, R, CW) M = fminf(M, fmaf(__saturatef(fmaf(R, R_GATE_BIG, CW)), R_GATE_HUGE, R))
+#else
+#define MKB_GATED_MIN(M, R, CW) gated_min(M, R, CW)
+#endif
+#define MKB_RUN_BODY(A, CW)                                                                       \
+    {                                                                                             \
+        const float dys = fmaf(fy, A.w, -A.y), dzs = fmaf(fz, A.w, -A.z);                         \
+        const float s2 = fmaf(dzs, dzs, dys * dys);                                               \
+        const float d0 = fmaf(-1.5f, A.w, -A.x), d1 = fmaf(-0.5f, A.w, -A.x);                     \
+        const float d2 = fmaf(0.5f, A.w, -A.x), d3 = fmaf(1.5f, A.w, -A.x);                       \
+        const float r0 = fmaf(d0, d0, s2), r1 = fmaf(d1, d1, s2), r2 = fmaf(d2, d2, s2), r3 = fmaf(d3, d3, s2); \
+        MKB_GATED_MIN(m0, r0, CW);                                                                \
+        MKB_GATED_MIN(m1, r1, CW);                                                                \
+        MKB_GATED_MIN(m2, r2, CW);                                                                \
+        MKB_GATED_MIN(m3, r3, CW);                                                                \
+    }
+                    float4 a = rec[0];
+                    float cwa = cwv[0];
+                    int i = 1;  // next record to load; i == np reads past the list (inside this warp's buffer), never used
+#pragma unroll 1
+                    for (int ri = 0; i <= np; ++ri) {
+                        float m0 = INF, m1 = INF, m2 = INF, m3 = INF;
+#pragma unroll 1
+                        for (;;) {
+                            const float4 b = rec[i];
+                            const float cwb = cwv[i];
+                            MKB_RUN_BODY(a, cwa)
+                            if (a.w < 0.0f) {  // the record that closes a run is negated (warp-uniform)
+                                a = b;
+                                cwa = cwb;
+                                i += 1;
+                                break;
+                            }
+                            a = rec[i + 1];
+                            cwa = cwv[i + 1];
+                            MKB_RUN_BODY(b, cwb)
+                            i += 2;
+                            if (b.w < 0.0f) break;
+                        }
+                        const unsigned mask = tmp[ri];
+#if MKB_R_FLUSH == 1
+                        MKB_NIB_SWITCH(mask & 15u, 0)
+                        MKB_NIB_SWITCH(mask >> 4, 4)
+#else
+#pragma unroll
+                        for (int h = 0; h < 8; ++h)
+                            if (mask & (1u << h)) {
+                                acc[h][0] = fminf(acc[h][0], m0); acc[h][1] = fminf(acc[h][1], m1);
+                                acc[h][2] = fminf(acc[h][2], m2); acc[h][3] = fminf(acc[h][3], m3);
+                            }
+#endif
+                    }
+#undef MKB_RUN_BODY
+                }
+                np = 0;
+                __syncwarp();
+            }
+
+            if (!touched) {
+                if (p.cmajor) {
+                    store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, z0 + lz);
+                } else {
+                    if (row_ok) bulk_store_row(row_dst, zero_sa, row_bytes);
+                    if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                continue;
+            }
+            // ---- epilogue: value = 1 - exp(-(1/r)^6) once per voxel-channel; channels empty across the warp skip it
+            if (pending) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                pending = false;
+            }
+            __syncwarp();
+            // The minima go to the stage (output layout: voxel-major, 8 channels = two float4) as they are; a compact loop
+            // then turns r into the value in place, 4 channels per lane and trip (an epilogue unrolled over the 32
+            // accumulators was 10 KB of code: with 28 warps in different phases the instruction cache did not hold it).
+            float4 *const stage = reinterpret_cast<float4 *>(wb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int v = ((k * 4 + ly) * 8 + lz) * 2;
+                stage[v] = make_float4(acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
+                stage[v + 1] = make_float4(acc[4][k], acc[5][k], acc[6][k], acc[7][k]);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+                float4 v = stage[it * 32 + lane];
+                const float LIVE = 0.5f * R_GATE_HUGE;  // r of a voxel-channel no atom reached: +inf (or 2^126 with the FMA gate)
+                const bool live = fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < LIVE;
+                if (__any_sync(0xffffffffu, live)) {
+                    v.x = occ_value(rcp_approx(v.x)); v.y = occ_value(rcp_approx(v.y));
+                    v.z = occ_value(rcp_approx(v.z)); v.w = occ_value(rcp_approx(v.w));
+                } else {
+                    v = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                stage[it * 32 + lane] = v;
+            }
+            if (p.cmajor) {  // channel-major grid: 8 lanes = one 32-byte segment per (channel, x, y)
+                __syncwarp();
+                const long long cs = (long long)nx * ny * nz;
+                if (y0 + ly < ny && z0 + lz < nz) {
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k)
+                        if (x0 + k < nx) {
+                            const int v = ((k * 4 + ly) * 8 + lz) * 2;
+                            const float4 lo4 = stage[v], hi4 = stage[v + 1];
+                            float *const o = p.out + out_offset * 8 + ((long long)(x0 + k) * ny + (y0 + ly)) * nz + (z0 + lz);
+                            __stcs(o, lo4.x); __stcs(o + cs, lo4.y); __stcs(o + 2 * cs, lo4.z); __stcs(o + 3 * cs, lo4.w);
+                            __stcs(o + 4 * cs, hi4.x); __stcs(o + 5 * cs, hi4.y); __stcs(o + 6 * cs, hi4.z); __stcs(o + 7 * cs, hi4.w);
+                        }
+                }
+                __syncwarp();  // the stage is the next block's record buffer
+                continue;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (row_ok) bulk_store_row(row_dst, stage_sa + lane * 256, row_bytes);
+            if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            pending = true;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the copies
+}
+#undef RG
+
+// ---------------------------------------------------------------------------------------------------------
+// Gate band pre-pass.  One thread per atom item walks the (y, z) lattice rows of the atom's cutoff sphere.  A row crosses
+// the sphere at x = px -+ sqrt(cut2 - s); only the lattice point nearest to a crossing can lie within the band
+// |d2 - cut2| <= band.  Such voxels get a bit in `bitmap` (bit = voxel index in the dense batch order); the first thread
+// to set a bit also appends the voxel to `list` (fix[0] = count, capacity `cap`: beyond it occ_fix_scan_kernel takes over).
+// ---------------------------------------------------------------------------------------------------------
+constexpr float R_FIND_BAND = 2.0e-6f;  // relative; fill error (< 1e-6) + this kernel's own float32 error
+constexpr int FIX_HDR = 4;              // words in front of the list: count, overflow flag
+
+__global__ void __launch_bounds__(128) occ_band_kernel(const float *__restrict__ coords, const GridDev *__restrict__ grids, int B,
+                                                       long long n_items, unsigned *__restrict__ bitmap,
+                                                       unsigned long long *__restrict__ fix, unsigned cap) {
+    const long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const int b = find_grid_item(grids, B, it);
+    const GridDev &g = grids[b];
+    const long long a = g.atom_begin + (it - g.item_base);
+    int ip[3];
+    float f[3];
+    bool live = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double pv = ((double)coords[3 * a + d] - g.origin[d]) * g.inv_vs;
+        live = live && (pv >= -(double)g.cutv - 1.0) && (pv <= (double)(g.dims[d] + g.cutv));
+        const double r = live ? rint(pv) : 0.0;
+        ip[d] = (int)r;
+        f[d] = (float)(pv - r);
+    }
+    if (!live) return;  // NaN or out of reach of every voxel
+    const float cut2 = g.cut2v;
+    const float band = R_FIND_BAND * cut2;
+    const int W = (int)(sqrtf(cut2) + 0.5f) + 1;  // |j - f| <= cut with |f| <= 0.5 (+1: rounding slack)
+    const float RND = 12582912.0f;                  // 1.5 * 2^23: (x + RND) - RND == rint(x) for |x| < 2^22
+    const int ny = g.dims[1], nz = g.dims[2];
+    for (int jy = -W; jy <= W; ++jy) {
+        const int iy = ip[1] + jy;
+        const float dy = (float)jy - f[1];
+        const float A = fmaf(-dy, dy, cut2);
+        if (A < -band || iy < 0 || iy >= ny) continue;
+        for (int jz = -W; jz <= W; ++jz) {
+            const float dz = (float)jz - f[2];
+            const float h2 = fmaf(-dz, dz, A);  // cut2 - s
+            if (h2 < -band) continue;           // the row misses the sphere
+            const float hp = fmaxf(h2, 0.0f);
+            const float hh = hp * rsqrtf(fmaxf(hp, 1e-30f));
+            const float jxa = (f[0] + hh + RND) - RND, jxb = (f[0] - hh + RND) - RND;
+            const float da = jxa - f[0], db = jxb - f[0];
+            const float ta = fmaf(da, da, -h2), tb = fmaf(db, db, -h2);
+            const bool fa = fabsf(ta) <= band, fb = (fabsf(tb) <= band) & (jxb != jxa);
+            if (fa | fb) {
+                const int iz = ip[2] + jz;
+                if (iz < 0 || iz >= nz) continue;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (q == 0 ? !fa : !fb) continue;
+                    const int ix = ip[0] + (int)(q == 0 ? jxa : jxb);
+                    if (ix < 0 || ix >= g.dims[0]) continue;
+                    const long long v = g.vox_base + (((long long)ix * ny + iy) * nz + iz);
+                    const unsigned bit = 1u << (v & 31);
+                    const unsigned old = atomicOr(bitmap + (v >> 5), bit);
+                    if (!(old & bit)) {
+                        const unsigned long long slot = atomicAdd(fix, 1ull);
+                        if (slot < cap) fix[FIX_HDR + slot] = (unsigned long long)v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// float64 re-evaluation of one voxel with the reference's operations (pyx:46-61): d2 as exact_gate, max of sigma^2/d2 per
+// channel, 1 - exp(-q^6).  One warp per flagged voxel.
+__device__ __forceinline__ void occ_fix_voxel(const GridDev *__restrict__ grids, int B, long long v, int lane,
+                                              const float *__restrict__ coords, const double *__restrict__ sigmas,
+                                              const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
+                                              const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ cell_start,
+                                              float *__restrict__ out, int cmajor) {
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (grids[mid].vox_base <= v) lo = mid; else hi = mid - 1;
+    }
+    const GridDev *g = grids + lo;
+    const long long lv = v - g->vox_base;
+    const int nz = g->dims[2], ny = g->dims[1];
+    const int iz = (int)(lv % nz), iy = (int)((lv / nz) % ny), ix = (int)(lv / ((long long)nz * ny));
+    const int cutv = g->cutv, cs = g->cell;
+    const int cx0 = ix / cs, cx1 = min((ix + 2 * cutv) / cs, g->cells[0] - 1);
+    const int cy0 = iy / cs, cy1 = min((iy + 2 * cutv) / cs, g->cells[1] - 1);
+    const int cz0 = iz / cs, cz1 = min((iz + 2 * cutv) / cs, g->cells[2] - 1);
+    const int ncy = cy1 - cy0 + 1, nrows = (cx1 - cx0 + 1) * ncy;
+    const double cx = __dadd_rn(__dmul_rn((double)ix, g->vs), g->origin[0]);
+    const double cy = __dadd_rn(__dmul_rn((double)iy, g->vs), g->origin[1]);
+    const double cz = __dadd_rn(__dmul_rn((double)iz, g->vs), g->origin[2]);
+    double q[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) q[h] = 0.0;
+    for (int r0 = 0; r0 < nrows; r0 += 32) {
+        unsigned a0 = 0, a1 = 0;
+        if (r0 + lane < nrows) {  // the rows' atom ranges, one row per lane
+            const int rx = (r0 + lane) / ncy, ry = (r0 + lane) - rx * ncy;
+            const long long cb = g->cell_base + ((long long)(cx0 + rx) * g->cells[1] + (cy0 + ry)) * g->cells[2];
+            a0 = __ldg(cell_start + cb + cz0);
+            a1 = __ldg(cell_start + cb + cz1 + 1);
+        }
+        const int nr = min(32, nrows - r0);
+        for (int r = 0; r < nr; ++r) {
+            const unsigned b0 = __shfl_sync(0xffffffffu, a0, r), b1 = __shfl_sync(0xffffffffu, a1, r);
+            for (unsigned i = b0 + lane; i < b1; i += 32) {
+                const unsigned a = __ldg(&rec_tag[i].y) & 0x7fffffffu;
+                const double dx = (double)coords[3ll * a + 0] - cx;
+                const double dy = (double)coords[3ll * a + 1] - cy;
+                const double dz = (double)coords[3ll * a + 2] - cz;
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (!(d2 < CUTOFF_A * CUTOFF_A)) continue;
+#pragma unroll
+                for (int h = 0; h < 8; ++h) {
+                    double s;
+                    if (sigmas) s = sigmas[(long long)a * 8 + h];
+                    else s = ((chanmask[a] >> h) & 1u) ? radii[a] : 0.0;
+                    if (s == 0.0 || s != s) continue;
+                    const double qq = (s * s) / d2;  // +inf at d2 == 0 -> value 1 (pyx:57)
+                    q[h] = qq > q[h] ? qq : q[h];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, q[h], o);
+            q[h] = t > q[h] ? t : q[h];
+        }
+    double mq = q[0];
+#pragma unroll
+    for (int h = 1; h < 8; ++h) mq = (lane == h) ? q[h] : mq;
+    if (lane < 8) {
+        const double q3 = mq * mq * mq;
+        const float val = (float)(-expm1(-(q3 * q3)));
+        if (cmajor) out[g->out_offset * 8 + (long long)lane * ((long long)g->dims[0] * ny * nz) + lv] = val;
+        else out[(g->out_offset + lv) * 8 + lane] = val;
+    }
+}
+
+__global__ void __launch_bounds__(256) occ_fix_list_kernel(const GridDev *__restrict__ grids, int B,
+                                                           const unsigned long long *__restrict__ fix, unsigned cap,
+                                                           const float *__restrict__ coords, const double *__restrict__ sigmas,
+                                                           const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
+                                                           const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ cell_start,
+                                                           float *__restrict__ out, int cmajor) {
+    const unsigned long long n = fix[0];
+    if (n > cap) return;  // the list overflowed: occ_fix_scan_kernel walks the bitmap instead
+    const int lane = threadIdx.x & 31;
+    const unsigned nw = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nw)
+        occ_fix_voxel(grids, B, (long long)fix[FIX_HDR + w], lane, coords, sigmas, radii, chanmask, rec_tag, cell_start, out, cmajor);
+}
+
+__global__ void __launch_bounds__(256) occ_fix_scan_kernel(const GridDev *__restrict__ grids, int B, long long n_words,
+                                                           const unsigned *__restrict__ bitmap,
+                                                           const unsigned long long *__restrict__ fix, unsigned cap,
+                                                           const float *__restrict__ coords, const double *__restrict__ sigmas,
+                                                           const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
+                                                           const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ cell_start,
+                                                           float *__restrict__ out, int cmajor) {
+    if (fix[0] <= cap) return;
+    const int lane = threadIdx.x & 31;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; w0 < n_words; w0 += nw * 32) {
+        const unsigned mine = (w0 + lane < n_words) ? __ldg(bitmap + w0 + lane) : 0u;
+        for (unsigned wm = __ballot_sync(0xffffffffu, mine != 0); wm; wm &= wm - 1) {
+            const int wl = __ffs(wm) - 1;
+            for (unsigned bits = __shfl_sync(0xffffffffu, mine, wl); bits; bits &= bits - 1)
+                occ_fix_voxel(grids, B, ((w0 + wl) << 5) + (__ffs(bits) - 1), lane, coords, sigmas, radii, chanmask, rec_tag,
+                              cell_start, out, cmajor);
+        }
+    }
+}
+
+}  // namespace mkb

@@ -49,6 +49,7 @@ struct GridDev {
     int cell;    // cell edge in voxels (8 for the tile kernels, 4 for the warp-per-block kernel)
     long long atom_begin, atom_end, out_offset;
     long long item_base, tile_base, cell_base;
+    long long vox_base;  // first voxel of this grid in the dense batch order (gate-band bitmap of the run kernel)
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -176,7 +177,10 @@ __global__ void occ_scatter_kernel(const float *__restrict__ coords, const doubl
     }
     const double sv = first * g.inv_vs;  // sigma in voxel units
     rec_pos[dst] = make_float4(rel[0], rel[1], rel[2], m ? fmaxf((float)(sv * sv), FLT_MIN) : 0.0f);
-    rec_tag[dst] = make_uint4(m, (unsigned)a | (multi ? 0x80000000u : 0u), (unsigned)cx | ((unsigned)cy << 10) | ((unsigned)cz << 20), 0u);
+    // tag.w: 1/|sigma| (voxel units) for the run kernel, which tracks min d2/sigma^2 on coordinates pre-scaled by it
+    const float sw = m ? (float)(1.0 / fabs(sv)) : 0.0f;
+    rec_tag[dst] = make_uint4(m, (unsigned)a | (multi ? 0x80000000u : 0u), (unsigned)cx | ((unsigned)cy << 10) | ((unsigned)cz << 20),
+                              __float_as_uint(sw));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1519,6 +1523,10 @@ __global__ void __launch_bounds__(128) occ_points_kernel(const double *__restric
     }
 }
 
+}  // namespace mkb
+#include "occ_runs.cuh"
+namespace mkb {
+
 static int scan_u32(mkb_ctx *h, cudaStream_t st, unsigned *in, unsigned *out, long long n) {
     size_t tmp_bytes = 0;
     MKB_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, st));
@@ -1566,7 +1574,7 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
     const int cellsz = (variant == 0) ? W_CELL : TILE;
 
     std::vector<GridDev> gd((size_t)B);
-    long long items = 0, tiles = 0, cells = 0;
+    long long items = 0, tiles = 0, cells = 0, voxels = 0;
     for (int b = 0; b < B; ++b) {
         const mkb_grid_desc &s = grids[b];
         GridDev &g = gd[b];
@@ -1606,6 +1614,8 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
         g.item_base = items;
         g.tile_base = tiles;
         g.cell_base = cells;
+        g.vox_base = voxels;
+        voxels += (long long)s.dims[0] * s.dims[1] * s.dims[2];
         items += s.atom_end - s.atom_begin;
         tiles += nt;
         cells += nc;
@@ -1654,6 +1664,78 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
     // opt-in (MKB_OCC_BULK_STORE=1): measured 21 % slower in this non-persistent kernel because the CTA has to wait for
     // the asynchronous smem read before it may retire; kept for the persistent variant
     fp.bulk_store = (fp.vec_ok && !(flags & MKB_OCC_ACCUMULATE) && getenv("MKB_OCC_BULK_STORE")) ? 1 : 0;
+
+    // ---- default for 8 channels: persistent mask-run kernel with TMA stores (occ_runs.cuh).  MKB_OCC_V6=1 or any of the
+    // older selectors keeps the v6 warp kernel (A/B runs, tests/test_occupancy_gpu.py::test_alternative_kernel_paths_agree).
+    bool use_runs = variant == 0 && C == 8 && !(flags & MKB_OCC_ACCUMULATE) && ((uintptr_t)out % 16 == 0) &&
+                    !getenv("MKB_OCC_V6") && !force_warp && !getenv("MKB_OCC_WARP32");
+    for (int b = 0; b < B && use_runs; ++b) {
+        const int r1 = (3 + 2 * gd[b].cutv) / 4 + 1;
+        if (r1 * r1 > R_ROWS) use_runs = false;
+    }
+    if (use_runs) {
+        // queue item = one (x, y) block column x R_ZC consecutive z blocks
+        std::vector<long long> ibase((size_t)B + 1, 0);
+        for (int b = 0; b < B; ++b) {
+            const long long nbz = (gd[b].dims[2] + R_BZ - 1) / R_BZ;
+            ibase[b + 1] = ibase[b] + (long long)((gd[b].dims[0] + 3) / 4) * ((gd[b].dims[1] + 3) / 4) * ((nbz + R_ZC - 1) / R_ZC);
+        }
+        if (ibase[B] >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "too many voxel blocks (%lld): split the batch", ibase[B]);
+        long long *d_ibase;
+        unsigned *d_bitmap, *d_queue;
+        unsigned long long *d_fix;
+        const long long n_words = cdiv(voxels, 32);
+        const unsigned fix_cap = (unsigned)std::min<long long>(voxels, 1ll << 22);
+        if ((rc = scratch_get(h, S_BLOCK_BASE, (size_t)B + 1, &d_ibase))) return rc;
+        if ((rc = scratch_get(h, S_BAND_BITMAP, (size_t)n_words, &d_bitmap))) return rc;
+        if ((rc = scratch_get(h, S_QUEUE, (size_t)4, &d_queue))) return rc;
+        if ((rc = scratch_get(h, S_FIX_LIST, (size_t)fix_cap + FIX_HDR, &d_fix))) return rc;
+        MKB_CUDA(h, cudaMemcpyAsync(d_ibase, ibase.data(), sizeof(long long) * ((size_t)B + 1), cudaMemcpyHostToDevice, st));
+        MKB_CUDA(h, cudaMemsetAsync(d_bitmap, 0, sizeof(unsigned) * (size_t)n_words, st));
+        MKB_CUDA(h, cudaMemsetAsync(d_queue, 0, sizeof(unsigned) * 4, st));
+        MKB_CUDA(h, cudaMemsetAsync(d_fix, 0, sizeof(unsigned long long) * FIX_HDR, st));
+        if (items > 0) {
+            occ_band_kernel<<<(unsigned)cdiv(items, 128), 128, 0, st>>>(coords, d_grids, B, items, d_bitmap, d_fix, fix_cap);
+            MKB_LAUNCHED(h);
+        }
+        RunParams rp;
+        rp.grids = d_grids; rp.B = B;
+        rp.rec_pos = rec_pos; rp.rec_tag = rec_tag; rp.cell_start = cell_start;
+        rp.sigmas = sigmas; rp.out = out;
+        rp.item_base = d_ibase; rp.queue = d_queue;
+        rp.total_items = (unsigned)ibase[B];
+        rp.cmajor = fp.cmajor;
+        bool uni = true;
+        const GridDev &g0 = gd[0];
+        const long long nvox0 = (long long)g0.dims[0] * g0.dims[1] * g0.dims[2];
+        const long long ncell0 = (long long)g0.cells[0] * g0.cells[1] * g0.cells[2];
+        for (int b = 0; b < B && uni; ++b) {
+            const GridDev &g = gd[b];
+            uni = g.dims[0] == g0.dims[0] && g.dims[1] == g0.dims[1] && g.dims[2] == g0.dims[2] && g.vs == g0.vs &&
+                  g.out_offset == g0.out_offset + b * nvox0 && g.cell_base == g0.cell_base + b * ncell0;
+        }
+        rp.u = g0;
+        rp.u_out_stride = nvox0;
+        rp.u_cell_stride = ncell0;
+        rp.u_ipg = (unsigned)(ibase[1] - ibase[0]);
+        rp.u_nby = (unsigned)((g0.dims[1] + 3) / 4);
+        rp.u_nzc = (unsigned)(((g0.dims[2] + R_BZ - 1) / R_BZ + R_ZC - 1) / R_ZC);
+        if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
+        const unsigned nctas = (unsigned)std::min<long long>((long long)h->sm_count * MKB_R_MIN_CTAS, cdiv(ibase[B], R_WARPS));
+        if (uni) occ_fill_runs_kernel<true><<<nctas, R_WARPS * 32, 0, st>>>(rp);
+        else occ_fill_runs_kernel<false><<<nctas, R_WARPS * 32, 0, st>>>(rp);
+        MKB_LAUNCHED(h);
+        if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));
+        if (items > 0) {
+            const unsigned fg = (unsigned)h->sm_count * 4;
+            occ_fix_list_kernel<<<fg, 256, 0, st>>>(d_grids, B, d_fix, fix_cap, coords, sigmas, radii, chanmask, rec_tag, cell_start, out, fp.cmajor);
+            MKB_LAUNCHED(h);
+            occ_fix_scan_kernel<<<fg, 256, 0, st>>>(d_grids, B, n_words, d_bitmap, d_fix, fix_cap, coords, sigmas, radii, chanmask,
+                                                    rec_tag, cell_start, out, fp.cmajor);
+            MKB_LAUNCHED(h);
+        }
+        return MKB_OK;
+    }
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
     const bool fast8 = (variant == 1);
     unsigned *tile_total = nullptr;

@@ -86,7 +86,10 @@ def test_cxyz_accumulate_and_batch_api():
     occ.occupancy_grid_batch(d_c, None, batch.descs, out, accumulate=True, layout="cxyz", radii=d_ch[0], chanmask=d_ch[1],
                              n_channels=8)
     got = batch.as_cxyz(out.cpu().numpy())
-    assert np.array_equal(got, np.maximum(np.stack(feats), np.float32(0.5)))
+    # accumulate runs the v6 warp kernel, the plain call the run kernel: each within 1e-5 of the oracle, not bit-identical
+    want = np.maximum(np.stack(feats), np.float32(0.5))
+    assert np.array_equal(got == 0.5, want == 0.5)
+    assert np.allclose(got, want, rtol=1.5e-5, atol=0)
 
 
 def test_masked_channels_equal_sigma_matrix():
