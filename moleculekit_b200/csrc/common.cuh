@@ -30,6 +30,8 @@ enum ScratchSlot {
     S_BAND_BITMAP,  // occupancy run kernel: one bit per voxel whose gate decision is re-done in float64
     S_QUEUE,        // occupancy run kernel: block queue counter
     S_FIX_LIST,     // occupancy run kernel: voxels re-evaluated in float64 (count + list)
+    S_BLK_ENT,      // occupancy run kernel: per-block candidate lists
+    S_BLK_SLOTS,    // occupancy run kernel: the slot of every (atom, block) insertion
     S_NSLOTS
 };
 
@@ -49,6 +51,9 @@ struct mkb_ctx {
     // optional per-kernel timing (bench.py roofline): events recorded on the launch stream
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before prep, before main kernel, after main kernel
+    // side stream of the occupancy run path (gate-band pre-pass beside the list build)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_ev[2] = {nullptr, nullptr};
     // K4: the count call leaves one ballot word per (row, 32 columns); the fill call that follows with the SAME arguments
     // reads them instead of evaluating every distance a second time
     struct K4Key {

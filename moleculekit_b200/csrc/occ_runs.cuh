@@ -1,33 +1,32 @@
-// occ_runs.cuh -- K1 v7, the default 8-channel fill: persistent "mask-run" kernel with TMA (cp.async.bulk) stores.
-// Included by occupancy.cu (after GridDev / exact_gate / occ_value).
+// occ_runs.cuh -- K1 v8, the default 8-channel fill: per-block candidate lists + persistent "mask-run" kernel with TMA
+// (cp.async.bulk) stores.  Included by occupancy.cu (after GridDev / occ_value).
 //
 // Replaces the inner loop of moleculekit/occupancy_utils/occupancy_utils.pyx:46-61.  What changed against v6
 // (occ_fill8v_kernel, 111 lane-instructions per in-gate (atom, voxel) pair, 16 predicated FMNMX per candidate):
 //
+//   * K2' (occ_prep_kernel / occ_blk_fill_kernel): every atom is appended to the candidate list of each 4x4x8-voxel
+//     block it can reach (~16 blocks per atom at 1 A) -- count, scan, fill.  The fill kernel reads its list; no block
+//     re-scans cell rows any more (v7 spent half its time there: 860 atoms scanned per block to keep 190).
 //   * The hot loop tracks  r = d2 / sigma^2  (a MIN; q = 1/r) instead of max q = sigma^2 / d2: no reciprocal per pair.
 //     The record of a candidate is pre-scaled by 1/sigma -- (x, y, z)/sigma in the block-centre frame plus 1/sigma --
 //     so r of a voxel is two FFMAs:  dxs = fma(x_k, 1/sigma, -x_a/sigma);  r = fma(dxs, dxs, dys^2 + dzs^2).
-//   * One warp owns a 4x4x8 voxel block; a lane owns the 4 voxels of one x-row (they share dys, dzs).  The candidate
-//     is WARP-UNIFORM (one LDS.128 broadcast), so its channel mask is uniform too: candidates are counting-sorted by
-//     mask into runs (lane-parallel, shared-memory histogram), a run keeps ONE scalar running minimum per voxel
-//     (FSETP gate + predicated FMNMX), and the 8-channel update happens once per run, not once per pair.
-//   * The 5 A gate is a plain float compare in the loop.  Pairs whose d2 lies within 4e-6 (relative) of the gate
+//   * One warp owns a block; a lane owns the 4 voxels of one x-row (they share dys, dzs).  The candidate is
+//     WARP-UNIFORM (one LDS.128 broadcast), so its channel mask is uniform too: candidates are counting-sorted by mask
+//     into runs (lane-parallel, shared-memory histogram), a run keeps ONE scalar running minimum per voxel (FSETP gate +
+//     predicated FMNMX), and the 8-channel update happens once per run, not once per pair.
+//   * The 5 A gate is a plain float compare in the loop.  Pairs whose d2 lies within 2e-6 (relative) of the gate
 //     -- where float32 could decide differently from the reference's float64 -- are found by a per-atom pre-pass
 //     (occ_band_kernel: the two lattice crossings of every (y, z) row of the cutoff sphere) and their voxels are
-//     recomputed in float64 with the reference's operation order by occ_fix_kernel after the fill.
-//   * Persistent CTAs (7 x 148 x 4 warps) pull blocks from an atomic queue; results are staged in shared memory in
-//     the output layout and leave the SM as cp.async.bulk.global.shared::cta row copies (SASS UBLKCP); the ~70 % of
-//     blocks without any atom in reach are 16 bulk copies from a zeroed shared-memory line, no CTA launch, no math.
+//     recomputed in float64 with the reference's operation order by occ_fix_*_kernel after the fill.
+//   * Persistent CTAs (7 x 148 x 4 warps) pull (x, y, 4 z-blocks) items from an atomic queue; results are staged in
+//     shared memory in the output layout and leave the SM as cp.async.bulk.global.shared::cta row copies (SASS UBLKCP);
+//     blocks without any atom in reach (~70 %) are bulk copies from a zeroed shared-memory line, no math.
 #pragma once
 
 namespace mkb {
 
 constexpr int R_BZ = 8;          // block = 4 x 4 x 8 voxels
-#ifndef MKB_R_CAP
-#define MKB_R_CAP 256            // candidates per round
-#endif
-constexpr int R_CAP = MKB_R_CAP;
-constexpr int R_ROWS = 64;       // cell rows (x, y) feeding one block: cutoff <= 14 voxels
+constexpr int R_CAP = 256;       // candidates per round (= the 4 KB output stage: 256 records of 16 bytes)
 #ifndef MKB_R_WARPS
 #define MKB_R_WARPS 4
 #endif
@@ -36,25 +35,25 @@ constexpr int R_WARPS = MKB_R_WARPS;
 #define MKB_R_MIN_CTAS 7
 #endif
 #ifndef MKB_R_ZC
-#define MKB_R_ZC 4               // consecutive z blocks per queue item (they share the x/y set-up of the halo rows)
+#define MKB_R_ZC 4               // consecutive z blocks per queue item
 #endif
 constexpr int R_ZC = MKB_R_ZC;
-constexpr int R_WARP_BYTES = ((R_CAP * 26 + 512 + R_ROWS * 4 + (R_ROWS + 4) * 4) + 127) / 128 * 128;
-static_assert(R_CAP * 16 >= 4096, "the 4 KB output stage aliases the candidate records (and only those)");
-static_assert(R_CAP <= 256 && R_CAP % 32 == 0, "ranks are bytes");
+// per warp: records 4096 | gate 1024 | ranks 256 | run masks 256 | histogram 512
+constexpr int R_WARP_BYTES = R_CAP * 16 + R_CAP * 4 + R_CAP + 256 + 512;
 #ifndef MKB_R_FMA_GATE
 #define MKB_R_FMA_GATE 0
 #endif
 constexpr float R_GATE_BIG = 1099511627776.0f;       // 2^40
-constexpr float R_GATE_HUGE = 8.507059173023462e37f;  // 2^126: what an out-of-range pair adds to r
-constexpr float R_BAND = 4e-6f;  // relative half-width of the band the float64 fix-up covers
+constexpr float R_GATE_HUGE = 8.507059173023462e37f;  // 2^126: what an out-of-range pair adds to r (FMA gate variant)
+constexpr float R_LIST_SLACK = 2e-4f;                 // relative slack of the block lists' reach test (float32 positions)
 
 struct RunParams {
     const GridDev *grids;
     int B;
-    const float4 *rec_pos;
-    const uint4 *rec_tag;
-    const unsigned *cell_start;
+    const float4 *rec_pos;       // per atom item: position minus its nearest lattice point (voxel units), -
+    const uint4 *rec_tag;        // mask | multi << 8 | lattice z << 16, atom row, lattice x | y << 16, 1/sigma
+    const unsigned *blk_start;   // [blocks + 1] exclusive offsets of the per-block candidate lists
+    const uint2 *blk_ent;        // (atom item, mask | multi << 8)
     const double *sigmas;        // multi-sigma atoms only
     float *out;
     const long long *item_base;  // [B + 1]: first queue item of every grid (item = 4 x 4 voxels in x, y and R_ZC blocks in z)
@@ -63,9 +62,110 @@ struct RunParams {
     int cmajor;                  // MKB_OCC_LAYOUT_CXYZ: grid stored [C][nx][ny][nz]; plain 32-byte-segment stores instead of TMA rows
     // uniform batches: descriptor of the first grid + strides (constant-bank operands)
     GridDev u;
-    long long u_out_stride, u_cell_stride;
-    unsigned u_ipg, u_nby, u_nzc;  // items per grid, y blocks, z chunks
+    long long u_out_stride;
+    unsigned u_ipg, u_nby, u_nzc, u_bpg;  // items per grid, y blocks, z chunks, blocks per grid
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// K2': records in atom order + per-block candidate lists.
+// ---------------------------------------------------------------------------------------------------------
+// blocks (4 x 4 x 8 voxels, voxel centres at integers) within `reach` of the point p; f(block id inside the grid)
+template <class F>
+__device__ __forceinline__ void for_each_block_in_reach(const GridDev &g, float px, float py, float pz, F f) {
+    const int nbx = (g.dims[0] + 3) >> 2, nby = (g.dims[1] + 3) >> 2, nbz = (g.dims[2] + R_BZ - 1) / R_BZ;
+    const float reach2 = g.cut2v * (1.0f + R_LIST_SLACK);
+    const float reach = sqrtf(reach2) * (1.0f + 1e-6f);
+    const int bx0 = max(0, (int)ceilf((px - reach - 3.0f) * 0.25f)), bx1 = min(nbx - 1, (int)floorf((px + reach) * 0.25f));
+    const int by0 = max(0, (int)ceilf((py - reach - 3.0f) * 0.25f)), by1 = min(nby - 1, (int)floorf((py + reach) * 0.25f));
+    const int bz0 = max(0, (int)ceilf((pz - reach - 7.0f) * 0.125f)), bz1 = min(nbz - 1, (int)floorf((pz + reach) * 0.125f));
+    for (int bx = bx0; bx <= bx1; ++bx) {
+        const float dx = fmaxf(fmaxf((float)(4 * bx) - px, px - (float)(4 * bx + 3)), 0.0f);
+        for (int by = by0; by <= by1; ++by) {
+            const float dy = fmaxf(fmaxf((float)(4 * by) - py, py - (float)(4 * by + 3)), 0.0f);
+            const float dxy = fmaf(dy, dy, dx * dx);
+            if (dxy > reach2) continue;
+            for (int bz = bz0; bz <= bz1; ++bz) {
+                const float dz = fmaxf(fmaxf((float)(R_BZ * bz) - pz, pz - (float)(R_BZ * bz + R_BZ - 1)), 0.0f);
+                if (fmaf(dz, dz, dxy) <= reach2) f((bx * nby + by) * nbz + bz);
+            }
+        }
+    }
+}
+
+// per atom item: record + block counts.  sigma handling as occ_scatter_kernel (one sigma + channel mask; several
+// distinct sigmas -> multi flag and the per-channel path of the fill kernel).
+__global__ void __launch_bounds__(128) occ_prep_kernel(const float *__restrict__ coords, const double *__restrict__ sigmas,
+                                                       const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
+                                                       const GridDev *__restrict__ grids, int B, long long n_items,
+                                                       float4 *__restrict__ rec_pos, uint4 *__restrict__ rec_tag,
+                                                       unsigned *__restrict__ blk_count) {
+    const long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const int b = find_grid_item(grids, B, it);
+    const GridDev &g = grids[b];
+    const long long a = g.atom_begin + (it - g.item_base);
+    int ip[3];
+    float f[3];
+    bool live = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double pv = ((double)coords[3 * a + d] - g.origin[d]) * g.inv_vs;
+        // atoms farther than the 5 A halo from the grid cannot touch any voxel (NaN fails both tests)
+        live = live && (pv >= -(double)g.cutv - 0.5) && (pv <= (double)(g.dims[d] - 1 + g.cutv) + 0.5);
+        const double r = live ? rint(pv) : 0.0;
+        ip[d] = (int)r;
+        f[d] = (float)(pv - r);  // |f| <= 0.5: absolute error <= 3e-8 voxel
+    }
+    double first = 0.0;
+    unsigned m = 0;
+    bool multi = false;
+    if (sigmas) {
+        const double *sg = sigmas + a * 8;
+        for (int h = 0; h < 8; ++h) {
+            const double s = sg[h];
+            if (s == 0.0 || s != s) continue;  // sigma == 0 skipped (pyx:56); NaN never wins the max (pyx:61)
+            if (m == 0) { first = s; m = 1u << h; }
+            else if (s == first) m |= 1u << h;
+            else multi = true;
+        }
+    } else {
+        const double r = radii[a];
+        const unsigned mm = chanmask[a] & 0xffu;
+        if (mm && !(r == 0.0 || r != r)) { first = r; m = mm; }
+    }
+    live = live && m != 0;
+    const double sv = first * g.inv_vs;  // sigma in voxel units
+    const float sw = m ? (float)(1.0 / fabs(sv)) : 0.0f;
+    const int off = g.cutv + 1;
+    rec_pos[it] = make_float4(f[0], f[1], f[2], 0.0f);
+    rec_tag[it] = make_uint4(live ? (m | (multi ? 0x100u : 0u) | ((unsigned)(ip[2] + off) << 16)) : 0u, (unsigned)a,
+                             live ? ((unsigned)(ip[0] + off) | ((unsigned)(ip[1] + off) << 16)) : 0u, __float_as_uint(sw));
+    if (!live) return;
+    unsigned *const bc = blk_count + g.tile_base;  // tile_base: first block of this grid
+    for_each_block_in_reach(g, (float)ip[0] + f[0], (float)ip[1] + f[1], (float)ip[2] + f[2], [&](int bid) { atomicAdd(bc + bid, 1u); });
+}
+
+// second pass: the same walk appends (item, mask | multi << 8) to the lists; blk_count counts down to zero.  (Keeping the
+// slots of the first pass instead -- no atomics here -- was slower: 178 + 154 us against 95 + 144 us per 256 pockets.)
+__global__ void __launch_bounds__(128) occ_blk_fill_kernel(const GridDev *__restrict__ grids, int B, long long n_items,
+                                                           const float4 *__restrict__ rec_pos, const uint4 *__restrict__ rec_tag,
+                                                           unsigned *__restrict__ blk_count, const unsigned *__restrict__ blk_start,
+                                                           uint2 *__restrict__ blk_ent) {
+    const long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const uint4 tg = rec_tag[it];
+    if ((tg.x & 0x1ffu) == 0) return;
+    const int b = find_grid_item(grids, B, it);
+    const GridDev &g = grids[b];
+    const float4 f = rec_pos[it];
+    const int off = g.cutv + 1;
+    const float px = (float)((int)(tg.z & 0xffffu) - off) + f.x, py = (float)((int)(tg.z >> 16) - off) + f.y,
+                pz = (float)((int)(tg.x >> 16) - off) + f.z;
+    unsigned *const bc = blk_count + g.tile_base;
+    const unsigned *const bs = blk_start + g.tile_base;
+    const uint2 ent = make_uint2((unsigned)it, tg.x & 0x1ffu);
+    for_each_block_in_reach(g, px, py, pz, [&](int bid) { blk_ent[bs[bid] + atomicSub(bc + bid, 1u) - 1u] = ent; });
+}
 
 __device__ __forceinline__ void bulk_store_row(float *dst, unsigned src_smem, int bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
@@ -85,13 +185,13 @@ __device__ __forceinline__ void store_cmajor_zero(float *grid, int nx, int ny, i
 __device__ __forceinline__ void gated_min(float &m, float r, float cw) {
     asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p min.f32 %0, %0, %1;\n\t}" : "+f"(m) : "f"(r), "f"(cw));
 }
-// run end: the run's four minima go into the channels of its mask.  One real (warp-uniform) branch per channel: a dead
-// channel costs a test and a jump, not four FMNMX issue slots (nvcc if-converts the C++ form into 32 predicated FMNMX),
-// and the code stays 50 instructions long (a jump table per mask nibble thrashed the instruction cache).
-// run end: the run's four minima go into the channels of its mask.  MKB_R_FLUSH 0: 32 predicated FMNMX (compact, but every
-// one issues whether its channel is live or not); 1: one jump per mask nibble into code with only the live channels.
+// run end: the run's four minima go into the channels of its mask.  MKB_R_FLUSH 0: 32 predicated FMNMX (compact; measured
+// faster than 1: one jump per mask nibble into code with only the live channels, which costs instruction-cache misses).
 #ifndef MKB_R_FLUSH
-#define MKB_R_FLUSH 1
+#define MKB_R_FLUSH 0
+#endif
+#ifndef MKB_R_EXP
+#define MKB_R_EXP 0  // timing experiments only (wrong results): 1 = no hot loop, 2 = no flush, 3 = no epilogue math
 #endif
 template <int M, int BASE>
 __device__ __forceinline__ void apply_nibble(float (&acc)[8][4], float m0, float m1, float m2, float m3) {
@@ -115,29 +215,25 @@ __device__ __forceinline__ void apply_nibble(float (&acc)[8][4], float m0, float
 template <bool UNIFORM>
 __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_kernel(const RunParams p) {
     __shared__ __align__(128) unsigned char s_raw[R_WARPS][R_WARP_BYTES];
-    __shared__ __align__(128) float s_zero[64];
+    __shared__ __align__(128) float s_zero[64 * R_ZC];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *const wb = s_raw[warp];
     float4 *const rec = reinterpret_cast<float4 *>(wb);                         // sorted candidates: (x, y, z)/sigma, 1/sigma
     float *const cwv = reinterpret_cast<float *>(wb + R_CAP * 16);              // gate in r units: cut2 / sigma^2
-    unsigned *const tmp = reinterpret_cast<unsigned *>(wb + R_CAP * 20);        // survivors (record index); then the run table
-    unsigned char *const key = wb + R_CAP * 24;
-    unsigned char *const rnk = wb + R_CAP * 25;
-    unsigned *const hist = reinterpret_cast<unsigned *>(wb + R_CAP * 26);       // 256 x 16-bit bins in 128 words
-    unsigned *const rpos = hist + 128;
-    unsigned *const rbase = rpos + R_ROWS;
+    unsigned char *const rnk = wb + R_CAP * 20;                                 // rank of a candidate inside its mask bin
+    unsigned char *const rmask = wb + R_CAP * 21;                               // run table: masks of the non-empty bins
+    unsigned *const hist = reinterpret_cast<unsigned *>(wb + R_CAP * 21 + 256); // 256 x 16-bit bins in 128 words
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(wb);
     const unsigned zero_sa = (unsigned)__cvta_generic_to_shared(s_zero);
 
-    if (threadIdx.x < 64) s_zero[threadIdx.x] = 0.0f;
+    for (int i = threadIdx.x; i < 64 * R_ZC; i += R_WARPS * 32) s_zero[i] = 0.0f;
     for (int i = lane; i < 128; i += 32) hist[i] = 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     const int ly = lane >> 3, lz = lane & 7;
     const float fy = (float)ly - 1.5f, fz = (float)lz - 3.5f;  // block frame: origin at the block centre
-    const unsigned lt = (1u << lane) - 1u;
     const float INF = __int_as_float(0x7f800000);
     bool pending = false;  // lanes 0..15: bulk copies still reading the stage
 
@@ -146,8 +242,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
         if (lane == 0) id = atomicAdd(p.queue, 1u);
         id = __shfl_sync(0xffffffffu, id, 0);
         if (id >= p.total_items) break;
-        // ---- decode the item: grid, (x, y) block column, chunk of R_ZC z blocks.  Everything that depends on x, y only
-        // (cell rows of the halo, output row pointers) is set up once for the R_ZC blocks.
+        // ---- decode the item: grid, (x, y) block column, chunk of R_ZC z blocks
         int gi;
         unsigned local;
         if (UNIFORM) {
@@ -175,63 +270,31 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
         const int rix = x0 + (lane >> 2), riy = y0 + (lane & 3);
         const bool row_ok = lane < 16 && rix < nx && riy < ny;
         float *const row_base = p.out + (out_offset + ((long long)rix * ny + riy) * nz) * 8;
-        // cell rows of the halo (cells of 4 voxels, rows run along z): lane -> rows lane and lane + 32
-        const int cutv = RG(cutv);
-        const int cN1 = RG(cells[1]), cN2 = RG(cells[2]);
-        const int cx0 = bxi, cx1 = min((x0 + 3 + 2 * cutv) >> 2, RG(cells[0]) - 1);
-        const int cy0 = byi, cy1 = min((y0 + 3 + 2 * cutv) >> 2, cN1 - 1);
-        const int ncy = cy1 - cy0 + 1;
-        const int nrows = (cx1 - cx0 + 1) * ncy;  // <= R_ROWS (host)
         const float cut2 = RG(cut2v);
-        const float cut_cull = cut2 * (1.0f + 1e-5f);
-        const unsigned *const cstart = p.cell_start + (UNIFORM ? p.u.cell_base + (long long)gi * p.u_cell_stride : __ldg(&gg->cell_base));
-        unsigned rowc[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int r = lane + 32 * q;
-            rowc[q] = 0xffffffffu;
-            if (r < nrows) {
-                const int rx = (int)(((float)r + 0.5f) / (float)ncy), ry = r - rx * ncy;
-                // corner rows further than the cutoff from the block's x/y extent cannot contribute
-                const int lox = (cx0 + rx) * 4 - cutv, loy = (cy0 + ry) * 4 - cutv;
-                const int gx = max(max(lox - (x0 + 3), x0 - (lox + 4)), 0);
-                const int gy = max(max(loy - (y0 + 3), y0 - (loy + 4)), 0);
-                if ((float)(gx * gx + gy * gy) <= cut_cull) rowc[q] = (unsigned)(((cx0 + rx) * cN1 + (cy0 + ry)) * cN2);
+        const int off = RG(cutv) + 1;
+        const int bz_begin = zc * R_ZC, bz_end = min(nbz, bz_begin + R_ZC);
+        // candidate list offsets of the item's blocks (consecutive block ids): lanes 0..R_ZC
+        const long long blk0 = (UNIFORM ? p.u.tile_base + (long long)gi * p.u_bpg : __ldg(&gg->tile_base)) + (long long)bxy * nbz + bz_begin;
+        const unsigned my_start = __ldg(p.blk_start + blk0 + min(lane, bz_end - bz_begin));
+        if (__shfl_sync(0xffffffffu, my_start, bz_end - bz_begin) == __shfl_sync(0xffffffffu, my_start, 0)) {
+            // no atom reaches any block of the item: one bulk copy of zeros per output row (TMA, nothing to wait for)
+            const int z0 = bz_begin * R_BZ;
+            if (p.cmajor) {
+                for (int bzi = bz_begin; bzi < bz_end; ++bzi) store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, bzi * R_BZ + lz);
+            } else {
+                if (row_ok) bulk_store_row(row_base + z0 * 8, zero_sa, (min(nz, bz_end * R_BZ) - z0) * 32);
+                if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            continue;
         }
-        const int sx = x0 + cutv, sy = y0 + cutv;
 
-        const int bz_end = min(nbz, (zc + 1) * R_ZC);
-        for (int bzi = zc * R_ZC; bzi < bz_end; ++bzi) {
+        for (int bzi = bz_begin; bzi < bz_end; ++bzi) {
             const int z0 = bzi * R_BZ;
             const int row_bytes = min(R_BZ, nz - z0) * 32;
             float *const row_dst = row_base + z0 * 8;
-
-            // ---- row lengths of this block's z range + scan
-            const int cz0 = bzi * 2, cz1 = min((z0 + R_BZ - 1 + 2 * cutv) >> 2, cN2 - 1);
-            unsigned total = 0;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (q * 32 < nrows) {  // warp-uniform
-                    unsigned v = 0, a = 0;
-                    if (rowc[q] != 0xffffffffu) {
-                        a = __ldg(cstart + rowc[q] + cz0);
-                        v = __ldg(cstart + rowc[q] + cz1 + 1) - a;
-                    }
-                    const unsigned len = v;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
-                        if (lane >= o) v += t;
-                    }
-                    rpos[lane + 32 * q] = a;
-                    rbase[lane + 32 * q + 1] = v + total;  // rows past nrows repeat the total
-                    (void)len;
-                    total += __shfl_sync(0xffffffffu, v, 31);
-                }
-            }
-            if (total == 0) {
-                // no atom in reach: 16 rows of zeros straight from the zero line (TMA, nothing to wait for)
+            const unsigned ls = __shfl_sync(0xffffffffu, my_start, bzi - bz_begin);
+            const unsigned n = __shfl_sync(0xffffffffu, my_start, bzi - bz_begin + 1) - ls;
+            if (n == 0) {
                 if (p.cmajor) {
                     store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, z0 + lz);
                 } else {
@@ -240,40 +303,42 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 }
                 continue;
             }
-            if (lane == 0) rbase[0] = 0;
-            __syncwarp();
 
             float acc[8][4];
 #pragma unroll
             for (int h = 0; h < 8; ++h)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[h][k] = INF;
-            bool touched = false;
-            const int sz = z0 + cutv;
-            int np = 0, row = 0;
-            for (unsigned k0 = 0; k0 < total; k0 += 32) {
-                // ---- gather 32 atoms of the concatenated rows; keep those within reach of the block
-                {
-                    const unsigned k = min(k0 + lane, total - 1);
-                    while (rbase[row + 1] <= k) ++row;
-                    const unsigned i = rpos[row] + (k - rbase[row]);
-                    const float4 e = __ldg(p.rec_pos + i);
-                    const uint4 tg = __ldg(p.rec_tag + i);
-                    const float ex = e.x + ((float)((int)(tg.z & 1023u) * 4 - sx) - 1.5f);
-                    const float ey = e.y + ((float)((int)((tg.z >> 10) & 1023u) * 4 - sy) - 1.5f);
-                    const float ez = e.z + ((float)((int)(tg.z >> 20) * 4 - sz) - 3.5f);
-                    const float ddx = fmaxf(fabsf(ex) - 1.5f, 0.f);
-                    const float ddy = fmaxf(fabsf(ey) - 1.5f, 0.f);
-                    const float ddz = fmaxf(fabsf(ez) - 3.5f, 0.f);
-                    const bool pass = (k0 + lane < total) & (tg.x != 0) & (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= cut_cull);
-                    const bool multi = pass & ((tg.y >> 31) != 0);
-                    const bool single = pass & !multi;
-                    // atoms with several distinct sigmas (user float channels): whole-warp per-channel path
+            // lattice point of the block corner in the records' offset frame
+            const int cx = x0 + off, cy = y0 + off, cz = z0 + off;
+
+            for (unsigned base = 0; base < n; base += R_CAP) {
+                const int np = (int)min((unsigned)R_CAP, n - base);
+                const uint2 *const ent = p.blk_ent + ls + base;
+                // ---- pass 1: histogram of the channel masks, rank of every candidate inside its bin
+                unsigned ey[R_CAP / 32], ex_multi = 0;
+#pragma unroll
+                for (int u = 0; u < R_CAP / 32; ++u) {  // all loads of the round in flight together
+                    const int j = u * 32 + lane;
+                    ey[u] = j < np ? __ldg(&ent[j].y) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < R_CAP / 32; ++u) {
+                    const int j0 = u * 32;
+                    if (j0 >= np) break;
+                    const int j = j0 + lane;
+                    uint2 e = make_uint2(0u, ey[u]);
+                    const bool multi = (e.y & 0x100u) != 0;
+                    if (__any_sync(0xffffffffu, multi)) e.x = j < np ? __ldg(&ent[j].x) : 0u;
+                    (void)ex_multi;
+                    // atoms with several distinct sigmas (user float channels): whole-warp per-channel path; they stay in
+                    // the list under mask 0 (a run that updates no channel)
                     for (unsigned bm = __ballot_sync(0xffffffffu, multi); bm; bm &= bm - 1) {
-                        const int sl = __ffs(bm) - 1;
-                        const float ax = __shfl_sync(0xffffffffu, ex, sl), ay = __shfl_sync(0xffffffffu, ey, sl),
-                                    az = __shfl_sync(0xffffffffu, ez, sl);
-                        const unsigned src = __shfl_sync(0xffffffffu, tg.y, sl) & 0x7fffffffu;
+                        const unsigned it = __shfl_sync(0xffffffffu, e.x, __ffs(bm) - 1);
+                        const float4 f = __ldg(p.rec_pos + it);
+                        const uint4 tg = __ldg(p.rec_tag + it);
+                        const float ax = (float)((int)(tg.z & 0xffffu) - cx) + (f.x - 1.5f), ay = (float)((int)(tg.z >> 16) - cy) + (f.y - 1.5f),
+                                    az = (float)((int)(tg.x >> 16) - cz) + (f.z - 3.5f);
                         const float dy = ay - fy, dz = az - fz;
                         const float s2 = fmaf(dz, dz, dy * dy);
                         const double ivs = RG(inv_vs);
@@ -285,42 +350,31 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                         }
 #pragma unroll
                         for (int h = 0; h < 8; ++h) {
-                            const double sv = __ldg(p.sigmas + (long long)src * 8 + h) * ivs;
+                            const double sv = __ldg(p.sigmas + (long long)tg.y * 8 + h) * ivs;
                             if (sv == 0.0 || sv != sv) continue;
                             const float w = (float)(1.0 / (sv * sv));
 #pragma unroll
                             for (int k2 = 0; k2 < 4; ++k2)
                                 if (d2[k2] < cut2) acc[h][k2] = fminf(acc[h][k2], d2[k2] * w);
                         }
-                        touched = true;
                     }
-                    const unsigned bal = __ballot_sync(0xffffffffu, single);
-                    if (single) {
-                        const int slot = np + __popc(bal & lt);
-                        const unsigned m = tg.x & 255u, sh = (m & 1u) * 16u;
-                        tmp[slot] = i;
-                        key[slot] = (unsigned char)m;
+                    if (j < np) {
+                        const unsigned m = multi ? 0u : (e.y & 255u), sh = (m & 1u) * 16u;
                         const unsigned old = atomicAdd(&hist[m >> 1], 1u << sh);
-                        rnk[slot] = (unsigned char)((old >> sh) & 0xffffu);
+                        rnk[j] = (unsigned char)((old >> sh) & 0xffffu);
                     }
-                    np += __popc(bal);
                 }
-                if (np <= R_CAP - 32 && k0 + 32 < total) continue;
-                if (np == 0) continue;
-                touched = true;
                 __syncwarp();
-
-                // ---- counting sort by channel mask: END offsets of the 256 bins (8 per lane); a survivor of rank r in its bin
-                // goes to end - 1 - r, so the rank-0 survivor closes the run
-                unsigned cnt[8], off[8];
-                unsigned ridx;
+                // ---- counting sort by channel mask: END offsets of the 256 bins (8 per lane); a candidate of rank r in its
+                // bin goes to end - 1 - r, so the rank-0 candidate closes the run
                 {
+                    unsigned cnt[8], off8[8];
                     const uint4 hw = *reinterpret_cast<const uint4 *>(hist + 4 * lane);
                     cnt[0] = hw.x & 0xffffu; cnt[1] = hw.x >> 16; cnt[2] = hw.y & 0xffffu; cnt[3] = hw.y >> 16;
                     cnt[4] = hw.z & 0xffffu; cnt[5] = hw.z >> 16; cnt[6] = hw.w & 0xffffu; cnt[7] = hw.w >> 16;
                     unsigned sum = 0, nzc2 = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { sum += cnt[j]; off[j] = sum; nzc2 += cnt[j] ? 1u : 0u; }
+                    for (int j = 0; j < 8; ++j) { sum += cnt[j]; off8[j] = sum; nzc2 += cnt[j] ? 1u : 0u; }
                     unsigned v = sum | (nzc2 << 16);
                     const unsigned mine = v;
 #pragma unroll
@@ -330,10 +384,14 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     }
                     const unsigned excl = v - mine;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) off[j] += excl & 0xffffu;
-                    ridx = excl >> 16;
+                    for (int j = 0; j < 8; ++j) off8[j] += excl & 0xffffu;
+                    unsigned ridx = excl >> 16;
                     *reinterpret_cast<uint4 *>(hist + 4 * lane) =
-                        make_uint4(off[0] | (off[1] << 16), off[2] | (off[3] << 16), off[4] | (off[5] << 16), off[6] | (off[7] << 16));
+                        make_uint4(off8[0] | (off8[1] << 16), off8[2] | (off8[3] << 16), off8[4] | (off8[5] << 16), off8[6] | (off8[7] << 16));
+                    // run table: the masks of the non-empty bins in order
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (cnt[j]) rmask[ridx++] = (unsigned char)(lane * 8 + j);
                 }
                 // the stage of the previous block aliases the records: its bulk copies must have read it
                 if (pending) {
@@ -345,17 +403,17 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 // The record that closes a run is stored NEGATED: every term of r is a square of a difference of record
                 // fields, so r is unchanged and the sign of .w is a free end-of-run flag.
                 for (int j = lane; j < np; j += 32) {
-                    const unsigned i = tmp[j];
-                    const unsigned m = key[j];
+                    const uint2 e = __ldg(ent + j);
+                    const unsigned m = (e.y & 0x100u) ? 0u : (e.y & 255u);
                     const unsigned rk = rnk[j];
                     const unsigned pos = ((hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu) - 1u - rk;
-                    const float4 e = __ldg(p.rec_pos + i);
-                    const uint4 tg = __ldg(p.rec_tag + i);
+                    const float4 f = __ldg(p.rec_pos + e.x);
+                    const uint4 tg = __ldg(p.rec_tag + e.x);
                     const float sw = __uint_as_float(tg.w);
                     const double dsw = rk == 0 ? -(double)sw : (double)sw;
-                    const double ex = (double)e.x + ((double)((int)(tg.z & 1023u) * 4 - sx) - 1.5);
-                    const double ey = (double)e.y + ((double)((int)((tg.z >> 10) & 1023u) * 4 - sy) - 1.5);
-                    const double ez = (double)e.z + ((double)((int)(tg.z >> 20) * 4 - sz) - 3.5);
+                    const double ex = (double)((int)(tg.z & 0xffffu) - cx) + ((double)f.x - 1.5);
+                    const double ey = (double)((int)(tg.z >> 16) - cy) + ((double)f.y - 1.5);
+                    const double ez = (double)((int)(tg.x >> 16) - cz) + ((double)f.z - 3.5);
                     rec[pos] = make_float4((float)(ex * dsw), (float)(ey * dsw), (float)(ez * dsw), (float)dsw);
 #if MKB_R_FMA_GATE
                     cwv[pos] = -(cut2 * (sw * sw)) * R_GATE_BIG;  // gate on the FMA pipe: sat((r - cw) 2^40) is 0 inside, 1 outside
@@ -364,10 +422,6 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
 #endif
                 }
                 __syncwarp();
-                // run table (tmp is free now): the masks of the non-empty bins in order; clear the histogram
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (cnt[j]) tmp[ridx++] = (unsigned)(lane * 8 + j);
                 *reinterpret_cast<uint4 *>(hist + 4 * lane) = make_uint4(0u, 0u, 0u, 0u);
                 __syncwarp();
 
@@ -395,7 +449,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     float cwa = cwv[0];
                     int i = 1;  // next record to load; i == np reads past the list (inside this warp's buffer), never used
 #pragma unroll 1
-                    for (int ri = 0; i <= np; ++ri) {
+                    for (int ri = 0; i <= np && MKB_R_EXP != 1; ++ri) {
                         float m0 = INF, m1 = INF, m2 = INF, m3 = INF;
 #pragma unroll 1
                         for (;;) {
@@ -414,7 +468,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                             i += 2;
                             if (b.w < 0.0f) break;
                         }
-                        const unsigned mask = tmp[ri];
+                        const unsigned mask = MKB_R_EXP == 2 ? 0u : rmask[ri];
 #if MKB_R_FLUSH == 1
                         MKB_NIB_SWITCH(mask & 15u, 0)
                         MKB_NIB_SWITCH(mask >> 4, 4)
@@ -428,29 +482,20 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
 #endif
                     }
 #undef MKB_RUN_BODY
+#undef MKB_GATED_MIN
                 }
-                np = 0;
                 __syncwarp();
             }
 
-            if (!touched) {
-                if (p.cmajor) {
-                    store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, z0 + lz);
-                } else {
-                    if (row_ok) bulk_store_row(row_dst, zero_sa, row_bytes);
-                    if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                continue;
-            }
-            // ---- epilogue: value = 1 - exp(-(1/r)^6) once per voxel-channel; channels empty across the warp skip it
+            // ---- epilogue: value = 1 - exp(-(1/r)^6) once per voxel-channel.  The minima go to the stage (output layout:
+            // voxel-major, 8 channels = two float4) as they are; a compact loop then turns r into the value in place, 4
+            // channels per lane and trip (an epilogue unrolled over the 32 accumulators was 10 KB of code: with 28 warps in
+            // different phases the instruction cache did not hold it).
             if (pending) {
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 pending = false;
             }
             __syncwarp();
-            // The minima go to the stage (output layout: voxel-major, 8 channels = two float4) as they are; a compact loop
-            // then turns r into the value in place, 4 channels per lane and trip (an epilogue unrolled over the 32
-            // accumulators was 10 KB of code: with 28 warps in different phases the instruction cache did not hold it).
             float4 *const stage = reinterpret_cast<float4 *>(wb);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -464,7 +509,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 float4 v = stage[it * 32 + lane];
                 const float LIVE = 0.5f * R_GATE_HUGE;  // r of a voxel-channel no atom reached: +inf (or 2^126 with the FMA gate)
                 const bool live = fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < LIVE;
-                if (__any_sync(0xffffffffu, live)) {
+                if (MKB_R_EXP != 3 && __any_sync(0xffffffffu, live)) {
                     v.x = occ_value(rcp_approx(v.x)); v.y = occ_value(rcp_approx(v.y));
                     v.z = occ_value(rcp_approx(v.z)); v.w = occ_value(rcp_approx(v.w));
                 } else {
@@ -507,7 +552,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
 // to set a bit also appends the voxel to `list` (fix[0] = count, capacity `cap`: beyond it occ_fix_scan_kernel takes over).
 // ---------------------------------------------------------------------------------------------------------
 constexpr float R_FIND_BAND = 2.0e-6f;  // relative; fill error (< 1e-6) + this kernel's own float32 error
-constexpr int FIX_HDR = 4;              // words in front of the list: count, overflow flag
+constexpr int FIX_HDR = 4;              // words in front of the list: count
 
 __global__ void __launch_bounds__(128) occ_band_kernel(const float *__restrict__ coords, const GridDev *__restrict__ grids, int B,
                                                        long long n_items, unsigned *__restrict__ bitmap,
@@ -570,13 +615,14 @@ __global__ void __launch_bounds__(128) occ_band_kernel(const float *__restrict__
     }
 }
 
-// float64 re-evaluation of one voxel with the reference's operations (pyx:46-61): d2 as exact_gate, max of sigma^2/d2 per
-// channel, 1 - exp(-q^6).  One warp per flagged voxel.
+// float64 re-evaluation of one voxel with the reference's operations (pyx:46-61): d2 as the reference computes it
+// (centres fl(fl(i*vs) + origin), voxeldescriptors.py:125-132,245), max of sigma^2/d2 per channel, 1 - exp(-q^6).
+// One warp per flagged voxel; the atoms are those of the voxel's block list.
 __device__ __forceinline__ void occ_fix_voxel(const GridDev *__restrict__ grids, int B, long long v, int lane,
                                               const float *__restrict__ coords, const double *__restrict__ sigmas,
                                               const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
-                                              const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ cell_start,
-                                              float *__restrict__ out, int cmajor) {
+                                              const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ blk_start,
+                                              const uint2 *__restrict__ blk_ent, float *__restrict__ out, int cmajor) {
     int lo = 0, hi = B - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -586,45 +632,30 @@ __device__ __forceinline__ void occ_fix_voxel(const GridDev *__restrict__ grids,
     const long long lv = v - g->vox_base;
     const int nz = g->dims[2], ny = g->dims[1];
     const int iz = (int)(lv % nz), iy = (int)((lv / nz) % ny), ix = (int)(lv / ((long long)nz * ny));
-    const int cutv = g->cutv, cs = g->cell;
-    const int cx0 = ix / cs, cx1 = min((ix + 2 * cutv) / cs, g->cells[0] - 1);
-    const int cy0 = iy / cs, cy1 = min((iy + 2 * cutv) / cs, g->cells[1] - 1);
-    const int cz0 = iz / cs, cz1 = min((iz + 2 * cutv) / cs, g->cells[2] - 1);
-    const int ncy = cy1 - cy0 + 1, nrows = (cx1 - cx0 + 1) * ncy;
+    const int nby = (ny + 3) >> 2, nbz = (nz + R_BZ - 1) / R_BZ;
+    const long long bid = g->tile_base + ((long long)(ix >> 2) * nby + (iy >> 2)) * nbz + iz / R_BZ;
+    const unsigned e0 = __ldg(blk_start + bid), e1 = __ldg(blk_start + bid + 1);
     const double cx = __dadd_rn(__dmul_rn((double)ix, g->vs), g->origin[0]);
     const double cy = __dadd_rn(__dmul_rn((double)iy, g->vs), g->origin[1]);
     const double cz = __dadd_rn(__dmul_rn((double)iz, g->vs), g->origin[2]);
     double q[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) q[h] = 0.0;
-    for (int r0 = 0; r0 < nrows; r0 += 32) {
-        unsigned a0 = 0, a1 = 0;
-        if (r0 + lane < nrows) {  // the rows' atom ranges, one row per lane
-            const int rx = (r0 + lane) / ncy, ry = (r0 + lane) - rx * ncy;
-            const long long cb = g->cell_base + ((long long)(cx0 + rx) * g->cells[1] + (cy0 + ry)) * g->cells[2];
-            a0 = __ldg(cell_start + cb + cz0);
-            a1 = __ldg(cell_start + cb + cz1 + 1);
-        }
-        const int nr = min(32, nrows - r0);
-        for (int r = 0; r < nr; ++r) {
-            const unsigned b0 = __shfl_sync(0xffffffffu, a0, r), b1 = __shfl_sync(0xffffffffu, a1, r);
-            for (unsigned i = b0 + lane; i < b1; i += 32) {
-                const unsigned a = __ldg(&rec_tag[i].y) & 0x7fffffffu;
-                const double dx = (double)coords[3ll * a + 0] - cx;
-                const double dy = (double)coords[3ll * a + 1] - cy;
-                const double dz = (double)coords[3ll * a + 2] - cz;
-                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if (!(d2 < CUTOFF_A * CUTOFF_A)) continue;
+    for (unsigned i = e0 + lane; i < e1; i += 32) {
+        const unsigned a = __ldg(&rec_tag[__ldg(&blk_ent[i].x)].y);
+        const double dx = (double)coords[3ll * a + 0] - cx;
+        const double dy = (double)coords[3ll * a + 1] - cy;
+        const double dz = (double)coords[3ll * a + 2] - cz;
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (!(d2 < CUTOFF_A * CUTOFF_A)) continue;
 #pragma unroll
-                for (int h = 0; h < 8; ++h) {
-                    double s;
-                    if (sigmas) s = sigmas[(long long)a * 8 + h];
-                    else s = ((chanmask[a] >> h) & 1u) ? radii[a] : 0.0;
-                    if (s == 0.0 || s != s) continue;
-                    const double qq = (s * s) / d2;  // +inf at d2 == 0 -> value 1 (pyx:57)
-                    q[h] = qq > q[h] ? qq : q[h];
-                }
-            }
+        for (int h = 0; h < 8; ++h) {
+            double s;
+            if (sigmas) s = sigmas[(long long)a * 8 + h];
+            else s = ((chanmask[a] >> h) & 1u) ? radii[a] : 0.0;
+            if (s == 0.0 || s != s) continue;
+            const double qq = (s * s) / d2;  // +inf at d2 == 0 -> value 1 (pyx:57)
+            q[h] = qq > q[h] ? qq : q[h];
         }
     }
 #pragma unroll
@@ -649,14 +680,14 @@ __global__ void __launch_bounds__(256) occ_fix_list_kernel(const GridDev *__rest
                                                            const unsigned long long *__restrict__ fix, unsigned cap,
                                                            const float *__restrict__ coords, const double *__restrict__ sigmas,
                                                            const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
-                                                           const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ cell_start,
-                                                           float *__restrict__ out, int cmajor) {
+                                                           const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ blk_start,
+                                                           const uint2 *__restrict__ blk_ent, float *__restrict__ out, int cmajor) {
     const unsigned long long n = fix[0];
     if (n > cap) return;  // the list overflowed: occ_fix_scan_kernel walks the bitmap instead
     const int lane = threadIdx.x & 31;
     const unsigned nw = (gridDim.x * blockDim.x) >> 5;
     for (unsigned long long w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nw)
-        occ_fix_voxel(grids, B, (long long)fix[FIX_HDR + w], lane, coords, sigmas, radii, chanmask, rec_tag, cell_start, out, cmajor);
+        occ_fix_voxel(grids, B, (long long)fix[FIX_HDR + w], lane, coords, sigmas, radii, chanmask, rec_tag, blk_start, blk_ent, out, cmajor);
 }
 
 __global__ void __launch_bounds__(256) occ_fix_scan_kernel(const GridDev *__restrict__ grids, int B, long long n_words,
@@ -664,8 +695,8 @@ __global__ void __launch_bounds__(256) occ_fix_scan_kernel(const GridDev *__rest
                                                            const unsigned long long *__restrict__ fix, unsigned cap,
                                                            const float *__restrict__ coords, const double *__restrict__ sigmas,
                                                            const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
-                                                           const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ cell_start,
-                                                           float *__restrict__ out, int cmajor) {
+                                                           const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ blk_start,
+                                                           const uint2 *__restrict__ blk_ent, float *__restrict__ out, int cmajor) {
     if (fix[0] <= cap) return;
     const int lane = threadIdx.x & 31;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -675,7 +706,7 @@ __global__ void __launch_bounds__(256) occ_fix_scan_kernel(const GridDev *__rest
             const int wl = __ffs(wm) - 1;
             for (unsigned bits = __shfl_sync(0xffffffffu, mine, wl); bits; bits &= bits - 1)
                 occ_fix_voxel(grids, B, ((w0 + wl) << 5) + (__ffs(bits) - 1), lane, coords, sigmas, radii, chanmask, rec_tag,
-                              cell_start, out, cmajor);
+                              blk_start, blk_ent, out, cmajor);
         }
     }
 }

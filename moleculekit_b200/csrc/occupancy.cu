@@ -1624,6 +1624,130 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
     if (cells >= (1ll << 31) - 2 || items >= (1ll << 31))
         return fail(h, MKB_ERR_BAD_ARG, "batch too large (%lld cells, %lld atom items): split it", cells, items);
 
+    // ---- default for 8 channels: per-block candidate lists + persistent mask-run kernel with TMA stores (occ_runs.cuh).
+    // MKB_OCC_V6=1 or any of the older selectors keeps the v6 warp kernel (A/B runs,
+    // tests/test_occupancy_gpu.py::test_alternative_kernel_paths_agree); accumulate calls stay on v6 as well.
+    bool use_runs = (variant == 0 || (variant == 1 && !getenv("MKB_OCC_TILE"))) && C == 8 && !(flags & MKB_OCC_ACCUMULATE) && ((uintptr_t)out % 16 == 0) &&
+                    !getenv("MKB_OCC_V6") && !force_warp && !getenv("MKB_OCC_WARP32");
+    long long run_blocks = 0, run_items = 0, ent_bound = 0;
+    std::vector<long long> ibase;  // [0, B]: first queue item of every grid; [B + 1, 2B + 1]: first slot word of every grid
+    if (use_runs) {
+        ibase.assign(2 * ((size_t)B + 1), 0);
+        for (int b = 0; b < B; ++b) {
+            GridDev &g = gd[b];
+            const long long nbx = (g.dims[0] + 3) / 4, nby = (g.dims[1] + 3) / 4, nbz = (g.dims[2] + R_BZ - 1) / R_BZ;
+            if (g.dims[0] + 2 * g.cutv + 2 >= 65536 || g.dims[1] + 2 * g.cutv + 2 >= 65536 || g.dims[2] + 2 * g.cutv + 2 >= 65536) use_runs = false;
+            g.tile_base = run_blocks;  // first 4x4x8 block of this grid
+            run_blocks += nbx * nby * nbz;
+            ibase[b + 1] = ibase[b] + nbx * nby * ((nbz + R_ZC - 1) / R_ZC);
+            // blocks one atom can reach: an interval of 2 cut voxels touches at most floor((2 cut + e - 1) / e) + 1 blocks of edge e
+            const double c2 = 2.0 * CUTOFF_A / g.vs;
+            const long long rx = std::min<long long>(nbx, (long long)((c2 + 3) / 4) + 1), ry = std::min<long long>(nby, (long long)((c2 + 3) / 4) + 1),
+                            rz = std::min<long long>(nbz, (long long)((c2 + R_BZ - 1) / R_BZ) + 1);
+            g.rcells = (int)(rx * ry * rz);  // slots per atom of this grid
+            ibase[(size_t)B + 1 + b] = ent_bound;
+            ent_bound += (g.atom_end - g.atom_begin) * rx * ry * rz;
+        }
+        ibase[2 * (size_t)B + 1] = ent_bound;
+        run_items = ibase[B];
+        if (run_blocks >= (1ll << 31) - 2 || ent_bound >= (1ll << 32) - 1) use_runs = false;
+        if (!use_runs) {  // restore the tile numbering of the other kernels
+            long long t = 0;
+            for (int b = 0; b < B; ++b) {
+                gd[b].tile_base = t;
+                t += (long long)gd[b].tiles[0] * gd[b].tiles[1] * gd[b].tiles[2];
+                gd[b].rcells = (TILE - 1 + 2 * gd[b].cutv) / TILE;
+            }
+        }
+    }
+    if (use_runs) {
+        GridDev *d_grids;
+        float4 *rec_pos;
+        uint4 *rec_tag;
+        unsigned *blk_count, *blk_start, *d_bitmap, *d_queue;
+        uint2 *blk_ent;
+        long long *d_ibase;
+        unsigned long long *d_fix;
+        int rc;
+        const size_t ni = (size_t)std::max<long long>(items, 1);
+        const long long n_words = cdiv(voxels, 32);
+        const unsigned fix_cap = (unsigned)std::min<long long>(voxels, 1ll << 22);
+        if ((rc = scratch_get(h, S_DESC, (size_t)B, &d_grids))) return rc;
+        if ((rc = scratch_get(h, S_SORT_PX, ni, &rec_pos))) return rc;
+        if ((rc = scratch_get(h, S_SORT_PY, ni, &rec_tag))) return rc;
+        if ((rc = scratch_get(h, S_CELL_COUNT, (size_t)run_blocks + 1, &blk_count))) return rc;
+        if ((rc = scratch_get(h, S_CELL_START, (size_t)run_blocks + 1, &blk_start))) return rc;
+        if ((rc = scratch_get(h, S_BLK_ENT, (size_t)std::max<long long>(ent_bound, 1), &blk_ent))) return rc;
+        if ((rc = scratch_get(h, S_BLOCK_BASE, 2 * ((size_t)B + 1), &d_ibase))) return rc;
+        if ((rc = scratch_get(h, S_BAND_BITMAP, (size_t)n_words, &d_bitmap))) return rc;
+        if ((rc = scratch_get(h, S_QUEUE, (size_t)4, &d_queue))) return rc;
+        if ((rc = scratch_get(h, S_FIX_LIST, (size_t)fix_cap + FIX_HDR, &d_fix))) return rc;
+        if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[0], st));
+        MKB_CUDA(h, cudaMemcpyAsync(d_grids, gd.data(), sizeof(GridDev) * (size_t)B, cudaMemcpyHostToDevice, st));
+        MKB_CUDA(h, cudaMemcpyAsync(d_ibase, ibase.data(), sizeof(long long) * 2 * ((size_t)B + 1), cudaMemcpyHostToDevice, st));
+        MKB_CUDA(h, cudaMemsetAsync(blk_count, 0, sizeof(unsigned) * ((size_t)run_blocks + 1), st));
+        MKB_CUDA(h, cudaMemsetAsync(d_bitmap, 0, sizeof(unsigned) * (size_t)n_words, st));
+        MKB_CUDA(h, cudaMemsetAsync(d_queue, 0, sizeof(unsigned) * 4, st));
+        MKB_CUDA(h, cudaMemsetAsync(d_fix, 0, sizeof(unsigned long long) * FIX_HDR, st));
+        if (items > 0) {
+            // the gate-band pre-pass (compute bound) runs beside the list build (atomic bound) on the handle's side stream
+            if (!h->aux_stream) {
+                MKB_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+                MKB_CUDA(h, cudaEventCreateWithFlags(&h->aux_ev[0], cudaEventDisableTiming));
+                MKB_CUDA(h, cudaEventCreateWithFlags(&h->aux_ev[1], cudaEventDisableTiming));
+            }
+            MKB_CUDA(h, cudaEventRecord(h->aux_ev[0], st));
+            MKB_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
+            occ_band_kernel<<<(unsigned)cdiv(items, 128), 128, 0, h->aux_stream>>>(coords, d_grids, B, items, d_bitmap, d_fix, fix_cap);
+            MKB_LAUNCHED(h);
+            MKB_CUDA(h, cudaEventRecord(h->aux_ev[1], h->aux_stream));
+            occ_prep_kernel<<<(unsigned)cdiv(items, 128), 128, 0, st>>>(coords, sigmas, radii, chanmask, d_grids, B, items, rec_pos, rec_tag, blk_count);
+            MKB_LAUNCHED(h);
+        }
+        if ((rc = scan_u32(h, st, blk_count, blk_start, run_blocks + 1))) return rc;
+        if (items > 0) {
+            occ_blk_fill_kernel<<<(unsigned)cdiv(items, 128), 128, 0, st>>>(d_grids, B, items, rec_pos, rec_tag, blk_count, blk_start, blk_ent);
+            MKB_LAUNCHED(h);
+        }
+        RunParams rp;
+        rp.grids = d_grids; rp.B = B;
+        rp.rec_pos = rec_pos; rp.rec_tag = rec_tag; rp.blk_start = blk_start; rp.blk_ent = blk_ent;
+        rp.sigmas = sigmas; rp.out = out;
+        rp.item_base = d_ibase; rp.queue = d_queue;
+        rp.total_items = (unsigned)run_items;
+        rp.cmajor = (flags & MKB_OCC_LAYOUT_CXYZ) ? 1 : 0;
+        bool uni = true;
+        const GridDev &g0 = gd[0];
+        const long long nvox0 = (long long)g0.dims[0] * g0.dims[1] * g0.dims[2];
+        for (int b = 0; b < B && uni; ++b) {
+            const GridDev &g = gd[b];
+            uni = g.dims[0] == g0.dims[0] && g.dims[1] == g0.dims[1] && g.dims[2] == g0.dims[2] && g.vs == g0.vs &&
+                  g.out_offset == g0.out_offset + b * nvox0;
+        }
+        rp.u = g0;
+        rp.u_out_stride = nvox0;
+        rp.u_ipg = (unsigned)(ibase[1] - ibase[0]);
+        rp.u_nby = (unsigned)((g0.dims[1] + 3) / 4);
+        rp.u_nzc = (unsigned)(((g0.dims[2] + R_BZ - 1) / R_BZ + R_ZC - 1) / R_ZC);
+        rp.u_bpg = (unsigned)(B > 1 ? gd[1].tile_base - gd[0].tile_base : run_blocks);
+        if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
+        const unsigned nctas = (unsigned)std::min<long long>((long long)h->sm_count * MKB_R_MIN_CTAS, cdiv(run_items, R_WARPS));
+        if (uni) occ_fill_runs_kernel<true><<<nctas, R_WARPS * 32, 0, st>>>(rp);
+        else occ_fill_runs_kernel<false><<<nctas, R_WARPS * 32, 0, st>>>(rp);
+        MKB_LAUNCHED(h);
+        if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));
+        if (items > 0) {
+            MKB_CUDA(h, cudaStreamWaitEvent(st, h->aux_ev[1], 0));
+            const unsigned fg = (unsigned)h->sm_count * 4;
+            occ_fix_list_kernel<<<fg, 256, 0, st>>>(d_grids, B, d_fix, fix_cap, coords, sigmas, radii, chanmask, rec_tag, blk_start, blk_ent, out, rp.cmajor);
+            MKB_LAUNCHED(h);
+            occ_fix_scan_kernel<<<fg, 256, 0, st>>>(d_grids, B, n_words, d_bitmap, d_fix, fix_cap, coords, sigmas, radii, chanmask,
+                                                    rec_tag, blk_start, blk_ent, out, rp.cmajor);
+            MKB_LAUNCHED(h);
+        }
+        return MKB_OK;
+    }
+
     GridDev *d_grids;
     int *item_cell;
     unsigned *item_slot, *cell_count, *cell_start;
@@ -1665,77 +1789,6 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
     // the asynchronous smem read before it may retire; kept for the persistent variant
     fp.bulk_store = (fp.vec_ok && !(flags & MKB_OCC_ACCUMULATE) && getenv("MKB_OCC_BULK_STORE")) ? 1 : 0;
 
-    // ---- default for 8 channels: persistent mask-run kernel with TMA stores (occ_runs.cuh).  MKB_OCC_V6=1 or any of the
-    // older selectors keeps the v6 warp kernel (A/B runs, tests/test_occupancy_gpu.py::test_alternative_kernel_paths_agree).
-    bool use_runs = variant == 0 && C == 8 && !(flags & MKB_OCC_ACCUMULATE) && ((uintptr_t)out % 16 == 0) &&
-                    !getenv("MKB_OCC_V6") && !force_warp && !getenv("MKB_OCC_WARP32");
-    for (int b = 0; b < B && use_runs; ++b) {
-        const int r1 = (3 + 2 * gd[b].cutv) / 4 + 1;
-        if (r1 * r1 > R_ROWS) use_runs = false;
-    }
-    if (use_runs) {
-        // queue item = one (x, y) block column x R_ZC consecutive z blocks
-        std::vector<long long> ibase((size_t)B + 1, 0);
-        for (int b = 0; b < B; ++b) {
-            const long long nbz = (gd[b].dims[2] + R_BZ - 1) / R_BZ;
-            ibase[b + 1] = ibase[b] + (long long)((gd[b].dims[0] + 3) / 4) * ((gd[b].dims[1] + 3) / 4) * ((nbz + R_ZC - 1) / R_ZC);
-        }
-        if (ibase[B] >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "too many voxel blocks (%lld): split the batch", ibase[B]);
-        long long *d_ibase;
-        unsigned *d_bitmap, *d_queue;
-        unsigned long long *d_fix;
-        const long long n_words = cdiv(voxels, 32);
-        const unsigned fix_cap = (unsigned)std::min<long long>(voxels, 1ll << 22);
-        if ((rc = scratch_get(h, S_BLOCK_BASE, (size_t)B + 1, &d_ibase))) return rc;
-        if ((rc = scratch_get(h, S_BAND_BITMAP, (size_t)n_words, &d_bitmap))) return rc;
-        if ((rc = scratch_get(h, S_QUEUE, (size_t)4, &d_queue))) return rc;
-        if ((rc = scratch_get(h, S_FIX_LIST, (size_t)fix_cap + FIX_HDR, &d_fix))) return rc;
-        MKB_CUDA(h, cudaMemcpyAsync(d_ibase, ibase.data(), sizeof(long long) * ((size_t)B + 1), cudaMemcpyHostToDevice, st));
-        MKB_CUDA(h, cudaMemsetAsync(d_bitmap, 0, sizeof(unsigned) * (size_t)n_words, st));
-        MKB_CUDA(h, cudaMemsetAsync(d_queue, 0, sizeof(unsigned) * 4, st));
-        MKB_CUDA(h, cudaMemsetAsync(d_fix, 0, sizeof(unsigned long long) * FIX_HDR, st));
-        if (items > 0) {
-            occ_band_kernel<<<(unsigned)cdiv(items, 128), 128, 0, st>>>(coords, d_grids, B, items, d_bitmap, d_fix, fix_cap);
-            MKB_LAUNCHED(h);
-        }
-        RunParams rp;
-        rp.grids = d_grids; rp.B = B;
-        rp.rec_pos = rec_pos; rp.rec_tag = rec_tag; rp.cell_start = cell_start;
-        rp.sigmas = sigmas; rp.out = out;
-        rp.item_base = d_ibase; rp.queue = d_queue;
-        rp.total_items = (unsigned)ibase[B];
-        rp.cmajor = fp.cmajor;
-        bool uni = true;
-        const GridDev &g0 = gd[0];
-        const long long nvox0 = (long long)g0.dims[0] * g0.dims[1] * g0.dims[2];
-        const long long ncell0 = (long long)g0.cells[0] * g0.cells[1] * g0.cells[2];
-        for (int b = 0; b < B && uni; ++b) {
-            const GridDev &g = gd[b];
-            uni = g.dims[0] == g0.dims[0] && g.dims[1] == g0.dims[1] && g.dims[2] == g0.dims[2] && g.vs == g0.vs &&
-                  g.out_offset == g0.out_offset + b * nvox0 && g.cell_base == g0.cell_base + b * ncell0;
-        }
-        rp.u = g0;
-        rp.u_out_stride = nvox0;
-        rp.u_cell_stride = ncell0;
-        rp.u_ipg = (unsigned)(ibase[1] - ibase[0]);
-        rp.u_nby = (unsigned)((g0.dims[1] + 3) / 4);
-        rp.u_nzc = (unsigned)(((g0.dims[2] + R_BZ - 1) / R_BZ + R_ZC - 1) / R_ZC);
-        if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
-        const unsigned nctas = (unsigned)std::min<long long>((long long)h->sm_count * MKB_R_MIN_CTAS, cdiv(ibase[B], R_WARPS));
-        if (uni) occ_fill_runs_kernel<true><<<nctas, R_WARPS * 32, 0, st>>>(rp);
-        else occ_fill_runs_kernel<false><<<nctas, R_WARPS * 32, 0, st>>>(rp);
-        MKB_LAUNCHED(h);
-        if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));
-        if (items > 0) {
-            const unsigned fg = (unsigned)h->sm_count * 4;
-            occ_fix_list_kernel<<<fg, 256, 0, st>>>(d_grids, B, d_fix, fix_cap, coords, sigmas, radii, chanmask, rec_tag, cell_start, out, fp.cmajor);
-            MKB_LAUNCHED(h);
-            occ_fix_scan_kernel<<<fg, 256, 0, st>>>(d_grids, B, n_words, d_bitmap, d_fix, fix_cap, coords, sigmas, radii, chanmask,
-                                                    rec_tag, cell_start, out, fp.cmajor);
-            MKB_LAUNCHED(h);
-        }
-        return MKB_OK;
-    }
     if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
     const bool fast8 = (variant == 1);
     unsigned *tile_total = nullptr;
