@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (C2 ligands, C5 fine grids, C4 distances)")
+    ap.add_argument("--no-scaling", action="store_true", help="skip the strong-scaling / NCCL gather / config-4 section")
     return ap.parse_args()
 
 
@@ -61,24 +62,56 @@ def make_workload(kind: str, batch: int, rank: int):
 
 
 # ----------------------------------------------------------------------------------------------------- CPU arm
+def host_cores() -> int:
+    """Cores this process may really use: scheduler affinity, capped by the cgroup CPU quota (os.cpu_count() reports the
+    box's logical CPUs even when a lease grants a fraction of them -- round 1's reference arm oversubscribed 128
+    processes onto far fewer cores and hit the driver's time limit)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+_CPU_FN = {}
+
+
 def _cpu_worker(args):
-    kind, coords, sigmas, boxsize, center, voxelsize = args
-    sys.path.insert(0, ROOT)
+    """One bounded sample item: the leading `nslab` x-planes of one grid of the workload (the reference kernel's cost is
+    atoms x centres, so a slab is the same work per voxel-channel)."""
+    kind, coords, sigmas, boxsize, center, voxelsize, nslab = args
+    if kind not in _CPU_FN:
+        sys.path.insert(0, ROOT)
+        if kind == "reference":
+            from oracle import build_ref
+
+            _CPU_FN[kind] = build_ref.load()[0].calculate_occupancy
+        else:
+            from oracle import cpu_oracle
+
+            _CPU_FN[kind] = cpu_oracle.calculate_occupancy
     from moleculekit_b200.tools.voxeldescriptors import _centers_from_spec, _grid_spec
 
     bb_min, nvox = _grid_spec(None, 0, boxsize, center, voxelsize)
-    centers = _centers_from_spec(bb_min, nvox, voxelsize)
+    per_plane = int(nvox[1]) * int(nvox[2])
+    centers = _centers_from_spec(bb_min, nvox, voxelsize)[: max(1, min(int(nvox[0]), nslab)) * per_plane]
     out = np.zeros((centers.shape[0], sigmas.shape[1]))
-    if kind == "reference":
-        from oracle import build_ref
-
-        fn = build_ref.load()[0].calculate_occupancy
-    else:
-        from oracle import cpu_oracle
-
-        fn = cpu_oracle.calculate_occupancy
+    c32 = np.ascontiguousarray(coords, dtype=np.float32)
+    s64 = np.ascontiguousarray(sigmas, dtype=np.float64)
     t0 = time.perf_counter()
-    fn(centers, np.ascontiguousarray(coords, dtype=np.float32), np.ascontiguousarray(sigmas, dtype=np.float64), out)
+    _CPU_FN[kind](np.ascontiguousarray(centers), c32, s64, out)
     return time.perf_counter() - t0, out.size
 
 
@@ -95,54 +128,77 @@ def cpu_kind():
     return "port"
 
 
-def _cpu_sample_once(w, n_items: int, procs: int, kind: str):
-    import multiprocessing as mp
+class CpuArm:
+    """The reference's CPU kernel on the host cores: `procs` single-threaded worker processes (the reference kernel is
+    single-threaded, setup.py:48), each step = one item per process.  A pilot item sizes the slab so that a step takes
+    about `step_seconds` of wall time -- fewer voxels per step, never fewer steps."""
 
-    jobs = [(kind, w["coords"][b], w["sigmas"][b], w["boxsize"], w["centers"][b], w["voxelsize"])
-            for b in range(n_items)]
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(processes=procs) as pool:
-        res = pool.map(_cpu_worker, jobs, chunksize=1)
-    wall = time.perf_counter() - t0
-    return sum(r[1] for r in res) / wall, wall, sum(r[0] for r in res)
+    MAX_PROCS = 32  # beyond this the kernel (a 6 MB centre array streamed per atom) is memory bound: 128 procs were slower than 32
 
+    def __init__(self, w, step_seconds: float):
+        import multiprocessing as mp
 
-def cpu_sample(w, n_items: int, procs: int):
-    """Time the CPU kernel on the first items of the workload, one single-threaded process per item (the reference
-    kernel is single-threaded: OpenMP is commented out in its setup.py:48).  The kernel streams a 6 MB centre array per
-    atom, so oversubscribing hyper-threads can LOWER throughput: two process counts are tried (all logical cores and a
-    quarter of them) and the better one is reported, with both in `sample`."""
-    kind = cpu_kind()
-    tried = []
-    for p in sorted({max(1, procs // 4), procs}):
-        n = min(n_items, p)
-        tried.append((p,) + _cpu_sample_once(w, n, p, kind))
-    best = max(tried, key=lambda t: t[1])
-    desc = "; ".join(f"{p} procs x 1 thread on {min(n_items, p)} items: {v:.3g} vc/s ({cs:.0f} core-s)" for p, v, _, cs in tried)
-    return dict(value=best[1], unit=UNIT, cores=best[0], kind=kind,
-                sample=f"kernel only (centres prebuilt), first items of the workload; {desc}"), best[2]
+        self.w, self.kind = w, cpu_kind()
+        self.cores = host_cores()
+        self.procs = max(1, min(self.cores, self.MAX_PROCS, len(w["coords"])))
+        self.pool = mp.get_context("fork").Pool(processes=self.procs)
+        # pilot: 2 planes of the first grid on one process
+        nx = self._nx()
+        t, n = self.pool.apply(_cpu_worker, (self._job(0, 2),))
+        rate1 = n / max(t, 1e-6)                                   # voxel-channels/s of one unloaded core
+        per_plane = n / 2
+        # under load a core delivers maybe half of that (shared memory bandwidth): size for step_seconds of wall time
+        self.target = step_seconds
+        self.nslab = int(max(1, min(nx, 0.5 * rate1 * step_seconds / per_plane)))
+        self.pilot = f"pilot {rate1:.3g} vc/s on 1 core"
+
+    def _nx(self):
+        from moleculekit_b200.tools.voxeldescriptors import _grid_spec
+
+        return int(_grid_spec(None, 0, self.w["boxsize"], self.w["centers"][0], self.w["voxelsize"])[1][0])
+
+    def _job(self, b, nslab):
+        w = self.w
+        return (self.kind, w["coords"][b], w["sigmas"][b], w["boxsize"], w["centers"][b], w["voxelsize"], nslab)
+
+    def step(self):
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, [self._job(b, self.nslab) for b in range(self.procs)], chunksize=1)
+        wall = time.perf_counter() - t0
+        value = sum(r[1] for r in res) / wall
+        if wall > 1.5 * self.target:  # the cores are slower than the pilot promised (shared host): shrink the slab, keep the steps
+            self.nslab = max(1, int(self.nslab * self.target / wall))
+        return value, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def describe(self, value):
+        return dict(value=value, unit=UNIT, cores=self.procs, kind=self.kind,
+                    sample=f"kernel only (centres prebuilt): {self.procs} single-threaded processes (host grants {self.cores} "
+                           f"cores), one grid each, leading {self.nslab} of {self._nx()} x-planes per step; {self.pilot}")
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    procs = os.cpu_count() or 1
     w = make_workload(a.workload, a.batch, 0)
-    n_items = min(len(w["coords"]), max(1, procs))
+    n_steps = max(1, a.steps) + max(0, a.warmup)
+    arm = CpuArm(w, step_seconds=min(8.0, 150.0 / n_steps))  # the whole run ends within ~3-4 minutes
     for _ in range(a.warmup):
-        cpu_sample(w, n_items, procs)
-    vals, walls, base = [], [], None
-    for _ in range(a.steps):
-        base, wall = cpu_sample(w, n_items, procs)   # each step = one bounded sample (best of two process counts)
-        vals.append(base["value"]); walls.append(wall)
-    base["value"] = float(np.mean(vals))
-    best = (base, float(np.mean(walls)))
+        arm.step()
+    vals, walls = [], []
+    for _ in range(max(1, a.steps)):
+        v, wall = arm.step()
+        vals.append(v); walls.append(wall)
+    arm.close()
+    base = arm.describe(float(np.mean(vals)))
     line = dict(impl="reference", metric=METRIC, value=base["value"], unit=UNIT, n_gpus=a.gpus, steps=len(vals),
-                warmup=a.warmup, ms_per_step=best[1] * 1e3, higher_is_better=True, scaling="weak",
+                warmup=a.warmup, ms_per_step=float(np.mean(walls)) * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=w["name"], sample_items=n_items), cpu_baseline=base,
+                config=dict(workload=w["name"], sample_items=arm.procs, sample_x_planes=arm.nslab), cpu_baseline=base,
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -414,6 +470,147 @@ def extra_workloads(dev, peak):
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa(index: int):
+    """Pin this rank to the CPUs next to its GPU (NVML affinity mask) before any pinned buffer is allocated, so the
+    page-locked staging memory is first touched on the GPU's NUMA node.  Round 1's end-to-end numbers at N=4/8 were
+    limited by ranks copying 2 GB per step into memory of the other socket."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cur = os.sched_getaffinity(0)
+        want = cpus & cur
+        if want:
+            os.sched_setaffinity(0, want)
+            return f"{len(want)} CPUs near GPU {index}"
+    except Exception as e:  # NVML missing or affinity not permitted: run unbound
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
+def scaling_section(a, dev, world, rank, peak):
+    """What SURVEY 8(e) / BASELINE.json's north star describe for N GPUs, measured at every N (so the driver's N=1,2,4,8
+    runs give STRONG scaling): (1) the ONE 256-pocket batch of config 3 sharded over the ranks, shards resident;
+    (2) the NCCL all_gather that assembles the (256 x 64^3 x 8) tensor on every rank when the caller asks for it;
+    (3) the same batch end to end (pinned host in, pinned host out, each rank its slice); (4) config 4: the 10k-frame
+    periodic contact map with frames sharded over the ranks, device resident and through MetricDistance.project with
+    host arrays.  Times are CUDA events / wall clock per rank, MAX over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from moleculekit_b200 import distance_utils as du, sharding, workloads
+    from moleculekit_b200.molecule_lite import MolLite
+    from moleculekit_b200.projections.metricdistance import MetricDistance
+    from moleculekit_b200.tools import voxeldescriptors as vd
+
+    def maxr(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return maxr(e0.elapsed_time(e1) / steps)
+
+    out = {}
+    # ---- (1) strong scaling of the one C3 batch
+    B = a.batch or 256
+    w = workloads.protein_pockets(B=B, seed=1000)
+    off = sharding.partition(B, world)
+    b0, b1 = int(off[rank]), int(off[rank + 1])
+    vb = vd.VoxelBatch(w["coords"][b0:b1], w["sigmas"][b0:b1], boxsize=w["boxsize"], centers=w["centers"][b0:b1], voxelsize=1.0)
+    d_c, d_s = vb.to_device(dev)
+    shard = torch.empty((vb.total_voxels, 8), dtype=torch.float32, device=dev)
+    ms = timed(lambda: vb.run(d_c, d_s, shard), steps=10, warm=3)
+    n_vc = B * 64 ** 3 * 8
+    out["c3_strong"] = dict(workload=f"C3: ONE batch of {B} pockets sharded over {world} GPU(s) ({b1 - b0} on rank 0), shards resident",
+                            ms_per_step=ms, voxel_channels_per_s=n_vc / (ms * 1e-3))
+    # ---- (2) NCCL gather of the shards (only when the caller wants the assembled tensor on every rank)
+    if world > 1 and B % world == 0:
+        full = torch.empty((B * 64 ** 3, 8), dtype=torch.float32, device=dev)
+        ms_g = timed(lambda: dist.all_gather_into_tensor(full, shard), steps=5, warm=2)
+        nbytes = full.numel() * 4
+        out["c3_gather"] = dict(collective="ncclAllGather (all_gather_into_tensor) of the per-rank grids", ms=ms_g, bytes_assembled=nbytes,
+                                algbw_gbs=nbytes / (ms_g * 1e-3) / 1e9, busbw_gbs=nbytes * (world - 1) / world / (ms_g * 1e-3) / 1e9,
+                                gather_over_compute=ms_g / ms)
+        del full
+    # ---- (3) the same batch end to end: every rank uploads its pockets and receives its slice in pinned host memory
+    h_c = vd.pinned_array(vb.coords.shape, np.float32); h_c[:] = vb.coords
+    h_s = vd.pinned_array(vb.sigmas.shape, np.float64); h_s[:] = vb.sigmas
+    h_o = vd.pinned_array((vb.total_voxels, 8), np.float32)
+    kw = dict(boxsize=w["boxsize"], centers=w["centers"][b0:b1], voxelsize=1.0, atom_offsets=vb.atom_offsets, device=dev, out=h_o)
+    for _ in range(2):
+        vd.getVoxelDescriptorsBatch(h_c, h_s, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        vd.getVoxelDescriptorsBatch(h_c, h_s, **kw)
+    torch.cuda.synchronize(dev)
+    dt = maxr((time.perf_counter() - t0) / 5)
+    out["c3_strong_e2e"] = dict(workload="same batch, pinned host in / out per rank (H2D + kernels + D2H in the timed region)",
+                                ms_per_step=dt * 1e3, voxel_channels_per_s=n_vc / dt,
+                                d2h_bytes_per_rank=int(vb.total_voxels * 32), h2d_bytes_per_rank=int(h_c.nbytes + h_s.nbytes))
+    del h_o, shard, d_c, d_s
+    # ---- (4) config 4: 10k frames x (256 x 1024) periodic contacts <= 12 A, frames sharded
+    F, n1, n2, nat = (2000 if a.batch else 10000), 256, 1024, 5000
+    foff = sharding.partition(F, world)
+    f0, f1 = int(foff[rank]), int(foff[rank + 1])
+    rng = np.random.default_rng(7)
+    L = 36.84
+    box = np.repeat((L * (1 + 0.002 * rng.normal(size=F))).astype(np.float32)[None, :], 3, axis=0)[:, f0:f1].copy()
+    # selected atoms: random walk (every rank draws the whole walk and keeps its frames); the other 3720 atoms ("water")
+    # are never read by the projection -- they only have to be there, as in a real solvated trajectory
+    sel = rng.uniform(0, L, size=(n1 + n2, 3, 1)).astype(np.float32) + \
+        np.cumsum(rng.normal(0, 0.3, size=(n1 + n2, 3, F)).astype(np.float32), axis=2)
+    coords = vd.pinned_array((nat, 3, f1 - f0), np.float32)
+    coords[: n1 + n2] = sel[:, :, f0:f1]
+    coords[n1 + n2:] = rng.random((nat - n1 - n2, 3, f1 - f0), dtype=np.float32) * L
+    del sel
+    chain = np.array(["A"] * n1 + ["B"] * n2 + ["W"] * (nat - n1 - n2), dtype=object)
+    m1 = np.zeros(nat, bool); m1[:n1] = True
+    m2 = np.zeros(nat, bool); m2[n1:n1 + n2] = True
+    mol = MolLite(coords, box=box, chain=chain)
+    d_c = torch.from_numpy(np.ascontiguousarray(coords[: n1 + n2])).to(dev); d_b = torch.from_numpy(box).to(dev)
+    s1 = torch.arange(0, n1, dtype=torch.int32, device=dev); s2 = torch.arange(n1, n1 + n2, dtype=torch.int32, device=dev)
+    ch = torch.ones(n1 + n2, dtype=torch.int32, device=dev); ch[n1:] = 2
+    o = torch.empty((f1 - f0, n1 * n2), dtype=torch.uint8, device=dev)
+    ms4 = timed(lambda: du.dist_trajectory_device(d_c, d_b, s1, s2, ch, False, True, metric="contacts", threshold=12.0, out=o), steps=5, warm=2)
+    out["c4_frames_sharded"] = dict(workload=f"C4: {F} frames x {n1}x{n2} periodic contacts <= 12 A, frames sharded over {world} GPU(s), resident",
+                                    ms_per_step=ms4, pair_frames_per_s=F * n1 * n2 / (ms4 * 1e-3))
+    del o, d_c
+    proj = MetricDistance(m1, m2, periodic="selections", metric="contacts", threshold=12)
+    proj.device = dev
+    for _ in range(2):
+        res = proj.project(mol)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        res = proj.project(mol)
+    dt4 = maxr((time.perf_counter() - t0) / 3)
+    out["c4_project_e2e"] = dict(workload=f"MetricDistance.project (host (N,3,F) float32 in, host (F,P) bool out), {nat} atoms, frames sharded over {world} GPU(s)",
+                                 ms_per_step=dt4 * 1e3, pair_frames_per_s=F * n1 * n2 / dt4, result_shape=list(res.shape),
+                                 d2h_bytes_per_rank=int(res.size), h2d_bytes_per_rank=int((n1 + n2) * 3 * (f1 - f0) * 4))
+    return out
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -423,6 +620,7 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -504,6 +702,18 @@ def run_ours(a):
                    api="moleculekit_b200.tools.voxeldescriptors.getVoxelDescriptorsBatch(out=pinned float32)")
         del h_out
 
+    # ---- strong scaling of the one batch, NCCL gather, config 4 frames-sharded (every rank takes part)
+    scaling = None
+    if not a.no_scaling:
+        try:
+            peak_s = HBM_FALLBACK_GBS
+            del out
+            torch.cuda.empty_cache()
+            scaling = scaling_section(a, dev, world, rank, peak_s)
+            scaling["numa"] = numa
+        except Exception as e:  # never let a side measurement break the headline line
+            scaling = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -519,19 +729,28 @@ def run_ours(a):
     alg_bytes = workloads.occupancy_algorithmic_bytes(batch.total_voxels, n_atoms, batch.C)
     fill_mean = float(np.mean(fill_ms))
     achieved = alg_bytes / (fill_mean * 1e-3) / 1e9
-    traffic = None
-    try:  # dram bytes of one launch of the same command, from the committed `ncu --set full` capture
+    # DRAM bytes of the fill kernel: measured in THIS run when bench.py is started under `ncu` by
+    # profiles/scripts/traffic.sh (it writes the sum next to the report); otherwise taken from the newest committed
+    # capture of the same kernel and workload and labelled as such -- never silently attached to another kernel
+    traffic, traffic_source = None, None
+    kname = _lib.last_fill_kernel(local) if hasattr(_lib, "last_fill_kernel") else "occ_fill_runs_kernel"
+    try:
         if a.workload == "c3" and not a.batch:
-            tr = 0.0
-            for ln in open(os.path.join(ROOT, "profiles", "r01_fill_v6_2vox_metrics.txt")):
+            fn = os.path.join(ROOT, "profiles", "r02_fill_v8_metrics.txt")
+            tr, kern_ok = 0.0, False
+            for ln in open(fn):
+                if ln.startswith("# kernel:"):
+                    kern_ok = kname.split("<")[0] in ln
                 f = ln.split()
                 if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     tr += float(f[1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
-            traffic = tr or None
+            if kern_ok and tr:
+                traffic, traffic_source = tr, "committed ncu --set full capture of the same kernel and workload (profiles/r02_fill_v8_metrics.txt)"
     except Exception:
         traffic = None
-    roofline = dict(bound="hbm", kernel=("occ_fill8v_kernel" if w["voxelsize"] >= 5.0 / 7 else "occ_fill8_kernel"), achieved=achieved, peak=peak, unit="GB/s",
-                    frac=achieved / peak, traffic=traffic, peak_source=f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
+    roofline = dict(bound="hbm", kernel=kname, achieved=achieved, peak=peak, unit="GB/s",
+                    frac=achieved / peak, traffic=traffic, traffic_source=traffic_source,
+                    peak_source=f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
                     algorithmic_bytes_per_launch=int(alg_bytes), kernel_ms_mean=fill_mean,
                     kernel_ms_min=float(np.min(fill_ms)), prep_ms_mean=float(np.mean(prep_ms)),
                     kernel_share_of_step=fill_mean / ms_step)
@@ -543,9 +762,11 @@ def run_ours(a):
             extra = {"error": repr(e)}
     cpu = None
     if not a.no_cpu and world == 1:
-        procs = os.cpu_count() or 1
-        n_items = min(batch.B, max(1, procs))
-        cpu, _ = cpu_sample(w, n_items, procs)
+        arm = CpuArm(w, step_seconds=6.0)  # ~10-30 s of CPU work in total (pilot + two bounded steps)
+        arm.step()
+        v, _ = arm.step()
+        arm.close()
+        cpu = arm.describe(v)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic",
@@ -553,7 +774,7 @@ def run_ours(a):
                             voxel_channels_per_gpu=int(n_vc),
                             l2="no flush needed: each step streams %.2f GB of grid output, >> 126 MB L2" % (n_vc * 4 / 1e9),
                             parallelism=f"batch sharded over {world} GPU(s), no collective"),
-                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk, extra=extra)
+                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk, scaling_detail=scaling, extra=extra)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

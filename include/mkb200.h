@@ -63,6 +63,8 @@ int64_t mkb_launch_count(mkb_handle_t h);
  * mkb_get_timing synchronises on the last event and returns the two intervals of the most recent call (ms). */
 int mkb_set_timing(mkb_handle_t h, int on);
 int mkb_get_timing(mkb_handle_t h, float *prep_ms, float *main_ms);
+/* name of the main kernel the most recent occupancy / distance entry point launched (static string; "" before any call) */
+const char *mkb_last_kernel(mkb_handle_t h);
 
 /* One regular voxel grid: centre of voxel (ix,iy,iz) = fl(fl(i*voxelsize) + origin[d]) in float64, exactly
  * as moleculekit/tools/voxeldescriptors.py:125-132,245 builds `centers`; flat voxel index

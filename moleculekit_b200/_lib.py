@@ -31,7 +31,7 @@ class Traj(C.Structure):
 
 EXPORTS = [
     "mkb_version", "mkb_create", "mkb_destroy", "mkb_last_error", "mkb_launch_count",
-    "mkb_set_timing", "mkb_get_timing",
+    "mkb_set_timing", "mkb_get_timing", "mkb_last_kernel",
     "mkb_occupancy_grid_batch", "mkb_occupancy_grid_batch_masked", "mkb_occupancy_points",
     "mkb_grid_centers", "mkb_rotate_coords",
     "mkb_dist_trajectory", "mkb_contacts_count", "mkb_contacts_fill", "mkb_dist_reduction",
@@ -68,6 +68,8 @@ def load():
     lib.mkb_launch_count.restype = i64
     lib.mkb_set_timing.argtypes = [vp, C.c_int]
     lib.mkb_get_timing.argtypes = [vp, C.POINTER(f32), C.POINTER(f32)]
+    lib.mkb_last_kernel.argtypes = [vp]
+    lib.mkb_last_kernel.restype = C.c_char_p
     lib.mkb_occupancy_grid_batch.argtypes = [vp, vp, vp, vp, i64, i32, vp, i32, vp, u32]
     lib.mkb_occupancy_points.argtypes = [vp, vp, vp, i64, vp, vp, i64, i32, vp, u32]
     lib.mkb_occupancy_grid_batch_masked.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, i32, vp, u32]
@@ -91,7 +93,7 @@ def load():
     lib.mkb_xtc_decode.argtypes = [vp, vp, vp, i64, vp, i64, i64, vp, i64, f32, vp]
     lib.mkb_wrap_box.argtypes = [vp, vp, tp, vp, i64, vp, i64, C.POINTER(C.c_float)]
     for name in EXPORTS:
-        if name in ("mkb_last_error", "mkb_launch_count", "mkb_version"):
+        if name in ("mkb_last_error", "mkb_launch_count", "mkb_version", "mkb_last_kernel"):
             continue
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -135,6 +137,11 @@ def get_timing(device: int = 0) -> tuple[float, float]:
     a, b = C.c_float(), C.c_float()
     check(load().mkb_get_timing(h, C.byref(a), C.byref(b)), h)
     return float(a.value), float(b.value)
+
+
+def last_fill_kernel(device: int = 0) -> str:
+    """Name of the main kernel the most recent occupancy / distance call launched on this device."""
+    return load().mkb_last_kernel(handle(device)).decode()
 
 
 def destroy_all() -> None:

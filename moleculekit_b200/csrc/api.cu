@@ -44,6 +44,8 @@ const char *mkb_last_error(mkb_handle_t h) { return h ? h->err.c_str() : "null h
 
 int64_t mkb_launch_count(mkb_handle_t h) { return h ? h->launches : -1; }
 
+const char *mkb_last_kernel(mkb_handle_t h) { return h ? h->last_kernel : ""; }
+
 int mkb_set_timing(mkb_handle_t h, int on) {
     MKB_ENTER(h);
     if (on && !h->ev[0])

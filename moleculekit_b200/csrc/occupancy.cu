@@ -1732,6 +1732,7 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
         rp.u_bpg = (unsigned)(B > 1 ? gd[1].tile_base - gd[0].tile_base : run_blocks);
         if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
         const unsigned nctas = (unsigned)std::min<long long>((long long)h->sm_count * MKB_R_MIN_CTAS, cdiv(run_items, R_WARPS));
+        h->last_kernel = "occ_fill_runs_kernel";
         if (uni) occ_fill_runs_kernel<true><<<nctas, R_WARPS * 32, 0, st>>>(rp);
         else occ_fill_runs_kernel<false><<<nctas, R_WARPS * 32, 0, st>>>(rp);
         MKB_LAUNCHED(h);
@@ -1854,6 +1855,7 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
                 memcpy(&fq.u_band_bits, &band, sizeof(float));
             }
             const dim3 wgrid((unsigned)cdiv(mz, W_WARPS), (unsigned)my, (unsigned)(nb << sh));
+            h->last_kernel = v64 ? "occ_fill8v_kernel" : "occ_fill8w_kernel";
             if (v64) {
                 const dim3 vgrid((unsigned)cdiv(mz, V_WARPS * V_ZPER), (unsigned)my, (unsigned)(nb << sh));
                 if (uni) occ_fill8v_kernel<true><<<vgrid, V_WARPS * 32, 0, st>>>(fq, d_bbase + b0, d_btotal);
@@ -1871,6 +1873,7 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
         long long mt = 0;
         for (int b = b0; b < b0 + nb; ++b) mt = std::max<long long>(mt, (long long)gd[b].tiles[0] * gd[b].tiles[1] * gd[b].tiles[2]);
         const dim3 grid((unsigned)mt, (unsigned)nb);
+        h->last_kernel = fast8 ? "occ_fill8_kernel" : "occ_fill_kernel";
         if (fast8) {
             occ_tile_total_kernel<<<dim3((unsigned)cdiv(mt, 128), (unsigned)nb), 128, 0, st>>>(fp.grids, cell_start, tile_total);
             MKB_LAUNCHED(h);

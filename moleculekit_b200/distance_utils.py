@@ -60,7 +60,7 @@ def dist_trajectory_device(coords, box, sel1, sel2, chains, selfdist: bool, pbc:
     P = n_columns(len(sel1), len(sel2), selfdist)
     mode = _lib.DIST_CONTACTS if metric == "contacts" else _lib.DIST_DISTANCES
     if out is None:
-        out = torch.zeros((F, P), dtype=torch.uint8 if mode else torch.float32, device=dev)
+        out = torch.empty((F, P), dtype=torch.uint8 if mode else torch.float32, device=dev)  # the kernel writes every element
     h = _lib.handle(dev.index)
     tr = _traj(coords, box)
     with torch.cuda.device(dev):
@@ -175,8 +175,13 @@ def upload_selected(coords, box, index_sets, digitized_chains=None, masses=None,
         raise IndexError("atom index out of range")
     remap = np.full(coords.shape[0], -1, dtype=np.int64)
     remap[used] = np.arange(used.size)
-    sub = np.ascontiguousarray(coords[used]) if used.size != coords.shape[0] else np.ascontiguousarray(coords)
-    d_coords = torch.from_numpy(sub).to(dev)
+    if used.size and used[-1] - used[0] + 1 == used.size and coords.flags["C_CONTIGUOUS"]:
+        # the selected rows are one slab of the (N, 3, F) array: copy it where it lies (no host gather; asynchronous and
+        # at full PCIe rate when the caller's array is page-locked, e.g. from tools.voxeldescriptors.pinned_array)
+        d_coords = torch.from_numpy(coords[int(used[0]):int(used[-1]) + 1]).to(dev, non_blocking=True)
+    else:
+        sub = np.ascontiguousarray(coords[used]) if used.size != coords.shape[0] else np.ascontiguousarray(coords)
+        d_coords = torch.from_numpy(sub).to(dev)
     d_box = torch.from_numpy(np.ascontiguousarray(box, dtype=np.float32)).to(dev)
     d_ch = None
     if digitized_chains is not None:
@@ -209,7 +214,12 @@ def dist_trajectory(coords, box, sel1, sel2, digitized_chains, selfdist, pbc, re
     out = dist_trajectory_device(d_coords, d_box, _sel_dev(sel1, remap, dev), _sel_dev(sel2, remap, dev), d_ch,
                                  selfdist, pbc, metric=metric, truncate=truncate, threshold=threshold)
     if metric == "contacts":
-        return out.cpu().numpy()
+        # page-locked result (torch's caching host allocator recycles the block once the array is dropped): the (F, P)
+        # map leaves the GPU at PCIe rate instead of through the driver's pageable staging
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return host.numpy()
     torch.from_numpy(results[:F, :P]).copy_(out) if results.flags["C_CONTIGUOUS"] and results.shape == (F, P) \
         else np.copyto(results[:F, :P], out.cpu().numpy())
     return results
