@@ -34,7 +34,8 @@ typedef enum {
     MKB_ERR_BAD_ARG = -1,
     MKB_ERR_CUDA = -2,
     MKB_ERR_NOMEM = -3,
-    MKB_ERR_CAPACITY = -4
+    MKB_ERR_CAPACITY = -4,
+    MKB_ERR_UNSUPPORTED = -5 /* a valid request this entry point cannot serve (e.g. compact output outside its domain) */
 } mkb_status;
 
 typedef struct mkb_ctx *mkb_handle_t;
@@ -98,6 +99,23 @@ int mkb_occupancy_grid_batch(mkb_handle_t h, void *stream, const float *coords, 
 int mkb_occupancy_grid_batch_masked(mkb_handle_t h, void *stream, const float *coords, const double *radii,
                                     const uint32_t *chanmask, int64_t n_atoms, int32_t C, const mkb_grid_desc *grids,
                                     int32_t B, float *out, uint32_t flags);
+
+/* K1 with a COMPACT result (end-to-end transfers): ~70 % of a pocket grid is empty, so instead of the dense grid the
+ * kernel emits one 4 KB record [4 x][4 y][8 z][8 channels] per 4x4x8-voxel block that has an atom within 5 A, and an
+ * index that says which blocks those are.  8 channels, voxel-major.  Block b of grid g (b = ((ix/4)*ceil(ny/4) +
+ * iy/4)*ceil(nz/8) + iz/8, grids in batch order) has a record iff blk_rank[b + 1] != blk_rank[b]; the record is
+ * records[1024 * blk_rank[b] ...].  records: device, room for mkb_occupancy_compact_blocks(grids, B) records in the
+ * worst case; blk_rank: device uint32 [rank_capacity >= blocks + 1].  Exactly one of sigmas / (radii, chanmask) is given.
+ * mkb_occupancy_expand_host rebuilds grids [g0, g1) of the dense float32 (sum M, 8) HOST array from host copies of the
+ * records (`records` points at record rec0) with n_threads threads; missing blocks are zero-filled; out_f64 != 0 writes
+ * float64 (the reference's result dtype).  The result is bit-identical to mkb_occupancy_grid_batch. */
+int mkb_occupancy_grid_batch_compact(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
+                                     const double *radii, const uint32_t *chanmask, int64_t n_atoms,
+                                     const mkb_grid_desc *grids, int32_t B, float *records, uint32_t *blk_rank,
+                                     int64_t rank_capacity);
+int64_t mkb_occupancy_compact_blocks(const mkb_grid_desc *grids, int32_t B);
+int mkb_occupancy_expand_host(const mkb_grid_desc *grids, int32_t g0, int32_t g1, const uint32_t *blk_rank,
+                              const float *records, int64_t rec0, void *out, int32_t out_f64, int32_t n_threads);
 
 /* Voxel centres on the device, exactly getCenters (voxeldescriptors.py:116-123,243-247):
  * centers[(out_offset_b + v) * 3 + d] = fl(fl(i_d * voxelsize) + origin[d]), v = (ix*ny + iy)*nz + iz; float64 device.

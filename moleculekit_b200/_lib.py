@@ -32,6 +32,7 @@ class Traj(C.Structure):
 EXPORTS = [
     "mkb_version", "mkb_create", "mkb_destroy", "mkb_last_error", "mkb_launch_count",
     "mkb_set_timing", "mkb_get_timing", "mkb_last_kernel",
+    "mkb_occupancy_grid_batch_compact", "mkb_occupancy_compact_blocks", "mkb_occupancy_expand_host",
     "mkb_occupancy_grid_batch", "mkb_occupancy_grid_batch_masked", "mkb_occupancy_points",
     "mkb_grid_centers", "mkb_rotate_coords",
     "mkb_dist_trajectory", "mkb_contacts_count", "mkb_contacts_fill", "mkb_dist_reduction",
@@ -45,6 +46,10 @@ _handles: dict[int, C.c_void_p] = {}
 
 class MkbError(RuntimeError):
     pass
+
+
+class MkbUnsupported(MkbError):
+    """MKB_ERR_UNSUPPORTED: a valid request outside the domain of the entry point (callers fall back to the general one)."""
 
 
 def load():
@@ -71,6 +76,10 @@ def load():
     lib.mkb_last_kernel.argtypes = [vp]
     lib.mkb_last_kernel.restype = C.c_char_p
     lib.mkb_occupancy_grid_batch.argtypes = [vp, vp, vp, vp, i64, i32, vp, i32, vp, u32]
+    lib.mkb_occupancy_grid_batch_compact.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, i32, vp, vp, i64]
+    lib.mkb_occupancy_compact_blocks.argtypes = [vp, i32]
+    lib.mkb_occupancy_compact_blocks.restype = i64
+    lib.mkb_occupancy_expand_host.argtypes = [vp, i32, i32, vp, vp, i64, vp, i32, i32]
     lib.mkb_occupancy_points.argtypes = [vp, vp, vp, i64, vp, vp, i64, i32, vp, u32]
     lib.mkb_occupancy_grid_batch_masked.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, i32, vp, u32]
     lib.mkb_grid_centers.argtypes = [vp, vp, vp, i32, vp]
@@ -93,7 +102,7 @@ def load():
     lib.mkb_xtc_decode.argtypes = [vp, vp, vp, i64, vp, i64, i64, vp, i64, f32, vp]
     lib.mkb_wrap_box.argtypes = [vp, vp, tp, vp, i64, vp, i64, C.POINTER(C.c_float)]
     for name in EXPORTS:
-        if name in ("mkb_last_error", "mkb_launch_count", "mkb_version", "mkb_last_kernel"):
+        if name in ("mkb_last_error", "mkb_launch_count", "mkb_version", "mkb_last_kernel", "mkb_occupancy_compact_blocks"):
             continue
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -119,7 +128,7 @@ def handle(device: int = 0):
 def check(rc: int, h) -> None:
     if rc != MKB_OK:
         msg = load().mkb_last_error(h)
-        raise MkbError(f"libmkb200 status {rc}: {msg.decode() if msg else '?'}")
+        raise (MkbUnsupported if rc == -5 else MkbError)(f"libmkb200 status {rc}: {msg.decode() if msg else '?'}")
 
 
 def launch_count(device: int = 0) -> int:

@@ -60,6 +60,9 @@ struct RunParams {
     unsigned *queue;
     unsigned total_items;
     int cmajor;                  // MKB_OCC_LAYOUT_CXYZ: grid stored [C][nx][ny][nz]; plain 32-byte-segment stores instead of TMA rows
+    const unsigned *blk_rank;    // compact output (mkb_occupancy_grid_batch_compact): exclusive count of non-empty blocks; block
+                                 // b with atoms in reach is one 4 KB record [4 x][4 y][8 z][8 ch] at out + 1024 * blk_rank[b],
+                                 // empty blocks are not written at all; nullptr = the dense grid
     // uniform batches: descriptor of the first grid + strides (constant-bank operands)
     GridDev u;
     long long u_out_stride;
@@ -165,6 +168,12 @@ __global__ void __launch_bounds__(128) occ_blk_fill_kernel(const GridDev *__rest
     const unsigned *const bs = blk_start + g.tile_base;
     const uint2 ent = make_uint2((unsigned)it, tg.x & 0x1ffu);
     for_each_block_in_reach(g, px, py, pz, [&](int bid) { blk_ent[bs[bid] + atomicSub(bc + bid, 1u) - 1u] = ent; });
+}
+
+// compact output: 1 for every block with a candidate list, then an exclusive scan gives its record index
+__global__ void occ_blk_flag_kernel(const unsigned *__restrict__ blk_start, long long n_blocks, unsigned *__restrict__ flag) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b <= n_blocks) flag[b] = (b < n_blocks && blk_start[b + 1] != blk_start[b]) ? 1u : 0u;
 }
 
 __device__ __forceinline__ void bulk_store_row(float *dst, unsigned src_smem, int bytes) {
@@ -279,7 +288,8 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
         if (__shfl_sync(0xffffffffu, my_start, bz_end - bz_begin) == __shfl_sync(0xffffffffu, my_start, 0)) {
             // no atom reaches any block of the item: one bulk copy of zeros per output row (TMA, nothing to wait for)
             const int z0 = bz_begin * R_BZ;
-            if (p.cmajor) {
+            if (p.blk_rank) {
+            } else if (p.cmajor) {
                 for (int bzi = bz_begin; bzi < bz_end; ++bzi) store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, bzi * R_BZ + lz);
             } else {
                 if (row_ok) bulk_store_row(row_base + z0 * 8, zero_sa, (min(nz, bz_end * R_BZ) - z0) * 32);
@@ -295,7 +305,8 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             const unsigned ls = __shfl_sync(0xffffffffu, my_start, bzi - bz_begin);
             const unsigned n = __shfl_sync(0xffffffffu, my_start, bzi - bz_begin + 1) - ls;
             if (n == 0) {
-                if (p.cmajor) {
+                if (p.blk_rank) {
+                } else if (p.cmajor) {
                     store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, z0 + lz);
                 } else {
                     if (row_ok) bulk_store_row(row_dst, zero_sa, row_bytes);
@@ -536,7 +547,9 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (row_ok) bulk_store_row(row_dst, stage_sa + lane * 256, row_bytes);
+            if (p.blk_rank) {  // compact output: the whole 4 KB stage is one record, one bulk copy
+                if (lane == 0) bulk_store_row(p.out + 1024ll * __ldg(p.blk_rank + blk0 + (bzi - bz_begin)), stage_sa, 4096);
+            } else if (row_ok) bulk_store_row(row_dst, stage_sa + lane * 256, row_bytes);
             if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             pending = true;
         }
@@ -622,7 +635,8 @@ __device__ __forceinline__ void occ_fix_voxel(const GridDev *__restrict__ grids,
                                               const float *__restrict__ coords, const double *__restrict__ sigmas,
                                               const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
                                               const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ blk_start,
-                                              const uint2 *__restrict__ blk_ent, float *__restrict__ out, int cmajor) {
+                                              const uint2 *__restrict__ blk_ent, float *__restrict__ out, int cmajor,
+                                              const unsigned *__restrict__ blk_rank) {
     int lo = 0, hi = B - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -671,7 +685,8 @@ __device__ __forceinline__ void occ_fix_voxel(const GridDev *__restrict__ grids,
     if (lane < 8) {
         const double q3 = mq * mq * mq;
         const float val = (float)(-expm1(-(q3 * q3)));
-        if (cmajor) out[g->out_offset * 8 + (long long)lane * ((long long)g->dims[0] * ny * nz) + lv] = val;
+        if (blk_rank) out[1024ll * __ldg(blk_rank + bid) + ((((ix & 3) * 4 + (iy & 3)) * 8 + (iz & 7)) * 8) + lane] = val;
+        else if (cmajor) out[g->out_offset * 8 + (long long)lane * ((long long)g->dims[0] * ny * nz) + lv] = val;
         else out[(g->out_offset + lv) * 8 + lane] = val;
     }
 }
@@ -681,13 +696,14 @@ __global__ void __launch_bounds__(256) occ_fix_list_kernel(const GridDev *__rest
                                                            const float *__restrict__ coords, const double *__restrict__ sigmas,
                                                            const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
                                                            const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ blk_start,
-                                                           const uint2 *__restrict__ blk_ent, float *__restrict__ out, int cmajor) {
+                                                           const uint2 *__restrict__ blk_ent, float *__restrict__ out, int cmajor,
+                                                           const unsigned *__restrict__ blk_rank) {
     const unsigned long long n = fix[0];
     if (n > cap) return;  // the list overflowed: occ_fix_scan_kernel walks the bitmap instead
     const int lane = threadIdx.x & 31;
     const unsigned nw = (gridDim.x * blockDim.x) >> 5;
     for (unsigned long long w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nw)
-        occ_fix_voxel(grids, B, (long long)fix[FIX_HDR + w], lane, coords, sigmas, radii, chanmask, rec_tag, blk_start, blk_ent, out, cmajor);
+        occ_fix_voxel(grids, B, (long long)fix[FIX_HDR + w], lane, coords, sigmas, radii, chanmask, rec_tag, blk_start, blk_ent, out, cmajor, blk_rank);
 }
 
 __global__ void __launch_bounds__(256) occ_fix_scan_kernel(const GridDev *__restrict__ grids, int B, long long n_words,
@@ -696,7 +712,8 @@ __global__ void __launch_bounds__(256) occ_fix_scan_kernel(const GridDev *__rest
                                                            const float *__restrict__ coords, const double *__restrict__ sigmas,
                                                            const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
                                                            const uint4 *__restrict__ rec_tag, const unsigned *__restrict__ blk_start,
-                                                           const uint2 *__restrict__ blk_ent, float *__restrict__ out, int cmajor) {
+                                                           const uint2 *__restrict__ blk_ent, float *__restrict__ out, int cmajor,
+                                                           const unsigned *__restrict__ blk_rank) {
     if (fix[0] <= cap) return;
     const int lane = threadIdx.x & 31;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -706,7 +723,7 @@ __global__ void __launch_bounds__(256) occ_fix_scan_kernel(const GridDev *__rest
             const int wl = __ffs(wm) - 1;
             for (unsigned bits = __shfl_sync(0xffffffffu, mine, wl); bits; bits &= bits - 1)
                 occ_fix_voxel(grids, B, ((w0 + wl) << 5) + (__ffs(bits) - 1), lane, coords, sigmas, radii, chanmask, rec_tag,
-                              blk_start, blk_ent, out, cmajor);
+                              blk_start, blk_ent, out, cmajor, blk_rank);
         }
     }
 }

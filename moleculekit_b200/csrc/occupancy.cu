@@ -23,6 +23,8 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -1544,7 +1546,8 @@ using namespace mkb;
 
 static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
                                      const double *radii, const uint32_t *chanmask, int64_t n_atoms, int32_t C,
-                                     const mkb_grid_desc *grids, int32_t B, float *out, uint32_t flags) {
+                                     const mkb_grid_desc *grids, int32_t B, float *out, uint32_t flags,
+                                     uint32_t *blk_rank = nullptr, int64_t rank_capacity = 0) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (B < 0 || n_atoms < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
@@ -1660,6 +1663,11 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             }
         }
     }
+    if (blk_rank && !use_runs)
+        return fail(h, MKB_ERR_UNSUPPORTED, "compact output needs the run kernel (8 channels, 16-byte aligned records, default kernel selection)");
+    if (blk_rank && (flags & MKB_OCC_LAYOUT_CXYZ)) return fail(h, MKB_ERR_BAD_ARG, "compact output is voxel-major");
+    if (blk_rank && rank_capacity < run_blocks + 1)
+        return fail(h, MKB_ERR_BAD_ARG, "blk_rank holds %lld entries, the batch has %lld blocks + 1", (long long)rank_capacity, run_blocks);
     if (use_runs) {
         GridDev *d_grids;
         float4 *rec_pos;
@@ -1716,6 +1724,12 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
         rp.item_base = d_ibase; rp.queue = d_queue;
         rp.total_items = (unsigned)run_items;
         rp.cmajor = (flags & MKB_OCC_LAYOUT_CXYZ) ? 1 : 0;
+        rp.blk_rank = blk_rank;
+        if (blk_rank) {  // record index of every non-empty block (blk_count is free again after the list fill)
+            occ_blk_flag_kernel<<<(unsigned)cdiv(run_blocks + 1, 256), 256, 0, st>>>(blk_start, run_blocks, blk_count);
+            MKB_LAUNCHED(h);
+            if ((rc = scan_u32(h, st, blk_count, blk_rank, run_blocks + 1))) return rc;
+        }
         bool uni = true;
         const GridDev &g0 = gd[0];
         const long long nvox0 = (long long)g0.dims[0] * g0.dims[1] * g0.dims[2];
@@ -1740,10 +1754,10 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
         if (items > 0) {
             MKB_CUDA(h, cudaStreamWaitEvent(st, h->aux_ev[1], 0));
             const unsigned fg = (unsigned)h->sm_count * 4;
-            occ_fix_list_kernel<<<fg, 256, 0, st>>>(d_grids, B, d_fix, fix_cap, coords, sigmas, radii, chanmask, rec_tag, blk_start, blk_ent, out, rp.cmajor);
+            occ_fix_list_kernel<<<fg, 256, 0, st>>>(d_grids, B, d_fix, fix_cap, coords, sigmas, radii, chanmask, rec_tag, blk_start, blk_ent, out, rp.cmajor, blk_rank);
             MKB_LAUNCHED(h);
             occ_fix_scan_kernel<<<fg, 256, 0, st>>>(d_grids, B, n_words, d_bitmap, d_fix, fix_cap, coords, sigmas, radii, chanmask,
-                                                    rec_tag, blk_start, blk_ent, out, rp.cmajor);
+                                                    rec_tag, blk_start, blk_ent, out, rp.cmajor, blk_rank);
             MKB_LAUNCHED(h);
         }
         return MKB_OK;
@@ -1914,6 +1928,110 @@ extern "C" int mkb_occupancy_grid_batch_masked(mkb_handle_t h, void *stream, con
                                                const mkb_grid_desc *grids, int32_t B, float *out, uint32_t flags) {
     if (h && n_atoms > 0 && (!radii || !chanmask)) return fail(h, MKB_ERR_BAD_ARG, "null radii/chanmask");
     return occupancy_grid_batch_impl(h, stream, coords, nullptr, radii, chanmask, n_atoms, C, grids, B, out, flags);
+}
+
+extern "C" int mkb_occupancy_grid_batch_compact(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
+                                                const double *radii, const uint32_t *chanmask, int64_t n_atoms,
+                                                const mkb_grid_desc *grids, int32_t B, float *records, uint32_t *blk_rank,
+                                                int64_t rank_capacity) {
+    if (h && n_atoms > 0 && !sigmas && (!radii || !chanmask)) return fail(h, MKB_ERR_BAD_ARG, "null sigmas and radii/chanmask");
+    if (h && !blk_rank) return fail(h, MKB_ERR_BAD_ARG, "null blk_rank");
+    return occupancy_grid_batch_impl(h, stream, coords, sigmas, sigmas ? nullptr : radii, sigmas ? nullptr : chanmask, n_atoms, 8, grids,
+                                     B, records, 0u, blk_rank, rank_capacity);
+}
+
+extern "C" int64_t mkb_occupancy_compact_blocks(const mkb_grid_desc *grids, int32_t B) {
+    int64_t n = 0;
+    for (int b = 0; b < B; ++b)
+        n += (int64_t)((grids[b].dims[0] + 3) / 4) * ((grids[b].dims[1] + 3) / 4) * ((grids[b].dims[2] + R_BZ - 1) / R_BZ);
+    return n;
+}
+
+// Host side of the compact transfer: grids [g0, g1) are rebuilt in the caller's dense (voxel-major, 8 channel) array from
+// the 4 KB block records; blocks without a record are zero-filled.  `blk_rank` is the whole batch's table (host copy),
+// `records` points at record `rec0` (the first record of grid g0: a chunk of grids is a contiguous range of records).
+// The expansion writes every byte of the dense array exactly once and never reads it back: non-temporal stores skip the
+// read-for-ownership of ordinary stores (half the memory traffic).  Rows start on 32-byte (voxel) boundaries.
+#if defined(__SSE2__) || defined(__x86_64__)
+#include <emmintrin.h>
+static inline void stream_zero(float *d, int n) {
+    const __m128i z = _mm_setzero_si128();
+    for (int i = 0; i < n; i += 4) _mm_stream_si128(reinterpret_cast<__m128i *>(d + i), z);
+}
+static inline void stream_zero(double *d, int n) {
+    const __m128i z = _mm_setzero_si128();
+    for (int i = 0; i < n; i += 2) _mm_stream_si128(reinterpret_cast<__m128i *>(d + i), z);
+}
+static inline void stream_copy(float *d, const float *s, int n) {
+    for (int i = 0; i < n; i += 4) _mm_stream_si128(reinterpret_cast<__m128i *>(d + i), _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i)));
+}
+static inline void stream_copy(double *d, const float *s, int n) {
+    for (int i = 0; i < n; i += 4) {
+        const __m128 v = _mm_loadu_ps(s + i);
+        _mm_stream_pd(d + i, _mm_cvtps_pd(v));
+        _mm_stream_pd(d + i + 2, _mm_cvtps_pd(_mm_movehl_ps(v, v)));
+    }
+}
+static inline void stream_fence() { _mm_sfence(); }
+#else
+static inline void stream_zero(float *d, int n) { memset(d, 0, (size_t)n * 4); }
+static inline void stream_zero(double *d, int n) { memset(d, 0, (size_t)n * 8); }
+static inline void stream_copy(float *d, const float *s, int n) { memcpy(d, s, (size_t)n * 4); }
+static inline void stream_copy(double *d, const float *s, int n) { for (int i = 0; i < n; ++i) d[i] = (double)s[i]; }
+static inline void stream_fence() {}
+#endif
+
+template <typename T>
+static int expand_host_impl(const mkb_grid_desc *grids, int32_t g0, int32_t g1, const uint32_t *blk_rank, const float *records,
+                            int64_t rec0, T *out, int32_t n_threads) {
+    std::vector<int64_t> bbase((size_t)g1 + 1, 0);
+    for (int b = 0; b < g1; ++b)
+        bbase[b + 1] = bbase[b] + (int64_t)((grids[b].dims[0] + 3) / 4) * ((grids[b].dims[1] + 3) / 4) * ((grids[b].dims[2] + R_BZ - 1) / R_BZ);
+    // work items: (grid, x block row); threads take them round robin
+    std::vector<std::pair<int, int>> items;
+    for (int b = g0; b < g1; ++b)
+        for (int bx = 0; bx < (grids[b].dims[0] + 3) / 4; ++bx) items.emplace_back(b, bx);
+    const int nt = std::max(1, std::min<int>(n_threads, (int)items.size()));
+    auto work = [&](int t) {
+        for (size_t i = (size_t)t; i < items.size(); i += (size_t)nt) {
+            const int b = items[i].first, bx = items[i].second;
+            const mkb_grid_desc &g = grids[b];
+            const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+            const int nby = (ny + 3) / 4, nbz = (nz + R_BZ - 1) / R_BZ;
+            T *const gout = out + g.out_offset * 8;
+            for (int by = 0; by < nby; ++by)
+                for (int k = 0; k < 4 && bx * 4 + k < nx; ++k)
+                    for (int l = 0; l < 4 && by * 4 + l < ny; ++l) {
+                        T *row = gout + ((int64_t)(bx * 4 + k) * ny + (by * 4 + l)) * nz * 8;
+                        const int64_t bid0 = bbase[b] + ((int64_t)bx * nby + by) * nbz;
+                        for (int bz = 0; bz < nbz; ++bz) {
+                            const int nfl = std::min(R_BZ, nz - bz * R_BZ) * 8;
+                            const uint32_t r = blk_rank[bid0 + bz];
+                            if (blk_rank[bid0 + bz + 1] != r) {
+                                const float *src = records + ((int64_t)r - rec0) * 1024 + (k * 4 + l) * 64;
+                                stream_copy(row + bz * 64, src, nfl);
+                            } else stream_zero(row + bz * 64, nfl);
+                        }
+                    }
+        }
+        stream_fence();
+    };
+    if (nt == 1) { work(0); return MKB_OK; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+    for (auto &x : th) x.join();
+    return MKB_OK;
+}
+
+// Host side of the compact transfer: grids [g0, g1) are rebuilt in the caller's dense (voxel-major, 8 channel) array from
+// the 4 KB block records; blocks without a record are zero-filled.  `blk_rank` is the whole batch's table (host copy),
+// `records` points at record `rec0` (the first record of grid g0: a chunk of grids is a contiguous range of records).
+// out_f64 != 0: `out` is float64 (the reference's dtype, voxeldescriptors.py:531) and the upcast happens here, threaded.
+extern "C" int mkb_occupancy_expand_host(const mkb_grid_desc *grids, int32_t g0, int32_t g1, const uint32_t *blk_rank,
+                                         const float *records, int64_t rec0, void *out, int32_t out_f64, int32_t n_threads) {
+    if (!grids || !blk_rank || !out || g0 < 0 || g1 < g0) return MKB_ERR_BAD_ARG;
+    if (out_f64) return expand_host_impl<double>(grids, g0, g1, blk_rank, records, rec0, static_cast<double *>(out), n_threads);
+    return expand_host_impl<float>(grids, g0, g1, blk_rank, records, rec0, static_cast<float *>(out), n_threads);
 }
 
 extern "C" int mkb_occupancy_points(mkb_handle_t h, void *stream, const double *centers, int64_t M,

@@ -110,6 +110,62 @@ def occupancy_grid_batch(coords: torch.Tensor, sigmas: torch.Tensor | None, desc
     return out
 
 
+def occupancy_grid_batch_compact(coords: torch.Tensor, sigmas: torch.Tensor | None, descs: np.ndarray,
+                                 radii: torch.Tensor | None = None, chanmask: torch.Tensor | None = None,
+                                 records: torch.Tensor | None = None, blk_rank: torch.Tensor | None = None):
+    """K2+K1 with the compact result of ``mkb_occupancy_grid_batch_compact`` (8 channels): returns (records, blk_rank),
+    ``records`` float32 cuda with one 4 KB row [4 x][4 y][8 z][8 ch] per 4x4x8-voxel block that has an atom within 5 A
+    (room for every block of the batch; only the first blk_rank[-1] rows are written) and ``blk_rank`` int32 (blocks + 1,)
+    the exclusive count of such blocks.  :func:`expand_compact_host` rebuilds the dense host array."""
+    dev = coords.device
+    assert coords.is_cuda and coords.dtype == torch.float32 and coords.is_contiguous() and coords.ndim == 2
+    descs = np.ascontiguousarray(descs, dtype=_lib.GRID_DESC)
+    lib = _lib.load()
+    nblk = int(lib.mkb_occupancy_compact_blocks(descs.ctypes.data_as(C.c_void_p), int(descs.shape[0])))
+    if records is None:
+        records = torch.empty((nblk, 1024), dtype=torch.float32, device=dev)
+    if blk_rank is None:
+        blk_rank = torch.empty(nblk + 1, dtype=torch.int32, device=dev)
+    assert records.is_cuda and records.dtype == torch.float32 and records.is_contiguous() and records.numel() >= nblk * 1024
+    assert blk_rank.is_cuda and blk_rank.dtype == torch.int32 and blk_rank.numel() >= nblk + 1
+    if sigmas is not None:
+        assert sigmas.is_cuda and sigmas.dtype == torch.float64 and sigmas.is_contiguous() and sigmas.shape == (coords.shape[0], 8)
+    else:
+        assert radii is not None and chanmask is not None and radii.dtype == torch.float64 and chanmask.dtype == torch.int32
+    h = _lib.handle(dev.index)
+    null = C.c_void_p(0)
+    with torch.cuda.device(dev):
+        rc = lib.mkb_occupancy_grid_batch_compact(
+            h, _stream_ptr(dev), C.c_void_p(coords.data_ptr()), C.c_void_p(sigmas.data_ptr()) if sigmas is not None else null,
+            C.c_void_p(radii.data_ptr()) if sigmas is None else null, C.c_void_p(chanmask.data_ptr()) if sigmas is None else null,
+            int(coords.shape[0]), descs.ctypes.data_as(C.c_void_p), int(descs.shape[0]), C.c_void_p(records.data_ptr()),
+            C.c_void_p(blk_rank.data_ptr()), int(blk_rank.numel()))
+    _lib.check(rc, h)
+    return records, blk_rank
+
+
+def expand_compact_host(descs: np.ndarray, g0: int, g1: int, blk_rank: np.ndarray, records: np.ndarray, rec0: int,
+                        out: np.ndarray, n_threads: int = 0) -> None:
+    """Host half of the compact transfer (``mkb_occupancy_expand_host``): grids [g0, g1) of the dense float32 (sum M, 8)
+    array ``out`` from the 4 KB block records (``records[0]`` is record ``rec0``).  Multi-threaded, releases the GIL."""
+    import os
+
+    descs = np.ascontiguousarray(descs, dtype=_lib.GRID_DESC)
+    assert blk_rank.dtype in (np.int32, np.uint32) and blk_rank.flags["C_CONTIGUOUS"]
+    assert records.dtype == np.float32 and records.flags["C_CONTIGUOUS"] and out.flags["C_CONTIGUOUS"]
+    assert out.dtype in (np.float32, np.float64)
+    if n_threads <= 0:
+        try:
+            n_threads = min(32, len(os.sched_getaffinity(0)))
+        except Exception:
+            n_threads = min(32, os.cpu_count() or 1)
+    rc = _lib.load().mkb_occupancy_expand_host(descs.ctypes.data_as(C.c_void_p), int(g0), int(g1), blk_rank.ctypes.data_as(C.c_void_p),
+                                               records.ctypes.data_as(C.c_void_p), int(rec0), out.ctypes.data_as(C.c_void_p),
+                                               1 if out.dtype == np.float64 else 0, int(n_threads))
+    if rc != 0:
+        raise ValueError("mkb_occupancy_expand_host: bad arguments")
+
+
 def grid_centers(descs: np.ndarray, device=None) -> torch.Tensor:
     """Voxel centres of a batch of grids on the device: (sum M_b, 3) float64 cuda, bit-identical to getCenters."""
     dev = _dev(device)

@@ -17,6 +17,7 @@ import logging
 import numpy as np
 import torch
 
+from .. import _lib as _lib_mod
 from .. import occupancy_utils as _occ
 from ..elements import vdw_radii_of
 
@@ -386,10 +387,63 @@ def pinned_array(shape, dtype=np.float32) -> np.ndarray:
     return t.numpy()
 
 
+def _compact_to_host(batch, d_coords, d_chan, dev, out, dtype, n_chunks: int = 8):
+    """Compact transfer: block records + index over PCIe in chunks, dense array rebuilt by host threads meanwhile."""
+    if isinstance(d_chan, tuple):
+        recs, rank = _occ.occupancy_grid_batch_compact(d_coords, None, batch.descs, radii=d_chan[0], chanmask=d_chan[1])
+    else:
+        recs, rank = _occ.occupancy_grid_batch_compact(d_coords, d_chan, batch.descs)
+    cur = torch.cuda.current_stream(dev)
+    h_rank_t = torch.empty(rank.shape, dtype=torch.int32, pin_memory=True)
+    h_rank_t.copy_(rank, non_blocking=True)
+    cur.synchronize()
+    h_rank = h_rank_t.numpy()
+    total = int(h_rank[-1])
+    h_recs_t = torch.empty((max(total, 1), 1024), dtype=torch.float32, pin_memory=True)
+    h_recs = h_recs_t.numpy()
+    if out is not None:
+        host = out
+    else:  # page-locked result from torch's caching host allocator: a fresh 4 GB numpy array would spend the call in page faults
+        host = torch.empty((batch.total_voxels, batch.C), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True).numpy()
+    # blocks per grid -> the record range of a chunk of grids
+    dims = batch.dims.astype(np.int64)
+    nblk = ((dims[:, 0] + 3) // 4) * ((dims[:, 1] + 3) // 4) * ((dims[:, 2] + 7) // 8)
+    bbase = np.concatenate([[0], np.cumsum(nblk)])
+    cuts = np.unique(np.linspace(0, batch.B, min(n_chunks, batch.B) + 1).astype(np.int64))
+    side = _side_stream(dev)
+    side.wait_stream(cur)
+    events = []
+    with torch.cuda.stream(side):
+        for g0, g1 in zip(cuts[:-1], cuts[1:]):
+            r0, r1 = int(h_rank[bbase[g0]]), int(h_rank[bbase[g1]])
+            if r1 > r0:
+                h_recs_t[r0:r1].copy_(recs[r0:r1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            events.append((int(g0), int(g1), r0, ev))
+    for g0, g1, r0, ev in events:
+        ev.synchronize()
+        _occ.expand_compact_host(batch.descs, g0, g1, h_rank, h_recs[r0:] if total else h_recs, r0, host)
+    recs.record_stream(side)
+    LAST_TRANSFER.update(mode="compact", d2h_bytes=int(total) * 4096 + int(h_rank.nbytes), records=total, blocks=int(len(h_rank) - 1))
+    return host
+
+
+_SIDE = {}
+LAST_TRANSFER = {}  # what the most recent getVoxelDescriptorsBatch moved device -> host (bench.py reports it)
+
+
+def _side_stream(dev):
+    key = (dev.index if isinstance(dev, torch.device) else int(dev))
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, buffer=0.0, voxelsize=1.0,
                              elements=None, radii=None, atom_offsets=None, device=None, return_tensor: bool = False,
                              dtype=np.float64, out: np.ndarray | None = None, layout: str = "xyzc",
-                             rotations=None, rotation_centers=None):
+                             rotations=None, rotation_centers=None, transfer: str = "auto"):
     """Voxelise a batch of molecules / pockets in one launch sequence (HOST arrays in, HOST arrays out).
 
     coords / channels: lists of per-item (N_b, 3) / (N_b, C) arrays, or concatenated arrays with ``atom_offsets``
@@ -402,7 +456,12 @@ def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, bu
     the device result directly -- or, with ``return_tensor=True``, ``(tensor, nvoxels, voxel_offsets)`` with one
     float32 CUDA tensor left on the device (the layout per-GPU consumers keep resident).  ``layout="cxyz"`` stores
     each grid channel-major: the list entries / tensor slices are then (C, X, Y, Z) (tensor: (B, C, X, Y, Z) when all
-    grids have the same size).  ``nvoxels`` is (B, 3)."""
+    grids have the same size).  ``nvoxels`` is (B, 3).
+
+    ``transfer``: how the grids cross PCIe.  "dense" copies the (sum M, C) float32 array; "compact" (8 channels,
+    voxel-major) copies only the 4x4x8-voxel blocks that have an atom within 5 A (~30 % of a protein pocket grid) plus a
+    block index, in chunks, while host threads rebuild the dense array -- float32 or, upcast on the fly, the reference's
+    float64 -- with identical bytes; "auto" takes the compact route when it applies."""
     batch = VoxelBatch(coords, channels, boxsize=boxsize, centers=centers, buffer=buffer, voxelsize=voxelsize,
                        elements=elements, radii=radii, atom_offsets=atom_offsets)
     dev = _occ._dev(device)
@@ -411,8 +470,24 @@ def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, bu
         if rotation_centers is None:
             raise ValueError("rotation_centers is required with rotations")
         d_coords = batch.rotate(d_coords, rotations, rotation_centers)
-    d_out = batch.run(d_coords, d_chan, layout=layout)
     cx = layout == "cxyz"
+    if transfer not in ("auto", "dense", "compact"):
+        raise ValueError("transfer must be 'auto', 'dense' or 'compact'")
+    want_dtype = np.float32 if out is not None else (np.dtype(dtype) if dtype is not None else np.dtype(np.float32))
+    compact_ok = (not return_tensor and not cx and batch.C == 8 and np.dtype(want_dtype) in (np.dtype(np.float32), np.dtype(np.float64))
+                  and batch.total_voxels > 0)
+    if transfer == "compact" and not compact_ok:
+        raise ValueError("transfer='compact' needs 8 channels, the voxel-major layout and host float32 / float64 results")
+    if compact_ok and transfer != "dense":
+        if out is not None and (out.dtype != np.float32 or out.shape != (batch.total_voxels, batch.C) or not out.flags["C_CONTIGUOUS"]):
+            raise ValueError(f"out must be a C-contiguous float32 array of shape {(batch.total_voxels, batch.C)}")
+        try:
+            host = _compact_to_host(batch, d_coords, d_chan, dev, out, want_dtype)
+            return batch.split(host), batch.dims.copy()
+        except _lib_mod.MkbUnsupported:
+            if transfer == "compact":
+                raise
+    d_out = batch.run(d_coords, d_chan, layout=layout)
     if return_tensor:
         if cx and (batch.dims == batch.dims[0]).all():
             d_out = batch.as_cxyz(d_out)
@@ -423,6 +498,7 @@ def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, bu
         torch.from_numpy(out).copy_(d_out, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         host = out
+        LAST_TRANSFER.update(mode="dense", d2h_bytes=int(out.nbytes), records=None, blocks=None)
     else:
         host = d_out.cpu().numpy()
         if dtype is not None and np.dtype(dtype) != np.float32:

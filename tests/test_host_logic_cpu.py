@@ -66,3 +66,42 @@ def test_wrap_argument_errors_without_gpu():
     assert wr.wrap(mol) is None  # zero box: logged no-op, never reaches the GPU
     with pytest.raises(ValueError, match="Buffer dtype mismatch"):
         wr.wrap_box(np.array([0, 4]), mol.coords, np.ones((3, 2), np.float32), np.zeros(0, np.uint32), np.zeros(3, np.float32))
+
+
+def test_expand_compact_host_matches_numpy():
+    """mkb_occupancy_expand_host (host half of the compact end-to-end transfer): dense grids rebuilt from 4 KB block records
+    + the block index, ragged dims, float32 and float64 targets, chunks of grids -- against a plain numpy scatter."""
+    from moleculekit_b200 import _lib, occupancy_utils as occ
+
+    rng = np.random.default_rng(5)
+    dims = np.array([[9, 6, 17], [4, 4, 8], [13, 10, 23]], dtype=np.int64)
+    nvox = dims.prod(axis=1)
+    off = np.concatenate([[0], np.cumsum(nvox)])
+    descs = np.zeros(3, dtype=_lib.GRID_DESC)
+    descs["dims"] = dims
+    descs["voxelsize"] = 1.0
+    descs["out_offset"] = off[:-1]
+    nblk = ((dims[:, 0] + 3) // 4) * ((dims[:, 1] + 3) // 4) * ((dims[:, 2] + 7) // 8)
+    bbase = np.concatenate([[0], np.cumsum(nblk)])
+    present = rng.random(bbase[-1]) < 0.4
+    rank = np.concatenate([[0], np.cumsum(present)]).astype(np.uint32)
+    recs = rng.random((int(rank[-1]), 1024)).astype(np.float32)
+    want = np.zeros((off[-1], 8), dtype=np.float32)
+    for g in range(3):
+        nx, ny, nz = dims[g]
+        nby, nbz = (ny + 3) // 4, (nz + 7) // 8
+        grid = want[off[g]:off[g + 1]].reshape(nx, ny, nz, 8)
+        for b in range(nblk[g]):
+            if not present[bbase[g] + b]:
+                continue
+            bz, by, bx = b % nbz, (b // nbz) % nby, b // (nbz * nby)
+            blk = recs[rank[bbase[g] + b]].reshape(4, 4, 8, 8)
+            x1, y1, z1 = min(4, nx - 4 * bx), min(4, ny - 4 * by), min(8, nz - 8 * bz)
+            grid[4 * bx:4 * bx + x1, 4 * by:4 * by + y1, 8 * bz:8 * bz + z1] = blk[:x1, :y1, :z1]
+    for dt in (np.float32, np.float64):
+        got = np.full((off[-1], 8), 7.0, dtype=dt)
+        # two chunks of grids, as the transfer does: [0, 1) then [1, 3)
+        occ.expand_compact_host(descs, 0, 1, rank, recs, 0, got, n_threads=3)
+        r0 = int(rank[bbase[1]])
+        occ.expand_compact_host(descs, 1, 3, rank, recs[r0:], r0, got, n_threads=2)
+        assert np.array_equal(got, want.astype(dt))

@@ -229,3 +229,27 @@ def test_nonuniform_batch_buffer_mode(vd, oracle):
         assert nv.tolist() == dims[b].tolist()
         want = np.zeros((centers.shape[0], 8)); oracle.calculate_occupancy(centers, coords[b], sigmas[b], want)
         _assert_occ_close(feats[b], want)
+
+
+def test_compact_transfer_equals_dense(vd):
+    """transfer="compact" (block records + index over PCIe, dense array rebuilt by host threads) returns the bytes of the
+    dense transfer: uniform and ragged batches, float32 into a caller's array and the reference-typed float64 lists."""
+    from moleculekit_b200 import workloads
+
+    w = workloads.protein_pockets(B=5, n_atoms=600, box=33.0, radius=10.0, seed=31)
+    for kw in (dict(boxsize=[33.0, 26.0, 41.0], centers=w["centers"], voxelsize=1.0),
+               dict(buffer=3.0, voxelsize=0.7)):
+        dense, dims = vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], transfer="dense", dtype=np.float32, **kw)
+        comp, dims2 = vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], transfer="compact", dtype=np.float32, **kw)
+        assert np.array_equal(dims, dims2)
+        for a, b in zip(dense, comp):
+            assert a.any() and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        f64, _ = vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], transfer="compact", **kw)
+        for a, b in zip(dense, f64):
+            assert b.dtype == np.float64 and np.array_equal(a.astype(np.float64), b)
+        total = int(sum(a.shape[0] for a in dense))
+        out = vd.pinned_array((total, 8), np.float32)
+        out[:] = 3.0
+        vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], out=out, **kw)  # "auto" takes the compact route
+        assert vd.LAST_TRANSFER["mode"] == "compact" and vd.LAST_TRANSFER["d2h_bytes"] < out.nbytes
+        assert np.array_equal(out, np.concatenate(dense))
