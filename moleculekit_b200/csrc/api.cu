@@ -32,6 +32,7 @@ int mkb_destroy(mkb_handle_t h) {
             if (s.ptr) cudaFree(s.ptr);
         for (auto &e : h->ev)
             if (e) cudaEventDestroy(e);
+        if (h->order_ev) cudaEventDestroy(h->order_ev);
         for (auto &e : h->aux_ev)
             if (e) cudaEventDestroy(e);
         if (h->aux_stream) cudaStreamDestroy(h->aux_stream);

@@ -185,6 +185,7 @@ extern "C" int mkb_within_distance(mkb_handle_t h, void *stream, const float *co
                                    uint8_t *results) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (n_atoms < 0 || n1 < 0 || n2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
     if (n_atoms >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "n_atoms must be < 2^31");
     if (cutoff != cutoff || std::isinf(cutoff)) return fail(h, MKB_ERR_BAD_ARG, "cutoff must be finite");
@@ -216,6 +217,7 @@ extern "C" int mkb_bonds_count(mkb_handle_t h, void *stream, const float *coords
                                int64_t *total_pairs) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     int rc = bond_args(h, coords, radii, is_hydrogen, n, pairdist);
     if (rc) return rc;
     if (!row_offsets || !total_pairs) return fail(h, MKB_ERR_BAD_ARG, "null row_offsets/total_pairs");
@@ -249,6 +251,7 @@ extern "C" int mkb_bonds_fill(mkb_handle_t h, void *stream, const float *coords,
                               uint32_t *pairs) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     int rc = bond_args(h, coords, radii, is_hydrogen, n, pairdist);
     if (rc) return rc;
     if (n == 0) return MKB_OK;

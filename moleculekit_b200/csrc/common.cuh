@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 
 #include "mkb200.h"
@@ -52,6 +53,13 @@ struct mkb_ctx {
     // optional per-kernel timing (bench.py roofline): events recorded on the launch stream
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before prep, before main kernel, after main kernel
+    // One handle = one set of grow-only scratch buffers.  Entry points may be called from several host threads and on
+    // several streams: the mutex serialises the host side of a call, and a call on a stream other than the previous one's
+    // first waits for the event recorded at the end of the previous call, so two calls never share scratch in flight.
+    std::recursive_mutex mtx;
+    cudaEvent_t order_ev = nullptr;
+    cudaStream_t order_stream = nullptr;
+    bool order_valid = false;
     // side stream of the occupancy run path (gate-band pre-pass beside the list build)
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t aux_ev[2] = {nullptr, nullptr};
@@ -136,6 +144,24 @@ struct DeviceGuard {
     if (!(h)) return MKB_ERR_BAD_ARG;                                       \
     mkb::DeviceGuard _guard((h)->device);                                   \
     if (!_guard.ok) return mkb::fail((h), MKB_ERR_CUDA, "cudaSetDevice(%d) failed", (h)->device)
+
+// scope guard of every entry point that enqueues work on a caller's stream (see mkb_ctx::mtx)
+struct StreamOrder {
+    mkb_ctx *h;
+    cudaStream_t st;
+    std::unique_lock<std::recursive_mutex> lock;
+    StreamOrder(mkb_ctx *h_, cudaStream_t st_) : h(h_), st(st_), lock(h_->mtx) {
+        if (h->order_valid && h->order_stream != st) cudaStreamWaitEvent(st, h->order_ev, 0);
+    }
+    ~StreamOrder() {
+        if (!h->order_ev && cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming) != cudaSuccess) return;
+        if (cudaEventRecord(h->order_ev, st) == cudaSuccess) {
+            h->order_stream = st;
+            h->order_valid = true;
+        }
+    }
+};
+#define MKB_STREAM_ORDER(h, st) mkb::StreamOrder _order((h), (st))
 
 #define MKB_LAUNCHED(h)                                                                                    \
     do {                                                                                                   \

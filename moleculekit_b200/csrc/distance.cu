@@ -577,6 +577,7 @@ extern "C" int mkb_dist_trajectory(mkb_handle_t h, void *stream, const mkb_traj 
                                    int32_t pbc, int32_t mode, float truncate, float threshold, void *out) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     int rc = check_traj(h, t);
     if (rc) return rc;
     if (n1 < 0 || n2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative selection size");
@@ -646,6 +647,7 @@ extern "C" int mkb_contacts_count(mkb_handle_t h, void *stream, const mkb_traj *
                                   int32_t pbc, float threshold, int64_t *row_offsets, int64_t *total_pairs) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (!row_offsets || !total_pairs) return fail(h, MKB_ERR_BAD_ARG, "null row_offsets/total_pairs");
     float4 *G1, *G2;
     int rc = contacts_common(h, st, t, sel1, n1, sel2, n2, chains, &G1, &G2);
@@ -695,6 +697,7 @@ extern "C" int mkb_contacts_fill(mkb_handle_t h, void *stream, const mkb_traj *t
                                  int32_t pbc, float threshold, const int64_t *row_offsets, uint32_t *pairs) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (!row_offsets) return fail(h, MKB_ERR_BAD_ARG, "null row_offsets");
     int rc = check_traj(h, t);
     if (rc) return rc;
@@ -737,6 +740,7 @@ extern "C" int mkb_dist_reduction(mkb_handle_t h, void *stream, const mkb_traj *
                                   float threshold, void *out) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     int rc = check_traj(h, t);
     if (rc) return rc;
     if (NG1 < 0 || NG2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative group count");
@@ -842,6 +846,7 @@ extern "C" int mkb_collisions_count(mkb_handle_t h, void *stream, const float *c
                                     int64_t n2, float threshold, int64_t *row_offsets, int64_t *total_pairs) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (n1 < 0 || n2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
     if (!row_offsets || !total_pairs) return fail(h, MKB_ERR_BAD_ARG, "null row_offsets/total_pairs");
     if (n1 > 0 && n2 > 0 && (!c1 || !c2)) return fail(h, MKB_ERR_BAD_ARG, "null coordinates");
@@ -883,6 +888,7 @@ extern "C" int mkb_shell_counts(mkb_handle_t h, void *stream, const mkb_traj *t,
                                 uint32_t *counts) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (numshells < 1 || numshells > 32) return fail(h, MKB_ERR_BAD_ARG, "numshells=%d: 1..32 supported", numshells);
     if (selfdist && n1 != n2) return fail(h, MKB_ERR_BAD_ARG, "selfdist needs sel1 == sel2");
     float4 *G1, *G2;

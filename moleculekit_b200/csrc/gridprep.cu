@@ -72,6 +72,7 @@ using namespace mkb;
 extern "C" int mkb_grid_centers(mkb_handle_t h, void *stream, const mkb_grid_desc *grids, int32_t B, double *centers) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (B < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
     if (B == 0) return MKB_OK;
     if (!grids || !centers) return fail(h, MKB_ERR_BAD_ARG, "null grids/centers");
@@ -107,6 +108,7 @@ extern "C" int mkb_rotate_coords(mkb_handle_t h, void *stream, const float *coor
                                  float *out_f32, double *out_f64) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (B < 0 || n_atoms < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
     if (n_atoms == 0 || B == 0) return MKB_OK;
     if (!coords || !atom_offsets || !matrices || !centers || (!out_f32 && !out_f64))

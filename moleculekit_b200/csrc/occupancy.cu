@@ -1550,6 +1550,7 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
                                      uint32_t *blk_rank = nullptr, int64_t rank_capacity = 0) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (B < 0 || n_atoms < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
     if (C < 1 || C > 32) return fail(h, MKB_ERR_BAD_ARG, "C=%d: 1..32 channels per call (split wider channel sets)", C);
     if (B == 0) return MKB_OK;
@@ -2039,6 +2040,7 @@ extern "C" int mkb_occupancy_points(mkb_handle_t h, void *stream, const double *
                                     float *out, uint32_t flags) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (M < 0 || n_atoms < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
     if (C < 1 || C > 32) return fail(h, MKB_ERR_BAD_ARG, "C=%d: 1..32 channels per call", C);
     if (M == 0) return MKB_OK;

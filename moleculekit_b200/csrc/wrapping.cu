@@ -310,6 +310,7 @@ extern "C" int mkb_wrap_box(mkb_handle_t h, void *stream, const mkb_traj *t, con
                             const uint32_t *centersel, int64_t n_centersel, const float *center) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (!t) return fail(h, MKB_ERR_BAD_ARG, "null trajectory");
     if (t->n_atoms < 0 || t->n_frames < 0 || n_groups < 0 || n_centersel < 0)
         return fail(h, MKB_ERR_BAD_ARG, "negative size");

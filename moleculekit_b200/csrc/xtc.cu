@@ -229,6 +229,7 @@ extern "C" int mkb_xtc_decode(mkb_handle_t h, void *stream, const uint8_t *file_
     static_assert(sizeof(mkb_xtc_frame) == sizeof(XtcFrame) && sizeof(XtcFrame) == 48, "frame descriptor layout");
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    MKB_STREAM_ORDER(h, st);
     if (n_frames < 0 || natoms < 0 || file_size < 0) return fail(h, MKB_ERR_BAD_ARG, "negative size");
     if (n_frames == 0 || natoms == 0) return MKB_OK;
     if (!file_bytes || !frames || !coords || !status) return fail(h, MKB_ERR_BAD_ARG, "null argument");

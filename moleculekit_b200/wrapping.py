@@ -49,6 +49,12 @@ def _check_index_ranges(groups, centersel, n_atoms):
         raise IndexError("group offset out of range")
     if centersel.size and int(centersel.max()) >= n_atoms:
         raise IndexError("centersel index out of range")
+    # K9 wraps all groups in parallel: the offsets must be ascending (disjoint [groups[i], groups[i+1]) ranges), as
+    # getBondedGroups + the reference's contiguous-molecule assumption produce.  The reference walks them sequentially and
+    # tolerates anything; overlapping ranges here would race, so they are rejected instead of wrapped nondeterministically.
+    if groups.size > 1 and np.any(np.diff(groups.astype(np.int64)) < 0):
+        raise ValueError("wrap_box: group offsets must be ascending (bonded groups have to be contiguous in atom order); "
+                         "reorder the atoms or wrap the offending groups separately")
 
 
 def wrap_box(groups, coords, box, centersel, center, device=None):

@@ -105,3 +105,14 @@ def test_expand_compact_host_matches_numpy():
         r0 = int(rank[bbase[1]])
         occ.expand_compact_host(descs, 1, 3, rank, recs[r0:], r0, got, n_threads=2)
         assert np.array_equal(got, want.astype(dt))
+
+
+def test_wrap_box_rejects_unordered_groups():
+    """K9 wraps groups in parallel, so overlapping / descending group offsets (which the reference walks sequentially) are
+    refused on the host before anything reaches the GPU."""
+    from moleculekit_b200.wrapping import wrap_box
+
+    xyz = np.zeros((10, 3, 2), np.float32)
+    box = np.full((3, 2), 10.0, np.float32)
+    with pytest.raises(ValueError, match="ascending"):
+        wrap_box(np.array([0, 6, 3, 10], np.uint32), xyz, box, np.arange(3, dtype=np.uint32), np.zeros(3, np.float32))
