@@ -178,6 +178,36 @@ __device__ __forceinline__ float pair_d2_fastwrap_flag(const float4 a, const flo
     return sq3(dx, dy, dz);
 }
 
+// Contact maps only need the BOOLEAN d2 <= T of the reference's float32 sequence, not its bits.  A fused estimate of d2
+// (3 instead of 8 instructions per axis) decides every pair whose estimate lies outside a 4e-6 band around T; pairs inside
+// the band, pairs with NaN / out-of-range quotients, and whole frames whose box is too small for the shortcut take the exact
+// sequence.  Why this is the reference's answer: (a) when the estimate's image integer n equals the reference's
+// roundf(fl(d/b)), the two d2 differ by < 1e-6 relative (a handful of float roundings); (b) when the integers differ, d/b
+// is within 1e-6 of a half-integer, so |w| >= b/2 (1 - 1e-5) in BOTH computations and both d2 exceed T as long as
+// (b/2)^2 (1 - 1e-4) > T -- checked once per frame (`shortcut`), else the exact sequence is used throughout.
+__device__ __forceinline__ bool contact_shortcut_ok(const BoxF &bx, float T) {
+    const float m = fminf(fminf(bx.hx, bx.hy), bx.hz);
+    return m * m * (1.0f - 1e-4f) > T;  // false for NaN / zero / negative boxes as well
+}
+__device__ __forceinline__ bool pair_contact(const float4 a, const float4 b, unsigned cb, const BoxF &bx, int pbc, float T,
+                                             bool shortcut) {
+    if (shortcut) {
+        float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+        float qm = 0.0f;
+        if (pbc && (__float_as_uint(a.w) != cb)) {
+            const float qx = dx * bx.rx, qy = dy * bx.ry, qz = dz * bx.rz;
+            dx = fmaf(-bx.bx, (qx + 12582912.0f) - 12582912.0f, dx);
+            dy = fmaf(-bx.by, (qy + 12582912.0f) - 12582912.0f, dy);
+            dz = fmaf(-bx.bz, (qz + 12582912.0f) - 12582912.0f, dz);
+            qm = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+        }
+        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        // decided unless the estimate is within the band, not a number, or the magic rounding left its range
+        if (fabsf(d2 - T) > 4e-6f * T && qm < 2097152.0f) return d2 <= T;
+    }
+    return pair_d2_fastwrap(a, b, cb, bx, pbc) <= T;
+}
+
 template <int MODE>
 __device__ __forceinline__ void emit_dist(void *out, long long idx, float d2, float truncate, float threshold) {
     if (MODE == DIST_CONTACTS_D2) reinterpret_cast<unsigned char *>(out)[idx] = (d2 <= threshold) ? 1 : 0;
@@ -212,6 +242,21 @@ __global__ void MKB_K3_BOUNDS dist_kernel(const float4 *__restrict__ G1, const f
     const BoxF bx = load_box(box, box_stride, f);
     const int rows = (int)(min(i0 + K3_ROWS, n1) - i0);
     const float4 *__restrict__ arow = G1 + f * n1 + i0;
+    if (MODE == DIST_CONTACTS_D2) {  // boolean map: fused estimate + exact re-check in the band (pair_contact)
+        const bool shortcut = contact_shortcut_ok(bx, threshold);
+        unsigned char *const o8 = reinterpret_cast<unsigned char *>(out);
+        long long idx = f * P + (SELF ? (i0 * n2 - (i0 * (i0 + 1)) / 2 + (j0 - i0 - 1)) : (i0 * n2 + j0));
+        long long step = SELF ? n2 - i0 - 2 : n2;
+#pragma unroll 2
+        for (int r = 0; r < rows; ++r) {
+            const float4 a = __ldg(arow + r);
+            if (!SELF || j0 > i0 + r) o8[idx] = pair_contact(a, b0, cb0, bx, pbc, threshold, shortcut) ? 1 : 0;
+            if (has1 && (!SELF || j1 > i0 + r)) o8[idx + K3_COLS] = pair_contact(a, b1, cb1, bx, pbc, threshold, shortcut) ? 1 : 0;
+            idx += step;
+            if (SELF) --step;
+        }
+        return;
+    }
     // running output index: non-self (i, j) -> i*n2 + j ; self -> i*n2 - i(i+1)/2 + (j - i - 1), step n2 - i - 2
     long long idx = f * P + (SELF ? (i0 * n2 - (i0 * (i0 + 1)) / 2 + (j0 - i0 - 1)) : (i0 * n2 + j0));
     if (SELF) {

@@ -56,6 +56,11 @@ class MetricShell(Projection):
             # unique first atoms of the pair map (metricshell.py:92-95): sel1's atoms; when sel1 == sel2 every atom of
             # the selection appears in some pair, which is the same set
             res["shellcenters"] = np.where(sel1)[0]
+            if not self.symmetrical and np.array_equal(sel1, sel2):
+                # two DIFFERENT selection strings that pick the same atoms: the reference's distance matrix is condensed
+                # (j > i pairs only) but its shell loop is keyed on string equality, so the centres are the first atoms
+                # of the pairs -- every selected atom but the last (metricshell.py:92-95,183-186)
+                res["shellcenters"] = res["shellcenters"][:-1]
         edges = np.arange(self.shellwidth * (self.numshells + 1), step=self.shellwidth)
         if "shelledges" in props:
             res["shelledges"] = edges
@@ -74,6 +79,8 @@ class MetricShell(Projection):
         if periodic == "chains":
             self.metricdistance._checkChains(mol, sel1, sel2)
         selfdist = np.array_equal(sel1, sel2)
+        if selfdist and not self.symmetrical:
+            return self._project_condensed_quirk(mol, props)
         i1 = np.where(sel1)[0].astype(np.uint32)
         i2 = np.where(sel2)[0].astype(np.uint32)
         coords, box = _box_for(mol, periodic, _NO_BOX)
@@ -82,6 +89,25 @@ class MetricShell(Projection):
                                  truncate=self.truncate, device=self.device)
         dens = counts / props["shellvol"][None, None, :]
         return dens.reshape(mol.numFrames, len(i1) * self.numshells)
+
+    def _project_condensed_quirk(self, mol, props):
+        """sel1 and sel2 are different strings selecting the SAME atoms.  The reference then counts, for centre i, only the
+        partners that come after it in the selection and has no row for the last atom (its `_shells` is keyed on string
+        equality while the distance matrix is condensed, metricshell.py:183-202).  Reproduced literally from the condensed
+        distances of K3: a rare configuration, correctness over speed."""
+        distances = self.metricdistance.project(mol)
+        if distances.ndim == 1:
+            distances = distances[np.newaxis, :]
+        idx = np.where(props["sel1"])[0]
+        first = np.repeat(idx[:-1], np.arange(len(idx) - 1, 0, -1))  # first atom of every condensed pair, row-major
+        centers, edges, vol = props["shellcenters"], props["shelledges"], props["shellvol"]
+        out = np.ones((distances.shape[0], len(centers) * self.numshells)) * -1
+        for i, c in enumerate(centers):
+            cols = first == c
+            for e in range(len(edges) - 1):
+                inshell = (distances[:, cols] > edges[e]) & (distances[:, cols] <= edges[e + 1])
+                out[:, i * self.numshells + e] = np.sum(inshell, axis=1) / vol[e]
+        return out
 
     def getMapping(self, mol):
         from pandas import DataFrame

@@ -201,6 +201,13 @@ def test_minimum_image_boundaries(du, oracle):
     assert bad[0].size == 0, (bad[0][:5], bad[1][:5], got[bad][:5], want[bad][:5])
     for thr in (3.0, 5.5):
         assert du.contacts_trajectory(c, bx, s1, s2, ch, False, True, thr) == oracle.contacts_trajectory(c, bx, s1, s2, ch, False, True, thr)
+    # the dense contact map decides most pairs on a fused estimate of d2 and re-checks a band around the threshold (and every
+    # frame whose box is too small for the shortcut) with the exact sequence: same booleans as `reference distance <= thr`
+    # on all of the above, for thresholds below, at and above half a box and exactly on values that occur
+    with np.errstate(all="ignore"):
+        for thr in (0.5, 2.5, 3.65, 5.0, 16.6665, 40.0, float(want[0, 30]), float(want[2, 11])):
+            gotc = du.dist_trajectory(c, bx, s1, s2, ch, False, True, None, metric="contacts", threshold=thr)
+            assert np.array_equal(gotc, want <= np.float32(thr)), thr
 
 
 def test_contacts_fill_from_cached_masks_equals_recomputation(du, oracle, monkeypatch):
@@ -500,6 +507,17 @@ def test_metricshell(mol, g_traj, oracle):
     assert np.allclose(d, [[0.01768388256576615, 0, 0, 0, 0.01768388256576615, 0, 0, 0, 0.01768388256576615, 0, 0, 0]])
     d = MetricShell("name CL", "name CL", numshells=2, shellwidth=1, periodic=None).project(tiny)
     assert np.allclose(d, [[0.23873241, 0.03410463, 0.23873241, 0.03410463, 0.0, 0.06820926]])
+
+    # two DIFFERENT strings that select the same atoms: the reference counts only later partners and has no row for the
+    # last atom (its shell loop is keyed on string equality, the matrix is condensed) -- pinned here
+    tiny2 = MolLite(xyz, name=["CL"] * 3, resname=["CL"] * 3, element=["Cl"] * 3, resid=np.arange(3),
+                    named_selections={"name CL": np.ones(3, bool), "resname CL": np.ones(3, bool)})
+    q = MetricShell("name CL", "resname CL", numshells=2, shellwidth=1, periodic=None)
+    d = q.project(tiny2)
+    vol = 4 / 3 * np.pi * np.array([1.0, 7.0])
+    # pairs (0,1) d=0.5, (0,2) d=1.5, (1,2) d=sqrt(2.5): centre 0 sees one atom per shell, centre 1 one in shell 2
+    assert np.allclose(d, [[1 / vol[0], 1 / vol[1], 0.0, 1 / vol[1]]])
+    assert q.getMapping(tiny2).shape == (2 * 2, 3)
 
     rng = np.random.default_rng(4)
     c = (rng.normal(size=(70, 3, 5)) * 6).astype(np.float32)
