@@ -36,6 +36,7 @@ int mkb_destroy(mkb_handle_t h) {
         for (auto &e : h->aux_ev)
             if (e) cudaEventDestroy(e);
         if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+        if (h->aux_stream2) cudaStreamDestroy(h->aux_stream2);
     }
     delete h;
     return MKB_OK;

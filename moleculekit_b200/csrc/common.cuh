@@ -61,8 +61,8 @@ struct mkb_ctx {
     cudaStream_t order_stream = nullptr;
     bool order_valid = false;
     // side stream of the occupancy run path (gate-band pre-pass beside the list build)
-    cudaStream_t aux_stream = nullptr;
-    cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+    cudaStream_t aux_stream = nullptr, aux_stream2 = nullptr;
+    cudaEvent_t aux_ev[2 + 16] = {};  // band fork / join, one per chunk of the list-build pipeline
     // K4: the count call leaves one ballot word per (row, 32 columns); the fill call that follows with the SAME arguments
     // reads them instead of evaluating every distance a second time
     struct K4Key {

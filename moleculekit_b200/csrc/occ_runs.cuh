@@ -57,6 +57,7 @@ struct RunParams {
     const double *sigmas;        // multi-sigma atoms only
     float *out;
     const long long *item_base;  // [B + 1]: first queue item of every grid (item = 4 x 4 voxels in x, y and R_ZC blocks in z)
+    unsigned item0;              // first item of this launch's chunk of grids (queue ids are chunk-local)
     unsigned *queue;
     unsigned total_items;
     int cmajor;                  // MKB_OCC_LAYOUT_CXYZ: grid stored [C][nx][ny][nz]; plain 32-byte-segment stores instead of TMA rows
@@ -99,11 +100,11 @@ __device__ __forceinline__ void for_each_block_in_reach(const GridDev &g, float 
 // distinct sigmas -> multi flag and the per-channel path of the fill kernel).
 __global__ void __launch_bounds__(128) occ_prep_kernel(const float *__restrict__ coords, const double *__restrict__ sigmas,
                                                        const double *__restrict__ radii, const unsigned *__restrict__ chanmask,
-                                                       const GridDev *__restrict__ grids, int B, long long n_items,
+                                                       const GridDev *__restrict__ grids, int B, long long it0, long long n_items,
                                                        float4 *__restrict__ rec_pos, uint4 *__restrict__ rec_tag,
                                                        unsigned *__restrict__ blk_count) {
-    const long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (it >= n_items) return;
+    const long long it = it0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (it >= it0 + n_items) return;
     const int b = find_grid_item(grids, B, it);
     const GridDev &g = grids[b];
     const long long a = g.atom_begin + (it - g.item_base);
@@ -150,12 +151,12 @@ __global__ void __launch_bounds__(128) occ_prep_kernel(const float *__restrict__
 
 // second pass: the same walk appends (item, mask | multi << 8) to the lists; blk_count counts down to zero.  (Keeping the
 // slots of the first pass instead -- no atomics here -- was slower: 178 + 154 us against 95 + 144 us per 256 pockets.)
-__global__ void __launch_bounds__(128) occ_blk_fill_kernel(const GridDev *__restrict__ grids, int B, long long n_items,
+__global__ void __launch_bounds__(128) occ_blk_fill_kernel(const GridDev *__restrict__ grids, int B, long long it0, long long n_items,
                                                            const float4 *__restrict__ rec_pos, const uint4 *__restrict__ rec_tag,
                                                            unsigned *__restrict__ blk_count, const unsigned *__restrict__ blk_start,
                                                            uint2 *__restrict__ blk_ent) {
-    const long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (it >= n_items) return;
+    const long long it = it0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (it >= it0 + n_items) return;
     const uint4 tg = rec_tag[it];
     if ((tg.x & 0x1ffu) == 0) return;
     const int b = find_grid_item(grids, B, it);
@@ -167,7 +168,8 @@ __global__ void __launch_bounds__(128) occ_blk_fill_kernel(const GridDev *__rest
     unsigned *const bc = blk_count + g.tile_base;
     const unsigned *const bs = blk_start + g.tile_base;
     const uint2 ent = make_uint2((unsigned)it, tg.x & 0x1ffu);
-    for_each_block_in_reach(g, px, py, pz, [&](int bid) { blk_ent[bs[bid] + atomicSub(bc + bid, 1u) - 1u] = ent; });
+    uint2 *const be = blk_ent + g.ent_base;
+    for_each_block_in_reach(g, px, py, pz, [&](int bid) { be[bs[bid] + atomicSub(bc + bid, 1u) - 1u] = ent; });
 }
 
 // compact output: 1 for every block with a candidate list, then an exclusive scan gives its record index
@@ -258,13 +260,14 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             gi = (int)(id / p.u_ipg);
             local = id - (unsigned)gi * p.u_ipg;
         } else {
+            const long long gid = (long long)id + p.item0;
             int lo = 0, hi = p.B - 1;
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
-                if (__ldg(p.item_base + mid) <= (long long)id) lo = mid; else hi = mid - 1;
+                if (__ldg(p.item_base + mid) <= gid) lo = mid; else hi = mid - 1;
             }
             gi = lo;
-            local = id - (unsigned)__ldg(p.item_base + gi);
+            local = (unsigned)(gid - __ldg(p.item_base + gi));
         }
         const GridDev *gg = p.grids + gi;
         const int nx = RG(dims[0]), ny = RG(dims[1]), nz = RG(dims[2]);
@@ -656,7 +659,7 @@ __device__ __forceinline__ void occ_fix_voxel(const GridDev *__restrict__ grids,
 #pragma unroll
     for (int h = 0; h < 8; ++h) q[h] = 0.0;
     for (unsigned i = e0 + lane; i < e1; i += 32) {
-        const unsigned a = __ldg(&rec_tag[__ldg(&blk_ent[i].x)].y);
+        const unsigned a = __ldg(&rec_tag[__ldg(&blk_ent[g->ent_base + i].x)].y);
         const double dx = (double)coords[3ll * a + 0] - cx;
         const double dy = (double)coords[3ll * a + 1] - cy;
         const double dz = (double)coords[3ll * a + 2] - cz;
