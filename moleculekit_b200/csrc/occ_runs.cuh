@@ -38,8 +38,8 @@ constexpr int R_WARPS = MKB_R_WARPS;
 #define MKB_R_ZC 4               // consecutive z blocks per queue item
 #endif
 constexpr int R_ZC = MKB_R_ZC;
-// per warp: records 4096 | gate 1024 | ranks 256 | run masks 256 | histogram 512
-constexpr int R_WARP_BYTES = R_CAP * 16 + R_CAP * 4 + R_CAP + 256 + 512;
+// per warp: records 4096 | (gate, mask) 2048 | ranks 256 | histogram 512
+constexpr int R_WARP_BYTES = R_CAP * 16 + R_CAP * 8 + R_CAP + 512;
 #ifndef MKB_R_FMA_GATE
 #define MKB_R_FMA_GATE 0
 #endif
@@ -231,10 +231,9 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *const wb = s_raw[warp];
     float4 *const rec = reinterpret_cast<float4 *>(wb);                         // sorted candidates: (x, y, z)/sigma, 1/sigma
-    float *const cwv = reinterpret_cast<float *>(wb + R_CAP * 16);              // gate in r units: cut2 / sigma^2
-    unsigned char *const rnk = wb + R_CAP * 20;                                 // rank of a candidate inside its mask bin
-    unsigned char *const rmask = wb + R_CAP * 21;                               // run table: masks of the non-empty bins
-    unsigned *const hist = reinterpret_cast<unsigned *>(wb + R_CAP * 21 + 256); // 256 x 16-bit bins in 128 words
+    float2 *const cwv = reinterpret_cast<float2 *>(wb + R_CAP * 16);            // gate in r units (cut2 / sigma^2), channel mask bits
+    unsigned char *const rnk = wb + R_CAP * 24;                                 // rank of a candidate inside its mask bin
+    unsigned *const hist = reinterpret_cast<unsigned *>(wb + R_CAP * 25);       // 256 x 16-bit bins in 128 words
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(wb);
     const unsigned zero_sa = (unsigned)__cvta_generic_to_shared(s_zero);
 
@@ -386,26 +385,20 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     const uint4 hw = *reinterpret_cast<const uint4 *>(hist + 4 * lane);
                     cnt[0] = hw.x & 0xffffu; cnt[1] = hw.x >> 16; cnt[2] = hw.y & 0xffffu; cnt[3] = hw.y >> 16;
                     cnt[4] = hw.z & 0xffffu; cnt[5] = hw.z >> 16; cnt[6] = hw.w & 0xffffu; cnt[7] = hw.w >> 16;
-                    unsigned sum = 0, nzc2 = 0;
+                    unsigned sum = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { sum += cnt[j]; off8[j] = sum; nzc2 += cnt[j] ? 1u : 0u; }
-                    unsigned v = sum | (nzc2 << 16);
-                    const unsigned mine = v;
+                    for (int j = 0; j < 8; ++j) { sum += cnt[j]; off8[j] = sum; }
+                    unsigned v = sum;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
                         if (lane >= o) v += t;
                     }
-                    const unsigned excl = v - mine;
+                    const unsigned excl = v - sum;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) off8[j] += excl & 0xffffu;
-                    unsigned ridx = excl >> 16;
+                    for (int j = 0; j < 8; ++j) off8[j] += excl;
                     *reinterpret_cast<uint4 *>(hist + 4 * lane) =
                         make_uint4(off8[0] | (off8[1] << 16), off8[2] | (off8[3] << 16), off8[4] | (off8[5] << 16), off8[6] | (off8[7] << 16));
-                    // run table: the masks of the non-empty bins in order
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (cnt[j]) rmask[ridx++] = (unsigned char)(lane * 8 + j);
                 }
                 // the stage of the previous block aliases the records: its bulk copies must have read it
                 if (pending) {
@@ -429,10 +422,11 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     const double ey = (double)((int)(tg.z >> 16) - cy) + ((double)f.y - 1.5);
                     const double ez = (double)((int)(tg.x >> 16) - cz) + ((double)f.z - 3.5);
                     rec[pos] = make_float4((float)(ex * dsw), (float)(ey * dsw), (float)(ez * dsw), (float)dsw);
+                    // the candidate's mask rides with its gate: the record that closes a run hands the run's mask to the flush
 #if MKB_R_FMA_GATE
-                    cwv[pos] = -(cut2 * (sw * sw)) * R_GATE_BIG;  // gate on the FMA pipe: sat((r - cw) 2^40) is 0 inside, 1 outside
+                    cwv[pos] = make_float2(-(cut2 * (sw * sw)) * R_GATE_BIG, __uint_as_float(m));  // FMA-pipe gate: sat((r - cw) 2^40)
 #else
-                    cwv[pos] = cut2 * (sw * sw);
+                    cwv[pos] = make_float2(cut2 * (sw * sw), __uint_as_float(m));
 #endif
                 }
                 __syncwarp();
@@ -460,17 +454,19 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
         MKB_GATED_MIN(m3, r3, CW);                                                                \
     }
                     float4 a = rec[0];
-                    float cwa = cwv[0];
+                    float2 cwa = cwv[0];
                     int i = 1;  // next record to load; i == np reads past the list (inside this warp's buffer), never used
 #pragma unroll 1
-                    for (int ri = 0; i <= np && MKB_R_EXP != 1; ++ri) {
+                    while (i <= np && MKB_R_EXP != 1) {
                         float m0 = INF, m1 = INF, m2 = INF, m3 = INF;
+                        unsigned mask;
 #pragma unroll 1
                         for (;;) {
                             const float4 b = rec[i];
-                            const float cwb = cwv[i];
-                            MKB_RUN_BODY(a, cwa)
+                            const float2 cwb = cwv[i];
+                            MKB_RUN_BODY(a, cwa.x)
                             if (a.w < 0.0f) {  // the record that closes a run is negated (warp-uniform)
+                                mask = __float_as_uint(cwa.y);
                                 a = b;
                                 cwa = cwb;
                                 i += 1;
@@ -478,11 +474,14 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                             }
                             a = rec[i + 1];
                             cwa = cwv[i + 1];
-                            MKB_RUN_BODY(b, cwb)
+                            MKB_RUN_BODY(b, cwb.x)
                             i += 2;
-                            if (b.w < 0.0f) break;
+                            if (b.w < 0.0f) {
+                                mask = __float_as_uint(cwb.y);
+                                break;
+                            }
                         }
-                        const unsigned mask = MKB_R_EXP == 2 ? 0u : rmask[ri];
+                        if (MKB_R_EXP == 2) mask = 0u;
 #if MKB_R_FLUSH == 1
                         MKB_NIB_SWITCH(mask & 15u, 0)
                         MKB_NIB_SWITCH(mask >> 4, 4)
