@@ -60,6 +60,11 @@ struct mkb_ctx {
     cudaEvent_t order_ev = nullptr;
     cudaStream_t order_stream = nullptr;
     bool order_valid = false;
+    // page-locked staging for the small per-call host -> device uploads (grid descriptors): a pageable cudaMemcpyAsync
+    // stages through the driver and costs tens of microseconds of host time per call
+    void *host_stage = nullptr;
+    size_t host_stage_cap = 0;
+    cudaEvent_t stage_ev = nullptr;
     // side stream of the occupancy run path (gate-band pre-pass beside the list build)
     cudaStream_t aux_stream = nullptr, aux_stream2 = nullptr;
     cudaEvent_t aux_ev[2 + 16] = {};  // band fork / join, one per chunk of the list-build pipeline
@@ -116,6 +121,22 @@ inline int scratch_get(mkb_ctx *h, ScratchSlot s, size_t bytes, void **out) {
         sc.cap = want;
     }
     *out = sc.ptr;
+    return MKB_OK;
+}
+
+// page-locked staging buffer of `bytes`; waits until the previous call's upload from it has left the host
+inline int host_stage_get(mkb_ctx *h, size_t bytes, void **out) {
+    if (h->stage_ev) MKB_CUDA(h, cudaEventSynchronize(h->stage_ev));
+    else MKB_CUDA(h, cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
+    if (bytes > h->host_stage_cap) {
+        if (h->host_stage) MKB_CUDA(h, cudaFreeHost(h->host_stage));
+        h->host_stage = nullptr;
+        h->host_stage_cap = 0;
+        const size_t want = bytes + bytes / 2 + 4096;
+        MKB_CUDA(h, cudaHostAlloc(&h->host_stage, want, cudaHostAllocDefault));
+        h->host_stage_cap = want;
+    }
+    *out = h->host_stage;
     return MKB_OK;
 }
 

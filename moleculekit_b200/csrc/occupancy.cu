@@ -1736,20 +1736,31 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             for (auto &e : h->aux_ev) MKB_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[0], st));
-        MKB_CUDA(h, cudaMemcpyAsync(d_grids, gd.data(), sizeof(GridDev) * (size_t)B, cudaMemcpyHostToDevice, st));
-        MKB_CUDA(h, cudaMemcpyAsync(d_ibase, ibase.data(), sizeof(long long) * ((size_t)B + 1), cudaMemcpyHostToDevice, st));
+        {   // descriptors + item table: one upload from page-locked staging
+            const size_t gbytes = sizeof(GridDev) * (size_t)B, ibytes = sizeof(long long) * ((size_t)B + 1);
+            void *stage = nullptr;
+            if ((rc = host_stage_get(h, gbytes + ibytes, &stage))) return rc;
+            memcpy(stage, gd.data(), gbytes);
+            memcpy(static_cast<char *>(stage) + gbytes, ibase.data(), ibytes);
+            MKB_CUDA(h, cudaMemcpyAsync(d_grids, stage, gbytes, cudaMemcpyHostToDevice, st));
+            MKB_CUDA(h, cudaMemcpyAsync(d_ibase, static_cast<char *>(stage) + gbytes, ibytes, cudaMemcpyHostToDevice, st));
+            MKB_CUDA(h, cudaEventRecord(h->stage_ev, st));
+        }
         MKB_CUDA(h, cudaMemsetAsync(blk_count, 0, sizeof(unsigned) * nslots, st));
         MKB_CUDA(h, cudaMemsetAsync(d_bitmap, 0, sizeof(unsigned) * (size_t)n_words, st));
         MKB_CUDA(h, cudaMemsetAsync(d_queue, 0, sizeof(unsigned) * 64, st));
         MKB_CUDA(h, cudaMemsetAsync(d_fix, 0, sizeof(unsigned long long) * FIX_HDR, st));
         cudaStream_t sk = n_chunks > 1 ? h->aux_stream2 : st;  // list builds
+        // the gate-band pre-pass (compute bound) runs beside the list build (atomic bound) on a side stream; small calls
+        // keep it on the caller's stream (the fork / join costs more host time than the overlap saves)
+        const bool band_aside = items >= 200000;
         if (items > 0) {
-            // the gate-band pre-pass (compute bound) and the list builds run beside the fill kernels on side streams
-            MKB_CUDA(h, cudaEventRecord(h->aux_ev[0], st));
-            MKB_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
-            occ_band_kernel<<<(unsigned)cdiv(items, 128), 128, 0, h->aux_stream>>>(coords, d_grids, B, items, d_bitmap, d_fix, fix_cap);
+            if (band_aside || sk != st) MKB_CUDA(h, cudaEventRecord(h->aux_ev[0], st));
+            cudaStream_t sb = band_aside ? h->aux_stream : st;
+            if (band_aside) MKB_CUDA(h, cudaStreamWaitEvent(sb, h->aux_ev[0], 0));
+            occ_band_kernel<<<(unsigned)cdiv(items, 128), 128, 0, sb>>>(coords, d_grids, B, items, d_bitmap, d_fix, fix_cap);
             MKB_LAUNCHED(h);
-            MKB_CUDA(h, cudaEventRecord(h->aux_ev[1], h->aux_stream));
+            if (band_aside) MKB_CUDA(h, cudaEventRecord(h->aux_ev[1], sb));
             if (sk != st) MKB_CUDA(h, cudaStreamWaitEvent(sk, h->aux_ev[0], 0));
         }
         h->last_kernel = "occ_fill_runs_kernel";
@@ -1809,7 +1820,7 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
         }
         if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));
         if (items > 0) {
-            MKB_CUDA(h, cudaStreamWaitEvent(st, h->aux_ev[1], 0));
+            if (band_aside) MKB_CUDA(h, cudaStreamWaitEvent(st, h->aux_ev[1], 0));
             const unsigned fg = (unsigned)h->sm_count * 4;
             const int cm = (flags & MKB_OCC_LAYOUT_CXYZ) ? 1 : 0;
             occ_fix_list_kernel<<<fg, 256, 0, st>>>(d_grids, B, d_fix, fix_cap, coords, sigmas, radii, chanmask, rec_tag, blk_start, blk_ent, out, cm, blk_rank);

@@ -250,9 +250,12 @@ def test_compact_transfer_equals_dense(vd):
         total = int(sum(a.shape[0] for a in dense))
         out = vd.pinned_array((total, 8), np.float32)
         out[:] = 3.0
-        vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], out=out, **kw)  # "auto" takes the compact route
+        vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], out=out, transfer="compact", **kw)
         assert vd.LAST_TRANSFER["mode"] == "compact" and vd.LAST_TRANSFER["d2h_bytes"] < out.nbytes
         assert np.array_equal(out, np.concatenate(dense))
+        out[:] = 5.0
+        vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], out=out, **kw)  # "auto": a batch this small goes dense
+        assert vd.LAST_TRANSFER["mode"] == "dense" and np.array_equal(out, np.concatenate(dense))
 
 
 def test_full_size_c2_all_poses_vs_oracle(vd, oracle):
