@@ -33,8 +33,10 @@ int mkb_destroy(mkb_handle_t h) {
         for (auto &e : h->ev)
             if (e) cudaEventDestroy(e);
         if (h->order_ev) cudaEventDestroy(h->order_ev);
-        if (h->stage_ev) cudaEventDestroy(h->stage_ev);
-        if (h->host_stage) cudaFreeHost(h->host_stage);
+        for (auto &e : h->stage_ev)
+            if (e) cudaEventDestroy(e);
+        for (auto &b : h->host_stage)
+            if (b) cudaFreeHost(b);
         for (auto &e : h->aux_ev)
             if (e) cudaEventDestroy(e);
         if (h->aux_stream) cudaStreamDestroy(h->aux_stream);

@@ -62,9 +62,11 @@ struct mkb_ctx {
     bool order_valid = false;
     // page-locked staging for the small per-call host -> device uploads (grid descriptors): a pageable cudaMemcpyAsync
     // stages through the driver and costs tens of microseconds of host time per call
-    void *host_stage = nullptr;
-    size_t host_stage_cap = 0;
-    cudaEvent_t stage_ev = nullptr;
+    static constexpr int N_STAGE = 4;  // a ring, so the host can run several calls ahead of the device
+    void *host_stage[N_STAGE] = {};
+    size_t host_stage_cap[N_STAGE] = {};
+    cudaEvent_t stage_ev[N_STAGE] = {};
+    int stage_next = 0;
     // side stream of the occupancy run path (gate-band pre-pass beside the list build)
     cudaStream_t aux_stream = nullptr, aux_stream2 = nullptr;
     cudaEvent_t aux_ev[2 + 16] = {};  // band fork / join, one per chunk of the list-build pipeline
@@ -124,19 +126,23 @@ inline int scratch_get(mkb_ctx *h, ScratchSlot s, size_t bytes, void **out) {
     return MKB_OK;
 }
 
-// page-locked staging buffer of `bytes`; waits until the previous call's upload from it has left the host
-inline int host_stage_get(mkb_ctx *h, size_t bytes, void **out) {
-    if (h->stage_ev) MKB_CUDA(h, cudaEventSynchronize(h->stage_ev));
-    else MKB_CUDA(h, cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
-    if (bytes > h->host_stage_cap) {
-        if (h->host_stage) MKB_CUDA(h, cudaFreeHost(h->host_stage));
-        h->host_stage = nullptr;
-        h->host_stage_cap = 0;
+// page-locked staging buffer of `bytes` (next slot of the ring); waits until the upload that last used the slot has left the
+// host.  The caller records *ev on its stream after enqueuing the copy.
+inline int host_stage_get(mkb_ctx *h, size_t bytes, void **out, cudaEvent_t **ev) {
+    const int k = h->stage_next;
+    h->stage_next = (k + 1) % mkb_ctx::N_STAGE;
+    if (h->stage_ev[k]) MKB_CUDA(h, cudaEventSynchronize(h->stage_ev[k]));
+    else MKB_CUDA(h, cudaEventCreateWithFlags(&h->stage_ev[k], cudaEventDisableTiming));
+    if (bytes > h->host_stage_cap[k]) {
+        if (h->host_stage[k]) MKB_CUDA(h, cudaFreeHost(h->host_stage[k]));
+        h->host_stage[k] = nullptr;
+        h->host_stage_cap[k] = 0;
         const size_t want = bytes + bytes / 2 + 4096;
-        MKB_CUDA(h, cudaHostAlloc(&h->host_stage, want, cudaHostAllocDefault));
-        h->host_stage_cap = want;
+        MKB_CUDA(h, cudaHostAlloc(&h->host_stage[k], want, cudaHostAllocDefault));
+        h->host_stage_cap[k] = want;
     }
-    *out = h->host_stage;
+    *out = h->host_stage[k];
+    *ev = &h->stage_ev[k];
     return MKB_OK;
 }
 

@@ -58,6 +58,7 @@ struct RunParams {
     float *out;
     const long long *item_base;  // [B + 1]: first queue item of every grid (item = 4 x 4 voxels in x, y and R_ZC blocks in z)
     unsigned item0;              // first item of this launch's chunk of grids (queue ids are chunk-local)
+    int zc;                      // z blocks per item: R_ZC, or fewer when the batch has too few items to balance 4144 warps
     unsigned *queue;
     unsigned total_items;
     int cmajor;                  // MKB_OCC_LAYOUT_CXYZ: grid stored [C][nx][ny][nz]; plain 32-byte-segment stores instead of TMA rows
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
         const GridDev *gg = p.grids + gi;
         const int nx = RG(dims[0]), ny = RG(dims[1]), nz = RG(dims[2]);
         const int nbz = (nz + R_BZ - 1) / R_BZ;
-        const unsigned nby = UNIFORM ? p.u_nby : (unsigned)(ny + 3) >> 2, nzc = UNIFORM ? p.u_nzc : (unsigned)(nbz + R_ZC - 1) / R_ZC;
+        const unsigned nby = UNIFORM ? p.u_nby : (unsigned)(ny + 3) >> 2, nzc = UNIFORM ? p.u_nzc : (unsigned)(nbz + p.zc - 1) / p.zc;
         const int zc = (int)(local % nzc);
         const unsigned bxy = local / nzc;
         const int byi = (int)(bxy % nby), bxi = (int)(bxy / nby);
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
         float *const row_base = p.out + (out_offset + ((long long)rix * ny + riy) * nz) * 8;
         const float cut2 = RG(cut2v);
         const int off = RG(cutv) + 1;
-        const int bz_begin = zc * R_ZC, bz_end = min(nbz, bz_begin + R_ZC);
+        const int bz_begin = zc * p.zc, bz_end = min(nbz, bz_begin + p.zc);
         // candidate list offsets of the item's blocks (consecutive block ids): lanes 0..R_ZC
         const long long blk0 = (UNIFORM ? p.u.tile_base + (long long)gi * p.u_bpg : __ldg(&gg->tile_base)) + (long long)bxy * nbz + bz_begin;
         const unsigned my_start = __ldg(p.blk_start + blk0 + min(lane, bz_end - bz_begin));

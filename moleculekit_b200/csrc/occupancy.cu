@@ -1643,14 +1643,25 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
     std::vector<int> cgrid;                // [n_chunks + 1] first grid of every chunk
     std::vector<long long> blk_off, ent_off, item_off, atom_item_off, ibase;
     long long run_blocks = 0, run_items = 0, ent_bound = 0;
+    int run_zc = R_ZC;
     if (use_runs) {
         std::vector<long long> nblk((size_t)B), nitem((size_t)B), nent((size_t)B);
+        // z blocks per queue item: 4 amortise the item set-up, but a small batch (strong scaling: 32 pockets per GPU) then
+        // has ~2 items per warp and the heavy ones decide the tail -> finer items when there are few
+        {
+            long long it4 = 0;
+            for (int b = 0; b < B; ++b)
+                it4 += (long long)((gd[b].dims[0] + 3) / 4) * ((gd[b].dims[1] + 3) / 4) * (((gd[b].dims[2] + R_BZ - 1) / R_BZ + R_ZC - 1) / R_ZC);
+            const long long warps = (long long)h->sm_count * MKB_R_MIN_CTAS * R_WARPS;
+            run_zc = it4 >= 8 * warps ? R_ZC : (it4 >= 3 * warps ? 2 : 1);
+            if (getenv("MKB_OCC_ZC")) run_zc = std::max(1, std::min(R_ZC, atoi(getenv("MKB_OCC_ZC"))));
+        }
         for (int b = 0; b < B; ++b) {
             const GridDev &g = gd[b];
             const long long nbx = (g.dims[0] + 3) / 4, nby = (g.dims[1] + 3) / 4, nbz = (g.dims[2] + R_BZ - 1) / R_BZ;
             if (g.dims[0] + 2 * g.cutv + 2 >= 65536 || g.dims[1] + 2 * g.cutv + 2 >= 65536 || g.dims[2] + 2 * g.cutv + 2 >= 65536) use_runs = false;
             nblk[b] = nbx * nby * nbz;
-            nitem[b] = nbx * nby * ((nbz + R_ZC - 1) / R_ZC);
+            nitem[b] = nbx * nby * ((nbz + run_zc - 1) / run_zc);
             // blocks one atom can reach: an interval of 2 cut voxels touches at most floor((2 cut + e - 1) / e) + 1 blocks of edge e
             const double c2 = 2.0 * CUTOFF_A / g.vs;
             const long long rx = std::min<long long>(nbx, (long long)((c2 + 3) / 4) + 1), ry = std::min<long long>(nby, (long long)((c2 + 3) / 4) + 1),
@@ -1739,12 +1750,13 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
         {   // descriptors + item table: one upload from page-locked staging
             const size_t gbytes = sizeof(GridDev) * (size_t)B, ibytes = sizeof(long long) * ((size_t)B + 1);
             void *stage = nullptr;
-            if ((rc = host_stage_get(h, gbytes + ibytes, &stage))) return rc;
+            cudaEvent_t *sev = nullptr;
+            if ((rc = host_stage_get(h, gbytes + ibytes, &stage, &sev))) return rc;
             memcpy(stage, gd.data(), gbytes);
             memcpy(static_cast<char *>(stage) + gbytes, ibase.data(), ibytes);
             MKB_CUDA(h, cudaMemcpyAsync(d_grids, stage, gbytes, cudaMemcpyHostToDevice, st));
             MKB_CUDA(h, cudaMemcpyAsync(d_ibase, static_cast<char *>(stage) + gbytes, ibytes, cudaMemcpyHostToDevice, st));
-            MKB_CUDA(h, cudaEventRecord(h->stage_ev, st));
+            MKB_CUDA(h, cudaEventRecord(*sev, st));
         }
         MKB_CUDA(h, cudaMemsetAsync(blk_count, 0, sizeof(unsigned) * nslots, st));
         MKB_CUDA(h, cudaMemsetAsync(d_bitmap, 0, sizeof(unsigned) * (size_t)n_words, st));
@@ -1809,7 +1821,8 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             rp.u_out_stride = nvox0;
             rp.u_ipg = (unsigned)(ibase[g0 + 1] - ibase[g0]);
             rp.u_nby = (unsigned)((g0d.dims[1] + 3) / 4);
-            rp.u_nzc = (unsigned)(((g0d.dims[2] + R_BZ - 1) / R_BZ + R_ZC - 1) / R_ZC);
+            rp.u_nzc = (unsigned)(((g0d.dims[2] + R_BZ - 1) / R_BZ + run_zc - 1) / run_zc);
+            rp.zc = run_zc;
             rp.u_bpg = (unsigned)(g1 - g0 > 1 ? gd[g0 + 1].tile_base - g0d.tile_base : 0);
             if (h->timing && c == 0) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
             const unsigned nctas = (unsigned)std::min<long long>((long long)h->sm_count * MKB_R_MIN_CTAS, cdiv((long long)rp.total_items, R_WARPS));

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import functools
 import logging
+import os
 
 import numpy as np
 import torch
@@ -482,7 +483,9 @@ def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, bu
         raise ValueError("transfer='compact' needs 8 channels, the voxel-major layout and host float32 / float64 results")
     # "auto": the compact route pays a block-index round trip and a host-thread expansion; it wins once the dense copy
     # is long enough to hide them (C3: 256 pockets 27 vs 40 ms, 32 pockets 7.2 vs 5.3 ms on one B200)
-    if transfer == "auto" and batch.total_voxels * batch.C * 4 < (512 << 20):
+    # and on a host shared by many ranks the expansion competes for the same memory bandwidth as the DMA it replaces
+    # (8 ranks x 256 pockets: 80 vs 58 ms), so "auto" keeps the dense copy there
+    if transfer == "auto" and (batch.total_voxels * batch.C * 4 < (512 << 20) or int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 2):
         compact_ok = False
     if compact_ok and transfer != "dense":
         if out is not None and (out.dtype != np.float32 or out.shape != (batch.total_voxels, batch.C) or not out.flags["C_CONTIGUOUS"]):
