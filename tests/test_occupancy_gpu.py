@@ -332,3 +332,22 @@ def test_two_streams_share_one_handle(vd):
     torch.cuda.synchronize()
     for a, b in zip(outs, want):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("vs", [1.0, 0.8, 0.5])
+def test_gate_decisions_on_many_random_grids(vd, oracle, vs):
+    """The run kernel decides the 5 A gate in float32 and repairs the +-2e-6 band in float64 (occ_band / occ_fix kernels):
+    16 random grids per voxel size (57 k voxels, 700 atoms each, ~6 M in-gate pairs in total) must reproduce the oracle's
+    zero pattern everywhere and its values to 1e-5."""
+    from moleculekit_b200 import workloads
+
+    n = int(round(36 * 1.0 / vs)) if vs >= 0.8 else 48
+    box = n * vs
+    w = workloads.protein_pockets(B=16, n_atoms=700, box=box, radius=0.38 * box, seed=int(1000 * vs) + 3)
+    feats, dims = vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], boxsize=[box] * 3, centers=w["centers"], voxelsize=vs,
+                                              dtype=np.float32)
+    assert dims.tolist() == [[n, n, n]] * 16
+    for b in range(16):
+        centers, _ = vd.getCenters(boxsize=[box] * 3, center=w["centers"][b], voxelsize=vs)
+        want = np.zeros((centers.shape[0], 8)); oracle.calculate_occupancy(centers, w["coords"][b], w["sigmas"][b], want)
+        _assert_occ_close(feats[b], want)
