@@ -56,9 +56,7 @@ __device__ __forceinline__ BoxF load_box(const float *box, long long stride, lon
     b.ry = __frcp_rn(b.by);
     b.rz = __frcp_rn(b.bz);
     b.hx = __fmul_rn(b.bx, 0.5f); b.hy = __fmul_rn(b.by, 0.5f); b.hz = __fmul_rn(b.bz, 0.5f);
-#ifdef MKB_K3_PIN_HALF
     asm volatile("" : "+f"(b.hx), "+f"(b.hy), "+f"(b.hz));  // keep the halves in registers (else recomputed per pair)
-#endif
     return b;
 }
 
@@ -160,6 +158,25 @@ __device__ __forceinline__ float pair_d2_fastwrap(const float4 a, const float4 b
     return sq3(dx, dy, dz);
 }
 
+// K3 hot loop variant: the rare exact re-wrap is an out-of-line call (the inlined form merged its registers back with a
+// dozen MOV / BSSY / BSYNC per pair), the half boxes live in registers, and the threshold folds |d| in with one FFMA:
+//   risky  <=>  |w| + 1e-6 |d| >= b/2  on some axis   (the same test as wrap_fast, rearranged)
+__device__ __noinline__ float pair_d2_rewrap(float dx, float dy, float dz, float bxx, float bxy, float bxz, float rx, float ry, float rz) {
+    return sq3(wrap_axis(dx, bxx, rx), wrap_axis(dy, bxy, ry), wrap_axis(dz, bxz, rz));
+}
+__device__ __forceinline__ float pair_d2_lean(const float4 a, const float4 b, unsigned cb, const BoxF &bx, int pbc) {
+    const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+    if (!(pbc && (__float_as_uint(a.w) != cb))) return sq3(dx, dy, dz);
+    const float nx = __fsub_rn(__fadd_rn(__fmul_rn(dx, bx.rx), 12582912.0f), 12582912.0f);
+    const float ny = __fsub_rn(__fadd_rn(__fmul_rn(dy, bx.ry), 12582912.0f), 12582912.0f);
+    const float nz = __fsub_rn(__fadd_rn(__fmul_rn(dz, bx.rz), 12582912.0f), 12582912.0f);
+    const float wx = __fsub_rn(dx, __fmul_rn(bx.bx, nx)), wy = __fsub_rn(dy, __fmul_rn(bx.by, ny)), wz = __fsub_rn(dz, __fmul_rn(bx.bz, nz));
+    const bool safe = (fmaf(1e-6f, fabsf(dx), fabsf(wx)) < bx.hx) & (fmaf(1e-6f, fabsf(dy), fabsf(wy)) < bx.hy) &
+                      (fmaf(1e-6f, fabsf(dz), fabsf(wz)) < bx.hz);
+    if (!safe) return pair_d2_rewrap(dx, dy, dz, bx.bx, bx.by, bx.bz, bx.rx, bx.ry, bx.rz);
+    return sq3(wx, wy, wz);
+}
+
 // same with the wrap decision made by the caller (group chains, K5)
 __device__ __forceinline__ float pair_d2_fastwrap_flag(const float4 a, const float4 b, const BoxF &bx, bool wrap) {
     float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
@@ -208,9 +225,10 @@ __device__ __forceinline__ bool pair_contact(const float4 a, const float4 b, uns
     return pair_d2_fastwrap(a, b, cb, bx, pbc) <= T;
 }
 
-template <int MODE>
+template <int MODE, bool TRUNC = true>
 __device__ __forceinline__ void emit_dist(void *out, long long idx, float d2, float truncate, float threshold) {
     if (MODE == DIST_CONTACTS_D2) reinterpret_cast<unsigned char *>(out)[idx] = (d2 <= threshold) ? 1 : 0;
+    else if (MODE == MKB_DIST_DISTANCES && !TRUNC) reinterpret_cast<float *>(out)[idx] = __fsqrt_rn(d2);  // no truncate given
     else store_dist<MODE>(out, idx, __fsqrt_rn(d2), truncate, threshold);
 }
 
@@ -224,7 +242,7 @@ __device__ __forceinline__ void emit_dist(void *out, long long idx, float d2, fl
 #else
 #define MKB_K3_BOUNDS __launch_bounds__(K3_COLS)
 #endif
-template <int MODE, bool SELF>
+template <int MODE, bool SELF, bool TRUNC = true>
 __global__ void MKB_K3_BOUNDS dist_kernel(const float4 *__restrict__ G1, const float4 *__restrict__ G2,
                                                         long long n1, long long n2, const float *__restrict__ box,
                                                         long long box_stride, int pbc, float truncate,
@@ -274,8 +292,8 @@ __global__ void MKB_K3_BOUNDS dist_kernel(const float4 *__restrict__ G1, const f
 #pragma unroll 2
         for (int r = 0; r < rows; ++r) {
             const float4 a = __ldg(arow + r);
-            emit_dist<MODE>(out, idx, pair_d2_fastwrap(a, b0, cb0, bx, pbc), truncate, threshold);
-            emit_dist<MODE>(out, idx + K3_COLS, pair_d2_fastwrap(a, b1, cb1, bx, pbc), truncate, threshold);
+            emit_dist<MODE, TRUNC>(out, idx, pair_d2_lean(a, b0, cb0, bx, pbc), truncate, threshold);
+            emit_dist<MODE, TRUNC>(out, idx + K3_COLS, pair_d2_lean(a, b1, cb1, bx, pbc), truncate, threshold);
             idx += n2;
         }
     } else {
@@ -658,7 +676,10 @@ extern "C" int mkb_dist_trajectory(mkb_handle_t h, void *stream, const mkb_traj 
 #define MKB_K3_LAUNCH(M, S)                                                                                       \
     dist_kernel<M, S><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box, pbc, truncate, kthr, P, out, f0)
         if (kmode == MKB_DIST_DISTANCES) {
-            if (selfdist) MKB_K3_LAUNCH(MKB_DIST_DISTANCES, true); else MKB_K3_LAUNCH(MKB_DIST_DISTANCES, false);
+            if (selfdist) MKB_K3_LAUNCH(MKB_DIST_DISTANCES, true);
+            else if (truncate != truncate)  // NaN = no truncate: the rectangular kernel without the compare / select per pair
+                dist_kernel<MKB_DIST_DISTANCES, false, false><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box, pbc, truncate, kthr, P, out, f0);
+            else MKB_K3_LAUNCH(MKB_DIST_DISTANCES, false);
         } else if (kmode == MKB_DIST_CONTACTS) {
             if (selfdist) MKB_K3_LAUNCH(MKB_DIST_CONTACTS, true); else MKB_K3_LAUNCH(MKB_DIST_CONTACTS, false);
         } else {
