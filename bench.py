@@ -471,24 +471,9 @@ def extra_workloads(dev, peak):
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
 def bind_to_gpu_numa(index: int):
-    """Pin this rank to the CPUs next to its GPU (NVML affinity mask) before any pinned buffer is allocated, so the
-    page-locked staging memory is first touched on the GPU's NUMA node.  Round 1's end-to-end numbers at N=4/8 were
-    limited by ranks copying 2 GB per step into memory of the other socket."""
-    try:
-        import pynvml
+    from moleculekit_b200 import sharding
 
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
-        cur = os.sched_getaffinity(0)
-        want = cpus & cur
-        if want:
-            os.sched_setaffinity(0, want)
-            return f"{len(want)} CPUs near GPU {index}"
-    except Exception as e:  # NVML missing or affinity not permitted: run unbound
-        return f"unbound ({type(e).__name__})"
-    return "unbound"
+    return sharding.bind_to_gpu_numa(index)
 
 
 def scaling_section(a, dev, world, rank, peak):
@@ -702,7 +687,8 @@ def run_ours(a):
             return dt
 
         # the call a user makes: host arrays in, the dense float32 (sum M, 8) host array out.  Default transfer ("auto"):
-        # only the 4x4x8 blocks with an atom in reach cross PCIe, host threads rebuild the dense array (identical bytes)
+        # only the 4x4x8 blocks with an atom in reach cross PCIe -- stored by the fill kernel straight into the page-locked
+        # result while host threads zero the other blocks (identical bytes to the dense copy)
         dt = e2e_time(n_e2e, out=h_out)
         d2h = int(vd.LAST_TRANSFER.get("d2h_bytes", h_out.nbytes))
         mode = vd.LAST_TRANSFER.get("mode")
@@ -713,6 +699,10 @@ def run_ours(a):
         if rank == 0 or world > 1:
             dt_dense = e2e_time(3, out=h_out, transfer="dense")
             e2e["dense_transfer"] = dict(ms_per_step=dt_dense * 1e3, value=world * n_vc / dt_dense, d2h_bytes_per_step=int(h_out.nbytes))
+            if mode == "direct":  # the staged variant of the same idea: 4 KB block records + host expansion
+                dt_c = e2e_time(3, out=h_out, transfer="compact")
+                e2e["compact_transfer"] = dict(ms_per_step=dt_c * 1e3, value=world * n_vc / dt_c,
+                                               d2h_bytes_per_step=int(vd.LAST_TRANSFER.get("d2h_bytes", 0)))
         if world == 1:  # the reference-typed result: a list of float64 (M, 8) arrays (voxeldescriptors.py:531)
             dt64 = e2e_time(2)
             e2e["float64_lists"] = dict(ms_per_step=dt64 * 1e3, value=n_vc / dt64,

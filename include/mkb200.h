@@ -107,13 +107,26 @@ int mkb_occupancy_grid_batch_masked(mkb_handle_t h, void *stream, const float *c
  * records[1024 * blk_rank[b] ...].  records: device, room for mkb_occupancy_compact_blocks(grids, B) records in the
  * worst case; blk_rank: device uint32 [rank_capacity >= blocks + 1].  Exactly one of sigmas / (radii, chanmask) is given.
  * mkb_occupancy_expand_host rebuilds grids [g0, g1) of the dense float32 (sum M, 8) HOST array from host copies of the
- * records (`records` points at record rec0) with n_threads threads; missing blocks are zero-filled; out_f64 != 0 writes
+ * records (`records` points at record rec0; NULL = only zero-fill the blocks without a record) with n_threads threads;
+ * missing blocks are zero-filled; out_f64 != 0 writes
  * float64 (the reference's result dtype).  The result is bit-identical to mkb_occupancy_grid_batch. */
 int mkb_occupancy_grid_batch_compact(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
                                      const double *radii, const uint32_t *chanmask, int64_t n_atoms,
                                      const mkb_grid_desc *grids, int32_t B, float *records, uint32_t *blk_rank,
                                      int64_t rank_capacity);
 int64_t mkb_occupancy_compact_blocks(const mkb_grid_desc *grids, int32_t B);
+/* K1 straight into the caller's HOST array (end-to-end callers with a page-locked result, e.g. cudaHostAlloc / torch
+ * pin_memory: under UVA such memory is device-accessible at the same address).  `out_mapped` is that dense float32
+ * (sum M, 8) host array: the kernel stores the blocks that have an atom within 5 A directly into it over PCIe (TMA bulk
+ * row copies, ~30 % of the bytes) and does not touch the others; the block index (as for the compact call) is computed before
+ * the fill kernel starts and copied to `host_rank` (page-locked, blocks + 1 words) on a side stream, so the host can
+ * zero-fill the empty blocks (mkb_occupancy_expand_host with records == NULL) WHILE the GPU computes and writes.
+ * mkb_occupancy_wait_index blocks until host_rank has arrived; the caller synchronises `stream` before reading `out`. */
+int mkb_occupancy_grid_batch_to_host(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
+                                     const double *radii, const uint32_t *chanmask, int64_t n_atoms,
+                                     const mkb_grid_desc *grids, int32_t B, float *out_mapped, uint32_t *blk_rank,
+                                     int64_t rank_capacity, uint32_t *host_rank);
+int mkb_occupancy_wait_index(mkb_handle_t h);
 int mkb_occupancy_expand_host(const mkb_grid_desc *grids, int32_t g0, int32_t g1, const uint32_t *blk_rank,
                               const float *records, int64_t rec0, void *out, int32_t out_f64, int32_t n_threads);
 

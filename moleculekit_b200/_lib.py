@@ -33,6 +33,7 @@ EXPORTS = [
     "mkb_version", "mkb_create", "mkb_destroy", "mkb_last_error", "mkb_launch_count",
     "mkb_set_timing", "mkb_get_timing", "mkb_last_kernel",
     "mkb_occupancy_grid_batch_compact", "mkb_occupancy_compact_blocks", "mkb_occupancy_expand_host",
+    "mkb_occupancy_grid_batch_to_host", "mkb_occupancy_wait_index",
     "mkb_occupancy_grid_batch", "mkb_occupancy_grid_batch_masked", "mkb_occupancy_points",
     "mkb_grid_centers", "mkb_rotate_coords",
     "mkb_dist_trajectory", "mkb_contacts_count", "mkb_contacts_fill", "mkb_dist_reduction",
@@ -77,6 +78,8 @@ def load():
     lib.mkb_last_kernel.restype = C.c_char_p
     lib.mkb_occupancy_grid_batch.argtypes = [vp, vp, vp, vp, i64, i32, vp, i32, vp, u32]
     lib.mkb_occupancy_grid_batch_compact.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, i32, vp, vp, i64]
+    lib.mkb_occupancy_grid_batch_to_host.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, i32, vp, vp, i64, vp]
+    lib.mkb_occupancy_wait_index.argtypes = [vp]
     lib.mkb_occupancy_compact_blocks.argtypes = [vp, i32]
     lib.mkb_occupancy_compact_blocks.restype = i64
     lib.mkb_occupancy_expand_host.argtypes = [vp, i32, i32, vp, vp, i64, vp, i32, i32]

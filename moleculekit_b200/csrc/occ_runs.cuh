@@ -65,6 +65,8 @@ struct RunParams {
     const unsigned *blk_rank;    // compact output (mkb_occupancy_grid_batch_compact): exclusive count of non-empty blocks; block
                                  // b with atoms in reach is one 4 KB record [4 x][4 y][8 z][8 ch] at out + 1024 * blk_rank[b],
                                  // empty blocks are not written at all; nullptr = the dense grid
+    int sparse_dense;            // with blk_rank: keep the DENSE addressing (out may be mapped host memory) and only skip the empty
+                                 // blocks -- the host zero-fills them meanwhile (mkb_occupancy_grid_batch_to_host)
     // uniform batches: descriptor of the first grid + strides (constant-bank operands)
     GridDev u;
     long long u_out_stride;
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (p.blk_rank) {  // compact output: the whole 4 KB stage is one record, one bulk copy
+            if (p.blk_rank && !p.sparse_dense) {  // compact output: the whole 4 KB stage is one record, one bulk copy
                 if (lane == 0) bulk_store_row(p.out + 1024ll * __ldg(p.blk_rank + blk0 + (bzi - bz_begin)), stage_sa, 4096);
             } else if (row_ok) bulk_store_row(row_dst, stage_sa + lane * 256, row_bytes);
             if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");

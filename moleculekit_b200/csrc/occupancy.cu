@@ -1548,7 +1548,7 @@ using namespace mkb;
 static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
                                      const double *radii, const uint32_t *chanmask, int64_t n_atoms, int32_t C,
                                      const mkb_grid_desc *grids, int32_t B, float *out, uint32_t flags,
-                                     uint32_t *blk_rank = nullptr, int64_t rank_capacity = 0) {
+                                     uint32_t *blk_rank = nullptr, int64_t rank_capacity = 0, uint32_t *host_rank = nullptr) {
     MKB_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
     MKB_STREAM_ORDER(h, st);
@@ -1796,6 +1796,13 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
                 MKB_LAUNCHED(h);
                 MKB_CUDA(h, cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, blk_count, blk_rank, (int)(run_blocks + 1), sk));
                 h->launches++;
+                if (host_rank) {  // the block index leaves for the host NOW (side stream), before the fill kernel starts
+                    MKB_CUDA(h, cudaEventRecord(h->aux_ev[2], sk));
+                    MKB_CUDA(h, cudaStreamWaitEvent(h->aux_stream2, h->aux_ev[2], 0));
+                    MKB_CUDA(h, cudaMemcpyAsync(host_rank, blk_rank, sizeof(uint32_t) * (size_t)(run_blocks + 1), cudaMemcpyDeviceToHost, h->aux_stream2));
+                    MKB_CUDA(h, cudaEventRecord(h->aux_ev[3], h->aux_stream2));
+                    h->index_pending = true;
+                }
             }
             if (sk != st) {
                 MKB_CUDA(h, cudaEventRecord(h->aux_ev[2 + c], sk));
@@ -1809,6 +1816,7 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             rp.total_items = (unsigned)(item_off[c + 1] - item_off[c]);
             rp.cmajor = (flags & MKB_OCC_LAYOUT_CXYZ) ? 1 : 0;
             rp.blk_rank = blk_rank;
+            rp.sparse_dense = host_rank ? 1 : 0;
             bool uni = true;
             const GridDev &g0d = gd[g0];
             const long long nvox0 = (long long)g0d.dims[0] * g0d.dims[1] * g0d.dims[2];
@@ -1836,10 +1844,11 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             if (band_aside) MKB_CUDA(h, cudaStreamWaitEvent(st, h->aux_ev[1], 0));
             const unsigned fg = (unsigned)h->sm_count * 4;
             const int cm = (flags & MKB_OCC_LAYOUT_CXYZ) ? 1 : 0;
-            occ_fix_list_kernel<<<fg, 256, 0, st>>>(d_grids, B, d_fix, fix_cap, coords, sigmas, radii, chanmask, rec_tag, blk_start, blk_ent, out, cm, blk_rank);
+            const uint32_t *fix_rank = host_rank ? nullptr : blk_rank;  // dense addressing in the to-host mode
+            occ_fix_list_kernel<<<fg, 256, 0, st>>>(d_grids, B, d_fix, fix_cap, coords, sigmas, radii, chanmask, rec_tag, blk_start, blk_ent, out, cm, fix_rank);
             MKB_LAUNCHED(h);
             occ_fix_scan_kernel<<<fg, 256, 0, st>>>(d_grids, B, n_words, d_bitmap, d_fix, fix_cap, coords, sigmas, radii, chanmask,
-                                                    rec_tag, blk_start, blk_ent, out, cm, blk_rank);
+                                                    rec_tag, blk_start, blk_ent, out, cm, fix_rank);
             MKB_LAUNCHED(h);
         }
         return MKB_OK;
@@ -2023,6 +2032,25 @@ extern "C" int mkb_occupancy_grid_batch_compact(mkb_handle_t h, void *stream, co
                                      B, records, 0u, blk_rank, rank_capacity);
 }
 
+extern "C" int mkb_occupancy_grid_batch_to_host(mkb_handle_t h, void *stream, const float *coords, const double *sigmas,
+                                                const double *radii, const uint32_t *chanmask, int64_t n_atoms,
+                                                const mkb_grid_desc *grids, int32_t B, float *out_mapped, uint32_t *blk_rank,
+                                                int64_t rank_capacity, uint32_t *host_rank) {
+    if (h && n_atoms > 0 && !sigmas && (!radii || !chanmask)) return fail(h, MKB_ERR_BAD_ARG, "null sigmas and radii/chanmask");
+    if (h && (!blk_rank || !host_rank)) return fail(h, MKB_ERR_BAD_ARG, "null blk_rank / host_rank");
+    return occupancy_grid_batch_impl(h, stream, coords, sigmas, sigmas ? nullptr : radii, sigmas ? nullptr : chanmask, n_atoms, 8, grids,
+                                     B, out_mapped, 0u, blk_rank, rank_capacity, host_rank);
+}
+
+extern "C" int mkb_occupancy_wait_index(mkb_handle_t h) {
+    MKB_ENTER(h);
+    if (h->index_pending) {
+        MKB_CUDA(h, cudaEventSynchronize(h->aux_ev[3]));
+        h->index_pending = false;
+    }
+    return MKB_OK;
+}
+
 extern "C" int64_t mkb_occupancy_compact_blocks(const mkb_grid_desc *grids, int32_t B) {
     int64_t n = 0;
     for (int b = 0; b < B; ++b)
@@ -2091,8 +2119,7 @@ static int expand_host_impl(const mkb_grid_desc *grids, int32_t g0, int32_t g1, 
                             const int nfl = std::min(R_BZ, nz - bz * R_BZ) * 8;
                             const uint32_t r = blk_rank[bid0 + bz];
                             if (blk_rank[bid0 + bz + 1] != r) {
-                                const float *src = records + ((int64_t)r - rec0) * 1024 + (k * 4 + l) * 64;
-                                stream_copy(row + bz * 64, src, nfl);
+                                if (records) stream_copy(row + bz * 64, records + ((int64_t)r - rec0) * 1024 + (k * 4 + l) * 64, nfl);
                             } else stream_zero(row + bz * 64, nfl);
                         }
                     }

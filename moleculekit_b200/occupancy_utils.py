@@ -144,12 +144,51 @@ def occupancy_grid_batch_compact(coords: torch.Tensor, sigmas: torch.Tensor | No
     return records, blk_rank
 
 
+def occupancy_grid_batch_to_host(coords: torch.Tensor, sigmas: torch.Tensor | None, descs: np.ndarray, out_host: torch.Tensor,
+                                 radii: torch.Tensor | None = None, chanmask: torch.Tensor | None = None):
+    """K2+K1 storing the non-empty 4x4x8 blocks straight into ``out_host`` -- a PINNED host float32 tensor (sum M, 8), device
+    accessible under UVA -- while the block index travels to the host ahead of the fill kernel
+    (``mkb_occupancy_grid_batch_to_host``).  Returns the pinned int32 index (blocks + 1,); call :func:`wait_index`, zero-fill
+    the empty blocks with :func:`expand_compact_host` (``records=None``) and synchronise the stream before reading."""
+    dev = coords.device
+    assert coords.is_cuda and coords.dtype == torch.float32 and coords.is_contiguous() and coords.ndim == 2
+    assert not out_host.is_cuda and out_host.is_pinned() and out_host.dtype == torch.float32 and out_host.is_contiguous()
+    descs = np.ascontiguousarray(descs, dtype=_lib.GRID_DESC)
+    lib = _lib.load()
+    nblk = int(lib.mkb_occupancy_compact_blocks(descs.ctypes.data_as(C.c_void_p), int(descs.shape[0])))
+    blk_rank = torch.empty(nblk + 1, dtype=torch.int32, device=dev)
+    host_rank = torch.empty(nblk + 1, dtype=torch.int32, pin_memory=True)
+    if sigmas is not None:
+        assert sigmas.is_cuda and sigmas.dtype == torch.float64 and sigmas.is_contiguous() and sigmas.shape == (coords.shape[0], 8)
+    else:
+        assert radii is not None and chanmask is not None and radii.dtype == torch.float64 and chanmask.dtype == torch.int32
+    h = _lib.handle(dev.index)
+    null = C.c_void_p(0)
+    with torch.cuda.device(dev):
+        rc = lib.mkb_occupancy_grid_batch_to_host(
+            h, _stream_ptr(dev), C.c_void_p(coords.data_ptr()), C.c_void_p(sigmas.data_ptr()) if sigmas is not None else null,
+            C.c_void_p(radii.data_ptr()) if sigmas is None else null, C.c_void_p(chanmask.data_ptr()) if sigmas is None else null,
+            int(coords.shape[0]), descs.ctypes.data_as(C.c_void_p), int(descs.shape[0]), C.c_void_p(out_host.data_ptr()),
+            C.c_void_p(blk_rank.data_ptr()), int(blk_rank.numel()), C.c_void_p(host_rank.data_ptr()))
+    _lib.check(rc, h)
+    return host_rank, blk_rank
+
+
+def wait_index(device) -> None:
+    """Block until the block index of the last ``occupancy_grid_batch_to_host`` call on this device has reached the host."""
+    h = _lib.handle(torch.device(device).index if not isinstance(device, int) else device)
+    _lib.check(_lib.load().mkb_occupancy_wait_index(h), h)
+
+
 def default_host_threads() -> int:
     """Host threads for the compact-transfer expansion: the CPUs this process may use, shared fairly between the ranks of a
     one-process-per-GPU job on this host (torchrun's LOCAL_WORLD_SIZE), at most 32 -- beyond that the expansion is bound
-    by memory bandwidth, and 8 ranks x 32 threads oversubscribed a 128-thread host (80 ms instead of 25 ms per step)."""
+    by memory bandwidth, and 8 ranks x 32 threads oversubscribed a 128-thread host (80 ms instead of 25 ms per step).
+    ``MKB_HOST_THREADS`` overrides."""
     import os
 
+    if os.environ.get("MKB_HOST_THREADS"):
+        return max(1, int(os.environ["MKB_HOST_THREADS"]))
     try:
         n = len(os.sched_getaffinity(0))
     except Exception:
@@ -162,17 +201,18 @@ def default_host_threads() -> int:
 def expand_compact_host(descs: np.ndarray, g0: int, g1: int, blk_rank: np.ndarray, records: np.ndarray, rec0: int,
                         out: np.ndarray, n_threads: int = 0) -> None:
     """Host half of the compact transfer (``mkb_occupancy_expand_host``): grids [g0, g1) of the dense float32 (sum M, 8)
-    array ``out`` from the 4 KB block records (``records[0]`` is record ``rec0``).  Multi-threaded, releases the GIL."""
+    array ``out`` from the 4 KB block records (``records[0]`` is record ``rec0``; ``records=None`` only zero-fills the blocks
+    that have no record).  Multi-threaded, releases the GIL."""
     import os
 
     descs = np.ascontiguousarray(descs, dtype=_lib.GRID_DESC)
     assert blk_rank.dtype in (np.int32, np.uint32) and blk_rank.flags["C_CONTIGUOUS"]
-    assert records.dtype == np.float32 and records.flags["C_CONTIGUOUS"] and out.flags["C_CONTIGUOUS"]
-    assert out.dtype in (np.float32, np.float64)
+    assert records is None or (records.dtype == np.float32 and records.flags["C_CONTIGUOUS"])
+    assert out.flags["C_CONTIGUOUS"] and out.dtype in (np.float32, np.float64)
     if n_threads <= 0:
         n_threads = default_host_threads()
     rc = _lib.load().mkb_occupancy_expand_host(descs.ctypes.data_as(C.c_void_p), int(g0), int(g1), blk_rank.ctypes.data_as(C.c_void_p),
-                                               records.ctypes.data_as(C.c_void_p), int(rec0), out.ctypes.data_as(C.c_void_p),
+                                               records.ctypes.data_as(C.c_void_p) if records is not None else C.c_void_p(0), int(rec0), out.ctypes.data_as(C.c_void_p),
                                                1 if out.dtype == np.float64 else 0, int(n_threads))
     if rc != 0:
         raise ValueError("mkb_occupancy_expand_host: bad arguments")

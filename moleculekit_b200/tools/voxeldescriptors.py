@@ -388,6 +388,24 @@ def pinned_array(shape, dtype=np.float32) -> np.ndarray:
     return t.numpy()
 
 
+def _direct_to_host(batch, d_coords, d_chan, dev, out):
+    """Zero-copy route for a PINNED float32 result: the fill kernel stores the non-empty blocks straight into ``out`` over
+    PCIe (~30 % of the bytes, no staging buffer, no host copy) while host threads zero-fill the empty blocks -- the block
+    index reaches the host before the fill kernel starts."""
+    t_out = torch.from_numpy(out)
+    if isinstance(d_chan, tuple):
+        h_rank_t, _keep = _occ.occupancy_grid_batch_to_host(d_coords, None, batch.descs, t_out, radii=d_chan[0], chanmask=d_chan[1])
+    else:
+        h_rank_t, _keep = _occ.occupancy_grid_batch_to_host(d_coords, d_chan, batch.descs, t_out)
+    _occ.wait_index(dev)
+    h_rank = h_rank_t.numpy()
+    _occ.expand_compact_host(batch.descs, 0, batch.B, h_rank, None, 0, out)   # zeros for the blocks the GPU does not write
+    torch.cuda.current_stream(dev).synchronize()
+    LAST_TRANSFER.update(mode="direct", d2h_bytes=int(h_rank[-1]) * 4096 + int(h_rank.nbytes), records=int(h_rank[-1]),
+                         blocks=int(len(h_rank) - 1))
+    return out
+
+
 def _compact_to_host(batch, d_coords, d_chan, dev, out, dtype, n_chunks: int = 0):
     """Compact transfer: block records + index over PCIe in chunks, dense array rebuilt by host threads meanwhile."""
     if isinstance(d_chan, tuple):
@@ -461,7 +479,9 @@ def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, bu
     each grid channel-major: the list entries / tensor slices are then (C, X, Y, Z) (tensor: (B, C, X, Y, Z) when all
     grids have the same size).  ``nvoxels`` is (B, 3).
 
-    ``transfer``: how the grids cross PCIe.  "dense" copies the (sum M, C) float32 array; "compact" (8 channels,
+    ``transfer``: how the grids cross PCIe.  "dense" copies the (sum M, C) float32 array; "direct" (chosen by "auto" when
+    ``out`` is page-locked, e.g. from :func:`pinned_array`) lets the fill kernel store the non-empty blocks straight into
+    ``out`` while host threads zero the others; "compact" (8 channels,
     voxel-major) copies only the 4x4x8-voxel blocks that have an atom within 5 A (~30 % of a protein pocket grid) plus a
     block index, in chunks, while host threads rebuild the dense array -- float32 or, upcast on the fly, the reference's
     float64 -- with identical bytes; "auto" takes the compact route when it applies."""
@@ -474,8 +494,10 @@ def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, bu
             raise ValueError("rotation_centers is required with rotations")
         d_coords = batch.rotate(d_coords, rotations, rotation_centers)
     cx = layout == "cxyz"
-    if transfer not in ("auto", "dense", "compact"):
-        raise ValueError("transfer must be 'auto', 'dense' or 'compact'")
+    if transfer not in ("auto", "dense", "compact", "direct"):
+        raise ValueError("transfer must be 'auto', 'dense', 'compact' or 'direct'")
+    if transfer == "direct" and (out is None or not torch.from_numpy(out).is_pinned()):
+        raise ValueError("transfer='direct' needs a page-locked float32 `out` (tools.voxeldescriptors.pinned_array)")
     want_dtype = np.float32 if out is not None else (np.dtype(dtype) if dtype is not None else np.dtype(np.float32))
     compact_ok = (not return_tensor and not cx and batch.C == 8 and np.dtype(want_dtype) in (np.dtype(np.float32), np.dtype(np.float64))
                   and batch.total_voxels > 0)
@@ -491,7 +513,10 @@ def getVoxelDescriptorsBatch(coords, channels, *, boxsize=None, centers=None, bu
         if out is not None and (out.dtype != np.float32 or out.shape != (batch.total_voxels, batch.C) or not out.flags["C_CONTIGUOUS"]):
             raise ValueError(f"out must be a C-contiguous float32 array of shape {(batch.total_voxels, batch.C)}")
         try:
-            host = _compact_to_host(batch, d_coords, d_chan, dev, out, want_dtype)
+            if transfer != "compact" and out is not None and torch.from_numpy(out).is_pinned():
+                host = _direct_to_host(batch, d_coords, d_chan, dev, out)
+            else:
+                host = _compact_to_host(batch, d_coords, d_chan, dev, out, want_dtype)
             return batch.split(host), batch.dims.copy()
         except _lib_mod.MkbUnsupported:
             if transfer == "compact":

@@ -253,6 +253,13 @@ def test_compact_transfer_equals_dense(vd):
         vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], out=out, transfer="compact", **kw)
         assert vd.LAST_TRANSFER["mode"] == "compact" and vd.LAST_TRANSFER["d2h_bytes"] < out.nbytes
         assert np.array_equal(out, np.concatenate(dense))
+        for fill in (7.0, np.nan):  # "direct": the fill kernel stores non-empty blocks into the pinned result, host zeros the rest
+            out[:] = fill
+            vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], out=out, transfer="direct", **kw)
+            assert vd.LAST_TRANSFER["mode"] == "direct" and vd.LAST_TRANSFER["d2h_bytes"] < out.nbytes
+            assert np.array_equal(out.view(np.uint32), np.concatenate(dense).view(np.uint32))
+        with pytest.raises(ValueError):
+            vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], out=np.empty((total, 8), np.float32), transfer="direct", **kw)
         out[:] = 5.0
         vd.getVoxelDescriptorsBatch(w["coords"], w["sigmas"], out=out, **kw)  # "auto": a batch this small goes dense
         assert vd.LAST_TRANSFER["mode"] == "dense" and np.array_equal(out, np.concatenate(dense))
