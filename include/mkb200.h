@@ -52,6 +52,9 @@ typedef struct mkb_ctx *mkb_handle_t;
 /* output modes of the distance entry points (host post-ops of projections/util.py:74-84 fused in) */
 #define MKB_DIST_DISTANCES 0 /* float32 distances, optionally truncated */
 #define MKB_DIST_CONTACTS 1  /* uint8 (bool) = distance <= threshold, after optional truncate */
+#define MKB_DIST_DISTANCES_FAST 4 /* float32 distances within 4 ulp of the reference's float32 sequence (the reference's
+                                     minimum-image roundings, fused sum of squares, approximate square root); same NaN
+                                     pattern; BASELINE north star asks for 1e-5 relative.  mkb_dist_trajectory only. */
 
 int mkb_version(void);
 int mkb_create(int device, mkb_handle_t *out);

@@ -15,6 +15,7 @@ OCC_ACCUMULATE = 1
 OCC_LAYOUT_CXYZ = 2
 DIST_DISTANCES = 0
 DIST_CONTACTS = 1
+DIST_DISTANCES_FAST = 4
 
 # numpy mirror of `mkb_grid_desc` (72 bytes, no padding)
 GRID_DESC = np.dtype(

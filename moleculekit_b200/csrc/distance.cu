@@ -225,9 +225,44 @@ __device__ __forceinline__ bool pair_contact(const float4 a, const float4 b, uns
     return pair_d2_fastwrap(a, b, cb, bx, pbc) <= T;
 }
 
+// MKB_DIST_DISTANCES_FAST: float32 distances within 4 ulp of the reference's sequence instead of its exact bits.
+// The minimum-image step keeps the reference's own roundings, w = fl(d - fl(b n)) with n = rint(d * fl(1/b)) -- so w is
+// bit-identical whenever n is the reference's roundf(fl(d/b)), and when the two integers differ (d/b within 2e-7 of a
+// half-integer) both |w| are b/2 (1 -+ 4e-7).  What is dropped: the test for that case, the unfused sum of squares
+// (two FFMA instead of four roundings) and the correctly rounded square root (MUFU.SQRT, <= 1 ulp + flush of subnormal
+// d2 to 0).  Same NaN behaviour (zero / non-finite boxes); quotients |d/b| >= 2^22 are outside the magic rounding's range.
+// 21 instead of 48 instructions per pair: the kernel becomes HBM-store bound.
+__device__ __forceinline__ float pair_d2_quick(const float4 a, const float4 b, unsigned cb, const BoxF &bx, int pbc) {
+    float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    if (pbc && (__float_as_uint(a.w) != cb)) {
+        const float nx = __fsub_rn(fmaf(dx, bx.rx, 12582912.0f), 12582912.0f);
+        const float ny = __fsub_rn(fmaf(dy, bx.ry, 12582912.0f), 12582912.0f);
+        const float nz = __fsub_rn(fmaf(dz, bx.rz, 12582912.0f), 12582912.0f);
+        dx = __fsub_rn(dx, __fmul_rn(bx.bx, nx));
+        dy = __fsub_rn(dy, __fmul_rn(bx.by, ny));
+        dz = __fsub_rn(dz, __fmul_rn(bx.bz, nz));
+    }
+    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+__device__ __forceinline__ float sqrt_quick(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+constexpr int DIST_QUICK = MKB_DIST_DISTANCES_FAST;
+
+template <int MODE>
+__device__ __forceinline__ float pair_d2_of(const float4 a, const float4 b, unsigned cb, const BoxF &bx, int pbc) {
+    return MODE == DIST_QUICK ? pair_d2_quick(a, b, cb, bx, pbc) : pair_d2_fastwrap(a, b, cb, bx, pbc);
+}
+
 template <int MODE, bool TRUNC = true>
 __device__ __forceinline__ void emit_dist(void *out, long long idx, float d2, float truncate, float threshold) {
-    if (MODE == DIST_CONTACTS_D2) reinterpret_cast<unsigned char *>(out)[idx] = (d2 <= threshold) ? 1 : 0;
+    if (MODE == DIST_QUICK) {
+        float d = sqrt_quick(d2);
+        if (TRUNC && d > truncate) d = truncate;
+        reinterpret_cast<float *>(out)[idx] = d;
+    } else if (MODE == DIST_CONTACTS_D2) reinterpret_cast<unsigned char *>(out)[idx] = (d2 <= threshold) ? 1 : 0;
     else if (MODE == MKB_DIST_DISTANCES && !TRUNC) reinterpret_cast<float *>(out)[idx] = __fsqrt_rn(d2);  // no truncate given
     else store_dist<MODE>(out, idx, __fsqrt_rn(d2), truncate, threshold);
 }
@@ -282,9 +317,9 @@ __global__ void MKB_K3_BOUNDS dist_kernel(const float4 *__restrict__ G1, const f
 #pragma unroll 2
         for (int r = 0; r < rows; ++r) {
             const float4 a = __ldg(arow + r);
-            if (j0 > i0 + r) emit_dist<MODE>(out, idx, pair_d2_fastwrap(a, b0, cb0, bx, pbc), truncate, threshold);
+            if (j0 > i0 + r) emit_dist<MODE>(out, idx, pair_d2_of<MODE>(a, b0, cb0, bx, pbc), truncate, threshold);
             if (has1 && j1 > i0 + r)
-                emit_dist<MODE>(out, idx + K3_COLS, pair_d2_fastwrap(a, b1, cb1, bx, pbc), truncate, threshold);
+                emit_dist<MODE>(out, idx + K3_COLS, pair_d2_of<MODE>(a, b1, cb1, bx, pbc), truncate, threshold);
             idx += step;
             --step;
         }
@@ -292,13 +327,13 @@ __global__ void MKB_K3_BOUNDS dist_kernel(const float4 *__restrict__ G1, const f
 #pragma unroll 2
         for (int r = 0; r < rows; ++r) {
             const float4 a = __ldg(arow + r);
-            emit_dist<MODE, TRUNC>(out, idx, pair_d2_lean(a, b0, cb0, bx, pbc), truncate, threshold);
-            emit_dist<MODE, TRUNC>(out, idx + K3_COLS, pair_d2_lean(a, b1, cb1, bx, pbc), truncate, threshold);
+            emit_dist<MODE, TRUNC>(out, idx, MODE == DIST_QUICK ? pair_d2_quick(a, b0, cb0, bx, pbc) : pair_d2_lean(a, b0, cb0, bx, pbc), truncate, threshold);
+            emit_dist<MODE, TRUNC>(out, idx + K3_COLS, MODE == DIST_QUICK ? pair_d2_quick(a, b1, cb1, bx, pbc) : pair_d2_lean(a, b1, cb1, bx, pbc), truncate, threshold);
             idx += n2;
         }
     } else {
         for (int r = 0; r < rows; ++r) {
-            emit_dist<MODE>(out, idx, pair_d2_fastwrap(__ldg(arow + r), b0, cb0, bx, pbc), truncate, threshold);
+            emit_dist<MODE>(out, idx, pair_d2_of<MODE>(__ldg(arow + r), b0, cb0, bx, pbc), truncate, threshold);
             idx += n2;
         }
     }
@@ -644,7 +679,8 @@ extern "C" int mkb_dist_trajectory(mkb_handle_t h, void *stream, const mkb_traj 
     int rc = check_traj(h, t);
     if (rc) return rc;
     if (n1 < 0 || n2 < 0) return fail(h, MKB_ERR_BAD_ARG, "negative selection size");
-    if (mode != MKB_DIST_DISTANCES && mode != MKB_DIST_CONTACTS) return fail(h, MKB_ERR_BAD_ARG, "bad mode %d", mode);
+    if (mode != MKB_DIST_DISTANCES && mode != MKB_DIST_CONTACTS && mode != MKB_DIST_DISTANCES_FAST)
+        return fail(h, MKB_ERR_BAD_ARG, "bad mode %d", mode);
     if (selfdist && n1 != n2) return fail(h, MKB_ERR_BAD_ARG, "selfdist needs sel1 == sel2");
     const long long P = selfdist ? (n1 * (n2 - 1)) / 2 : n1 * n2;
     if (t->n_frames == 0 || P <= 0) return MKB_OK;
@@ -682,6 +718,11 @@ extern "C" int mkb_dist_trajectory(mkb_handle_t h, void *stream, const mkb_traj 
             else MKB_K3_LAUNCH(MKB_DIST_DISTANCES, false);
         } else if (kmode == MKB_DIST_CONTACTS) {
             if (selfdist) MKB_K3_LAUNCH(MKB_DIST_CONTACTS, true); else MKB_K3_LAUNCH(MKB_DIST_CONTACTS, false);
+        } else if (kmode == DIST_QUICK) {
+            if (selfdist) MKB_K3_LAUNCH(DIST_QUICK, true);
+            else if (truncate != truncate)
+                dist_kernel<DIST_QUICK, false, false><<<grid, K3_COLS, 0, st>>>(G1, G2, n1, n2, t->box, t->frame_stride_box, pbc, truncate, kthr, P, out, f0);
+            else MKB_K3_LAUNCH(DIST_QUICK, false);
         } else {
             if (selfdist) MKB_K3_LAUNCH(DIST_CONTACTS_D2, true); else MKB_K3_LAUNCH(DIST_CONTACTS_D2, false);
         }

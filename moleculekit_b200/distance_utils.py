@@ -53,14 +53,17 @@ def n_columns(n1: int, n2: int, selfdist: bool) -> int:
 
 # ------------------------------------------------------------------------------------------------ device level
 def dist_trajectory_device(coords, box, sel1, sel2, chains, selfdist: bool, pbc: bool, *, metric: str = "distances",
-                           truncate: float | None = None, threshold: float = 8.0, out: torch.Tensor | None = None):
-    """K3 on CUDA tensors.  Returns (F, P) float32 distances or bool contacts (post-ops fused, util.py:74-84)."""
+                           truncate: float | None = None, threshold: float = 8.0, out: torch.Tensor | None = None,
+                           exact: bool = True):
+    """K3 on CUDA tensors.  Returns (F, P) float32 distances or bool contacts (post-ops fused, util.py:74-84).
+    ``exact=False`` (distances only): MKB_DIST_DISTANCES_FAST, within 4 ulp of the reference's float32 values instead of
+    bit-identical (contact maps are always the reference's booleans)."""
     dev = coords.device
     F = coords.shape[2]
     P = n_columns(len(sel1), len(sel2), selfdist)
-    mode = _lib.DIST_CONTACTS if metric == "contacts" else _lib.DIST_DISTANCES
+    mode = _lib.DIST_CONTACTS if metric == "contacts" else (_lib.DIST_DISTANCES if exact else _lib.DIST_DISTANCES_FAST)
     if out is None:
-        out = torch.empty((F, P), dtype=torch.uint8 if mode else torch.float32, device=dev)  # the kernel writes every element
+        out = torch.empty((F, P), dtype=torch.uint8 if mode == _lib.DIST_CONTACTS else torch.float32, device=dev)  # the kernel writes every element
     h = _lib.handle(dev.index)
     tr = _traj(coords, box)
     with torch.cuda.device(dev):
@@ -69,7 +72,7 @@ def dist_trajectory_device(coords, box, sel1, sel2, chains, selfdist: bool, pbc:
             int(bool(selfdist)), int(bool(pbc)), mode, _NAN if truncate is None else float(truncate),
             float(threshold), _ptr(out))
     _lib.check(rc, h)
-    return out.view(torch.bool) if mode else out
+    return out.view(torch.bool) if mode == _lib.DIST_CONTACTS else out
 
 
 def contacts_trajectory_device(coords, box, sel1, sel2, chains, selfdist: bool, pbc: bool, dist_threshold: float):
@@ -197,9 +200,10 @@ def _sel_dev(sel, remap, dev):
 
 
 def dist_trajectory(coords, box, sel1, sel2, digitized_chains, selfdist, pbc, results, device=None,
-                    metric: str = "distances", truncate=None, threshold: float = 8.0):
+                    metric: str = "distances", truncate=None, threshold: float = 8.0, exact: bool = True):
     """Drop-in for distance_utils.pyx:126-155 (results (F, P) float32 filled in place).  The optional keywords fuse the
-    post-ops of pp_calcDistances; with metric="contacts" a new bool array is returned instead."""
+    post-ops of pp_calcDistances; with metric="contacts" a new bool array is returned instead.  ``exact=False``: distances
+    within 4 ulp of the reference's float32 values (about twice the kernel throughput) instead of bit-identical."""
     _check("coords", coords, np.float32, 3); _check("box", box, np.float32, 2)
     _check("sel1", sel1, np.uint32, 1); _check("sel2", sel2, np.uint32, 1)
     _check("digitized_chains", digitized_chains, np.uint32, 1)
@@ -212,7 +216,7 @@ def dist_trajectory(coords, box, sel1, sel2, digitized_chains, selfdist, pbc, re
     d_coords, d_box, remap, d_ch, _ = upload_selected(coords, box, [sel1, sel2], digitized_chains, device=device)
     dev = d_coords.device
     out = dist_trajectory_device(d_coords, d_box, _sel_dev(sel1, remap, dev), _sel_dev(sel2, remap, dev), d_ch,
-                                 selfdist, pbc, metric=metric, truncate=truncate, threshold=threshold)
+                                 selfdist, pbc, metric=metric, truncate=truncate, threshold=threshold, exact=exact)
     if metric == "contacts":
         # page-locked result (torch's caching host allocator recycles the block once the array is dropped): the (F, P)
         # map leaves the GPU at PCIe rate instead of through the driver's pageable staging

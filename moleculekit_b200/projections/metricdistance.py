@@ -41,6 +41,9 @@ class MetricDistance(Projection):
         self.metric, self.threshold, self.truncate = metric, threshold, truncate
         self.groupreduce1, self.groupreduce2, self.pairs = groupreduce1, groupreduce2, pairs
         self.device = None  # CUDA device for project(); None = current device
+        # True: float32 distances bit-identical to the reference.  False: atom-atom distances within 4 ulp of them
+        # (MKB_DIST_DISTANCES_FAST, about twice the kernel throughput); contacts and group reductions are unaffected
+        self.exact = True
 
     # ------------------------------------------------------------------ selections
     def _calculateMolProp(self, mol, props="all"):
@@ -118,7 +121,7 @@ class MetricDistance(Projection):
             if self.pairs:
                 raise RuntimeError("Pairs calculation not implemented without groups")
             return pp_calcDistances(mol, sel1, sel2, self.periodic, self.metric, self.threshold,
-                                    truncate=self.truncate, device=self.device)
+                                    truncate=self.truncate, device=self.device, exact=self.exact)
         return get_reduced_distances(mol, sel1, sel2, self.periodic, self.metric, self.threshold,
                                      truncate=self.truncate, reduction1=self.groupreduce1,
                                      reduction2=self.groupreduce2, pairs=self.pairs, device=self.device)

@@ -49,7 +49,7 @@ def digitize_chains(mol, periodic, sel2_atoms):
 
 
 def pp_calcDistances(mol, sel1, sel2, periodic, metric: str = "distances", threshold: float = 8, gap=1,
-                     truncate=None, device=None):
+                     truncate=None, device=None, exact: bool = True):
     """(F, n1*n2 | n1(n2-1)/2) float32 distances or bool contacts between two boolean atom masks."""
     selfdist = np.array_equal(sel1, sel2)
     sel1 = np.where(sel1)[0].astype(np.uint32)
@@ -61,7 +61,7 @@ def pp_calcDistances(mol, sel1, sel2, periodic, metric: str = "distances", thres
     shape = (mol.numFrames, _du.n_columns(len(sel1), len(sel2), selfdist))
     results = np.zeros(shape, dtype=np.float32)
     res = _du.dist_trajectory(coords, box, sel1, sel2, chains, selfdist, periodic is not None, results,
-                              device=device, metric=metric, truncate=truncate, threshold=threshold)
+                              device=device, metric=metric, truncate=truncate, threshold=threshold, exact=exact)
     return res
 
 

@@ -162,6 +162,89 @@ def test_random_vs_oracle_large_wraps_and_half_ties(du, oracle):
         assert du.contacts_trajectory(c, bx, a, b, ch, selfd, True, 9.5) == oracle.contacts_trajectory(c, bx, a, b, ch, selfd, True, 9.5)
 
 
+def _ulps(got, want):
+    """distance in float32 units in the last place (finite, non-negative values)"""
+    return np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+
+
+def test_fast_distances_within_tolerance(du, oracle, mol, g_traj):
+    """exact=False (MKB_DIST_DISTANCES_FAST): the reference's minimum-image roundings, a fused sum of squares and MUFU.SQRT.
+    Tolerance written here: 2e-6 relative (BASELINE's north star allows 1e-5), >= 99.9 % of the values within 4 ulp, the
+    same NaN and zero pattern; pairs whose quotient |d/box| reaches 2^21 are outside the mode's stated domain."""
+    rng = np.random.default_rng(23)
+    N, F = 200, 41
+    c = np.cumsum(rng.normal(size=(N, 3, F)).astype(np.float32) * 3, axis=2) + (rng.normal(size=(N, 3, 1)) * 60).astype(np.float32)
+    c[:30] = np.round(c[:30])
+    c[5] = c[4]  # coincident atoms: distance exactly 0
+    bx = np.abs(rng.normal(size=(3, F)) * 6 + 31).astype(np.float32)
+    bx[:, :5] = np.array([[2.0], [4.0], [6.0]], np.float32)  # exact half-integer quotients with the integer coordinates
+    bx[2, -1] = 0.0   # NaN frame
+    bx[0, -2] = np.inf
+    ch = rng.integers(0, 3, N).astype(np.uint32)
+    s1 = np.sort(rng.choice(N, 80, replace=False)).astype(np.uint32); s1[:2] = (4, 5); s1.sort()
+    s2 = np.sort(rng.choice(N, 130, replace=False)).astype(np.uint32)
+    worst = 0
+    for selfd, a, b, tr in ((False, s1, s2, None), (True, s1, s1, None), (False, s1, s2, 17.25), (False, s1[:3], s2[:1], None)):
+        P = du.n_columns(len(a), len(b), selfd)
+        want = np.zeros((F, P), np.float32)
+        with np.errstate(all="ignore"):
+            oracle.dist_trajectory(c, bx, a, b, ch, selfd, True, want)
+        if tr is not None:
+            want[want > tr] = tr
+        got = np.full((F, P), -1.0, np.float32)
+        du.dist_trajectory(c, bx, a, b, ch, selfd, True, got, truncate=tr, exact=False)
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(want).any()
+        ok = ~np.isnan(want)
+        assert np.array_equal(got[ok] == 0, want[ok] == 0) and (selfd or tr is not None or P < 10 or (want[ok] == 0).any())
+        np.testing.assert_allclose(got[ok], want[ok], rtol=2e-6, atol=0)
+        u = _ulps(got[ok], want[ok])
+        assert (u <= 4).mean() >= 0.999, (u.max(), (u > 4).mean())
+        worst = max(worst, int(u.max()))
+        exact = np.zeros((F, P), np.float32); du.dist_trajectory(c, bx, a, b, ch, selfd, True, exact, truncate=tr)
+        assert np.array_equal(_bits(exact), _bits(want))   # the default stays bit-identical on the same inputs
+    assert worst <= 32
+
+    # differences within +-3 ulp of 0.5, 1.5, 2.5 ... box lengths (the image integer may differ from the reference's there)
+    boxes = np.array([10.0, 7.3, 33.333, 8.0, 3e4, -5.0, np.nan, np.inf, 0.0], np.float32)
+    Fb = len(boxes)
+    mults = [0.0, 0.25, 0.5, 0.75, 1.0, 1.4998, 1.4999, 1.49995, 1.5, 2.0, 2.5, 3.5, 100.5]
+    cols = []
+    for f in range(Fb):
+        bb = boxes[f] if np.isfinite(boxes[f]) and boxes[f] != 0 else np.float32(6.0)
+        vals = []
+        for m in mults:
+            v = np.float32(np.float32(m) * np.abs(bb))
+            for k in range(-3, 4):
+                w = v
+                for _ in range(abs(k)):
+                    w = np.nextafter(w, np.float32(np.inf if k > 0 else -np.inf), dtype=np.float32)
+                vals += [w, -w]
+        cols.append(np.array(vals, np.float32))
+    n2 = len(cols[0])
+    cb = np.zeros((1 + n2, 3, Fb), np.float32)
+    for f in range(Fb):
+        cb[1:, 0, f] = cols[f]; cb[1:, 1, f] = cols[f][::-1]; cb[1:, 2, f] = np.roll(cols[f], 5)
+    bxb = np.repeat(boxes[None, :], 3, axis=0).copy()
+    sa = np.array([0], np.uint32); sb = np.arange(1, 1 + n2, dtype=np.uint32)
+    chb = np.zeros(1 + n2, np.uint32); chb[1:] = 1
+    want = np.zeros((Fb, n2), np.float32)
+    with np.errstate(all="ignore"):
+        oracle.dist_trajectory(cb, bxb, sa, sb, chb, False, True, want)
+    got = np.zeros((Fb, n2), np.float32); du.dist_trajectory(cb, bxb, sa, sb, chb, False, True, got, exact=False)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(want).any() and np.isfinite(want).any()
+    ok = ~np.isnan(want)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=2e-6, atol=0)
+
+    # through the projection: MetricDistance.exact = False against the frozen output of the reference's compiled kernel
+    from moleculekit_b200.projections.metricdistance import MetricDistance
+
+    m = MetricDistance("protein and name CA", "resname MOL and noh", metric="distances", periodic="selections")
+    m.exact = False
+    data = m.project(mol)
+    np.testing.assert_allclose(data, g_traj["ref_distances"], rtol=2e-6, atol=0)
+    assert (_ulps(data, g_traj["ref_distances"]) <= 4).mean() >= 0.999
+
+
 def test_minimum_image_boundaries(du, oracle):
     """The dense kernels take n = rint(d * (1/b)) and verify it with |d - b n| < b/2 - 1e-6 |d|: differences placed
     within a few ulps of b/2, 1.4999 b, 1.5 b, 2.5 b (both signs), boxes that are powers of two / arbitrary / tiny / huge /
