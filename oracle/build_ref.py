@@ -33,6 +33,7 @@ MODULES = {
     "wrapping": "moleculekit/wrapping/wrapping.pyx",
     "atomselect_utils": "moleculekit/atomselect_utils/atomselect_utils.pyx",
     "xtc": "moleculekit/fileformats/xtc/xtc.pyx",
+    "hbonds": "moleculekit/interactions/hbonds/hbonds.pyx",
 }
 
 # extra C++ sources / include directories of a module (the reference's setup.py:55-66 lists the same files)

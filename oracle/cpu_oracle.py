@@ -11,7 +11,7 @@ order mirror the reference's Cython modules so parity tests read like the refere
   moleculekit/distance_utils/distance_utils.pyx:286    dist_trajectory_reduction_pairs
   moleculekit/distance_utils/distance_utils.pyx:355+   cdist / pdist / squareform
 
-Parity status: PINNED (oracle/pin_oracle.py; tests/test_oracle_golden.py).
+Parity status: PINNED (tests/test_oracle_golden.py).
 """
 from __future__ import annotations
 
@@ -48,6 +48,8 @@ def lib():
         _lib.oracle_get_collisions.restype = C.c_int64
         _lib.oracle_squareform_dim.restype = C.c_int64
         _lib.oracle_bond_grid_search.restype = C.c_int64
+        _lib.oracle_wrap_compact.restype = C.c_int64
+        _lib.oracle_hbonds.restype = C.c_int64
     return _lib
 
 
@@ -230,6 +232,63 @@ def wrap_box(groups, coords, box, centersel, center):
     assert box.shape == (3, F)
     lib().oracle_wrap_box(_p(groups), C.c_int64(len(groups)), _p(coords), _p(box), C.c_int64(F),
                           _p(centersel), C.c_int64(len(centersel)), _p(center))
+
+
+WRAP_MAX_ITER = 1 << 20  # bound of the reference's unbounded `while` loops (same bound in the CUDA kernels)
+
+
+def _tric_args(groups, coords, boxvectors, centersel, center):
+    assert coords.dtype == np.float32 and coords.flags["C_CONTIGUOUS"] and coords.ndim == 3 and coords.shape[1] == 3
+    groups, centersel = _u32(groups), _u32(centersel)
+    bv = np.ascontiguousarray(boxvectors, dtype=np.float64)
+    center = _f32(center)
+    F = coords.shape[2]
+    assert bv.shape == (3, 3, F)
+    return groups, bv, centersel, center, F
+
+
+def wrap_triclinic_unitcell(groups, coords, boxvectors, centersel, center):
+    """moleculekit/wrapping/wrapping.pyx:147-250 (same arguments); coords (N, 3, F) float32 C-contiguous, in place."""
+    groups, bv, centersel, center, F = _tric_args(groups, coords, boxvectors, centersel, center)
+    lib().oracle_wrap_triclinic(_p(groups), C.c_int64(len(groups)), _p(coords), C.c_int64(coords.shape[0]), _p(bv),
+                                C.c_int64(F), _p(centersel), C.c_int64(len(centersel)), _p(center),
+                                C.c_int64(WRAP_MAX_ITER))
+
+
+def wrap_compact_unitcell(groups, coords, boxvectors, centersel, center, mode):
+    """moleculekit/wrapping/wrapping.pyx:255-344 (same arguments); mode 0 = rectangular, 1 = compact; in place."""
+    groups, bv, centersel, center, F = _tric_args(groups, coords, boxvectors, centersel, center)
+    rc = lib().oracle_wrap_compact(_p(groups), C.c_int64(len(groups)), _p(coords), C.c_int64(coords.shape[0]), _p(bv),
+                                   C.c_int64(F), _p(centersel), C.c_int64(len(centersel)), _p(center), C.c_int(mode),
+                                   C.c_int64(WRAP_MAX_ITER))
+    if rc < 0:
+        raise ValueError("Too many triclinic vectors!!")
+
+
+def hbonds_calculate(donors, acceptors, coords, box, sel1, sel2, dist_threshold=2.5, angle_threshold=120, intra=False,
+                     ignore_hs=False):
+    """moleculekit/interactions/hbonds/hbonds.pyx:25-134 `calculate` (same arguments): list over frames of flat int lists
+    (heavy, hydrogen | -1, acceptor, ...)."""
+    donors = np.ascontiguousarray(donors, dtype=np.uint32).reshape(len(donors), -1)
+    if donors.shape[1] == 1:  # ignore_hs callers pass (n, 1)
+        donors = np.ascontiguousarray(np.hstack([donors, donors]))
+    acceptors, sel1, sel2 = _u32(acceptors), _u32(sel1), _u32(sel2)
+    coords, box = _f32(coords), _f32(box)
+    F = coords.shape[2]
+    counts = np.zeros(F, dtype=np.int64)
+    args = lambda out, cap: (_p(donors), C.c_int64(len(donors)), _p(acceptors), C.c_int64(len(acceptors)), _p(coords),
+                             _p(box), C.c_int64(F), _p(sel1), _p(sel2), C.c_float(dist_threshold),
+                             C.c_float(angle_threshold), C.c_int(int(intra)), C.c_int(int(ignore_hs)), _p(counts),
+                             _p(out), C.c_int64(cap))
+    dummy = np.zeros(3, dtype=np.int32)
+    total = lib().oracle_hbonds(*args(dummy, 0))
+    out = np.zeros(max(3 * total, 3), dtype=np.int32)
+    lib().oracle_hbonds(*args(out, total))
+    res, pos = [], 0
+    for f in range(F):
+        res.append(out[3 * pos:3 * (pos + counts[f])].tolist())
+        pos += int(counts[f])
+    return res
 
 
 def within_distance(coords, cutoff, sel1, sel2, sel2_min_coords, sel2_max_coords, results):

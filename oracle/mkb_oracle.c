@@ -5,7 +5,7 @@
  * --impl reference legs of bench.py may load this library.  The product path
  * (moleculekit_b200/) never links, imports or calls it and has no CPU fallback.
  *
- * Parity is PINNED: oracle/pin_oracle.py checks every function below bit-for-bit against the
+ * Parity is PINNED: tests/test_oracle_golden.py checks every function below bit-for-bit against the
  * reference's own Cython kernels compiled from /root/reference (oracle/_ref, see
  * oracle/build_ref.py) and against the reference's golden vectors (tests/golden/).
  *
@@ -632,4 +632,296 @@ EXPORT int oracle_xtc_decode_block(const uint8_t *data, int64_t nbytes, int64_t 
         sizesmall[0] = sizesmall[1] = sizesmall[2] = (uint32_t)xtc_magic[smallidx];
     }
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Triclinic / compact wrapping -- moleculekit/wrapping/wrapping.pyx:147-344 (Molecule.wrap for cells
+ * with a box angle != 90, moleculekit/molecule.py:2078-2090).  coords (n_atoms, 3, F) float32 frame
+ * minor, in place; boxvectors (3, 3, F) float64, row i = box vector i.  The reference mixes float32
+ * state (wrap_center, box_middle, grp_center) with float64 box arithmetic; every assignment below keeps
+ * the C type the generated code has (float op float -> float, float op double -> double, rounded to
+ * float on store).  The running means are as in wrap_box.
+ * ------------------------------------------------------------------------------------------------ */
+static void tric_frame_setup(const double *bv, int64_t F, int64_t f, float *coords, int64_t n_atoms,
+                             const uint32_t *centersel, int64_t n_centersel, float wrap_center[3],
+                             double box[3][3], float box_middle[3])
+{
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) box[i][j] = bv[(i * 3 + j) * F + f];
+    if (n_centersel > 0) {                                                    /* pyx:180-185 / 271-276 */
+        for (int i = 0; i < 3; ++i) wrap_center[i] = 0.f;
+        for (int64_t n = 0; n < n_centersel; ++n)
+            for (int i = 0; i < 3; ++i) {
+                const float x = coords[((int64_t)centersel[n] * 3 + i) * F + f];
+                wrap_center[i] = wrap_center[i] + (x - wrap_center[i]) / (float)(n + 1);
+            }
+    }
+    for (int i = 0; i < 3; ++i) box_middle[i] = 0.f;                          /* pyx:187-191 / 278-282 */
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) box_middle[j] = (float)((double)box_middle[j] + 0.5 * box[i][j]);
+    (void)n_atoms;
+}
+
+/* pyx:147-250 wrap_triclinic_unitcell.  The while loops of the reference never end for a box whose
+ * diagonal element is <= 0 while the centre is outside; `max_iter` bounds them here (the GPU kernel
+ * uses the same bound) -- inputs that reach it have no reference result. */
+EXPORT void oracle_wrap_triclinic(const uint32_t *groups, int64_t n_groups, float *coords, int64_t n_atoms,
+                                  const double *boxvectors, int64_t F, const uint32_t *centersel,
+                                  int64_t n_centersel, const float *center, int64_t max_iter)
+{
+    float wrap_center[3] = {0.f, 0.f, 0.f}, box_middle[3], grp_center[3], grp_center_init[3] = {0.f, 0.f, 0.f};
+    double box[3][3], shift_center[3];
+    if (n_centersel == 0)
+        for (int i = 0; i < 3; ++i) wrap_center[i] = center[i];
+    for (int64_t f = 0; f < F; ++f) {
+        tric_frame_setup(boxvectors, F, f, coords, n_atoms, centersel, n_centersel, wrap_center, box, box_middle);
+        const double shm01 = box[1][0] / box[1][1];                           /* pyx:198-200 */
+        const double shm02 = (box[1][1] * box[2][0] - box[2][1] * box[1][0]) / (box[1][1] * box[2][2]);
+        const double shm12 = box[2][1] / box[2][2];
+        for (int i = 0; i < 3; ++i) shift_center[i] = 0.0;                    /* pyx:203-213 */
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) shift_center[j] = shift_center[j] + box[i][j];
+        for (int i = 0; i < 3; ++i) shift_center[i] = shift_center[i] * 0.5;
+        for (int i = 0; i < 3; ++i) shift_center[i] = (double)box_middle[i] - shift_center[i];
+        shift_center[0] = shm01 * shift_center[1] + shm02 * shift_center[2];  /* pyx:216-218 */
+        shift_center[1] = shm12 * shift_center[2];
+        shift_center[2] = 0.0;
+        for (int64_t a = 0; a < n_atoms; ++a)                                 /* pyx:221-223 */
+            for (int i = 0; i < 3; ++i) {
+                float *x = &coords[(a * 3 + i) * F + f];
+                *x = (*x - wrap_center[i]) + box_middle[i];
+            }
+        for (int64_t g = 0; g + 1 < n_groups; ++g) {
+            const int64_t s = groups[g], e = groups[g + 1];
+            for (int i = 0; i < 3; ++i) grp_center[i] = 0.f;
+            int64_t n = 0;
+            for (int64_t k = s; k < e; ++k, ++n)                              /* pyx:230-237 */
+                for (int i = 0; i < 3; ++i) {
+                    grp_center[i] = grp_center[i] + (coords[(k * 3 + i) * F + f] - grp_center[i]) / (float)(n + 1);
+                    grp_center_init[i] = grp_center[i];   /* (keeps the previous group's value for an empty group) */
+                }
+            for (int m = 2; m >= 0; --m) {                                    /* pyx:239-259 */
+                double shift = shift_center[m];
+                if (m == 0) shift += shm01 * (double)grp_center[1] + shm02 * (double)grp_center[2];
+                else if (m == 1) shift += shm12 * (double)grp_center[2];
+                int64_t it = 0;
+                while ((double)grp_center[m] - shift < 0 && it++ < max_iter)
+                    for (int d = 0; d <= m; ++d) grp_center[d] = (float)((double)grp_center[d] + box[m][d]);
+                it = 0;
+                while ((double)grp_center[m] - shift >= box[m][m] && it++ < max_iter)
+                    for (int d = 0; d <= m; ++d) grp_center[d] = (float)((double)grp_center[d] - box[m][d]);
+                for (int64_t a = s; a < e; ++a) {
+                    float *x = &coords[(a * 3 + m) * F + f];
+                    *x = *x - (grp_center_init[m] - grp_center[m]);
+                }
+            }
+        }
+    }
+}
+
+static double tric_norm2(const double *v) { return v[0] * v[0] + v[1] * v[1] + v[2] * v[2]; }
+static double tric_min(double a, double b) { return a < b ? a : b; }
+static double tric_max(double a, double b) { return a > b ? a : b; }
+
+/* pyx:357-451 get_pbc (GROMACS low_set_pbc): up to 12 correction vectors; returns ntric_vec or -1 for the
+ * reference's ValueError("Too many triclinic vectors!!"). */
+static int tric_get_pbc(double box[3][3], double tric_vec[12][3], double *max_cutoff2_out)
+{
+    static const int order[3] = {0, -1, 1};
+    const double skew = 1.001;
+    double hbox[3], trial[3], pos[3];
+    int ntric = 0;
+    for (int i = 0; i < 3; ++i) hbox[i] = box[i][i] * 0.5;
+    double min_hv2 = 0.25 * tric_min(tric_norm2(box[0]), tric_norm2(box[1]));
+    min_hv2 = tric_min(min_hv2, 0.25 * tric_norm2(box[2]));
+    const double min_ss = tric_min(box[0][0], tric_min(box[1][1] - fabs(box[2][1]), box[2][2]));
+    *max_cutoff2_out = tric_min(min_hv2, min_ss * min_ss);
+    for (int kk = 0; kk < 3; ++kk) {
+        const int k = order[kk];
+        for (int jj = 0; jj < 3; ++jj) {
+            const int j = order[jj];
+            for (int ii = 0; ii < 3; ++ii) {
+                const int i = order[ii];
+                if (!(j != 0 || k != 0)) continue;
+                double d2old = 0, d2new = 0;
+                for (int d = 0; d < 3; ++d) {
+                    trial[d] = i * box[0][d] + j * box[1][d] + k * box[2][d];
+                    if (trial[d] < 0) pos[d] = tric_min(hbox[d], -trial[d]);
+                    else pos[d] = tric_max(-hbox[d], -trial[d]);
+                    d2old += pos[d] * pos[d];
+                    d2new += (pos[d] + trial[d]) * (pos[d] + trial[d]);
+                }
+                if (skew * d2new < d2old) {
+                    int use = 1;
+                    for (int dd = 0; dd < 3; ++dd) {
+                        const int shift = dd == 0 ? i : (dd == 1 ? j : k);
+                        if (shift) {
+                            double d2c = 0;
+                            for (int e = 0; e < 3; ++e) {
+                                const double t = pos[e] + trial[e] - shift * box[dd][e];
+                                d2c += t * t;
+                            }
+                            if (d2c <= skew * d2new) { use = 0; break; }
+                        }
+                    }
+                    if (use) {
+                        if (ntric >= 12) return -1;
+                        for (int e = 0; e < 3; ++e) tric_vec[ntric][e] = trial[e];
+                        ++ntric;
+                    }
+                }
+            }
+        }
+    }
+    return ntric;
+}
+
+/* pyx:454-505 pbc_dx (note: in mode 1 the correction-vector search sits INSIDE the loop over the axes) */
+static void tric_pbc_dx(const float *x1, const float *x2, double box[3][3], const double *hbox,
+                        double tric_vec[12][3], double max_cutoff2, int ntric, int mode, double *dx, int64_t max_iter)
+{
+    double dx_start[3], trial[3];
+    for (int i = 0; i < 3; ++i) dx[i] = (double)(x1[i] - x2[i]);
+    if (mode == 0) {
+        for (int i = 0; i < 3; ++i) {
+            int64_t it = 0;
+            while (dx[i] > hbox[i] && it++ < max_iter) dx[i] -= box[i][i];
+            it = 0;
+            while (dx[i] <= -hbox[i] && it++ < max_iter) dx[i] += box[i][i];
+        }
+    } else if (mode == 1) {
+        for (int i = 2; i >= 0; --i) {
+            int64_t it = 0;
+            while (dx[i] > hbox[i] && it++ < max_iter)
+                for (int j = i; j >= 0; --j) dx[j] -= box[i][j];
+            it = 0;
+            while (dx[i] <= -hbox[i] && it++ < max_iter)
+                for (int j = i; j >= 0; --j) dx[j] += box[i][j];
+            double d2min = tric_norm2(dx);
+            if (d2min > max_cutoff2) {
+                for (int j = 0; j < 3; ++j) dx_start[j] = dx[j];
+                int k = 0;
+                while (d2min > max_cutoff2 && k < ntric) {
+                    for (int j = 0; j < 3; ++j) trial[j] = dx_start[j] + tric_vec[k][j];
+                    const double d2trial = tric_norm2(trial);
+                    if (d2trial < d2min) {
+                        for (int j = 0; j < 3; ++j) dx[j] = trial[j];
+                        d2min = d2trial;
+                    }
+                    ++k;
+                }
+            }
+        }
+    }
+}
+
+/* pyx:255-344 wrap_compact_unitcell; mode 0 = "rectangular" cell of a triclinic box, 1 = "compact".
+ * Returns 0, or -1 - f for the frame whose box yields more than 12 correction vectors. */
+EXPORT int64_t oracle_wrap_compact(const uint32_t *groups, int64_t n_groups, float *coords, int64_t n_atoms,
+                                   const double *boxvectors, int64_t F, const uint32_t *centersel,
+                                   int64_t n_centersel, const float *center, int mode, int64_t max_iter)
+{
+    float wrap_center[3] = {0.f, 0.f, 0.f}, box_middle[3], grp_center[3];
+    double box[3][3], tric_vec[12][3], hbox[3], dx[3], max_cutoff2;
+    if (n_centersel == 0)
+        for (int i = 0; i < 3; ++i) wrap_center[i] = center[i];
+    for (int64_t f = 0; f < F; ++f) {
+        tric_frame_setup(boxvectors, F, f, coords, n_atoms, centersel, n_centersel, wrap_center, box, box_middle);
+        for (int i = 0; i < 3; ++i) hbox[i] = box[i][i] * 0.5;
+        for (int64_t a = 0; a < n_atoms; ++a)
+            for (int i = 0; i < 3; ++i) {
+                float *x = &coords[(a * 3 + i) * F + f];
+                *x = (*x - wrap_center[i]) + box_middle[i];
+            }
+        memset(tric_vec, 0, sizeof tric_vec);
+        const int ntric = tric_get_pbc(box, tric_vec, &max_cutoff2);
+        if (ntric < 0) return -1 - f;
+        for (int64_t g = 0; g + 1 < n_groups; ++g) {
+            const int64_t s = groups[g], e = groups[g + 1];
+            for (int i = 0; i < 3; ++i) grp_center[i] = 0.f;
+            int64_t n = 0;
+            for (int64_t a = s; a < e; ++a, ++n)
+                for (int i = 0; i < 3; ++i)
+                    grp_center[i] = grp_center[i] + (coords[(a * 3 + i) * F + f] - grp_center[i]) / (float)(n + 1);
+            tric_pbc_dx(grp_center, box_middle, box, hbox, tric_vec, max_cutoff2, ntric, mode, dx, max_iter);
+            for (int64_t a = s; a < e; ++a)
+                for (int i = 0; i < 3; ++i) {
+                    float *x = &coords[(a * 3 + i) * F + f];
+                    *x = (float)((double)((*x - grp_center[i]) + box_middle[i]) + dx[i]);
+                }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Hydrogen bonds -- moleculekit/interactions/hbonds/hbonds.pyx:25-134 (called by hbonds_calculate,
+ * moleculekit/interactions/interactions.py:365-467).  donors (n_donors, 2) = (heavy, hydrogen),
+ * acceptors (n_acceptors), sel1 / sel2 0/1 flags per atom, coords (N, 3, F) f32, box (3, F) f32.
+ * Per frame, donor-major / acceptor-minor, a triple (heavy, hydrogen | -1, acceptor) is emitted when the
+ * hydrogen (heavy atom with ignore_hs) is within dist_threshold of the acceptor and the
+ * heavy-hydrogen-acceptor angle exceeds angle_threshold.  Types as generated: `val`, the squared
+ * distances, the dot product and `angle` are float; the wrap goes through double (libc round on the
+ * float quotient, float * double), and so do sqrt / acos (results rounded to float on assignment).
+ * counts[f] receives the number of triples of frame f; up to `capacity` triples are written; the total
+ * is returned.
+ * ------------------------------------------------------------------------------------------------ */
+EXPORT int64_t oracle_hbonds(const uint32_t *donors, int64_t n_donors, const uint32_t *acceptors, int64_t n_acceptors,
+                             const float *coords, const float *box, int64_t F, const uint32_t *sel1,
+                             const uint32_t *sel2, float dist_threshold, float angle_threshold, int intra,
+                             int ignore_hs, int64_t *counts, int32_t *out, int64_t capacity)
+{
+    float dist_vec_a[3], dist_vec_b[3], half_box[3];
+    int64_t total = 0;
+    dist_threshold = dist_threshold * dist_threshold;                          /* pyx:49 */
+    angle_threshold = (float)((double)angle_threshold / 57.29578);            /* pyx:50 */
+    for (int64_t f = 0; f < F; ++f) {
+        int64_t nf = 0;
+        for (int i = 0; i < 3; ++i) half_box[i] = box[i * F + f] / 2;
+        for (int64_t d = 0; d < n_donors; ++d)
+            for (int64_t a = 0; a < n_acceptors; ++a) {
+                const uint32_t a_idx = acceptors[a], d_idx_d = donors[2 * d];
+                uint32_t d_idx = d_idx_d, d_idx_h = 0;
+                if (!ignore_hs) { d_idx_h = donors[2 * d + 1]; d_idx = d_idx_h; }
+                if (a_idx == d_idx_d) continue;
+                if (intra) {
+                    if (sel1[a_idx] == 0 || sel1[d_idx_d] == 0) continue;
+                } else if (!((sel1[a_idx] == 1 && sel2[d_idx_d] == 1) || (sel2[a_idx] == 1 && sel1[d_idx_d] == 1)))
+                    continue;
+                float dist2_a = 0, dist2_b = 0;
+                for (int i = 0; i < 3; ++i) {
+                    const float b = box[i * F + f];
+                    float val = coords[((int64_t)a_idx * 3 + i) * F + f] - coords[((int64_t)d_idx * 3 + i) * F + f];
+                    if (fabsf(val) > half_box[i] && b != 0) val = (float)((double)val - (double)b * round((double)(val / b)));
+                    dist_vec_a[i] = val;
+                    dist2_a = dist2_a + (val * val);
+                }
+                if (dist2_a > dist_threshold) continue;
+                if (ignore_hs) {
+                    if (total < capacity) { out[3 * total] = (int32_t)d_idx_d; out[3 * total + 1] = -1; out[3 * total + 2] = (int32_t)a_idx; }
+                    ++total; ++nf;
+                    continue;
+                }
+                for (int i = 0; i < 3; ++i) {
+                    const float b = box[i * F + f];
+                    float val = coords[((int64_t)d_idx_d * 3 + i) * F + f] - coords[((int64_t)d_idx_h * 3 + i) * F + f];
+                    if (fabsf(val) > half_box[i] && b != 0) val = (float)((double)val - (double)b * round((double)(val / b)));
+                    dist_vec_b[i] = val;
+                    dist2_b = dist2_b + (val * val);
+                }
+                if (dist2_a == 0 || dist2_b == 0) continue;
+                float dotprod = 0;
+                for (int i = 0; i < 3; ++i) dotprod = dotprod + dist_vec_a[i] * dist_vec_b[i];
+                float angle = (float)((double)dotprod / (sqrt((double)dist2_a) * sqrt((double)dist2_b)));
+                if (angle > 1) angle = 1;
+                if (angle < -1) angle = -1;
+                angle = (float)acos((double)angle);
+                if (angle > angle_threshold) {
+                    if (total < capacity) { out[3 * total] = (int32_t)d_idx_d; out[3 * total + 1] = (int32_t)d_idx_h; out[3 * total + 2] = (int32_t)a_idx; }
+                    ++total; ++nf;
+                }
+            }
+        counts[f] = nf;
+    }
+    return total;
 }
