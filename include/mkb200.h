@@ -277,6 +277,37 @@ int mkb_within_distance(mkb_handle_t h, void *stream, const float *coords, int64
 int mkb_wrap_box(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *groups, int64_t n_groups,
                  const uint32_t *centersel, int64_t n_centersel, const float *center);
 
+/* K9b: wrapping of bonded groups in triclinic cells, replaces wrap_triclinic_unitcell (moleculekit/wrapping/wrapping.pyx:147-250,
+ * unitcell = 2) and wrap_compact_unitcell (pyx:255-344 with get_pbc pyx:357-451 and pbc_dx pyx:454-505; unitcell = 0 is
+ * its mode 0 "rectangular", 1 its mode 1 "compact") -- the calls Molecule.wrap makes when a box angle differs from 90
+ * (moleculekit/molecule.py:2078-2090).  t->coords is MODIFIED IN PLACE (t->box is not used); boxvectors [3][3][stride]
+ * float64 device, row i = box vector i, frame minor like Molecule.boxvectors.  groups / centersel / center as in
+ * mkb_wrap_box; every atom is first centred on the wrap centre (also atoms outside all groups), then each group is
+ * translated as the reference does it, float32 centres against float64 cell arithmetic: bit-identical coordinates.
+ * Returns MKB_ERR_BAD_ARG "Too many triclinic vectors!!" where the reference raises that ValueError (pyx:439-441).  The
+ * reference's unbounded while loops are capped at 2^20 iterations (only reached by cells without a positive diagonal). */
+int mkb_wrap_triclinic(mkb_handle_t h, void *stream, const mkb_traj *t, const double *boxvectors,
+                       int64_t bv_frame_stride, const uint32_t *groups, int64_t n_groups, const uint32_t *centersel,
+                       int64_t n_centersel, const float *center, int32_t unitcell);
+
+/* K12: hydrogen bonds over a trajectory, replaces hbonds.calculate (moleculekit/interactions/hbonds/hbonds.pyx:25-134; called
+ * by hbonds_calculate, moleculekit/interactions/interactions.py:365-467).  donors [n_donors][2] uint32 device = (heavy atom,
+ * hydrogen); acceptors [n_acceptors] uint32 device; sel1 / sel2 [n_atoms] uint32 device 0/1 flags; t->box is the
+ * orthorhombic box (3, F).  intra != 0: both atoms in sel1 (pyx:70-73), else one in sel1 and the other in sel2
+ * (pyx:74-77).  ignore_hs != 0: the heavy atom's distance is tested, no angle, hydrogen reported as -1 (pyx:101-105).
+ * Two calls like K4 -- count: row_offsets [n_frames*n_donors + 1] int64 device = exclusive scan of the per-(frame, donor)
+ * hit counts, *total_triples (HOST) the total (synchronises the stream); fill: triples [total][3] int32 device =
+ * (heavy, hydrogen | -1, acceptor) in the reference's order (frame, donor, acceptor ascending).  Same booleans as the
+ * reference binary: float / double operations as in the generated C, the acos comparison as a precomputed cosine bound. */
+int mkb_hbonds_count(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *donors, int64_t n_donors,
+                     const uint32_t *acceptors, int64_t n_acceptors, const uint32_t *sel1, const uint32_t *sel2,
+                     float dist_threshold, float angle_threshold, int32_t intra, int32_t ignore_hs, int64_t *row_offsets,
+                     int64_t *total_triples);
+int mkb_hbonds_fill(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *donors, int64_t n_donors,
+                    const uint32_t *acceptors, int64_t n_acceptors, const uint32_t *sel1, const uint32_t *sel2,
+                    float dist_threshold, float angle_threshold, int32_t intra, int32_t ignore_hs,
+                    const int64_t *row_offsets, int32_t *triples);
+
 #ifdef __cplusplus
 }
 #endif

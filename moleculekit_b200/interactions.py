@@ -1,16 +1,18 @@
-"""Contact-type interaction detectors on top of the GPU contact kernel (K4) -- SURVEY 8f row 2, second half.
+"""Interaction detectors on top of the GPU contact kernel (K4) and the hydrogen-bond kernel (K12) -- SURVEY 8f row 2.
 
-Mirrors of the three detectors in the reference that are thin consumers of ``calculate_contacts``
+Mirrors of the detectors in the reference that are thin consumers of ``calculate_contacts`` or ``hbonds.calculate``
 (moleculekit/interactions/interactions.py):
 
+  hbonds_calculate                :365-467     donor-H ... acceptor distance + angle test per frame (K12)
   saltbridge_calculate            :724-788     charged atoms within `threshold`, one positive + one negative per pair
   hydrophobic_calculate           :949-992     carbon - carbon contacts
   metal_coordination_calculate    :995-1056    metal - (N, O, S, halogen) contacts, both directions
   get_protein_charged / get_metal_charged      :292-306  (pure table look-ups on resname / name / element)
 
 Selections are boolean masks / index arrays, or strings resolved by ``mol.atomselect``; the pair search itself is
-``mkb_contacts_count`` + ``mkb_contacts_fill`` (bit-exact index output, reference order).  The ring / angle based detectors
-(pi-pi, cation-pi, sigma holes, hydrogen bonds) are a different algorithm family and stay with moleculekit.
+``mkb_contacts_count`` + ``mkb_contacts_fill`` (bit-exact index output, reference order); hydrogen bonds run in
+``mkb_hbonds_count`` + ``mkb_hbonds_fill``.  The ring based detectors (pi-pi, cation-pi, sigma holes) are a different
+algorithm family and stay with moleculekit.
 """
 from __future__ import annotations
 
@@ -82,3 +84,36 @@ def metal_coordination_calculate(mol, sel1, sel2, dist_threshold: float = 3.5, d
     inter1 = calculate_contacts(mol, m1 & is_metal, m2 & is_coord, periodic, dist_threshold, device=device)
     inter2 = calculate_contacts(mol, m1 & is_coord, m2 & is_metal, periodic, dist_threshold, device=device)
     return [np.vstack((inter1[f], inter2[f])) for f in range(mol.numFrames)]
+
+
+def hbonds_calculate(mol, donors, acceptors, sel1="all", sel2=None, dist_threshold: float = 2.5,
+                     angle_threshold: float = 120, ignore_hs: bool = False, device=None):
+    """interactions.py:365-467: per frame the (n, 3) int64 array of (donor heavy atom, donor hydrogen | -1, acceptor)."""
+    from . import hbonds
+
+    if mol.box.shape[1] != mol.coords.shape[2]:
+        raise RuntimeError("mol.box should have same number of frames as mol.coords")
+    donors, acceptors = np.asarray(donors), np.asarray(acceptors)
+    if len(donors) == 0 or len(acceptors) == 0:
+        return [np.empty((0, 3), dtype=np.int64) for _ in range(mol.numFrames)]
+    s1 = _mask(mol, sel1).astype(np.uint32)
+    if sel2 is None:
+        s2 = s1.copy()
+        intra = True
+    else:
+        s2 = _mask(mol, sel2).astype(np.uint32)
+        intra = False
+    if len(s1) != mol.numAtoms or len(s2) != mol.numAtoms:
+        raise RuntimeError("Selections must be boolean of size equal to number of atoms in the molecule")
+    # donors / acceptors outside both selections can never pass (interactions.py:439-442)
+    sel_idx = np.where(s1 | s2)[0]
+    donors = donors[np.all(np.isin(donors, sel_idx), axis=1)]
+    acceptors = acceptors[np.isin(acceptors, sel_idx)]
+    if ignore_hs:
+        donors = np.unique(donors[:, 0])[:, None]
+    off, tri = hbonds.calculate_arrays(
+        np.ascontiguousarray(donors.astype(np.uint32)), np.ascontiguousarray(acceptors.astype(np.uint32)),
+        np.ascontiguousarray(mol.coords.astype(np.float32)), np.ascontiguousarray(mol.box.astype(np.float32)), s1, s2,
+        dist_threshold=float(dist_threshold), angle_threshold=float(angle_threshold), intra=bool(intra),
+        ignore_hs=bool(ignore_hs), device=device)
+    return [tri[off[f]:off[f + 1]].astype(np.int64).reshape(-1, 3) for f in range(mol.numFrames)]

@@ -107,6 +107,16 @@ def g_wrap():
 
 
 @pytest.fixture(scope="session")
+def g_tric():
+    return _npz("tric.npz")
+
+
+@pytest.fixture(scope="session")
+def g_hbonds():
+    return _npz("hbonds.npz")
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import cpu_oracle
 

@@ -115,6 +115,185 @@ def wrapping_fixture():
     np.savez_compressed(os.path.join(HERE, "wrap.npz"), **w)
 
 
+def triclinic_fixture():
+    """tric.npz (K9b): the reference's triclinic test system tests/test_readers/dodecahedral_box (tests/test_wrapping.py:26-44),
+    cut to the protein + the first solvent groups and 3 frames, with (a) the output of the reference's compiled
+    wrap_triclinic_unitcell / wrap_compact_unitcell (modes 0, 1) on that cut (bit-exact targets) and (b) the same atoms /
+    frames of the reference's STORED goldens output_{triclinic,compact,rectangular}_wrapped.xtc (atol 1e-2, the reference
+    test's tolerance); plus a fixed-centre variant and seeded random cases (rhombic dodecahedron, truncated octahedron,
+    general reduced cells; empty groups, atoms outside all groups)."""
+    from oracle import build_ref
+
+    wref = build_ref.load()[3]
+    from moleculekit.molecule import Molecule, getBondedGroups
+
+    d = os.path.join(REFT, "test_readers", "dodecahedral_box")
+    mol = Molecule(os.path.join(d, "3ptb_dodecahedron.psf"))
+    mol.read(scratch_copy(os.path.join(d, "output.xtc")))
+    groups, _ = getBondedGroups(mol)
+    centersel = mol.atomselect("protein", indexes=True, guessBonds=False).astype(np.uint32)
+    ncut_groups = int(np.searchsorted(groups, centersel.max() + 1)) + 800
+    K = int(groups[ncut_groups])
+    assert centersel.max() < K
+    frames = [0, mol.numFrames // 2, mol.numFrames - 1]
+    w = {}
+    w["coords"] = np.ascontiguousarray(mol.coords[:K][:, :, frames])
+    w["box"] = np.ascontiguousarray(mol.box[:, frames])
+    w["boxangles"] = np.ascontiguousarray(mol.boxangles[:, frames])
+    w["boxvectors"] = np.ascontiguousarray(mol.boxvectors[:, :, frames])
+    w["groups"] = groups[: ncut_groups + 1].copy()
+    w["centersel"] = centersel
+    zero = np.zeros(3, np.float32)
+    for name, fn in (("triclinic", lambda c: wref.wrap_triclinic_unitcell(w["groups"], c, w["boxvectors"], centersel, zero)),
+                     ("compact", lambda c: wref.wrap_compact_unitcell(w["groups"], c, w["boxvectors"], centersel, zero, 1)),
+                     ("rectangular", lambda c: wref.wrap_compact_unitcell(w["groups"], c, w["boxvectors"], centersel, zero, 0))):
+        out = w["coords"].copy()
+        fn(out)
+        w[f"ref_{name}"] = out
+        gold = Molecule(scratch_copy(os.path.join(d, f"output_{name}_wrapped.xtc")))
+        w[f"gold_{name}_xtc"] = np.ascontiguousarray(gold.coords[:K][:, :, frames])
+        # the cut reproduces the stored golden: a group's translation depends only on its own atoms and the protein centre
+        assert np.max(np.abs(out - w[f"gold_{name}_xtc"])) < 1e-2, name
+        assert not np.array_equal(out, w["coords"])
+    cen = np.array([12.5, -3.0, 40.25], dtype=np.float32)
+    w["center_fixed"] = cen
+    for name, mode in (("triclinic", None), ("compact", 1), ("rectangular", 0)):
+        out = w["coords"].copy()
+        if mode is None:
+            wref.wrap_triclinic_unitcell(w["groups"], out, w["boxvectors"], np.zeros(0, np.uint32), cen)
+        else:
+            wref.wrap_compact_unitcell(w["groups"], out, w["boxvectors"], np.zeros(0, np.uint32), cen, mode)
+        w[f"ref_{name}_fixed"] = out
+    rng = np.random.default_rng(2024)
+    ncase = 9
+    for c in range(ncase):
+        N = int(rng.integers(5, 300)); F = int(rng.integers(1, 7))
+        cuts = np.unique(np.concatenate([[0], rng.integers(0, N, size=int(rng.integers(0, 40))), [N]])).astype(np.uint32)
+        if c == 1:
+            cuts = np.sort(np.concatenate([cuts, cuts[1:3]])).astype(np.uint32)  # repeated offsets = empty groups
+        if c == 2 and len(cuts) > 3:
+            cuts = cuts[1:-1].copy()  # atoms before the first / after the last group are only centred
+        bv = np.zeros((3, 3, F))
+        for f in range(F):
+            L = rng.uniform(20, 40)
+            if c % 3 == 0:    # rhombic dodecahedron (GROMACS xy-square form)
+                vec = [[L, 0, 0], [0, L, 0], [L / 2, L / 2, L * np.sqrt(2) / 2]]
+            elif c % 3 == 1:  # truncated octahedron
+                vec = [[L, 0, 0], [L / 3, 2 * np.sqrt(2) * L / 3, 0], [-L / 3, np.sqrt(2) * L / 3, np.sqrt(6) * L / 3]]
+            else:             # a mildly skewed reduced cell
+                vec = [[L, 0, 0], [rng.uniform(-.3, .3) * L, L * rng.uniform(.9, 1.1), 0],
+                       [rng.uniform(-.3, .3) * L, rng.uniform(-.3, .3) * L, L * rng.uniform(.9, 1.1)]]
+            bv[:, :, f] = np.array(vec) * (1 + 0.001 * rng.normal())
+        xyz = rng.normal(0, 45, size=(N, 3, F)).astype(np.float32)
+        cs = np.zeros(0, np.uint32) if c % 2 else np.sort(rng.choice(N, size=min(N, 17), replace=False)).astype(np.uint32)
+        cen = rng.normal(0, 4, 3).astype(np.float32)
+        for k, v in (("groups", cuts), ("coords", xyz), ("boxvectors", bv), ("centersel", cs), ("center", cen)):
+            w[f"r{c}_{k}"] = v
+        for name, mode in (("triclinic", None), ("compact", 1), ("rectangular", 0)):
+            o = xyz.copy()
+            if mode is None:
+                wref.wrap_triclinic_unitcell(cuts, o, bv, cs, cen)
+            else:
+                wref.wrap_compact_unitcell(cuts, o, bv, cs, cen, mode)
+            w[f"r{c}_ref_{name}"] = o
+    w["ncase"] = np.array(ncase)
+    np.savez_compressed(os.path.join(HERE, "tric.npz"), **w)
+    print("tric.npz", K, "atoms", len(frames), "frames")
+
+
+def hbonds_fixture():
+    """hbonds.npz (K12): the reference's hydrogen-bond test (tests/test_interactions.py:7-55) rebuilt without rdkit: the
+    protein's donors / acceptors come from the reference's get_donors_acceptors, the benzamidine ligand is read from the SDF
+    by hand (its donors are the four N-H pairs the test's expected rows name, it has no acceptors).  Stored: coordinates
+    (two identical frames as in the test), donors, acceptors, selection masks, the reference's hbonds_calculate outputs --
+    whose 'protein' vs 'resname BEN' rows equal the constants in the reference test and whose 'all' result has its 178
+    rows -- plus ignore_hs / threshold variants and seeded random periodic cases from the compiled hbonds.calculate."""
+    from oracle import build_ref
+
+    href = build_ref.load()[6]
+    from moleculekit.interactions.interactions import get_donors_acceptors, hbonds_calculate
+    from moleculekit.molecule import Molecule
+
+    d = os.path.join(REFT, "test_interactions")
+    mol = Molecule(os.path.join(d, "3PTB_prepared.pdb"))
+    mol.guessBonds()
+    donors, acceptors = get_donors_acceptors(mol, exclude_water=True, exclude_backbone=False)
+    lines = open(os.path.join(d, "3PTB_BEN.sdf")).read().splitlines()
+    na, nb = int(lines[3][:3]), int(lines[3][3:6])
+    xyz = np.array([[float(l[0:10]), float(l[10:20]), float(l[20:30])] for l in lines[4:4 + na]], dtype=np.float32)
+    elem = [l[31:34].strip() for l in lines[4:4 + na]]
+    lbonds = np.array([[int(l[0:3]) - 1, int(l[3:6]) - 1] for l in lines[4 + na:4 + na + nb]])
+    lig = Molecule().empty(na)
+    lig.coords = xyz[:, :, None].copy()
+    lig.element[:] = elem
+    lig.name[:] = [f"{e}{i}" for i, e in enumerate(elem)]
+    lig.resname[:] = "BEN"
+    lig.record[:] = "HETATM"
+    lig.resid[:] = 1
+    lig.bonds = lbonds.astype(np.uint32)
+    lig.bondtype = np.array(["1"] * nb, dtype=object)
+    mol.append(lig)
+    lig_idx = np.where(mol.resname == "BEN")[0][0]
+    lig_don = np.array([[a, b] if elem[a] == "N" else [b, a] for a, b in lbonds
+                        if {elem[a], elem[b]} == {"N", "H"}], dtype=np.uint32)
+    mol.bonds = mol._guessBonds()
+    mol.coords = np.tile(mol.coords, (1, 1, 2)).copy()
+    mol.box = np.tile(mol.box, (1, 2)).copy()
+    donors = np.vstack((donors, lig_don + lig_idx)).astype(np.uint32)
+    acceptors = np.asarray(acceptors, dtype=np.uint32)
+    w = {"coords": mol.coords.astype(np.float32), "box": mol.box.astype(np.float32), "donors": donors,
+         "acceptors": acceptors, "protein": mol.atomselect("protein"), "ben": mol.atomselect("resname BEN")}
+    hb = hbonds_calculate(mol, donors, acceptors, "protein", "resname BEN")
+    expected = np.array([[3414, 3421, 2471], [3414, 3422, 2789], [3415, 3423, 2472], [3415, 3424, 2482]])
+    assert len(hb) == 2 and np.array_equal(hb[0], expected) and np.array_equal(hb[1], expected), hb  # test_interactions.py:41-51
+    w["hb_prot_ben"] = hb[0]
+    hb = hbonds_calculate(mol, donors, acceptors, "all")
+    assert np.array(hb[0]).shape == (178, 3)  # test_interactions.py:53-55
+    w["hb_all"] = hb[0]
+    w["hb_all_nohs"] = hbonds_calculate(mol, donors, acceptors, "all", ignore_hs=True)[0]
+    w["hb_all_wide"] = hbonds_calculate(mol, donors, acceptors, "all", dist_threshold=3.2, angle_threshold=100)[1]
+    w["hb_prot_ben_nohs"] = hbonds_calculate(mol, donors, acceptors, "protein", "resname BEN", ignore_hs=True,
+                                             dist_threshold=3.5)[0]
+    rng = np.random.default_rng(77)
+    ncase = 8
+    for c in range(ncase):
+        N = int(rng.integers(30, 250)); F = int(rng.integers(1, 6))
+        L = rng.uniform(8, 15, size=(3, F)).astype(np.float32)
+        if c == 1:
+            L[1, 0] = 0
+        if c == 2:
+            L[:] = 0
+        xyz = (rng.uniform(0, 1, size=(N, 3, F)) * 12).astype(np.float32) if c % 2 else rng.normal(0, 6, size=(N, 3, F)).astype(np.float32)
+        nd = int(rng.integers(1, 60)); nacc = int(rng.integers(1, 60))
+        heavy = rng.integers(0, N, nd); hyd = rng.integers(0, N, nd)
+        for k in range(nd):
+            if hyd[k] != heavy[k]:
+                v = rng.normal(size=(3, F)); v /= np.linalg.norm(v, axis=0)
+                xyz[hyd[k]] = xyz[heavy[k]] + v.astype(np.float32)
+        if c == 3:
+            xyz[hyd[0]] = xyz[heavy[0]]  # overlapping donor pair (dist2_b == 0)
+        if c == 4:
+            xyz[5, 1, 0] = np.nan
+        dn = np.stack([heavy, hyd], 1).astype(np.uint32)
+        acc = rng.integers(0, N, nacc).astype(np.uint32)
+        s1 = (rng.random(N) < .6).astype(np.uint32); s2 = (rng.random(N) < .6).astype(np.uint32)
+        dth = float(rng.uniform(2, 6)); ath = float(rng.uniform(60, 150))
+        for k, v in (("coords", xyz), ("box", L), ("donors", dn), ("acceptors", acc), ("sel1", s1), ("sel2", s2),
+                     ("thr", np.array([dth, ath]))):
+            w[f"r{c}_{k}"] = v
+        for intra in (0, 1):
+            for ign in (0, 1):
+                dd = dn if not ign else np.unique(dn[:, 0])[:, None].astype(np.uint32)
+                with np.errstate(all="ignore"):
+                    r = href.calculate(dd, acc, xyz, L, s1, s2, dist_threshold=dth, angle_threshold=ath, intra=bool(intra),
+                                       ignore_hs=bool(ign))
+                w[f"r{c}_out_{intra}{ign}_counts"] = np.array([len(x) // 3 for x in r])
+                w[f"r{c}_out_{intra}{ign}"] = np.array([v for x in r for v in x], dtype=np.int32).reshape(-1, 3)
+    w["ncase"] = np.array(ncase)
+    np.savez_compressed(os.path.join(HERE, "hbonds.npz"), **w)
+    print("hbonds.npz", mol.numAtoms, "atoms,", len(donors), "donors,", len(acceptors), "acceptors")
+
+
 def rotation_fixture():
     """rotate.npz: outputs of the reference's rotateCoordinates (tools/voxeldescriptors.py:78-114) and rotationMatrix
     (util.py:70-117) on seeded inputs -- the float64 targets of mkb_rotate_coords."""
@@ -304,6 +483,14 @@ def main():
         return
     if "--only-rotation" in sys.argv:
         rotation_fixture()
+        return
+    if "--only-triclinic" in sys.argv:
+        assert build_ref.build()
+        triclinic_fixture()
+        return
+    if "--only-hbonds" in sys.argv:
+        assert build_ref.build()
+        hbonds_fixture()
         return
     if "--only-wrapping" in sys.argv:
         assert build_ref.build()

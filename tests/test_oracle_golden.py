@@ -237,6 +237,145 @@ def test_wrap_box_oracle_vs_live_reference(oracle, refmods):
         assert np.array_equal(_fbits(a), _fbits(b)), trial
 
 
+
+# ------------------------------------------------------------------------- K9b: triclinic / compact wrapping
+TRIC_MODES = (("triclinic", None), ("compact", 1), ("rectangular", 0))
+
+
+def _oracle_tric(oracle, name, mode, groups, coords, bv, cs, cen):
+    if mode is None:
+        oracle.wrap_triclinic_unitcell(groups, coords, bv, cs, cen)
+    else:
+        oracle.wrap_compact_unitcell(groups, coords, bv, cs, cen, mode)
+
+
+def test_triclinic_wrapping_oracle_vs_golden(oracle, g_tric):
+    """oracle_wrap_triclinic / oracle_wrap_compact against (a) the outputs of the reference's compiled kernels on the cut of
+    its dodecahedral test system (bit-exact), (b) the reference's stored goldens output_{triclinic,compact,rectangular}_
+    wrapped.xtc at the reference test's tolerance (tests/test_wrapping.py:31-44) and (c) seeded reference outputs."""
+    g = g_tric
+    zero = np.zeros(3, np.float32)
+    for name, mode in TRIC_MODES:
+        out = g["coords"].copy()
+        _oracle_tric(oracle, name, mode, g["groups"], out, g["boxvectors"], g["centersel"], zero)
+        assert np.array_equal(_fbits(out), _fbits(g[f"ref_{name}"])), name
+        assert np.max(np.abs(out - g[f"gold_{name}_xtc"])) < 1e-2, name
+        out = g["coords"].copy()
+        _oracle_tric(oracle, name, mode, g["groups"], out, g["boxvectors"], np.zeros(0, np.uint32), g["center_fixed"])
+        assert np.array_equal(_fbits(out), _fbits(g[f"ref_{name}_fixed"])), name
+        for c in range(int(g["ncase"])):
+            out = g[f"r{c}_coords"].copy()
+            _oracle_tric(oracle, name, mode, g[f"r{c}_groups"], out, g[f"r{c}_boxvectors"], g[f"r{c}_centersel"],
+                         g[f"r{c}_center"])
+            assert np.array_equal(_fbits(out), _fbits(g[f"r{c}_ref_{name}"])), (name, c)
+
+
+def test_triclinic_wrapping_oracle_vs_live_reference(oracle, refmods):
+    if refmods is None or len(refmods) < 4:
+        pytest.skip("oracle/_ref not built")
+    wref = refmods[3]
+    rng = np.random.default_rng(6)
+    for trial in range(9):
+        N, F = int(rng.integers(1, 400)), int(rng.integers(1, 6))
+        cuts = np.unique(np.concatenate([[0], rng.integers(0, N, size=int(rng.integers(0, 60))), [N]])).astype(np.uint32)
+        L = rng.uniform(20, 40)
+        vec = [[L, 0, 0], [0, L, 0], [L / 2, L / 2, L * np.sqrt(2) / 2]] if trial % 2 else \
+            [[L, 0, 0], [L / 3, 2 * np.sqrt(2) * L / 3, 0], [-L / 3, np.sqrt(2) * L / 3, np.sqrt(6) * L / 3]]
+        bv = np.repeat(np.array(vec)[:, :, None], F, axis=2) * (1 + 0.001 * rng.normal(size=(1, 1, F)))
+        xyz = rng.normal(0, 60, size=(N, 3, F)).astype(np.float32)
+        cs = np.zeros(0, np.uint32) if trial % 3 == 0 else \
+            np.sort(rng.choice(N, size=min(N, 23), replace=False)).astype(np.uint32)
+        cen = rng.normal(0, 5, 3).astype(np.float32)
+        for name, mode in TRIC_MODES:
+            a, b = xyz.copy(), xyz.copy()
+            if mode is None:
+                wref.wrap_triclinic_unitcell(cuts, a, bv, cs, cen)
+            else:
+                wref.wrap_compact_unitcell(cuts, a, bv, cs, cen, mode)
+            _oracle_tric(oracle, name, mode, cuts, b, bv, cs, cen)
+            assert np.array_equal(_fbits(a), _fbits(b)), (trial, name)
+
+
+def test_box_vectors_host_mirror(g_tric):
+    """wrapping.box_vectors == Molecule.boxvectors of the reference on its dodecahedral system (stored in the fixture)."""
+    from moleculekit_b200.wrapping import box_vectors
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = box_vectors(g_tric["box"], g_tric["boxangles"])
+    assert got.dtype == np.float64 and np.array_equal(got, g_tric["boxvectors"])
+
+
+# ------------------------------------------------------------------------------------------- K12: hydrogen bonds
+def _hb_arrays(res):
+    return np.array([len(x) // 3 for x in res]), np.array([v for x in res for v in x], dtype=np.int32).reshape(-1, 3)
+
+
+def test_hbonds_oracle_vs_golden(oracle, g_hbonds):
+    """oracle_hbonds against the reference's hydrogen-bond test (tests/test_interactions.py:7-55; the fixture asserts its
+    expected rows and its 178-row count when it is generated) and seeded outputs of the compiled hbonds.calculate incl. zero
+    boxes, an overlapping donor pair and a NaN coordinate."""
+    g = g_hbonds
+    prot, ben = g["protein"].astype(np.uint32), g["ben"].astype(np.uint32)
+    everything = np.ones_like(prot)
+
+    def run(s1, s2, intra, ign=False, dth=2.5, ath=120):
+        don, acc = g["donors"], g["acceptors"]
+        sel_idx = np.where(s1.astype(bool) | s2.astype(bool))[0]           # interactions.py:439-447
+        don = don[np.all(np.isin(don, sel_idx), axis=1)]
+        acc = acc[np.isin(acc, sel_idx)]
+        if ign:
+            don = np.unique(don[:, 0])[:, None].astype(np.uint32)
+        return oracle.hbonds_calculate(don, acc, g["coords"], g["box"], s1, s2, dth, ath, intra, ign)
+
+    r = run(prot, ben, False)
+    assert np.array_equal(np.array(r[0]).reshape(-1, 3), g["hb_prot_ben"]) and r[0] == r[1]
+    assert np.array_equal(g["hb_prot_ben"], [[3414, 3421, 2471], [3414, 3422, 2789], [3415, 3423, 2472], [3415, 3424, 2482]])
+    r = run(everything, everything, True)
+    assert np.array_equal(np.array(r[0]).reshape(-1, 3), g["hb_all"]) and len(r[0]) == 3 * 178
+    assert np.array_equal(np.array(run(everything, everything, True, ign=True)[0]).reshape(-1, 3), g["hb_all_nohs"])
+    assert np.array_equal(np.array(run(everything, everything, True, dth=3.2, ath=100)[1]).reshape(-1, 3), g["hb_all_wide"])
+    assert np.array_equal(np.array(run(prot, ben, False, ign=True, dth=3.5)[0]).reshape(-1, 3), g["hb_prot_ben_nohs"])
+    for c in range(int(g["ncase"])):
+        dth, ath = (float(x) for x in g[f"r{c}_thr"])
+        for intra in (0, 1):
+            for ign in (0, 1):
+                dn = g[f"r{c}_donors"] if not ign else np.unique(g[f"r{c}_donors"][:, 0])[:, None].astype(np.uint32)
+                res = oracle.hbonds_calculate(dn, g[f"r{c}_acceptors"], g[f"r{c}_coords"], g[f"r{c}_box"], g[f"r{c}_sel1"],
+                                              g[f"r{c}_sel2"], dth, ath, bool(intra), bool(ign))
+                counts, tri = _hb_arrays(res)
+                assert np.array_equal(counts, g[f"r{c}_out_{intra}{ign}_counts"]), (c, intra, ign)
+                assert np.array_equal(tri, g[f"r{c}_out_{intra}{ign}"]), (c, intra, ign)
+
+
+def test_hbonds_oracle_vs_live_reference(oracle, refmods):
+    if refmods is None or len(refmods) < 7:
+        pytest.skip("oracle/_ref (hbonds) not built")
+    href = refmods[6]
+    rng = np.random.default_rng(8)
+    for trial in range(10):
+        N, F = int(rng.integers(20, 200)), int(rng.integers(1, 5))
+        L = rng.uniform(8, 15, size=(3, F)).astype(np.float32)
+        xyz = (rng.uniform(0, 1, size=(N, 3, F)) * 12).astype(np.float32)
+        nd, na = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        heavy, hyd = rng.integers(0, N, nd), rng.integers(0, N, nd)
+        for k in range(nd):
+            if hyd[k] != heavy[k]:
+                v = rng.normal(size=(3, F)); v /= np.linalg.norm(v, axis=0)
+                xyz[hyd[k]] = xyz[heavy[k]] + v.astype(np.float32)
+        dn = np.stack([heavy, hyd], 1).astype(np.uint32)
+        acc = rng.integers(0, N, na).astype(np.uint32)
+        s1, s2 = (rng.random(N) < .6).astype(np.uint32), (rng.random(N) < .6).astype(np.uint32)
+        dth, ath = float(rng.uniform(2, 6)), float(rng.uniform(60, 150))
+        for intra in (False, True):
+            for ign in (False, True):
+                dd = dn if not ign else np.unique(dn[:, 0])[:, None].astype(np.uint32)
+                want = [list(x) for x in href.calculate(dd, acc, xyz, L, s1, s2, dist_threshold=dth, angle_threshold=ath,
+                                                        intra=intra, ignore_hs=ign)]
+                assert oracle.hbonds_calculate(dd, acc, xyz, L, s1, s2, dth, ath, intra, ign) == want, (trial, intra, ign)
+
+
 def test_bonded_groups_host_mirror(g_wrap, refmods):
     """getBondedGroups (host logic of the wrap path) reproduces the reference's group offsets on the cut of its own
     test system, and the union-find keeps the reference's root identities on a scrambled bond list."""

@@ -139,9 +139,18 @@ def test_molecule_wrap_mirror(g_wrap, oracle, caplog):
     mol = MolLite(g["coords"].copy(), box=g["box"][:, :2], bonds=g["bonds"])
     with pytest.raises(RuntimeError, match="different number of simulation frames"):
         wr.wrap(mol, wrapsel=mask)
-    tri = MolLite(g["coords"].copy(), box=g["box"], bonds=g["bonds"], boxangles=np.full((3, 3), 60.0, np.float32))
-    with pytest.raises(NotImplementedError):
-        wr.wrap(tri, wrapsel=mask)
+    # a cell with angles != 90 goes to the triclinic kernels (molecule.py:2078-2090); 60/60/90 = rhombic dodecahedron
+    ang = np.repeat(np.array([[60.0], [60.0], [90.0]], np.float32), g["box"].shape[1], axis=1)
+    bx = np.repeat(g["box"][:1], 3, axis=0)
+    tri = MolLite(g["coords"].copy(), box=bx, bonds=g["bonds"], boxangles=ang)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        wr.wrap(tri, wrapsel=mask, unitcell="compact")
+        bv = wr.box_vectors(bx, ang)
+    want = g["coords"].copy()
+    oracle.wrap_compact_unitcell(g["groups"], want, bv, g["centersel"], np.zeros(3, np.float32), 1)
+    assert np.array_equal(_fbits(tri.coords), _fbits(want))
 
 
 def test_argument_checks():
@@ -182,3 +191,151 @@ def test_exact_division_sequence(tmp_path):
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "mismatches=0" in r.stdout
+
+
+# ------------------------------------------------------------------------- K9b: triclinic / compact wrapping
+TRIC_MODES = (("triclinic", None), ("compact", 1), ("rectangular", 0))
+
+
+def _gpu_tric(mode, groups, coords, bv, cs, cen):
+    from moleculekit_b200.wrapping import wrap_compact_unitcell, wrap_triclinic_unitcell
+
+    if mode is None:
+        assert wrap_triclinic_unitcell(groups, coords, bv, cs, cen) is None
+    else:
+        assert wrap_compact_unitcell(groups, coords, bv, cs, cen, mode) is None
+
+
+def _oracle_tric(oracle, mode, groups, coords, bv, cs, cen):
+    if mode is None:
+        oracle.wrap_triclinic_unitcell(groups, coords, bv, cs, cen)
+    else:
+        oracle.wrap_compact_unitcell(groups, coords, bv, cs, cen, mode)
+
+
+def test_triclinic_reference_golden(g_tric):
+    """tests/test_wrapping.py:26-44 on the committed cut of the reference's dodecahedral system, all three unit cells:
+    bit-identical to the reference kernels, within the reference test's tolerance of its stored goldens; the fixed-centre
+    variant; seeded reference cases incl. empty groups and atoms outside every group."""
+    g = g_tric
+    zero = np.zeros(3, np.float32)
+    for name, mode in TRIC_MODES:
+        out = g["coords"].copy()
+        _gpu_tric(mode, g["groups"], out, g["boxvectors"], g["centersel"], zero)
+        assert np.array_equal(_fbits(out), _fbits(g[f"ref_{name}"])), name
+        assert np.max(np.abs(out - g[f"gold_{name}_xtc"])) < 1e-2, name
+        out = g["coords"].copy()
+        _gpu_tric(mode, g["groups"], out, g["boxvectors"], np.zeros(0, np.uint32), g["center_fixed"])
+        assert np.array_equal(_fbits(out), _fbits(g[f"ref_{name}_fixed"])), name
+        for c in range(int(g["ncase"])):
+            out = g[f"r{c}_coords"].copy()
+            _gpu_tric(mode, g[f"r{c}_groups"], out, g[f"r{c}_boxvectors"], g[f"r{c}_centersel"], g[f"r{c}_center"])
+            assert np.array_equal(_fbits(out), _fbits(g[f"r{c}_ref_{name}"])), (name, c)
+
+
+def _dodecahedron(rng, F, L=62.0):
+    vec = np.array([[L, 0, 0], [0, L, 0], [L / 2, L / 2, L * np.sqrt(2) / 2]])
+    return np.repeat(vec[:, :, None], F, axis=2) * (1 + 0.002 * rng.normal(size=(1, 1, F)))
+
+
+def test_triclinic_large_vs_oracle_and_device_api(oracle):
+    """a solvated system (one 700-atom group, 2500 waters that diffused several cells away) over 70 frames in a rhombic
+    dodecahedron vs the oracle, all three unit cells; the device entry on a resident tensor and on a frame shard."""
+    import torch
+    from moleculekit_b200.wrapping import wrap_triclinic_device
+
+    rng = np.random.default_rng(23)
+    groups, coords, _ = _solvated(rng, 700, 2500, 70, box_edge=60.0)
+    bv = _dodecahedron(rng, 70)
+    centersel = np.arange(0, 700, 3, dtype=np.uint32)
+    zero = np.zeros(3, np.float32)
+    for name, mode in TRIC_MODES:
+        want = coords.copy()
+        _oracle_tric(oracle, mode, groups, want, bv, centersel, zero)
+        got = coords.copy()
+        _gpu_tric(mode, groups, got, bv, centersel, zero)
+        assert np.array_equal(_fbits(got), _fbits(want)), name
+        # wrapped groups sit in the cell: wrapping the result again moves (almost) nothing
+        if name != "triclinic":
+            again = got.copy()
+            _gpu_tric(mode, groups, again, bv, centersel, zero)
+            assert np.max(np.abs(again - got)) < 1e-2
+    # device API, frames 16..48 of a resident trajectory (frame_stride 70 > 32 frames)
+    dev = torch.device("cuda:0")
+    d = torch.from_numpy(coords).to(dev)
+    dbv = torch.from_numpy(bv).to(dev)
+    dg = torch.from_numpy(groups.view(np.int32)).to(dev)
+    dcs = torch.from_numpy(centersel.view(np.int32)).to(dev)
+    out = wrap_triclinic_device(d[:, :, 16:48], dbv[:, :, 16:48], dg, dcs, None, "compact")
+    assert out.data_ptr() == d[:, :, 16:48].data_ptr()
+    want = coords.copy()
+    sub = np.ascontiguousarray(coords[:, :, 16:48])
+    oracle.wrap_compact_unitcell(groups, sub, np.ascontiguousarray(bv[:, :, 16:48]), centersel, zero, 1)
+    want[:, :, 16:48] = sub
+    assert np.array_equal(_fbits(d.cpu().numpy()), _fbits(want))
+
+
+def test_triclinic_long_groups_and_edge_cases(oracle):
+    """a 20 000-atom group (many pipeline stages), odd frame counts, groups of every small size, a fixed centre far from
+    the cell, and the reference's ValueError for a cell with more than 12 correction vectors."""
+    from moleculekit_b200.wrapping import wrap_compact_unitcell
+
+    rng = np.random.default_rng(31)
+    for F in (1, 33):
+        sizes = [20000, 1, 2, 3, 4, 5, 37, 1, 260]
+        groups = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+        N = int(groups[-1])
+        coords = (rng.normal(0, 5, size=(N, 3, F)) + rng.uniform(-200, 200, size=(1, 3, F))).astype(np.float32)
+        for k in range(1, len(sizes)):
+            coords[groups[k]:groups[k + 1]] += rng.uniform(-150, 150, size=(1, 3, F)).astype(np.float32)
+        L = 48.0
+        vec = np.array([[L, 0, 0], [L / 3, 2 * np.sqrt(2) * L / 3, 0], [-L / 3, np.sqrt(2) * L / 3, np.sqrt(6) * L / 3]])
+        bv = np.repeat(vec[:, :, None], F, axis=2) * (1 + 0.002 * rng.normal(size=(1, 1, F)))
+        cen = np.array([300.0, -120.0, 55.5], np.float32)
+        for name, mode in TRIC_MODES:
+            for cs in (np.zeros(0, np.uint32), np.arange(10, 19000, 7, dtype=np.uint32)):
+                want, got = coords.copy(), coords.copy()
+                _oracle_tric(oracle, mode, groups, want, bv, cs, cen)
+                _gpu_tric(mode, groups, got, bv, cs, cen)
+                assert np.array_equal(_fbits(got), _fbits(want)), (F, name, len(cs))
+    # heavily skewed, unreduced cell: get_pbc finds more than 12 vectors (wrapping.pyx:439-441)
+    bad = np.array([[30.0, 0, 0], [11.9, 27.0, 0], [-11.8, 11.9, 33.0]])[:, :, None].copy()
+    xyz = rng.normal(0, 30, size=(10, 3, 1)).astype(np.float32)
+    g2 = np.array([0, 5, 10], np.uint32)
+    try:
+        oracle.wrap_compact_unitcell(g2, xyz.copy(), bad, np.zeros(0, np.uint32), np.zeros(3, np.float32), 1)
+        raised = False
+    except ValueError:
+        raised = True
+    if raised:
+        with pytest.raises(ValueError, match="Too many triclinic vectors"):
+            wrap_compact_unitcell(g2, xyz.copy(), bad, np.zeros(0, np.uint32), np.zeros(3, np.float32), 1)
+
+
+def test_wrap_mirror_dispatches_on_boxangles(g_tric):
+    """wrapping.wrap (Molecule.wrap mirror, molecule.py:2075-2090) takes the triclinic kernels when a box angle != 90 and
+    builds the box vectors from lengths / angles when the container has no boxvectors attribute."""
+    import warnings
+
+    from moleculekit_b200.wrapping import wrap
+
+    g = g_tric
+
+    class Mol:
+        pass
+
+    for unitcell in ("triclinic", "compact", "rectangular"):
+        m = Mol()
+        m.coords = g["coords"].copy()
+        m.box, m.boxangles = g["box"], g["boxangles"]
+        m.numAtoms = m.coords.shape[0]
+        # one "bond" chain per group so that getBondedGroups reproduces the fixture's groups
+        gr = g["groups"].astype(np.int64)
+        m.bonds = np.concatenate([np.stack([np.arange(a, b - 1), np.arange(a + 1, b)], 1) for a, b in zip(gr[:-1], gr[1:])
+                                  if b - a > 1]).astype(np.uint32)
+        sel = np.zeros(m.numAtoms, bool)
+        sel[g["centersel"]] = True
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            wrap(m, wrapsel=sel, unitcell=unitcell)
+        assert np.array_equal(_fbits(m.coords), _fbits(g[f"ref_{unitcell}"])), unitcell
