@@ -374,7 +374,45 @@ def extra_workloads(dev, peak):
                           frac_of_peak=nb / (main * 1e-3) / 1e9 / peak,
                           whole_call_gbs=(nb + n_prot * 3 * F * 4) / ((main + prep) * 1e-3) / 1e9,
                           whole_call_frac_of_peak=(nb + n_prot * 3 * F * 4) / ((main + prep) * 1e-3) / 1e9 / peak)
-    del d_c, d_orig, d_b
+    # C6b: the same system in a rhombic dodecahedron (K9b): every coordinate is centred and rewritten, the group translation
+    # is the triclinic / compact / rectangular rule of wrap_triclinic_unitcell / wrap_compact_unitcell
+    vec = torch.tensor([[L, 0, 0], [0, L, 0], [L / 2, L / 2, L * 2 ** 0.5 / 2]], dtype=torch.float64, device=dev)
+    d_bv = vec[:, :, None].repeat(1, 1, F).contiguous()
+    c6b = {}
+    for cell in ("triclinic", "compact", "rectangular"):
+        kms = []
+        for it in range(4):
+            d_c.copy_(d_orig)
+            wr.wrap_triclinic_device(d_c, d_bv, groups, csel, None, cell)
+            prep, main = _lib.get_timing(dev.index)
+            if it:
+                kms.append(prep + main)
+        ms = float(np.mean(kms))
+        nbt = 2 * N * 3 * F * 4 + n_prot * 3 * F * 4  # read + write every coordinate, the centre selection read once more
+        c6b[cell] = dict(ms_per_call=ms, atom_frames_per_s=N * F / (ms * 1e-3), gbs=nbt / (ms * 1e-3) / 1e9,
+                         frac_of_peak=nbt / (ms * 1e-3) / 1e9 / peak)
+    out["c6b_wrap_triclinic"] = dict(workload=f"C6b: wrap in a rhombic dodecahedron, {N} atoms ({n_wat + 1} bonded groups) x {F} frames, "
+                                              f"centre = {n_prot} solute atoms; unit cells triclinic / compact / rectangular", **c6b)
+    del d_bv
+    # C10: hydrogen bonds (K12) between the waters of the system: 2 x n_wat donor pairs x n_wat acceptors per frame, 64 frames
+    from moleculekit_b200 import hbonds as hbm
+
+    Fh = 64
+    ow = n_prot + 3 * torch.arange(n_wat, dtype=torch.int32, device=dev)
+    donors = torch.cat([torch.stack([ow, ow + 1], 1), torch.stack([ow, ow + 2], 1)]).contiguous()
+    d_wr = d_orig[:, :, :Fh].contiguous()
+    wr.wrap_box_device(d_wr, d_b[:, :Fh].contiguous(), groups, csel)
+    selw = torch.ones(N, dtype=torch.int32, device=dev)
+    resh = {}
+
+    def run_hb():
+        resh["r"] = hbm.calculate_device(d_wr, d_b[:, :Fh].contiguous(), donors, ow.contiguous(), selw, selw, 2.5, 120, True, False)
+
+    ms = _time_cuda(run_hb, warm=1, steps=3)
+    out["c10_hbonds"] = dict(workload=f"C10: hydrogen bonds, {Fh} frames x {2 * n_wat} donor pairs x {n_wat} acceptors, periodic, "
+                                      "count + ordered fill", ms_per_call=ms, pair_tests_per_s=2.0 * Fh * 2 * n_wat * n_wat / (ms * 1e-3),
+                             bonds_per_frame=float(resh["r"][1].shape[0]) / Fh)
+    del d_c, d_orig, d_b, d_wr
     # C7: `within 5 of <solute>` (K10) on one frame of a 96k-atom solvated system (the reference: 96k x 5.5k brute force)
     from moleculekit_b200 import atomselect_utils as asel
 
