@@ -26,7 +26,8 @@
 
 namespace mkb {
 
-// G[f][k] = (coords[idx[k], 0..2, f], selection bits of idx[k]); bit0: sel1 != 0, bit1: sel1 == 1, bit2: sel2 == 1
+// G[f][k] = (coords[idx[k], 0..2, f], tag of idx[k]); tag bit0: sel1 != 0, bit1: sel1 == 1, bit2: sel2 == 1, bits 3..31: the
+// atom index itself (n_atoms < 2^29), so the pair loop needs no second load
 __global__ void hb_gather_kernel(const float *__restrict__ coords, long long stride, long long n_frames,
                                  const unsigned *__restrict__ idx, long long n, const unsigned *__restrict__ sel1,
                                  const unsigned *__restrict__ sel2, float4 *__restrict__ G) {
@@ -47,19 +48,34 @@ __global__ void hb_gather_kernel(const float *__restrict__ coords, long long str
         if (k < n && f < n_frames) {
             const long long a = (long long)idx[k];
             const unsigned s1 = sel1[a], s2 = sel2[a];
-            const unsigned t = (s1 != 0u ? 1u : 0u) | (s1 == 1u ? 2u : 0u) | (s2 == 1u ? 4u : 0u);
+            const unsigned t = (s1 != 0u ? 1u : 0u) | (s1 == 1u ? 2u : 0u) | (s2 == 1u ? 4u : 0u) | ((unsigned)a << 3);
             G[f * n + k] = make_float4(tile[0][lane][ff], tile[1][lane][ff], tile[2][lane][ff], __uint_as_float(t));
         }
     }
 }
 
-// pyx:88-94: one component of a minimum-image vector, through double exactly as the generated C
-__device__ __forceinline__ float hb_wrap(float val, float b, float hb) {
+// pyx:88-94: one component of a minimum-image vector, through double exactly as the generated C (general path)
+__device__ __noinline__ float hb_wrap_exact(float val, float b, float hb) {
     if (fabsf(val) > hb && b != 0.f) {
         const float n = roundf(__fdiv_rn(val, b));  // round((double)q) of a float q is the same value
         val = __double2float_rn(__dsub_rn((double)val, __dmul_rn((double)b, (double)n)));
     }
     return val;
+}
+
+// Branch-free form of the same step for the pair loop (the scheme of K3's wrap_fast, csrc/distance.cu).  n = rint(val * fl(1/b))
+// by the magic-number trick; w = fmaf(-b, n, val) is the reference's (float)((double)val - (double)b * n): the double
+// product and difference are exact (24-bit operands, |n| < 2^22), so only the final rounding to float remains.  n is the
+// reference's round(fl(val / b)) whenever |w| < b/2 - 1e-6 |val|: were the integers different, val / b would lie within 2e-7
+// of a half-integer and |w| >= b/2 - 3e-7 |val|.  Exact ties, huge quotients, NaN and non-positive boxes fail the test; such
+// pairs set `risky` and are redone with hb_wrap_exact.  No wrap (|val| <= b/2 or b == 0) leaves val untouched, as there.
+__device__ __forceinline__ float hb_wrap_fast(float val, float b, float rb, float hb, bool &risky) {
+    const bool w = fabsf(val) > hb && b != 0.f;
+    const float MAGIC = 12582912.f;  // 1.5 * 2^23
+    const float n = __fsub_rn(__fadd_rn(__fmul_rn(val, rb), MAGIC), MAGIC);
+    const float r = __fmaf_rn(-b, n, val);
+    risky = risky || (w && !(fabsf(r) < __fmaf_rn(-1e-6f, fabsf(val), hb)));
+    return w ? r : val;
 }
 
 struct HbArgs {
@@ -86,33 +102,42 @@ __global__ void __launch_bounds__(256) hbond_kernel(const HbArgs A, long long *_
     const unsigned dbits = __float_as_uint(ph.w);
     const float bx = A.box[f], by = A.box[A.fsb + f], bz = A.box[2 * A.fsb + f];
     const float hx = __fdiv_rn(bx, 2.f), hy = __fdiv_rn(by, 2.f), hz = __fdiv_rn(bz, 2.f);
+    const float rbx = __frcp_rn(bx), rby = __frcp_rn(by), rbz = __frcp_rn(bz);
     const float4 pd = A.ignore_hs ? ph : pH;  // the atom whose distance to the acceptor is tested (pyx:60-64)
     // heavy -> hydrogen vector: the same for every acceptor of the row (pyx:107-114)
     float b0 = 0.f, b1 = 0.f, b2 = 0.f, d2b = 0.f;
     if (!A.ignore_hs) {
-        b0 = hb_wrap(__fsub_rn(ph.x, pH.x), bx, hx);
-        b1 = hb_wrap(__fsub_rn(ph.y, pH.y), by, hy);
-        b2 = hb_wrap(__fsub_rn(ph.z, pH.z), bz, hz);
+        b0 = hb_wrap_exact(__fsub_rn(ph.x, pH.x), bx, hx);
+        b1 = hb_wrap_exact(__fsub_rn(ph.y, pH.y), by, hy);
+        b2 = hb_wrap_exact(__fsub_rn(ph.z, pH.z), bz, hz);
         d2b = __fadd_rn(__fadd_rn(__fmul_rn(b0, b0), __fmul_rn(b1, b1)), __fmul_rn(b2, b2));
     }
     long long base = FILL ? row_offsets[row] : 0;
+    const long long row_end = FILL ? row_offsets[row + 1] : 0;
+    if (FILL && base == row_end) return;  // most (frame, donor) rows have no bond: the count pass already knows
     long long total = 0;
     const float4 *ga = A.GA + f * A.na;
-    for (long long a0 = 0; a0 < A.na; a0 += 32) {
-        const long long a = a0 + lane;
+    const int na = (int)A.na;
+    for (int a0 = 0; a0 < na; a0 += 32) {
+        const int a = a0 + lane;
         bool hit = false;
         unsigned a_idx = 0;
-        if (a < A.na) {
+        if (a < na) {
             const float4 pa = ga[a];
-            a_idx = A.acceptors[a];
             const unsigned abits = __float_as_uint(pa.w);
+            a_idx = abits >> 3;
             bool ok = a_idx != d_heavy;                                            // pyx:67-68
             if (A.intra) ok = ok && (abits & 1u) && (dbits & 1u);                  // pyx:70-73
             else ok = ok && (((abits & 2u) && (dbits & 4u)) || ((abits & 4u) && (dbits & 2u)));  // pyx:74-77
             if (ok) {
-                const float a0v = hb_wrap(__fsub_rn(pa.x, pd.x), bx, hx);
-                const float a1v = hb_wrap(__fsub_rn(pa.y, pd.y), by, hy);
-                const float a2v = hb_wrap(__fsub_rn(pa.z, pd.z), bz, hz);
+                const float v0 = __fsub_rn(pa.x, pd.x), v1 = __fsub_rn(pa.y, pd.y), v2 = __fsub_rn(pa.z, pd.z);
+                bool risky = false;
+                float a0v = hb_wrap_fast(v0, bx, rbx, hx, risky);
+                float a1v = hb_wrap_fast(v1, by, rby, hy, risky);
+                float a2v = hb_wrap_fast(v2, bz, rbz, hz, risky);
+                if (risky) {  // quotient next to a half-integer, or huge: the exactly rounded division
+                    a0v = hb_wrap_exact(v0, bx, hx); a1v = hb_wrap_exact(v1, by, hy); a2v = hb_wrap_exact(v2, bz, hz);
+                }
                 const float d2a = __fadd_rn(__fadd_rn(__fmul_rn(a0v, a0v), __fmul_rn(a1v, a1v)), __fmul_rn(a2v, a2v));
                 if (!(d2a > A.thr2)) {                                             // pyx:97-98 (NaN passes, as there)
                     if (A.ignore_hs) {
@@ -139,6 +164,7 @@ __global__ void __launch_bounds__(256) hbond_kernel(const HbArgs A, long long *_
                 o[2] = (int)a_idx;
             }
             base += __popc(m);
+            if (base == row_end) break;  // every bond of the row is out (warp-uniform)
         } else {
             total += __popc(m);
         }
@@ -185,6 +211,7 @@ static int hb_setup(mkb_ctx *h, cudaStream_t st, const mkb_traj *t, const uint32
         return fail(h, MKB_ERR_BAD_ARG, "frame_stride smaller than n_frames");
     const long long F = t->n_frames, rows = F * n_donors;
     if (rows >= (1ll << 31) / 32) return fail(h, MKB_ERR_BAD_ARG, "frames x donors too large for one call (%lld)", rows);
+    if (t->n_atoms >= (1ll << 29) || n_acceptors >= (1ll << 31)) return fail(h, MKB_ERR_BAD_ARG, "n_atoms must be < 2^29");
     A->F = F; A->fsb = t->frame_stride_box; A->nd = n_donors; A->na = n_acceptors;
     A->box = t->box; A->donors = donors; A->acceptors = acceptors;
     A->thr2 = dist_threshold * dist_threshold;                                            // pyx:49 (float product)
