@@ -166,6 +166,65 @@ def project_sharded(projection, mol, *, gather: bool = True, group=None):
     return res.astype(bool) if local.dtype == bool else res
 
 
+def wrap_sharded(mol, *, gather: bool = True, group=None, wrap_fn=None, **wrap_kwargs):
+    """Molecule.wrap (moleculekit/molecule.py:1987-2090) with the frames split across ranks: frames are independent
+    (wrapping.pyx loops over them outermost), so every rank wraps its block with `wrapping.wrap` (orthorhombic K9 or the
+    triclinic K9b kernels, chosen by the box angles) and no data-path collective is needed.  gather=True leaves the fully
+    wrapped (N, 3, F) array in ``mol.coords`` on every rank (all_gather of the (F_r, 3N) row blocks); gather=False wraps
+    only this rank's frames of ``mol.coords`` in place and returns (f0, f1).  ``wrap_fn(view, **kwargs)`` defaults to
+    `moleculekit_b200.wrapping.wrap` (the gloo tests pass a CPU stand-in)."""
+    if wrap_fn is None:
+        from .wrapping import wrap as wrap_fn
+    world, rank = world_info(group)
+    F = mol.coords.shape[2]
+    off = partition(F, world)
+    f0, f1 = int(off[rank]), int(off[rank + 1])
+    view = _frame_view(mol, f0, f1)
+    for name in ("boxangles", "boxvectors"):  # per-frame cell data follows the frames
+        a = getattr(mol, name, None)
+        if isinstance(a, np.ndarray) and a.shape[-1] == F:
+            try:
+                setattr(view, name, np.ascontiguousarray(a[..., f0:f1]))
+            except AttributeError:  # a read-only property derived from box / boxangles
+                pass
+    if f1 > f0:
+        wrap_fn(view, **wrap_kwargs)
+    mol.coords[:, :, f0:f1] = view.coords
+    if not gather or world == 1:
+        return (f0, f1)
+    N = mol.coords.shape[0]
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    rows = torch.from_numpy(np.ascontiguousarray(np.moveaxis(view.coords, 2, 0)).reshape(f1 - f0, 3 * N)).to(dev)
+    full = gather_rows(rows, [int(off[r + 1] - off[r]) for r in range(world)], group=group)
+    mol.coords[...] = np.moveaxis(full.cpu().numpy().reshape(F, N, 3), 0, 2)
+    return (0, F)
+
+
+def hbonds_sharded(mol, donors, acceptors, sel1="all", sel2=None, *, gather: bool = True, group=None, hbonds_fn=None,
+                   **hb_kwargs):
+    """hbonds_calculate (moleculekit/interactions/interactions.py:365-467) with the frames split across ranks.  Returns the
+    per-frame list of (n, 3) arrays for all frames on every rank (gather=True; the ragged lists travel with
+    all_gather_object, they are small) or this rank's frames and (f0, f1).  ``hbonds_fn`` defaults to
+    `moleculekit_b200.interactions.hbonds_calculate`."""
+    import torch.distributed as dist
+
+    if hbonds_fn is None:
+        from .interactions import hbonds_calculate as hbonds_fn
+    world, rank = world_info(group)
+    F = mol.coords.shape[2]
+    off = partition(F, world)
+    f0, f1 = int(off[rank]), int(off[rank + 1])
+    view = _frame_view(mol, f0, f1)
+    if hasattr(view, "numFrames") and not isinstance(getattr(type(view), "numFrames", None), property):
+        view.numFrames = f1 - f0
+    local = hbonds_fn(view, donors, acceptors, sel1, sel2, **hb_kwargs) if f1 > f0 else []
+    if not gather or world == 1:
+        return (local, (f0, f1)) if not gather else local
+    parts = [None] * world
+    dist.all_gather_object(parts, local, group=group)
+    return [fr for part in parts for fr in part]
+
+
 def _frame_view(mol, f0: int, f1: int):
     """A shallow copy of `mol` restricted to frames [f0, f1) (coords / box sliced, topology shared)."""
     import copy

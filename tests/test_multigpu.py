@@ -31,6 +31,29 @@ g = np.random.default_rng(1)
 mol = MolLite((g.normal(size=(40, 3, 9)) * 6).astype(np.float32), box=np.full((3, 9), 11.0, np.float32))
 m = MetricDistance(np.arange(0, 15), np.arange(15, 40), periodic="selections")
 assert np.array_equal(project_sharded(m, mol, gather=True), m.project(mol))
+# frame-sharded wrapping (orthorhombic K9 and triclinic K9b) and hydrogen bonds (K12) against the single-GPU call
+from moleculekit_b200.sharding import wrap_sharded, hbonds_sharded
+from moleculekit_b200 import wrapping as wr
+from moleculekit_b200.interactions import hbonds_calculate
+N, F = 90, 9
+xyz = (g.normal(size=(N, 3, F)) * 25).astype(np.float32)
+bonds = np.array([[3 * k, 3 * k + 1] for k in range(30)] + [[3 * k, 3 * k + 2] for k in range(30)], dtype=np.uint32)
+sel = np.zeros(N, bool); sel[:12] = True
+for angles in (None, np.repeat(np.array([[60.0], [60.0], [90.0]], np.float32), F, axis=1)):
+    for cell in ("rectangular", "compact", "triclinic"):
+        a = MolLite(xyz.copy(), box=np.full((3, F), 14.0, np.float32), bonds=bonds, boxangles=angles)
+        b = MolLite(xyz.copy(), box=np.full((3, F), 14.0, np.float32), bonds=bonds, boxangles=angles)
+        wr.wrap(a, wrapsel=sel, unitcell=cell)
+        assert wrap_sharded(b, wrapsel=sel, unitcell=cell) == (0, F)
+        assert np.array_equal(a.coords.view(np.uint32), b.coords.view(np.uint32)), (cell, angles is None)
+hx = (g.uniform(0, 1, size=(N, 3, F)) * 9).astype(np.float32)
+don = np.stack([np.arange(0, N, 3), np.arange(1, N, 3)], 1).astype(np.uint32)
+hx[don[:, 1]] = hx[don[:, 0]] + (g.normal(size=(30, 3, F)) * 0.55).astype(np.float32)
+hm = MolLite(hx, box=np.full((3, F), 9.0, np.float32))
+acc = np.arange(2, N, 3, dtype=np.uint32)
+one = hbonds_calculate(hm, don, acc, np.ones(N, bool), dist_threshold=3.0, angle_threshold=100.0)
+two = hbonds_sharded(hm, don, acc, np.ones(N, bool), dist_threshold=3.0, angle_threshold=100.0)
+assert len(two) == F and all(np.array_equal(x, y) for x, y in zip(one, two)) and sum(len(x) for x in one) > 0
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

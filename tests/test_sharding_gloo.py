@@ -87,6 +87,45 @@ def _worker(rank, world, port, tmpdir):
         assert res.shape == (7, 35) and np.array_equal(res, OracleDistance().project(mol))
         part, (f0, f1) = project_sharded(OracleDistance(), mol, gather=False)
         assert (f0, f1) == ((0, 4) if rank == 0 else (4, 7)) and np.array_equal(part, res[f0:f1])
+        # frame-sharded wrapping (orthorhombic and triclinic stand-ins on the oracle) and hydrogen bonds
+        from moleculekit_b200.sharding import hbonds_sharded, wrap_sharded
+
+        groups = np.arange(0, 13, 3, dtype=np.uint32)
+        L = 9.0
+        bv = np.repeat(np.array([[L, 0, 0], [0, L, 0], [L / 2, L / 2, L * 2 ** 0.5 / 2]])[:, :, None], 7, axis=2)
+
+        def oracle_wrap(m, mode=None):
+            if mode is None:
+                cpu_oracle.wrap_box(groups, m.coords, m.box, np.arange(3, dtype=np.uint32), np.zeros(3, np.float32))
+            else:
+                cpu_oracle.wrap_compact_unitcell(groups, m.coords, m.boxvectors, np.arange(3, dtype=np.uint32),
+                                                 np.zeros(3, np.float32), mode)
+
+        for mode in (None, 1):
+            want = MolLite(mol.coords.copy(), box=mol.box.copy()); want.boxvectors = bv
+            oracle_wrap(want, mode)
+            got = MolLite(mol.coords.copy(), box=mol.box.copy()); got.boxvectors = bv
+            assert wrap_sharded(got, wrap_fn=oracle_wrap, mode=mode) == (0, 7)
+            assert np.array_equal(got.coords, want.coords), mode
+            part = MolLite(mol.coords.copy(), box=mol.box.copy()); part.boxvectors = bv
+            f0, f1 = wrap_sharded(part, gather=False, wrap_fn=oracle_wrap, mode=mode)
+            assert (f0, f1) == ((0, 4) if rank == 0 else (4, 7))
+            assert np.array_equal(part.coords[:, :, f0:f1], want.coords[:, :, f0:f1])
+            other = np.ones(7, bool); other[f0:f1] = False
+            assert np.array_equal(part.coords[:, :, other], mol.coords[:, :, other])
+
+        don = np.array([[0, 1], [3, 4], [6, 7]], dtype=np.uint32); acc = np.array([2, 5, 8, 11], dtype=np.uint32)
+        ones = np.ones(12, np.uint32)
+
+        def oracle_hb(m, donors, acceptors, sel1, sel2, **kw):
+            r = cpu_oracle.hbonds_calculate(donors, acceptors, m.coords, m.box, ones, ones, 6.0, 20.0, True, False)
+            return [np.array(x, dtype=np.int64).reshape(-1, 3) for x in r]
+
+        want = oracle_hb(mol, don, acc, None, None)
+        got = hbonds_sharded(mol, don, acc, hbonds_fn=oracle_hb)
+        assert len(got) == 7 and all(np.array_equal(a, b) for a, b in zip(got, want)) and sum(len(x) for x in want) > 0
+        loc, (f0, f1) = hbonds_sharded(mol, don, acc, gather=False, hbonds_fn=oracle_hb)
+        assert len(loc) == f1 - f0 and all(np.array_equal(a, b) for a, b in zip(loc, want[f0:f1]))
         open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
