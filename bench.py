@@ -248,6 +248,55 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------- side measurements
+def cpu_next_rows(extra):
+    """One core of the reference's own compiled kernels (oracle/_ref; else the C port) on bounded samples of the K9b / K12
+    bench workloads (~1 s each), beside the GPU numbers of extra['c6b_wrap_triclinic'] / extra['c10_hbonds']."""
+    from oracle import build_ref, cpu_oracle
+
+    mods = build_ref.load()
+    kind = "reference" if mods is not None and len(mods) >= 7 else "port"
+    rng = np.random.default_rng(3)
+    out = {"kind": kind, "cores": 1}
+    # wrapping: 6000 atoms (1 solute of 600 + 1800 waters) x 4 frames in a rhombic dodecahedron
+    n_prot, n_wat, F, L = 600, 1800, 4, 82.0
+    N = n_prot + 3 * n_wat
+    xyz = (rng.normal(0, 120, size=(N, 3, F))).astype(np.float32)
+    groups = np.concatenate([[0], n_prot + 3 * np.arange(n_wat + 1)]).astype(np.uint32)
+    bv = np.repeat(np.array([[L, 0, 0], [0, L, 0], [L / 2, L / 2, L * 2 ** 0.5 / 2]])[:, :, None], F, axis=2)
+    cs, zero = np.arange(n_prot, dtype=np.uint32), np.zeros(3, np.float32)
+    for name, mode in (("triclinic", None), ("compact", 1), ("rectangular", 0)):
+        c = xyz.copy()
+        t0 = time.perf_counter()
+        if kind == "reference":
+            (mods[3].wrap_triclinic_unitcell(groups, c, bv, cs, zero) if mode is None else
+             mods[3].wrap_compact_unitcell(groups, c, bv, cs, zero, mode))
+        else:
+            (cpu_oracle.wrap_triclinic_unitcell(groups, c, bv, cs, zero) if mode is None else
+             cpu_oracle.wrap_compact_unitcell(groups, c, bv, cs, zero, mode))
+        dt = time.perf_counter() - t0
+        g = extra.get("c6b_wrap_triclinic", {}).get(name, {}).get("atom_frames_per_s")
+        out[f"wrap_{name}"] = dict(atom_frames_per_s=N * F / dt, sample=f"{N} atoms x {F} frames",
+                                   gpu_over_one_core=(g / (N * F / dt)) if g else None)
+    # hydrogen bonds: 1 frame, 2400 donor pairs x 1200 acceptors of a periodic water box
+    nw = 1200
+    O = rng.uniform(0, 33.0, size=(nw, 3, 1))
+    h = rng.normal(size=(2, nw, 3, 1)); h /= np.linalg.norm(h, axis=2, keepdims=True)
+    c = np.empty((3 * nw, 3, 1), np.float32); c[0::3] = O; c[1::3] = O + 0.96 * h[0]; c[2::3] = O + 0.96 * h[1]
+    o = np.arange(0, 3 * nw, 3)
+    don = np.concatenate([np.stack([o, o + 1], 1), np.stack([o, o + 2], 1)]).astype(np.uint32)
+    acc, ones, box = o.astype(np.uint32), np.ones(3 * nw, np.uint32), np.full((3, 1), 33.0, np.float32)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        mods[6].calculate(don, acc, c, box, ones, ones, dist_threshold=2.5, angle_threshold=120, intra=True, ignore_hs=False)
+    else:
+        cpu_oracle.hbonds_calculate(don, acc, c, box, ones, ones, 2.5, 120, True, False)
+    dt = time.perf_counter() - t0
+    g = extra.get("c10_hbonds", {}).get("pair_tests_per_s")
+    out["hbonds"] = dict(pair_tests_per_s=len(don) * len(acc) / dt, sample=f"1 frame x {len(don)} donor pairs x {len(acc)} acceptors",
+                         gpu_over_one_core=(g / (len(don) * len(acc) / dt)) if g else None)
+    return out
+
+
 def _time_cuda(fn, warm=3, steps=10):
     import torch
 
@@ -815,6 +864,11 @@ def run_ours(a):
         v, _ = arm.step()
         arm.close()
         cpu = arm.describe(v)
+        if isinstance(extra, dict) and "error" not in extra:
+            try:
+                extra["cpu_reference_next_rows"] = cpu_next_rows(extra)
+            except Exception as e:
+                extra["cpu_reference_next_rows"] = {"error": repr(e)}
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic",

@@ -4,6 +4,7 @@ Mirrors of the detectors in the reference that are thin consumers of ``calculate
 (moleculekit/interactions/interactions.py):
 
   hbonds_calculate                :365-467     donor-H ... acceptor distance + angle test per frame (K12)
+  waterbridge_calculate           :470-618     chains of hydrogen bonds through waters (host graph search over K12 shells)
   saltbridge_calculate            :724-788     charged atoms within `threshold`, one positive + one negative per pair
   hydrophobic_calculate           :949-992     carbon - carbon contacts
   metal_coordination_calculate    :995-1056    metal - (N, O, S, halogen) contacts, both directions
@@ -117,3 +118,67 @@ def hbonds_calculate(mol, donors, acceptors, sel1="all", sel2=None, dist_thresho
         dist_threshold=float(dist_threshold), angle_threshold=float(angle_threshold), intra=bool(intra),
         ignore_hs=bool(ignore_hs), device=device)
     return [tri[off[f]:off[f + 1]].astype(np.int64).reshape(-1, 3) for f in range(mol.numFrames)]
+
+
+def waterbridge_calculate(mol, donors, acceptors, sel1, sel2, order: int = 1, dist_threshold: float = 2.5,
+                          angle_threshold: float = 120, ignore_hs: bool = False, water="water", device=None):
+    """interactions.py:470-618: per frame the list of atom-index paths from a sel1 atom to a sel2 atom whose intermediate
+    atoms are all water; the hydrogen-bond shells run on K12, the path search is the reference's networkx walk.  ``water``:
+    selection of the water atoms (string for ``mol.atomselect``, mask or indices; the reference hard-codes "water")."""
+    import networkx as nx
+
+    if len(donors) == 0 or len(acceptors) == 0:
+        return [[] for _ in range(mol.numFrames)]
+    sel1_b, sel2_b, water_b = _mask(mol, sel1), _mask(mol, sel2), _mask(mol, water)
+    args = dict(mol=mol, donors=donors, acceptors=acceptors, dist_threshold=dist_threshold,
+                angle_threshold=angle_threshold, ignore_hs=ignore_hs, device=device)
+    water_goal = water_b | sel2_b
+    water_goal_idx = np.where(water_goal)[0]
+    water_idx = np.where(water_b)[0]
+    order += 1  # an order-1 bridge needs two shells to reach the target (interactions.py:556-557)
+    edges = [[] for _ in range(mol.numFrames)]
+    sel1_b_curr = sel1_b.copy()
+    for _ in range(order):
+        curr_shell = hbonds_calculate(sel1=sel1_b_curr, sel2=water_goal, **args)
+        for f in range(mol.numFrames):
+            curr_shell[f] = np.array(curr_shell[f])
+            if len(curr_shell[f]) == 0:
+                continue
+            has_water = np.any(np.isin(curr_shell[f], water_idx), axis=1)  # keep interactions with at least one water
+            curr_shell[f] = curr_shell[f][has_water, :]
+            if ignore_hs:
+                edges[f].append(curr_shell[f][:, [0, 2]])
+            else:
+                edges[f].append(curr_shell[f][:, :2])
+                edges[f].append(curr_shell[f][:, 1:])
+        curr_shell = [cs for cs in curr_shell if len(cs) > 0]
+        if len(curr_shell) == 0:
+            break
+        shell = np.vstack(curr_shell)[:, [0, 2]]
+        sel1_b_curr = np.zeros(mol.numAtoms, dtype=bool)
+        interacted = np.unique(shell[np.isin(shell, water_goal_idx)])
+        if len(interacted) == 0:
+            break
+        sel1_b_curr[interacted] = True
+    sel1_idx, sel2_idx = np.where(sel1_b)[0], np.where(sel2_b)[0]
+    water_bridges = []
+    for f in range(mol.numFrames):
+        water_bridges.append([])
+        if len(edges[f]) == 0:
+            continue
+        ee = np.vstack(edges[f])
+        starts = np.unique(ee[np.isin(ee, sel1_idx)])
+        ends = np.unique(ee[np.isin(ee, sel2_idx)])
+        if not (np.any(starts) and np.any(ends)):  # (the reference's test: also skips when the only index is 0)
+            continue
+        network = nx.Graph()
+        network.add_edges_from(ee)
+        for st in starts:
+            for en in ends:
+                for pp in nx.all_simple_paths(network, source=st, target=en):
+                    if len(pp) < 3:
+                        continue
+                    if not np.all(np.isin(pp[1:-1], water_idx)):
+                        continue
+                    water_bridges[f].append(pp)
+    return water_bridges

@@ -112,6 +112,11 @@ def g_tric():
 
 
 @pytest.fixture(scope="session")
+def g_waterbridge():
+    return _npz("waterbridge.npz")
+
+
+@pytest.fixture(scope="session")
 def g_hbonds():
     return _npz("hbonds.npz")
 

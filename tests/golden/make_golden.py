@@ -294,6 +294,64 @@ def hbonds_fixture():
     print("hbonds.npz", mol.numAtoms, "atoms,", len(donors), "donors,", len(acceptors), "acceptors")
 
 
+def _sdf_molecule(path, resname):
+    """A Molecule from a V2000 SDF read by hand (no rdkit): coordinates, elements, bonds."""
+    from moleculekit.molecule import Molecule
+
+    lines = open(path).read().splitlines()
+    na, nb = int(lines[3][:3]), int(lines[3][3:6])
+    xyz = np.array([[float(l[0:10]), float(l[10:20]), float(l[20:30])] for l in lines[4:4 + na]], dtype=np.float32)
+    elem = [l[31:34].strip() for l in lines[4:4 + na]]
+    lbonds = np.array([[int(l[0:3]) - 1, int(l[3:6]) - 1] for l in lines[4 + na:4 + na + nb]])
+    lig = Molecule().empty(na)
+    lig.coords = xyz[:, :, None].copy()
+    lig.element[:] = elem
+    lig.name[:] = [f"{e}{i}" for i, e in enumerate(elem)]
+    lig.resname[:] = resname
+    lig.record[:] = "HETATM"
+    lig.resid[:] = 1
+    lig.bonds = lbonds.astype(np.uint32)
+    lig.bondtype = np.array(["1"] * nb, dtype=object)
+    return lig, elem, lbonds
+
+
+def waterbridge_fixture():
+    """waterbridge.npz: the reference's water-bridge test (tests/test_interactions.py:255-326) rebuilt without rdkit (the
+    glycerol ligand read from the SDF by hand).  Stored: coordinates, donors / acceptors of the reference's
+    get_donors_acceptors(exclude_water=False), the selection masks the test uses, and the reference's outputs -- asserted
+    equal to the constants written in the test before they are stored."""
+    from moleculekit.interactions.interactions import get_donors_acceptors, waterbridge_calculate
+    from moleculekit.molecule import Molecule
+
+    d = os.path.join(REFT, "test_interactions")
+    mol = Molecule(os.path.join(d, "5gw6_receptor_H_wet.pdb"))
+    mol.bonds = mol._guessBonds()
+    lig, _, _ = _sdf_molecule(os.path.join(d, "5gw6_ligand-RDK.sdf"), "GOL")
+    mol.append(lig)
+    donors, acceptors = get_donors_acceptors(mol, exclude_water=False, exclude_backbone=False)
+    asn = "protein and resname ASN and resid 155"
+    w = {"coords": mol.coords.astype(np.float32), "box": mol.box.astype(np.float32), "donors": donors, "acceptors": acceptors,
+         "gol": mol.atomselect("resname GOL"), "asn155": mol.atomselect(asn), "protein": mol.atomselect("protein"),
+         "water": mol.atomselect("water")}
+    kw = dict(dist_threshold=3.8, ignore_hs=True)
+    wb1 = waterbridge_calculate(mol, donors, acceptors, "resname GOL", asn, order=1, **kw)
+    assert np.array_equal(wb1, [[[3140, 2899, 2024]]]), wb1
+    wb2 = waterbridge_calculate(mol, donors, acceptors, "resname GOL", asn, order=2, **kw)
+    assert [list(map(int, p)) for p in wb2[0]] == [[3140, 2899, 2944, 2023], [3140, 2899, 2024]], wb2
+    wb3 = waterbridge_calculate(mol, donors, acceptors, "resname GOL", "protein", order=1, **kw)
+    assert np.array_equal(wb3, [[[3140, 2899, 2024], [3142, 2857, 1317], [3142, 2857, 2720], [3142, 2857, 2737],
+                                 [3142, 2857, 2789]]]), wb3
+    wb4 = waterbridge_calculate(mol, donors, acceptors, "resname GOL", "protein", order=1, dist_threshold=2.6)  # with hydrogens
+
+    def flat(wb):  # ragged paths of frame 0 -> (lengths, concatenated indices)
+        return np.array([len(p) for p in wb[0]], dtype=np.int64), np.array([i for p in wb[0] for i in p], dtype=np.int64)
+
+    for name, wb in (("wb1", wb1), ("wb2", wb2), ("wb3", wb3), ("wb4", wb4)):
+        w[f"{name}_len"], w[f"{name}_idx"] = flat(wb)
+    np.savez_compressed(os.path.join(HERE, "waterbridge.npz"), **w)
+    print("waterbridge.npz", mol.numAtoms, "atoms", len(donors), "donors", len(acceptors), "acceptors; with-H bridges:", len(wb4[0]))
+
+
 def rotation_fixture():
     """rotate.npz: outputs of the reference's rotateCoordinates (tools/voxeldescriptors.py:78-114) and rotationMatrix
     (util.py:70-117) on seeded inputs -- the float64 targets of mkb_rotate_coords."""
@@ -487,6 +545,9 @@ def main():
     if "--only-triclinic" in sys.argv:
         assert build_ref.build()
         triclinic_fixture()
+        return
+    if "--only-waterbridge" in sys.argv:
+        waterbridge_fixture()
         return
     if "--only-hbonds" in sys.argv:
         assert build_ref.build()

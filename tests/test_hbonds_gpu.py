@@ -111,3 +111,30 @@ def test_angle_threshold_sweep_vs_oracle(oracle):
         want = oracle.hbonds_calculate(donors, acc, coords, box, s1, s1, 3.0, ath, True, False)
         got = hbonds.calculate(donors, acc, coords, box, s1, s1, dist_threshold=3.0, angle_threshold=ath, intra=True)
         assert got == want, ath
+
+
+def _paths(g, name):
+    out, pos = [], 0
+    for n in g[f"{name}_len"]:
+        out.append([int(i) for i in g[f"{name}_idx"][pos:pos + n]])
+        pos += int(n)
+    return out
+
+
+def test_waterbridge_reference_test_case(g_waterbridge):
+    """tests/test_interactions.py:255-326 through the waterbridge_calculate mirror (K12 shells + the reference's graph walk):
+    the paths written in the reference test for order 1 / 2 and for the whole protein, plus a with-hydrogens variant."""
+    from moleculekit_b200.interactions import waterbridge_calculate
+
+    g = g_waterbridge
+    mol = _Mol(g["coords"], g["box"])
+    kw = dict(dist_threshold=3.8, ignore_hs=True, water=g["water"])
+    wb = waterbridge_calculate(mol, g["donors"], g["acceptors"], g["gol"], g["asn155"], order=1, **kw)
+    assert [list(map(int, p)) for p in wb[0]] == [[3140, 2899, 2024]] == _paths(g, "wb1")
+    wb = waterbridge_calculate(mol, g["donors"], g["acceptors"], g["gol"], g["asn155"], order=2, **kw)
+    assert [list(map(int, p)) for p in wb[0]] == [[3140, 2899, 2944, 2023], [3140, 2899, 2024]] == _paths(g, "wb2")
+    wb = waterbridge_calculate(mol, g["donors"], g["acceptors"], g["gol"], g["protein"], order=1, **kw)
+    assert [list(map(int, p)) for p in wb[0]] == _paths(g, "wb3") and len(wb[0]) == 5
+    wb = waterbridge_calculate(mol, g["donors"], g["acceptors"], g["gol"], g["protein"], order=1, dist_threshold=2.6,
+                               water=g["water"])
+    assert [list(map(int, p)) for p in wb[0]] == _paths(g, "wb4")

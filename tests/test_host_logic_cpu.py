@@ -116,3 +116,38 @@ def test_wrap_box_rejects_unordered_groups():
     box = np.full((3, 2), 10.0, np.float32)
     with pytest.raises(ValueError, match="ascending"):
         wrap_box(np.array([0, 6, 3, 10], np.uint32), xyz, box, np.arange(3, dtype=np.uint32), np.zeros(3, np.float32))
+
+
+def test_waterbridge_host_logic(g_waterbridge, oracle, monkeypatch):
+    """The graph walk of the waterbridge_calculate mirror (interactions.py:470-618) with the hydrogen-bond shells supplied by
+    the CPU oracle instead of K12 (test stand-in): the paths written in tests/test_interactions.py:279-326."""
+    from moleculekit_b200 import interactions as it
+
+    g = g_waterbridge
+
+    class Mol:
+        coords, box = g["coords"], g["box"]
+        numAtoms, numFrames = g["coords"].shape[0], g["coords"].shape[2]
+
+    def hb_stand_in(mol, donors, acceptors, sel1="all", sel2=None, dist_threshold=2.5, angle_threshold=120, ignore_hs=False,
+                    device=None):
+        s1 = np.asarray(sel1, bool).astype(np.uint32)
+        s2 = s1.copy() if sel2 is None else np.asarray(sel2, bool).astype(np.uint32)
+        sel_idx = np.where(s1.astype(bool) | s2.astype(bool))[0]
+        donors = donors[np.all(np.isin(donors, sel_idx), axis=1)]
+        acceptors = acceptors[np.isin(acceptors, sel_idx)]
+        if ignore_hs:
+            donors = np.unique(donors[:, 0])[:, None]
+        r = oracle.hbonds_calculate(donors.astype(np.uint32), acceptors.astype(np.uint32), mol.coords, mol.box, s1, s2,
+                                    float(dist_threshold), float(angle_threshold), sel2 is None, bool(ignore_hs))
+        return [np.asarray(x, dtype=np.int64).reshape(-1, 3) for x in r]
+
+    monkeypatch.setattr(it, "hbonds_calculate", hb_stand_in)
+    kw = dict(dist_threshold=3.8, ignore_hs=True, water=g["water"])
+    wb = it.waterbridge_calculate(Mol, g["donors"], g["acceptors"], g["gol"], g["asn155"], order=1, **kw)
+    assert [list(map(int, p)) for p in wb[0]] == [[3140, 2899, 2024]]
+    wb = it.waterbridge_calculate(Mol, g["donors"], g["acceptors"], g["gol"], g["asn155"], order=2, **kw)
+    assert [list(map(int, p)) for p in wb[0]] == [[3140, 2899, 2944, 2023], [3140, 2899, 2024]]
+    wb = it.waterbridge_calculate(Mol, g["donors"], g["acceptors"], g["gol"], g["protein"], order=1, **kw)
+    assert [list(map(int, p)) for p in wb[0]] == [[3140, 2899, 2024], [3142, 2857, 1317], [3142, 2857, 2720],
+                                                  [3142, 2857, 2737], [3142, 2857, 2789]]
