@@ -298,7 +298,8 @@ int mkb_wrap_triclinic(mkb_handle_t h, void *stream, const mkb_traj *t, const do
  * Two calls like K4 -- count: row_offsets [n_frames*n_donors + 1] int64 device = exclusive scan of the per-(frame, donor)
  * hit counts, *total_triples (HOST) the total (synchronises the stream); fill: triples [total][3] int32 device =
  * (heavy, hydrogen | -1, acceptor) in the reference's order (frame, donor, acceptor ascending).  Same booleans as the
- * reference binary: float / double operations as in the generated C, the acos comparison as a precomputed cosine bound. */
+ * reference binary (built as C++: round / sqrt / acos on float arguments are the float overloads), the acosf comparison as
+ * a precomputed cosine bound. */
 int mkb_hbonds_count(mkb_handle_t h, void *stream, const mkb_traj *t, const uint32_t *donors, int64_t n_donors,
                      const uint32_t *acceptors, int64_t n_acceptors, const uint32_t *sel1, const uint32_t *sel2,
                      float dist_threshold, float angle_threshold, int32_t intra, int32_t ignore_hs, int64_t *row_offsets,
@@ -307,6 +308,26 @@ int mkb_hbonds_fill(mkb_handle_t h, void *stream, const mkb_traj *t, const uint3
                     const uint32_t *acceptors, int64_t n_acceptors, const uint32_t *sel1, const uint32_t *sel2,
                     float dist_threshold, float angle_threshold, int32_t intra, int32_t ignore_hs,
                     const int64_t *row_offsets, int32_t *triples);
+
+/* K13: ring-based interaction detectors over a trajectory.  mode 0 replaces pipi.calculate
+ * (moleculekit/interactions/pipi/pipi.pyx:86-185), mode 1 cationpi.calculate (interactions/cationpi/cationpi.pyx:91-173),
+ * mode 2 sigmahole.calculate (interactions/sigmahole/sigmahole.pyx:91-174); callers pipi_calculate / cationpi_calculate /
+ * sigmahole_calculate (moleculekit/interactions/interactions.py:621-946).  rings_atoms uint32 device: concatenated ring atom
+ * indexes; starts1 [n_rings1 + 1] uint32 device: ring start indexes of the first set.  second, uint32 device: mode 0 the start
+ * indexes [n_second + 1] of the second ring set inside the same rings_atoms; mode 1 cation atom indexes [n_second]; mode 2
+ * (halogen, bonded partner) pairs [n_second][2].  p0..p3: mode 0 dist_threshold1, angle_threshold1_max, dist_threshold2,
+ * angle_threshold2_min; modes 1 / 2 dist_threshold, angle_threshold_min (p2, p3 unused).  Two calls like K4 -- count:
+ * row_offsets [n_frames*n_rings1 + 1] int64 device, *total_pairs (HOST; synchronises the stream); fill: pairs [total][2]
+ * int32 device = (ring index, second ring index | cation atom | halogen atom) and distangles [total][2] float32 device =
+ * (distance, angle in degrees), in the reference's order (frame, ring, partner ascending).  Pairs and distances are the
+ * reference binary's; the reported angle is within a few ulp (it comes from the device's acos, the reference's from glibc's
+ * acosf). */
+int mkb_ring_pairs_count(mkb_handle_t h, void *stream, int32_t mode, const mkb_traj *t, const uint32_t *rings_atoms,
+                         const uint32_t *starts1, int64_t n_rings1, const uint32_t *second, int64_t n_second, float p0,
+                         float p1, float p2, float p3, int64_t *row_offsets, int64_t *total_pairs);
+int mkb_ring_pairs_fill(mkb_handle_t h, void *stream, int32_t mode, const mkb_traj *t, const uint32_t *rings_atoms,
+                        const uint32_t *starts1, int64_t n_rings1, const uint32_t *second, int64_t n_second, float p0,
+                        float p1, float p2, float p3, const int64_t *row_offsets, int32_t *pairs, float *distangles);
 
 #ifdef __cplusplus
 }

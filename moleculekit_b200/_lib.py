@@ -40,7 +40,7 @@ EXPORTS = [
     "mkb_dist_trajectory", "mkb_contacts_count", "mkb_contacts_fill", "mkb_dist_reduction",
     "mkb_cdist", "mkb_pdist", "mkb_squareform", "mkb_collisions_count", "mkb_collisions_fill",
     "mkb_bonds_count", "mkb_bonds_fill", "mkb_shell_counts", "mkb_wrap_box", "mkb_within_distance", "mkb_xtc_decode",
-    "mkb_wrap_triclinic", "mkb_hbonds_count", "mkb_hbonds_fill",
+    "mkb_wrap_triclinic", "mkb_hbonds_count", "mkb_hbonds_fill", "mkb_ring_pairs_count", "mkb_ring_pairs_fill",
 ]
 
 _lib = None
@@ -109,6 +109,8 @@ def load():
     lib.mkb_wrap_triclinic.argtypes = [vp, vp, tp, vp, i64, vp, i64, vp, i64, C.POINTER(C.c_float), i32]
     lib.mkb_hbonds_count.argtypes = [vp, vp, tp, vp, i64, vp, i64, vp, vp, f32, f32, i32, i32, vp, C.POINTER(i64)]
     lib.mkb_hbonds_fill.argtypes = [vp, vp, tp, vp, i64, vp, i64, vp, vp, f32, f32, i32, i32, vp, vp]
+    lib.mkb_ring_pairs_count.argtypes = [vp, vp, i32, tp, vp, vp, i64, vp, i64, f32, f32, f32, f32, vp, C.POINTER(i64)]
+    lib.mkb_ring_pairs_fill.argtypes = [vp, vp, i32, tp, vp, vp, i64, vp, i64, f32, f32, f32, f32, vp, vp, vp]
     for name in EXPORTS:
         if name in ("mkb_last_error", "mkb_launch_count", "mkb_version", "mkb_last_kernel", "mkb_occupancy_compact_blocks"):
             continue

@@ -7,16 +7,18 @@
 // ORDER of the output is sequential, so this is the count -> scan -> ordered-fill scheme of K4 (one warp per
 // (frame, donor) row, ballot + popc ranks inside the row).
 //
-// Bit parity.  The generated C keeps `val`, the squared lengths, the dot product and `angle` in float and goes through
-// double for the wrap (libc round on the float quotient, float * double product), the square roots and acos:
-//   val  = a - d (float);  if |val| > box/2 and box != 0:  val = (float)((double)val - (double)box * round((double)(val / box)))
-//   d2   = (v0*v0 + v1*v1) + v2*v2 (float, each op rounded);  skip when d2 > thr*thr  (a NaN d2 is NOT skipped)
-//   cosv = (float)((double)dot / (sqrt((double)d2a) * sqrt((double)d2b))), clamped to [-1, 1]
-//   hit  = (float)acos((double)cosv) > (float)(angle_threshold / 57.29578)
-// Every operation above has an IEEE counterpart on the device (__f*_rn / __d*_rn, roundf == round on a float value)
-// except acos.  (float)acos((double)c) is a non-increasing function of the float c, so the host finds, with the same libm
-// the reference calls, the largest float c* whose rounded arc cosine still exceeds the threshold; the device tests
-// c <= c* -- the same booleans without a device acos (the trick K3 uses for sqrt).
+// Bit parity.  The reference is compiled as C++ (setup.py: language="c++"): the unqualified round / sqrt / acos of the generated
+// code, called on float arguments, resolve to the FLOAT overloads of <cmath>.  So
+//   val  = a - d;  if |val| > box/2 and box != 0:  val = val - fl(box * roundf(fl(val / box)))      (every op rounded to float,
+//                                                                                                   the _dist of distance_utils)
+//   d2   = (v0*v0 + v1*v1) + v2*v2 (float);  skip when d2 > thr*thr  (a NaN d2 is NOT skipped)
+//   cosv = (float)((double)dot / (double)fl(sqrtf(d2a) * sqrtf(d2b))), clamped to [-1, 1]
+//   hit  = acosf(cosv) > (float)(angle_threshold / 57.29578)
+// (a restatement that went through double, as the .pyx reads in C, differs from the reference binary in ~2 bonds per
+// 10 million; tests/test_oracle_golden.py::test_hbonds_float_overloads).  Every operation has an IEEE counterpart on the
+// device (__f*_rn, __ddiv_rn) except acosf.  acosf is a non-increasing function of its float argument, so the host finds,
+// with the same libm the reference calls, the largest float c* whose arc cosine still exceeds the threshold; the device
+// tests c <= c* -- the same booleans without a device acos (the trick K3 uses for sqrt).
 #include <cmath>
 #include <cstring>
 
@@ -54,26 +56,22 @@ __global__ void hb_gather_kernel(const float *__restrict__ coords, long long str
     }
 }
 
-// pyx:88-94: one component of a minimum-image vector, through double exactly as the generated C (general path)
+// pyx:88-94: one component of a minimum-image vector, every operation rounded to float (general path)
 __device__ __noinline__ float hb_wrap_exact(float val, float b, float hb) {
-    if (fabsf(val) > hb && b != 0.f) {
-        const float n = roundf(__fdiv_rn(val, b));  // round((double)q) of a float q is the same value
-        val = __double2float_rn(__dsub_rn((double)val, __dmul_rn((double)b, (double)n)));
-    }
+    if (fabsf(val) > hb && b != 0.f) val = __fsub_rn(val, __fmul_rn(b, roundf(__fdiv_rn(val, b))));
     return val;
 }
 
-// Branch-free form of the same step for the pair loop (the scheme of K3's wrap_fast, csrc/distance.cu).  n = rint(val * fl(1/b))
-// by the magic-number trick; w = fmaf(-b, n, val) is the reference's (float)((double)val - (double)b * n): the double
-// product and difference are exact (24-bit operands, |n| < 2^22), so only the final rounding to float remains.  n is the
-// reference's round(fl(val / b)) whenever |w| < b/2 - 1e-6 |val|: were the integers different, val / b would lie within 2e-7
-// of a half-integer and |w| >= b/2 - 3e-7 |val|.  Exact ties, huge quotients, NaN and non-positive boxes fail the test; such
-// pairs set `risky` and are redone with hb_wrap_exact.  No wrap (|val| <= b/2 or b == 0) leaves val untouched, as there.
+// Branch-free form of the same step for the pair loop: K3's wrap_fast (csrc/distance.cu).  n = rint(val * fl(1/b)) by the
+// magic-number trick, r = val - fl(b n) as the reference rounds it, and ONE test that n is the reference's
+// roundf(fl(val / b)):  |r| < b/2 - 1e-6 |val|.  Were the integers different, val / b would lie within 2e-7 of a half-integer
+// and |r| >= b/2 - 3e-7 |val|.  Exact ties, |val / b| >= 2^22, NaN and non-positive boxes fail the test; such pairs set
+// `risky` and are redone with hb_wrap_exact.  No wrap (|val| <= b/2 or b == 0) leaves val untouched, as there.
 __device__ __forceinline__ float hb_wrap_fast(float val, float b, float rb, float hb, bool &risky) {
     const bool w = fabsf(val) > hb && b != 0.f;
     const float MAGIC = 12582912.f;  // 1.5 * 2^23
     const float n = __fsub_rn(__fadd_rn(__fmul_rn(val, rb), MAGIC), MAGIC);
-    const float r = __fmaf_rn(-b, n, val);
+    const float r = __fsub_rn(val, __fmul_rn(b, n));
     risky = risky || (w && !(fabsf(r) < __fmaf_rn(-1e-6f, fabsf(val), hb)));
     return w ? r : val;
 }
@@ -147,10 +145,10 @@ __global__ void __launch_bounds__(256) hbond_kernel(const HbArgs A, long long *_
                         dot = __fadd_rn(dot, __fmul_rn(a1v, b1));
                         dot = __fadd_rn(dot, __fmul_rn(a2v, b2));
                         float c = __double2float_rn(
-                            __ddiv_rn((double)dot, __dmul_rn(__dsqrt_rn((double)d2a), __dsqrt_rn((double)d2b))));
+                            __ddiv_rn((double)dot, (double)__fmul_rn(__fsqrt_rn(d2a), __fsqrt_rn(d2b))));  // sqrtf * sqrtf in float
                         if (c > 1.f) c = 1.f;
                         if (c < -1.f) c = -1.f;
-                        hit = c <= A.cstar;                                        // (float)acos(c) > angle threshold
+                        hit = c <= A.cstar;                                        // acosf(c) > angle threshold
                     }
                 }
             }
@@ -176,9 +174,10 @@ __global__ void hb_set_last_zero(long long *p, long long n) {
     if (threadIdx.x == 0 && blockIdx.x == 0) p[n] = 0;
 }
 
-// largest float c in [-1, 1] with (float)acos((double)c) > athr (host libm = the reference's); -inf when none
+// largest float c in [-1, 1] with acosf(c) > athr (host libm = the reference's); -inf when none.  glibc's acosf is
+// non-increasing over all 2.13e9 floats of [-1, 1] (checked exhaustively on glibc 2.39), so one bound is exact.
 static float hb_cos_threshold(float athr) {
-    auto passes = [&](float c) { return (float)acos((double)c) > athr; };
+    auto passes = [&](float c) { return acosf(c) > athr; };
     if (!passes(-1.f)) return -INFINITY;
     if (passes(1.f)) return 1.f;
     auto key = [](float x) {  // order-preserving integer image of a float

@@ -5,6 +5,7 @@ Mirrors of the detectors in the reference that are thin consumers of ``calculate
 
   hbonds_calculate                :365-467     donor-H ... acceptor distance + angle test per frame (K12)
   waterbridge_calculate           :470-618     chains of hydrogen bonds through waters (host graph search over K12 shells)
+  pipi_calculate / cationpi_calculate / sigmahole_calculate   :621-946   ring centroid / normal tests per frame (K13)
   saltbridge_calculate            :724-788     charged atoms within `threshold`, one positive + one negative per pair
   hydrophobic_calculate           :949-992     carbon - carbon contacts
   metal_coordination_calculate    :995-1056    metal - (N, O, S, halogen) contacts, both directions
@@ -12,8 +13,9 @@ Mirrors of the detectors in the reference that are thin consumers of ``calculate
 
 Selections are boolean masks / index arrays, or strings resolved by ``mol.atomselect``; the pair search itself is
 ``mkb_contacts_count`` + ``mkb_contacts_fill`` (bit-exact index output, reference order); hydrogen bonds run in
-``mkb_hbonds_count`` + ``mkb_hbonds_fill``.  The ring based detectors (pi-pi, cation-pi, sigma holes) are a different
-algorithm family and stay with moleculekit.
+``mkb_hbonds_count`` + ``mkb_hbonds_fill``, the ring detectors in ``mkb_ring_pairs_count`` + ``mkb_ring_pairs_fill``.  The
+perception helpers that need rdkit or residue templates (get_ligand_rings, get_protein_rings, ...) stay with moleculekit:
+rings, cations and halogen bonds are inputs here, as they are for the reference's Cython kernels.
 """
 from __future__ import annotations
 
@@ -182,3 +184,73 @@ def waterbridge_calculate(mol, donors, acceptors, sel1, sel2, order: int = 1, di
                         continue
                     water_bridges[f].append(pp)
     return water_bridges
+
+
+def _ring_lists(mol, rings, off, pairs, da, return_rings, second_rings=None):
+    index_list, dist_ang_list = [], []
+    for f in range(mol.numFrames):
+        pp = pairs[off[f]:off[f + 1]].tolist()
+        if return_rings:
+            index_list.append([[rings[a], second_rings[b] if second_rings is not None else b] for a, b in pp])
+        else:
+            index_list.append(pp)
+        dist_ang_list.append(da[off[f]:off[f + 1]].tolist())
+    return index_list, dist_ang_list
+
+
+def pipi_calculate(mol, rings1, rings2, dist_threshold1: float = 4.4, angle_threshold1_max: float = 30,
+                   dist_threshold2: float = 5.5, angle_threshold2_min: float = 60, return_rings: bool = False, device=None):
+    """interactions.py:621-721: per frame the [ring1 index, ring2 index] pairs (or the rings themselves) and their
+    [centroid distance, angle between the planes]."""
+    from . import ringpairs
+
+    if angle_threshold1_max < 0 or angle_threshold1_max > 90 or angle_threshold2_min < 0 or angle_threshold2_min > 90:
+        raise RuntimeError("Values for angles should be [0, 90] degrees")
+    if len(rings1) == 0 or len(rings2) == 0:
+        return [[] for _ in range(mol.numFrames)], [[] for _ in range(mol.numFrames)]
+    ring_atoms = np.hstack((np.hstack(rings1), np.hstack(rings2)))
+    ring_starts1 = np.insert(np.cumsum([len(rr) for rr in rings1]), 0, 0)
+    ring_starts2 = np.insert(np.cumsum([len(rr) for rr in rings2]), 0, 0)
+    ring_starts2 += ring_starts1.max()
+    off, pairs, da = ringpairs.calculate_arrays(
+        ringpairs.PIPI, ring_atoms.astype(np.uint32), ring_starts1.astype(np.uint32), ring_starts2.astype(np.uint32),
+        np.ascontiguousarray(mol.coords, dtype=np.float32), np.ascontiguousarray(mol.box, dtype=np.float32),
+        dist_threshold1, angle_threshold1_max, dist_threshold2, angle_threshold2_min, device=device)
+    return _ring_lists(mol, rings1, off, pairs, da, return_rings, second_rings=rings2)
+
+
+def cationpi_calculate(mol, rings, cations, dist_threshold: float = 5, angle_threshold_min: float = 60,
+                       return_rings: bool = False, device=None):
+    """interactions.py:791-868: per frame [ring index, cation atom] and [centroid-cation distance, angle to the ring plane]."""
+    from . import ringpairs
+
+    if angle_threshold_min < 0 or angle_threshold_min > 90:
+        raise RuntimeError("Values for angles should be [0, 90] degrees")
+    if len(rings) == 0 or len(cations) == 0:
+        return [[] for _ in range(mol.numFrames)], [[] for _ in range(mol.numFrames)]
+    ring_atoms = np.hstack(rings)
+    ring_starts = np.insert(np.cumsum([len(rr) for rr in rings]), 0, 0)
+    off, pairs, da = ringpairs.calculate_arrays(
+        ringpairs.CATIONPI, ring_atoms.astype(np.uint32), ring_starts.astype(np.uint32), np.array(cations, dtype=np.uint32),
+        np.ascontiguousarray(mol.coords, dtype=np.float32), np.ascontiguousarray(mol.box, dtype=np.float32), dist_threshold,
+        angle_threshold_min, device=device)
+    return _ring_lists(mol, rings, off, pairs, da, return_rings)
+
+
+def sigmahole_calculate(mol, rings, halides, dist_threshold: float = 4.5, angle_threshold_min: float = 60,
+                        return_rings: bool = False, device=None):
+    """interactions.py:871-946: per frame [ring index, halogen atom] and [centroid-halogen distance, angle of the halogen's
+    bond to the ring plane]; ``halides``: (halogen, bonded atom) index pairs."""
+    from . import ringpairs
+
+    if angle_threshold_min < 0 or angle_threshold_min > 90:
+        raise RuntimeError("Values for angles should be [0, 90] degrees")
+    if len(rings) == 0 or len(halides) == 0:
+        return [[] for _ in range(mol.numFrames)], [[] for _ in range(mol.numFrames)]
+    ring_atoms = np.hstack(rings)
+    ring_starts = np.insert(np.cumsum([len(rr) for rr in rings]), 0, 0)
+    off, pairs, da = ringpairs.calculate_arrays(
+        ringpairs.SIGMAHOLE, ring_atoms.astype(np.uint32), ring_starts.astype(np.uint32),
+        np.array(halides, dtype=np.uint32).reshape(-1, 2), np.ascontiguousarray(mol.coords, dtype=np.float32),
+        np.ascontiguousarray(mol.box, dtype=np.float32), dist_threshold, angle_threshold_min, device=device)
+    return _ring_lists(mol, rings, off, pairs, da, return_rings)

@@ -34,6 +34,9 @@ MODULES = {
     "atomselect_utils": "moleculekit/atomselect_utils/atomselect_utils.pyx",
     "xtc": "moleculekit/fileformats/xtc/xtc.pyx",
     "hbonds": "moleculekit/interactions/hbonds/hbonds.pyx",
+    "pipi": "moleculekit/interactions/pipi/pipi.pyx",
+    "cationpi": "moleculekit/interactions/cationpi/cationpi.pyx",
+    "sigmahole": "moleculekit/interactions/sigmahole/sigmahole.pyx",
 }
 
 # extra C++ sources / include directories of a module (the reference's setup.py:55-66 lists the same files)

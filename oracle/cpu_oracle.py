@@ -50,6 +50,7 @@ def lib():
         _lib.oracle_bond_grid_search.restype = C.c_int64
         _lib.oracle_wrap_compact.restype = C.c_int64
         _lib.oracle_hbonds.restype = C.c_int64
+        _lib.oracle_ring_interactions.restype = C.c_int64
     return _lib
 
 
@@ -289,6 +290,31 @@ def hbonds_calculate(donors, acceptors, coords, box, sel1, sel2, dist_threshold=
         res.append(out[3 * pos:3 * (pos + counts[f])].tolist())
         pos += int(counts[f])
     return res
+
+
+def ring_interactions(mode, rings_atoms, starts1, second, coords, box, p0, p1=0.0, p2=0.0, p3=0.0):
+    """pipi.calculate (mode 0: pipi.pyx:86-185), cationpi.calculate (1: cationpi.pyx:91-173), sigmahole.calculate
+    (2: sigmahole.pyx:91-174) with their positional arguments; returns (results, distangles) as the reference: per frame a flat
+    int list and a flat float list."""
+    rings_atoms, starts1 = _u32(rings_atoms), _u32(starts1)
+    second = np.ascontiguousarray(second, dtype=np.uint32)
+    coords, box = _f32(coords), _f32(box)
+    F = coords.shape[2]
+    n1 = len(starts1) - 1
+    n2 = len(second) - 1 if mode == 0 else len(second)
+    counts = np.zeros(F, dtype=np.int64)
+    call = lambda pairs, da, cap: lib().oracle_ring_interactions(
+        C.c_int(mode), _p(rings_atoms), _p(starts1), C.c_int64(n1), _p(second), C.c_int64(n2), _p(coords), _p(box),
+        C.c_int64(F), C.c_float(p0), C.c_float(p1), C.c_float(p2), C.c_float(p3), _p(counts), _p(pairs), _p(da), C.c_int64(cap))
+    total = call(np.zeros(2, np.int32), np.zeros(2, np.float32), 0)
+    pairs, da = np.zeros(max(2 * total, 2), np.int32), np.zeros(max(2 * total, 2), np.float32)
+    call(pairs, da, total)
+    res, dist, pos = [], [], 0
+    for f in range(F):
+        res.append(pairs[2 * pos:2 * (pos + counts[f])].tolist())
+        dist.append(da[2 * pos:2 * (pos + counts[f])].tolist())
+        pos += int(counts[f])
+    return res, dist
 
 
 def within_distance(coords, cutoff, sel1, sel2, sel2_min_coords, sel2_max_coords, results):

@@ -861,11 +861,24 @@ EXPORT int64_t oracle_wrap_compact(const uint32_t *groups, int64_t n_groups, flo
  * Per frame, donor-major / acceptor-minor, a triple (heavy, hydrogen | -1, acceptor) is emitted when the
  * hydrogen (heavy atom with ignore_hs) is within dist_threshold of the acceptor and the
  * heavy-hydrogen-acceptor angle exceeds angle_threshold.  Types as generated: `val`, the squared
- * distances, the dot product and `angle` are float; the wrap goes through double (libc round on the
- * float quotient, float * double), and so do sqrt / acos (results rounded to float on assignment).
+ * distances, the dot product and `angle` are float; see the note on the C++ float overloads below.
  * counts[f] receives the number of triples of frame f; up to `capacity` triples are written; the total
  * is returned.
  * ------------------------------------------------------------------------------------------------ */
+/* The reference is compiled as C++ (setup.py: language="c++"), where the unqualified round / sqrt / acos the generated
+ * code calls on float arguments resolve to the float overloads of <cmath>: the wrap is val - fl(box * roundf(fl(val / box)))
+ * with every operation rounded to float (as distance_utils._dist), the norms are sqrtf with a float product, and the angle is
+ * acosf.  (A first restatement went through double as the .pyx reads in C; index outputs rarely tell the two apart --
+ * tests/test_oracle_golden.py::test_hbonds_float_overloads pins the difference on ~1e9 pair tests.)  hb_model_double = 1
+ * selects that discarded model, for that test only. */
+static int hb_model_double = 0;
+EXPORT void oracle_hbonds_set_model(int use_double) { hb_model_double = use_double; }
+static float hb_wrap_val(float val, float b)
+{
+    if (hb_model_double) return (float)((double)val - (double)b * round((double)(val / b)));
+    return val - b * roundf(val / b);
+}
+
 EXPORT int64_t oracle_hbonds(const uint32_t *donors, int64_t n_donors, const uint32_t *acceptors, int64_t n_acceptors,
                              const float *coords, const float *box, int64_t F, const uint32_t *sel1,
                              const uint32_t *sel2, float dist_threshold, float angle_threshold, int intra,
@@ -892,7 +905,7 @@ EXPORT int64_t oracle_hbonds(const uint32_t *donors, int64_t n_donors, const uin
                 for (int i = 0; i < 3; ++i) {
                     const float b = box[i * F + f];
                     float val = coords[((int64_t)a_idx * 3 + i) * F + f] - coords[((int64_t)d_idx * 3 + i) * F + f];
-                    if (fabsf(val) > half_box[i] && b != 0) val = (float)((double)val - (double)b * round((double)(val / b)));
+                    if (fabsf(val) > half_box[i] && b != 0) val = hb_wrap_val(val, b);
                     dist_vec_a[i] = val;
                     dist2_a = dist2_a + (val * val);
                 }
@@ -905,21 +918,144 @@ EXPORT int64_t oracle_hbonds(const uint32_t *donors, int64_t n_donors, const uin
                 for (int i = 0; i < 3; ++i) {
                     const float b = box[i * F + f];
                     float val = coords[((int64_t)d_idx_d * 3 + i) * F + f] - coords[((int64_t)d_idx_h * 3 + i) * F + f];
-                    if (fabsf(val) > half_box[i] && b != 0) val = (float)((double)val - (double)b * round((double)(val / b)));
+                    if (fabsf(val) > half_box[i] && b != 0) val = hb_wrap_val(val, b);
                     dist_vec_b[i] = val;
                     dist2_b = dist2_b + (val * val);
                 }
                 if (dist2_a == 0 || dist2_b == 0) continue;
                 float dotprod = 0;
                 for (int i = 0; i < 3; ++i) dotprod = dotprod + dist_vec_a[i] * dist_vec_b[i];
-                float angle = (float)((double)dotprod / (sqrt((double)dist2_a) * sqrt((double)dist2_b)));
+                float angle = hb_model_double ? (float)((double)dotprod / (sqrt((double)dist2_a) * sqrt((double)dist2_b)))
+                                              : (float)((double)dotprod / (double)(sqrtf(dist2_a) * sqrtf(dist2_b)));
                 if (angle > 1) angle = 1;
                 if (angle < -1) angle = -1;
-                angle = (float)acos((double)angle);
+                angle = hb_model_double ? (float)acos((double)angle) : acosf(angle);
                 if (angle > angle_threshold) {
                     if (total < capacity) { out[3 * total] = (int32_t)d_idx_d; out[3 * total + 1] = (int32_t)d_idx_h; out[3 * total + 2] = (int32_t)a_idx; }
                     ++total; ++nf;
                 }
+            }
+        counts[f] = nf;
+    }
+    return total;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Ring interactions -- moleculekit/interactions/pipi/pipi.pyx:86-185 (mode 0), cationpi/cationpi.pyx:91-173
+ * (mode 1), sigmahole/sigmahole.pyx:91-174 (mode 2); callers pipi_calculate / cationpi_calculate /
+ * sigmahole_calculate, moleculekit/interactions/interactions.py:621-946.
+ * rings_atoms + starts1 [n1 + 1]: the rings of the first set.  `second`: mode 0 ring start indexes
+ * [n2 + 1] into the same rings_atoms; mode 1 cation atom indexes [n2]; mode 2 (halogen, bonded
+ * partner) pairs [n2][2].  Helpers shared by the three files: ring centroid = float sum in atom order /
+ * (float)count (pyx:23-41); wrapped distance (pyx:46-62), cross product and normalisation (pyx:67-83) in
+ * float -- the modules are C++, so round / sqrt / acos on float arguments are the float overloads (see
+ * oracle_hbonds).  `angle` is an untyped (double) variable: (double)acosf(dot) * 57.29578, folded to
+ * [0, 90], for modes 1 / 2 turned into the angle to the plane.
+ * Emits per frame, ring-major: (r1, r2 | cation atom | halogen atom) and (sqrt(dist2), angle) as floats.
+ * ------------------------------------------------------------------------------------------------ */
+static void ring_mean(const float *coords, int64_t F, int64_t f, const uint32_t *atoms, int64_t s, int64_t e, float *m)
+{
+    for (int i = 0; i < 3; ++i) m[i] = 0.f;
+    for (int64_t r = s; r < e; ++r)
+        for (int i = 0; i < 3; ++i) m[i] = m[i] + coords[((int64_t)atoms[r] * 3 + i) * F + f];
+    for (int i = 0; i < 3; ++i) m[i] = m[i] / (float)(e - s);
+}
+static float ring_wrapped_dist(const float *p1, const float *p2, const float *half_box, const float *box, int64_t F, int64_t f)
+{
+    float dist2 = 0.f;
+    for (int i = 0; i < 3; ++i) {
+        const float b = box[i * F + f];
+        float val = p1[i] - p2[i];
+        if (fabsf(val) > half_box[i] && b != 0) val = val - b * roundf(val / b);   /* C++ float overload of round */
+        dist2 = dist2 + (val * val);
+    }
+    return dist2;
+}
+static void ring_normalize(float *v)
+{
+    float n = 0.f;
+    for (int i = 0; i < 3; ++i) n = n + (v[i] * v[i]);
+    n = sqrtf(n);
+    for (int i = 0; i < 3; ++i) v[i] = v[i] / n;
+}
+static void ring_normal(const float *coords, int64_t F, int64_t f, const uint32_t *atoms, int64_t s, float *res)
+{
+    float a[3], b[3];
+    for (int i = 0; i < 3; ++i) {
+        a[i] = coords[((int64_t)atoms[s] * 3 + i) * F + f] - coords[((int64_t)atoms[s + 2] * 3 + i) * F + f];
+        b[i] = coords[((int64_t)atoms[s + 1] * 3 + i) * F + f] - coords[((int64_t)atoms[s + 2] * 3 + i) * F + f];
+    }
+    res[0] = a[1] * b[2] - a[2] * b[1];
+    res[1] = a[2] * b[0] - a[0] * b[2];
+    res[2] = a[0] * b[1] - a[1] * b[0];
+    ring_normalize(res);
+}
+
+EXPORT int64_t oracle_ring_interactions(int mode, const uint32_t *rings_atoms, const uint32_t *starts1, int64_t n1,
+                                        const uint32_t *second, int64_t n2, const float *coords, const float *box,
+                                        int64_t F, float p0, float p1, float p2, float p3, int64_t *counts,
+                                        int32_t *pairs, float *distangles, int64_t capacity)
+{
+    float half_box[3], m1[3], m2[3], nrm1[3], nrm2[3], t1[3], t2[3];
+    int64_t total = 0;
+    const float d1 = p0 * p0;                       /* pipi: dist_threshold1^2; others: dist_threshold^2 */
+    const float d2 = mode == 0 ? p2 * p2 : 0.f;     /* pipi: dist_threshold2^2 */
+    for (int64_t f = 0; f < F; ++f) {
+        int64_t nf = 0;
+        for (int i = 0; i < 3; ++i) half_box[i] = box[i * F + f] / 2;
+        for (int64_t r1 = 0; r1 < n1; ++r1)
+            for (int64_t r2 = 0; r2 < n2; ++r2) {
+                const int64_t s1 = starts1[r1], e1 = starts1[r1 + 1];
+                float dist2;
+                double angle;
+                int32_t second_id;
+                if (mode == 0) {
+                    const int64_t s2 = second[r2], e2 = second[r2 + 1];
+                    if (s1 == s2 && e1 == e2) continue;                       /* identical rings */
+                    for (int i = 0; i < 3; ++i) {
+                        t1[i] = coords[((int64_t)rings_atoms[s1] * 3 + i) * F + f];
+                        t2[i] = coords[((int64_t)rings_atoms[s2] * 3 + i) * F + f];
+                    }
+                    if (ring_wrapped_dist(t1, t2, half_box, box, F, f) > 225) continue;
+                    ring_mean(coords, F, f, rings_atoms, s1, e1, m1);
+                    ring_mean(coords, F, f, rings_atoms, s2, e2, m2);
+                    dist2 = ring_wrapped_dist(m1, m2, half_box, box, F, f);
+                    if (dist2 > d2) continue;
+                    ring_normal(coords, F, f, rings_atoms, s1, nrm1);
+                    ring_normal(coords, F, f, rings_atoms, s2, nrm2);
+                    float dot = 0.f;
+                    for (int i = 0; i < 3; ++i) dot = dot + nrm1[i] * nrm2[i];
+                    angle = (double)acosf(dot) * 57.29578;
+                    if (angle > 90) angle = 180 - angle;
+                    if (!((dist2 < d1 && angle <= (double)p1) || (dist2 < d2 && angle >= (double)p3))) continue;
+                    second_id = (int32_t)r2;
+                } else {
+                    const uint32_t atom = mode == 1 ? second[r2] : second[2 * r2];
+                    ring_mean(coords, F, f, rings_atoms, s1, e1, m1);
+                    for (int i = 0; i < 3; ++i) m2[i] = coords[((int64_t)atom * 3 + i) * F + f];
+                    dist2 = ring_wrapped_dist(m1, m2, half_box, box, F, f);
+                    if (dist2 > d1) continue;
+                    ring_normal(coords, F, f, rings_atoms, s1, nrm1);
+                    if (mode == 1) {
+                        for (int i = 0; i < 3; ++i) t1[i] = m2[i] - m1[i];                     /* ring -> cation */
+                    } else {
+                        const uint32_t partner = second[2 * r2 + 1];
+                        for (int i = 0; i < 3; ++i) t1[i] = m2[i] - coords[((int64_t)partner * 3 + i) * F + f];
+                    }
+                    ring_normalize(t1);
+                    float dot = 0.f;
+                    for (int i = 0; i < 3; ++i) dot = dot + nrm1[i] * t1[i];
+                    angle = (double)acosf(dot) * 57.29578;
+                    if (angle > 90) angle = 180 - angle;
+                    angle = 90 - angle;
+                    if (!(angle >= (double)p1)) continue;
+                    second_id = (int32_t)atom;
+                }
+                if (total < capacity) {
+                    pairs[2 * total] = (int32_t)r1; pairs[2 * total + 1] = second_id;
+                    distangles[2 * total] = sqrtf(dist2); distangles[2 * total + 1] = (float)angle;
+                }
+                ++total; ++nf;
             }
         counts[f] = nf;
     }

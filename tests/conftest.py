@@ -112,6 +112,11 @@ def g_tric():
 
 
 @pytest.fixture(scope="session")
+def g_rings():
+    return _npz("rings.npz")
+
+
+@pytest.fixture(scope="session")
 def g_waterbridge():
     return _npz("waterbridge.npz")
 

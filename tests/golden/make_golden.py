@@ -352,6 +352,92 @@ def waterbridge_fixture():
     print("waterbridge.npz", mol.numAtoms, "atoms", len(donors), "donors", len(acceptors), "acceptors; with-H bridges:", len(wb4[0]))
 
 
+def rings_fixture():
+    """rings.npz (K13): (a) the reference's pipi_calculate / cationpi_calculate on a real structure -- the protein of its
+    interaction tests (tests/test_interactions/3PTB_prepared.pdb, two frames: the second one jittered), rings from the
+    reference's get_protein_rings, cations from get_protein_charged, wide thresholds so that the lists are not empty --
+    and (b) seeded synthetic systems (planar 5/6-rings, cations above ring centres, halogen bonds; periodic boxes incl. zero
+    components) through the compiled pipi / cationpi / sigmahole kernels.  The reference's own tests for these detectors
+    need rdkit for the ligand rings (tests/test_interactions.py:57-253), so their constants cannot be rebuilt here."""
+    from oracle import build_ref
+
+    mods = build_ref.load()
+    pipi, cat, sig = mods[7], mods[8], mods[9]
+    from moleculekit.interactions.interactions import (cationpi_calculate, get_protein_charged, get_protein_rings,
+                                                       pipi_calculate)
+    from moleculekit.molecule import Molecule
+
+    mol = Molecule(os.path.join(REFT, "test_interactions", "3PTB_prepared.pdb"))
+    rng = np.random.default_rng(4)
+    mol.coords = np.concatenate([mol.coords, mol.coords + rng.normal(0, 0.15, size=mol.coords.shape).astype(np.float32)], axis=2)
+    mol.box = np.zeros((3, 2), np.float32)
+    rings = get_protein_rings(mol)
+    pos, _ = get_protein_charged(mol)
+    w = {"p_coords": mol.coords.astype(np.float32), "p_box": mol.box, "p_ring_atoms": np.hstack(rings).astype(np.uint32),
+         "p_ring_starts": np.insert(np.cumsum([len(r) for r in rings]), 0, 0).astype(np.uint32), "p_cations": pos}
+    pp, da = pipi_calculate(mol, rings, rings, dist_threshold1=6.0, angle_threshold1_max=40, dist_threshold2=7.0,
+                            angle_threshold2_min=50)
+    cp, cda = cationpi_calculate(mol, rings, pos, dist_threshold=7.0, angle_threshold_min=30)
+    for f in range(2):
+        w[f"p_pipi_{f}"] = np.array(pp[f], dtype=np.int32).reshape(-1, 2); w[f"p_pipi_da_{f}"] = np.array(da[f], dtype=np.float32).reshape(-1, 2)
+        w[f"p_cat_{f}"] = np.array(cp[f], dtype=np.int32).reshape(-1, 2); w[f"p_cat_da_{f}"] = np.array(cda[f], dtype=np.float32).reshape(-1, 2)
+    assert len(pp[0]) > 3 and len(cp[0]) > 3, (len(pp[0]), len(cp[0]))
+    rng = np.random.default_rng(11)
+    ncase = 10
+    for c in range(ncase):
+        N = int(rng.integers(80, 300)); F = int(rng.integers(1, 5))
+        L = rng.uniform(14, 25, size=(3, F)).astype(np.float32)
+        if c == 0:
+            L[:] = 0
+        if c == 3:
+            L[2, 0] = 0
+        xyz = (rng.uniform(0, 1, size=(N, 3, F)) * 16 + rng.integers(-2, 3, size=(N, 3, 1)) * L[None]).astype(np.float32)
+        rings_c, used = [], 0
+        for r in range(int(rng.integers(4, 14))):
+            k = int(rng.choice([5, 6])); idx = np.arange(used, used + k)
+            if used + k > N - 12:
+                break
+            used += k
+            ctr = rng.uniform(0, 16, size=(3, 1)); u = rng.normal(size=3); u /= np.linalg.norm(u)
+            v = np.cross(u, rng.normal(size=3)); v /= np.linalg.norm(v)
+            for j, a in enumerate(idx):
+                ang = 2 * np.pi * j / k
+                xyz[a] = (ctr + 1.39 * (np.cos(ang) * u[:, None] + np.sin(ang) * v[:, None]) + rng.normal(0, .05, size=(3, F))).astype(np.float32)
+            rings_c.append(idx)
+        k = len(rings_c) // 2
+        if c % 3 == 0:   # a set against itself: identical rings are skipped
+            ra = np.hstack(rings_c).astype(np.uint32)
+            s1 = np.insert(np.cumsum([len(r) for r in rings_c]), 0, 0).astype(np.uint32); s2 = s1.copy()
+        else:
+            ra = np.hstack(rings_c).astype(np.uint32)
+            s1 = np.insert(np.cumsum([len(r) for r in rings_c[:k]]), 0, 0).astype(np.uint32)
+            s2 = (np.insert(np.cumsum([len(r) for r in rings_c[k:]]), 0, 0) + s1.max()).astype(np.uint32)
+        sa = np.insert(np.cumsum([len(r) for r in rings_c]), 0, 0).astype(np.uint32)
+        cations = rng.integers(used, N, size=int(rng.integers(2, 14))).astype(np.uint32)
+        for q in cations[:4]:
+            rr = rings_c[int(rng.integers(len(rings_c)))]
+            ctr = xyz[rr].mean(axis=0); n = np.cross(xyz[rr[0]] - xyz[rr[2]], xyz[rr[1]] - xyz[rr[2]], axis=0); n /= np.linalg.norm(n, axis=0)
+            xyz[q] = (ctr + 3.5 * n + rng.normal(0, .4, size=ctr.shape)).astype(np.float32)
+        hal = np.stack([cations, rng.integers(used, N, size=len(cations))], 1).astype(np.uint32)
+        th = np.array([rng.uniform(3.5, 8), rng.uniform(10, 50), rng.uniform(5, 10), rng.uniform(40, 80),
+                       rng.uniform(4, 7), rng.uniform(20, 70)], dtype=np.float64)
+        for kname, v in (("coords", xyz), ("box", L), ("ring_atoms", ra), ("s1", s1), ("s2", s2), ("sa", sa), ("cations", cations),
+                         ("hal", hal), ("th", th)):
+            w[f"r{c}_{kname}"] = v
+        with np.errstate(all="ignore"):
+            outs = (pipi.calculate(ra, s1, s2, xyz, L, *[float(x) for x in th[:4]]),
+                    cat.calculate(ra, sa, cations, xyz, L, float(th[4]), float(th[5])),
+                    sig.calculate(ra, sa, hal, xyz, L, float(th[4]), float(th[5]) / 4))
+        for name, (res, da_) in zip(("pipi", "cat", "sig"), outs):
+            w[f"r{c}_{name}_counts"] = np.array([len(x) // 2 for x in res])
+            w[f"r{c}_{name}"] = np.array([v for x in res for v in x], dtype=np.int32).reshape(-1, 2)
+            w[f"r{c}_{name}_da"] = np.array([v for x in da_ for v in x], dtype=np.float32).reshape(-1, 2)
+    w["ncase"] = np.array(ncase)
+    np.savez_compressed(os.path.join(HERE, "rings.npz"), **w)
+    print("rings.npz", len(rings), "protein rings,", len(pos), "cations; pipi", len(pp[0]), "cation-pi", len(cp[0]),
+          "synthetic hits", sum(int(w[f"r{c}_{n}_counts"].sum()) for c in range(ncase) for n in ("pipi", "cat", "sig")))
+
+
 def rotation_fixture():
     """rotate.npz: outputs of the reference's rotateCoordinates (tools/voxeldescriptors.py:78-114) and rotationMatrix
     (util.py:70-117) on seeded inputs -- the float64 targets of mkb_rotate_coords."""
@@ -545,6 +631,10 @@ def main():
     if "--only-triclinic" in sys.argv:
         assert build_ref.build()
         triclinic_fixture()
+        return
+    if "--only-rings" in sys.argv:
+        assert build_ref.build()
+        rings_fixture()
         return
     if "--only-waterbridge" in sys.argv:
         waterbridge_fixture()

@@ -100,6 +100,19 @@ def test_water_box_vs_oracle(oracle):
     assert total > 5000  # the case is not vacuous
 
 
+def test_dense_boundary_case_vs_oracle(oracle):
+    """5e6 pair tests with minimum-image integers up to 8 and a third of the pairs bonded (the case that separates the
+    reference's float overloads of round / sqrt / acos from a double restatement, tests/test_oracle_golden.py::
+    test_hbonds_float_overloads): identical triples."""
+    from moleculekit_b200 import hbonds
+    from test_oracle_golden import _hb_dense_case
+
+    don, acc, xyz, L, ones = _hb_dense_case(8, seed=19)
+    want = oracle.hbonds_calculate(don, acc, xyz, L, ones, ones, 5.5, 95.0, True, False)
+    got = hbonds.calculate(don, acc, xyz, L, ones, ones, dist_threshold=5.5, angle_threshold=95.0, intra=True)
+    assert sum(map(len, want)) // 3 > 1_000_000 and got == want
+
+
 def test_angle_threshold_sweep_vs_oracle(oracle):
     """the acos comparison is a precomputed cosine bound: sweep thresholds incl. 0, 180, > 180 and negative ones"""
     from moleculekit_b200 import hbonds

@@ -151,3 +151,22 @@ def test_waterbridge_host_logic(g_waterbridge, oracle, monkeypatch):
     wb = it.waterbridge_calculate(Mol, g["donors"], g["acceptors"], g["gol"], g["protein"], order=1, **kw)
     assert [list(map(int, p)) for p in wb[0]] == [[3140, 2899, 2024], [3142, 2857, 1317], [3142, 2857, 2720],
                                                   [3142, 2857, 2737], [3142, 2857, 2789]]
+
+
+def test_ring_decision_intervals(tmp_path):
+    """rings.cu turns the reference's tests on the double angle into intervals of the float dot product (host code, bisection
+    with libm's acosf): tests/cuda/ringsets.cu checks them against the direct evaluation on 6e6 floats."""
+    import os
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "ringsets")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", f"-I{root}/include",
+                    f"-I{root}/moleculekit_b200/csrc", os.path.join(root, "tests", "cuda", "ringsets.cu"), "-o", exe],
+                   check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout[-500:]

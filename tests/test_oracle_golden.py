@@ -376,6 +376,113 @@ def test_hbonds_oracle_vs_live_reference(oracle, refmods):
                 assert oracle.hbonds_calculate(dd, acc, xyz, L, s1, s2, dth, ath, intra, ign) == want, (trial, intra, ign)
 
 
+
+def _hb_dense_case(F, seed=7):
+    """800 donor pairs x 800 acceptors in a ~9 A box with molecules displaced by up to 8 boxes (minimum-image integers up to
+    8: box * n is inexact in float) and thresholds that let a third of the pairs through: every rounding of the wrap, the
+    norms and the arc cosine gets exercised close to a decision boundary somewhere."""
+    rng = np.random.default_rng(seed)
+    N = 2400
+    L = rng.uniform(7, 11, size=(3, F)).astype(np.float32)
+    base = (rng.uniform(0, 1, size=(N, 3, F)) * 9).astype(np.float32)
+    xyz = (base + rng.integers(-8, 9, size=(N, 3, 1)).astype(np.float32) * L[None]).astype(np.float32)
+    heavy = np.arange(0, 1600, 2); hyd = heavy + 1
+    v = rng.normal(size=(800, 3, F)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    xyz[hyd] = xyz[heavy] + v.astype(np.float32)
+    return np.stack([heavy, hyd], 1).astype(np.uint32), np.arange(1600, 2400).astype(np.uint32), xyz, L, np.ones(N, np.uint32)
+
+
+def test_hbonds_float_overloads(oracle, refmods):
+    """The reference is built as C++: round / sqrt / acos on float arguments are the float overloads.  On 2.6e7 pair tests
+    (9.4e6 bonds) the oracle's float model equals the compiled reference exactly, while the model that goes through double
+    (the .pyx read as C) does not -- index outputs alone rarely tell them apart, this case does."""
+    import ctypes as C
+
+    if refmods is None or len(refmods) < 7:
+        pytest.skip("oracle/_ref (hbonds) not built")
+    don, acc, xyz, L, ones = _hb_dense_case(40)
+    want = [list(x) for x in refmods[6].calculate(don, acc, xyz, L, ones, ones, dist_threshold=5.5, angle_threshold=95.0,
+                                                  intra=True, ignore_hs=False)]
+    assert sum(map(len, want)) // 3 > 5_000_000
+    assert oracle.hbonds_calculate(don, acc, xyz, L, ones, ones, 5.5, 95.0, True, False) == want
+    oracle.lib().oracle_hbonds_set_model(C.c_int(1))
+    try:
+        assert oracle.hbonds_calculate(don, acc, xyz, L, ones, ones, 5.5, 95.0, True, False) != want
+    finally:
+        oracle.lib().oracle_hbonds_set_model(C.c_int(0))
+
+
+
+# ---------------------------------------------------------------------- K13: pi-pi, cation-pi, sigma-hole kernels
+def _ring_arrays(res):
+    pairs, da = res
+    return (np.array([len(x) // 2 for x in pairs]), np.array([v for x in pairs for v in x], dtype=np.int32).reshape(-1, 2),
+            np.array([v for x in da for v in x], dtype=np.float32).reshape(-1, 2))
+
+
+def _ring_cases(g):
+    """(name, mode, args) of every stored case: the protein of the reference's interaction tests + the seeded systems"""
+    for f in range(2):
+        c, b = np.ascontiguousarray(g["p_coords"][:, :, f:f + 1]), np.ascontiguousarray(g["p_box"][:, f:f + 1])
+        # pipi_calculate concatenates the two ring lists (interactions.py:690-694): the same set twice is NOT "identical rings"
+        ra2 = np.concatenate([g["p_ring_atoms"], g["p_ring_atoms"]])
+        st2 = (g["p_ring_starts"] + g["p_ring_starts"].max()).astype(np.uint32)
+        yield f"p_pipi_{f}", f"p_pipi_da_{f}", None, 0, (ra2, g["p_ring_starts"], st2, c, b, 6.0, 40.0, 7.0, 50.0)
+        yield f"p_cat_{f}", f"p_cat_da_{f}", None, 1, (g["p_ring_atoms"], g["p_ring_starts"], g["p_cations"], c, b, 7.0, 30.0)
+    for c in range(int(g["ncase"])):
+        th = [float(x) for x in g[f"r{c}_th"]]
+        xyz, L, ra = g[f"r{c}_coords"], g[f"r{c}_box"], g[f"r{c}_ring_atoms"]
+        yield f"r{c}_pipi", f"r{c}_pipi_da", f"r{c}_pipi_counts", 0, (ra, g[f"r{c}_s1"], g[f"r{c}_s2"], xyz, L, *th[:4])
+        yield f"r{c}_cat", f"r{c}_cat_da", f"r{c}_cat_counts", 1, (ra, g[f"r{c}_sa"], g[f"r{c}_cations"], xyz, L, th[4], th[5])
+        yield f"r{c}_sig", f"r{c}_sig_da", f"r{c}_sig_counts", 2, (ra, g[f"r{c}_sa"], g[f"r{c}_hal"], xyz, L, th[4], th[5] / 4)
+
+
+def test_ring_interactions_oracle_vs_golden(oracle, g_rings):
+    """oracle_ring_interactions (pipi / cationpi / sigmahole .pyx) against the reference's outputs: pairs, distances AND
+    angles bit for bit -- on the protein of the reference's interaction tests (rings of its get_protein_rings) and on the
+    seeded periodic systems."""
+    g = g_rings
+    total = 0
+    for name, da_name, cnt_name, mode, args in _ring_cases(g):
+        counts, pairs, da = _ring_arrays(oracle.ring_interactions(mode, *args))
+        assert np.array_equal(pairs, g[name]), name
+        assert np.array_equal(_fbits(da), _fbits(g[da_name])), name
+        if cnt_name:
+            assert np.array_equal(counts, g[cnt_name]), name
+        total += len(pairs)
+    assert total > 300
+
+
+def test_ring_interactions_oracle_vs_live_reference(oracle, refmods):
+    if refmods is None or len(refmods) < 10:
+        pytest.skip("oracle/_ref (pipi / cationpi / sigmahole) not built")
+    rng = np.random.default_rng(12)
+    hits = 0
+    for trial in range(12):
+        N, F = 120, int(rng.integers(1, 4))
+        L = rng.uniform(10, 18, size=(3, F)).astype(np.float32)
+        xyz = (rng.uniform(0, 1, size=(N, 3, F)) * 12).astype(np.float32)
+        starts = np.arange(0, 61, 6, dtype=np.uint32)
+        ra = np.arange(60, dtype=np.uint32)
+        for r in range(10):
+            ctr = rng.uniform(0, 12, size=(3, 1)); u = rng.normal(size=3); u /= np.linalg.norm(u)
+            v = np.cross(u, rng.normal(size=3)); v /= np.linalg.norm(v)
+            for j in range(6):
+                xyz[6 * r + j] = (ctr + 1.39 * (np.cos(j * np.pi / 3) * u[:, None] + np.sin(j * np.pi / 3) * v[:, None])
+                                  + rng.normal(0, .05, size=(3, F))).astype(np.float32)
+        cations = rng.integers(60, N, size=9).astype(np.uint32)
+        hal = np.stack([cations, rng.integers(60, N, size=9)], 1).astype(np.uint32)
+        for mode, mod, args in ((0, refmods[7], (ra, starts, starts, xyz, L, 6.5, 35.0, 8.0, 45.0)),
+                                (1, refmods[8], (ra, starts, cations, xyz, L, 7.5, 15.0)),
+                                (2, refmods[9], (ra, starts, hal, xyz, L, 7.5, 5.0))):
+            want = _ring_arrays(mod.calculate(*args))
+            got = _ring_arrays(oracle.ring_interactions(mode, *args))
+            assert np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1]), (trial, mode)
+            assert np.array_equal(_fbits(want[2]), _fbits(got[2])), (trial, mode)
+            hits += len(want[1])
+    assert hits > 100
+
+
 def test_bonded_groups_host_mirror(g_wrap, refmods):
     """getBondedGroups (host logic of the wrap path) reproduces the reference's group offsets on the cut of its own
     test system, and the union-find keeps the reference's root identities on a scrambled bond list."""
