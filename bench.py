@@ -294,6 +294,20 @@ def cpu_next_rows(extra):
     g = extra.get("c10_hbonds", {}).get("pair_tests_per_s")
     out["hbonds"] = dict(pair_tests_per_s=len(don) * len(acc) / dt, sample=f"1 frame x {len(don)} donor pairs x {len(acc)} acceptors",
                          gpu_over_one_core=(g / (len(don) * len(acc) / dt)) if g else None)
+    # pi-pi: 300 six-rings against themselves, 4 frames
+    nr, Fr = 300, 4
+    xyz = (rng.uniform(0, 60, size=(6 * nr, 3, Fr))).astype(np.float32)
+    ra, st = np.arange(6 * nr, dtype=np.uint32), np.arange(0, 6 * nr + 1, 6, dtype=np.uint32)
+    boxr = np.full((3, Fr), 60.0, np.float32)
+    t0 = time.perf_counter()
+    if kind == "reference" and len(mods) >= 10:
+        mods[7].calculate(ra, st, st, xyz, boxr, 4.4, 30.0, 5.5, 60.0)
+    else:
+        cpu_oracle.ring_interactions(0, ra, st, st, xyz, boxr, 4.4, 30.0, 5.5, 60.0)
+    dt = time.perf_counter() - t0
+    g = extra.get("c11_ring_detectors", {}).get("pipi_pair_tests_per_s")
+    out["pipi"] = dict(pair_tests_per_s=Fr * nr * nr / dt, sample=f"{Fr} frames x {nr} x {nr} rings",
+                       gpu_over_one_core=(g / (Fr * nr * nr / dt)) if g else None)
     return out
 
 
@@ -461,6 +475,31 @@ def extra_workloads(dev, peak):
     out["c10_hbonds"] = dict(workload=f"C10: hydrogen bonds, {Fh} frames x {2 * n_wat} donor pairs x {n_wat} acceptors, periodic, "
                                       "count + ordered fill", ms_per_call=ms, pair_tests_per_s=2.0 * Fh * 2 * n_wat * n_wat / (ms * 1e-3),
                              bonds_per_frame=float(resh["r"][1].shape[0]) / Fh)
+    # C11: ring detectors (K13): 400 six-rings against themselves (pi-pi) and against 2000 cations (cation-pi), 1000 frames
+    from moleculekit_b200 import ringpairs as rp
+
+    nr, nc, Fr = 400, 2000, 1000
+    Nr = 6 * nr + nc
+    ctr = torch.rand((nr, 1, 3, 1), generator=g, device=dev) * 60 + torch.cumsum(torch.randn((nr, 1, 3, Fr), generator=g, device=dev) * 0.1, dim=3)
+    ang = torch.arange(6, device=dev, dtype=torch.float32) * (3.14159265 / 3)
+    u = torch.nn.functional.normalize(torch.randn((nr, 3), generator=g, device=dev), dim=1)
+    v = torch.nn.functional.normalize(torch.linalg.cross(u, torch.randn((nr, 3), generator=g, device=dev)), dim=1)
+    ring_xyz = ctr + 1.39 * (torch.cos(ang)[None, :, None, None] * u[:, None, :, None] + torch.sin(ang)[None, :, None, None] * v[:, None, :, None])
+    d_rc = torch.empty((Nr, 3, Fr), dtype=torch.float32, device=dev)
+    d_rc[:6 * nr] = ring_xyz.reshape(6 * nr, 3, Fr)
+    d_rc[6 * nr:] = torch.rand((nc, 3, 1), generator=g, device=dev) * 60 + torch.cumsum(torch.randn((nc, 3, Fr), generator=g, device=dev) * 0.1, dim=2)
+    d_rb = torch.full((3, Fr), 60.0, dtype=torch.float32, device=dev)
+    r_atoms = torch.arange(6 * nr, dtype=torch.int32, device=dev)
+    r_st = torch.arange(0, 6 * nr + 1, 6, dtype=torch.int32, device=dev)
+    cat_idx = 6 * nr + torch.arange(nc, dtype=torch.int32, device=dev)
+    resr = {}
+    ms_pp = _time_cuda(lambda: resr.__setitem__("pp", rp.calculate_device(rp.PIPI, d_rc, d_rb, r_atoms, r_st, r_st, 4.4, 30.0, 5.5, 60.0)), warm=1, steps=3)
+    ms_cp = _time_cuda(lambda: resr.__setitem__("cp", rp.calculate_device(rp.CATIONPI, d_rc, d_rb, r_atoms, r_st, cat_idx, 5.0, 60.0)), warm=1, steps=3)
+    out["c11_ring_detectors"] = dict(
+        workload=f"C11: {Fr} frames, {nr} rings: pi-pi against themselves and cation-pi against {nc} cations, periodic, count + fill",
+        pipi_ms=ms_pp, pipi_pair_tests_per_s=Fr * nr * nr / (ms_pp * 1e-3), pipi_hits_per_frame=float(resr["pp"][1].shape[0]) / Fr,
+        cationpi_ms=ms_cp, cationpi_pair_tests_per_s=Fr * nr * nc / (ms_cp * 1e-3), cationpi_hits_per_frame=float(resr["cp"][1].shape[0]) / Fr)
+    del d_rc, ring_xyz, ctr
     del d_c, d_orig, d_b, d_wr
     # C7: `within 5 of <solute>` (K10) on one frame of a 96k-atom solvated system (the reference: 96k x 5.5k brute force)
     from moleculekit_b200 import atomselect_utils as asel
