@@ -41,11 +41,14 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_sass_excerpts.txt"), "w") as f:
             f.write(f"# TMA bulk stores (cp.async.bulk.global.shared::cta) in the DEFAULT fill kernel: {len(ub)} UBLKCP\n")
             f.write("\n".join(ub) + "\n")
             # the hot loop: the two LDS.128 of the ping-pong records up to the run-end flush
-            lds = [i for i, l in enumerate(lines) if "LDS.128" in l]
-            if len(lds) >= 3:
-                lo = lds[-2] - 25
-                hi = lo + 120
-                f.write("# hot loop (two candidates per trip: FFMA x11, FSETP x5, predicated FMNMX x4 per candidate) and the run-end flush\n")
+            # (v9: FSETP compares against |gate| -- the sign of the gate flags the end of a high-nibble group)
+            hot = [i for i, l in enumerate(lines) if "FSETP.GEU.AND" in l and ", |R" in l]
+            hot = [i for i in hot if hot[-1] - i < 120]
+            if hot:
+                lo = hot[0] - 16
+                hi = hot[-1] + 75
+                f.write("# hot loop (two candidates per trip; per candidate FFMA / FMUL x8, FSETP x5, predicated FMNMX x4, LDS.128 x2) and the\n"
+                        "# two-level run-end flush (low nibble: 16 predicated FMNMX + 4 folds; high nibble once per group)\n")
                 f.write("\n".join(lines[lo:hi]) + "\n")
         if "dist_kernelILi0ELb0" in name:
             f.write(f"\n## {name}: {len(lines)} instructions (K3 distances, bit-exact minimum image: FMUL/FADD/FSUB, no FFMA in the wrap)\n")
