@@ -215,6 +215,13 @@ __device__ __forceinline__ void gated_min(float &m, float r, float cw) {
 __device__ __forceinline__ void gated_min_abs(float &m, float r, float cw) {
     asm("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tabs.f32 t, %2;\n\tsetp.lt.f32 p, %1, t;\n\t@p min.f32 %0, %0, %1;\n\t}" : "+f"(m) : "f"(r), "f"(cw));
 }
+// record load through a pinned shared address (MKB_R_PIN >= 2).  Volatile: stays between the __syncwarp()s around the hot loop,
+// i.e. after the stores of the record pass and before the next round's.
+__device__ __forceinline__ float4 lds_rec4(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
 // run end: the run's four minima go into the channels of its mask.  MKB_R_FLUSH 0: 32 predicated FMNMX (compact; measured
 // faster than 1: one jump per mask nibble into code with only the live channels, which costs instruction-cache misses).
 // MKB_R_FLUSH 2 (needs MKB_R_PRE): two-level flush.  Candidates are sorted by mask value, so runs with the same HIGH nibble
@@ -224,6 +231,11 @@ __device__ __forceinline__ void gated_min_abs(float &m, float r, float cw) {
 // Measured on C3 (with MKB_R_PRE): 0.913 -> 0.889 ms at 7 CTAs / 72 registers, 0.876 ms at 6 CTAs / 80 registers; default.
 #ifndef MKB_R_FLUSH
 #define MKB_R_FLUSH (MKB_R_PRE ? 2 : 0)
+#endif
+// MKB_R_PIN: 1 pins fy / fz, 2 also the record base (loads through a pinned shared address).  ptxas otherwise rebuilds them
+// from the lane / warp id at the head of every run.  Measured on C3: 0.879 -> 0.857 (1) -> 0.844 ms (2); default 2.
+#ifndef MKB_R_PIN
+#define MKB_R_PIN (MKB_R_PRE ? 2 : 0)
 #endif
 #ifndef MKB_R_EXP
 #define MKB_R_EXP 0  // timing experiments only (wrong results): 1 = no hot loop, 2 = no flush, 3 = no epilogue math
@@ -264,6 +276,10 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
     // SR_TID / SR_CgaCtaId at every run end: ten instructions and two slow special-register reads per run)
     unsigned msk_sa = (unsigned)__cvta_generic_to_shared(msk);
     asm volatile("mov.b32 %0, %0;" : "+r"(msk_sa));
+#if MKB_R_PIN >= 2
+    unsigned rec_sa = (unsigned)__cvta_generic_to_shared(wb);  // same for the record base: the hot loop loads through it
+    asm volatile("mov.b32 %0, %0;" : "+r"(rec_sa));
+#endif
 #else
     float2 *const cwv = reinterpret_cast<float2 *>(wb + R_CAP * 16);            // gate in r units (cut2 / sigma^2), channel mask bits
     unsigned char *const rnk = wb + R_CAP * 24;                                 // rank of a candidate inside its mask bin
@@ -278,7 +294,13 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
     __syncthreads();
 
     const int ly = lane >> 3, lz = lane & 7;
-    const float fy = (float)ly - 1.5f, fz = (float)lz - 3.5f;  // block frame: origin at the block centre
+    float fy = (float)ly - 1.5f, fz = (float)lz - 3.5f;  // block frame: origin at the block centre
+#if MKB_R_PIN
+    // ptxas rebuilds fy / fz from the lane id (SHF, LOP3, I2FP, FADD) at the head of every run instead of keeping two registers
+    // alive: an opaque move pins them (8 instructions per run, 3 % of the kernel)
+    asm volatile("mov.b32 %0, %0;" : "+f"(fy));
+    asm volatile("mov.b32 %0, %0;" : "+f"(fz));
+#endif
     const float INF = __int_as_float(0x7f800000);
     bool pending = false;  // lanes 0..15: bulk copies still reading the stage
 
@@ -497,6 +519,13 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
 #define MKB_GATED_MIN(M, R, CW) gated_min(M, R, CW)
 #endif
 #if MKB_R_PRE
+#if MKB_R_PIN >= 2
+#define MKB_LDREC(I) lds_rec4(rec_sa + 16u * (unsigned)(I))
+#define MKB_LDRECY(I) lds_rec4(rec_sa + (unsigned)(R_CAP * 16) + 16u * (unsigned)(I))
+#else
+#define MKB_LDREC(I) rec[I]
+#define MKB_LDRECY(I) recy[I]
+#endif
 #define MKB_RUN_BODY(D, Y)                                                                        \
     {                                                                                             \
         const float dys = fmaf(fy, Y.z, -Y.x), dzs = fmaf(fz, Y.z, -Y.y);                         \
@@ -507,7 +536,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
         MKB_GATED_MIN(m2, r2, Y.w);                                                               \
         MKB_GATED_MIN(m3, r3, Y.w);                                                               \
     }
-                    float4 a = rec[0], ya = recy[0];
+                    float4 a = MKB_LDREC(0), ya = MKB_LDRECY(0);
                     int i = 1;  // next record to load; i == np reads past the list (inside this warp's buffer), never used
 #if MKB_R_FLUSH == 2
                     float M0 = INF, M1 = INF, M2 = INF, M3 = INF, gclose;
@@ -518,7 +547,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                         unsigned mask;
 #pragma unroll 1
                         for (;;) {
-                            const float4 b = rec[i], yb = recy[i];
+                            const float4 b = MKB_LDREC(i), yb = MKB_LDRECY(i);
                             MKB_RUN_BODY(a, ya)
                             if (ya.z < 0.0f) {  // the record that closes a run is negated (warp-uniform)
                                 asm volatile("ld.shared.u8 %0, [%1+-1];" : "=r"(mask) : "r"(msk_sa + i));
@@ -530,8 +559,8 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                                 i += 1;
                                 break;
                             }
-                            a = rec[i + 1];
-                            ya = recy[i + 1];
+                            a = MKB_LDREC(i + 1);
+                            ya = MKB_LDRECY(i + 1);
                             MKB_RUN_BODY(b, yb)
                             i += 2;
                             if (yb.z < 0.0f) {
