@@ -229,10 +229,10 @@ static long long last_true(long long ka, long long kb, P pred) {
     }
     return lo;
 }
-// `decide(angle)` is the reference's test on the folded double angle; kind = +1 when it is true for SMALL angles
-// (angle <= t, 90 - angle >= t), -1 when true for LARGE angles (angle >= t).  `to_plane`: modes 1 / 2 (90 - angle).
+// `decide(angle)` is the reference's test on the folded double angle (monotone in the angle); `to_plane`: modes 1 / 2
+// (90 - angle).  Returns the floats x in [-1, 1] for which decide(folded(x)) holds, as two closed intervals.
 template <class D>
-static RingSet ring_decision_set(D decide, int kind, bool to_plane) {
+static RingSet ring_decision_set(D decide, bool to_plane) {
     auto raw = [](float x) { return (double)acosf(x) * 57.29578; };  // the C++ float overload the reference calls
     auto folded = [&](float x) {
         double a = raw(x);
@@ -240,7 +240,6 @@ static RingSet ring_decision_set(D decide, int kind, bool to_plane) {
         if (to_plane) a = 90.0 - a;
         return a;
     };
-    (void)kind;
     const long long kmin = fkey(-1.f), kmax = fkey(1.f);
     // lower branch: the floats whose raw angle exceeds 90 (a prefix of [-1, 1]: acosf is non-increasing)
     const long long kb = last_true(kmin, kmax, [&](float x) { return raw(x) > 90.0; });
@@ -285,11 +284,11 @@ static int ring_setup(mkb_ctx *h, cudaStream_t st, int32_t mode, const mkb_traj 
     A->d2 = mode == RING_PIPI ? p2 * p2 : 0.f;
     if (mode == RING_PIPI) {
         const double t1 = (double)p1, t2 = (double)p3;
-        A->c1 = ring_decision_set([=](double a) { return a <= t1; }, +1, false);  // pyx:176
-        A->c2 = ring_decision_set([=](double a) { return a >= t2; }, -1, false);  // pyx:177
+        A->c1 = ring_decision_set([=](double a) { return a <= t1; }, false);  // pyx:176
+        A->c2 = ring_decision_set([=](double a) { return a >= t2; }, false);  // pyx:177
     } else {
         const double tmin = (double)p1;
-        A->c1 = ring_decision_set([=](double a) { return a >= tmin; }, +1, true);  // cationpi.pyx:165 on 90 - angle
+        A->c1 = ring_decision_set([=](double a) { return a >= tmin; }, true);  // cationpi.pyx:165 on 90 - angle
         A->c2 = A->c1;
     }
     if (rows == 0 || n2 == 0) return MKB_OK;

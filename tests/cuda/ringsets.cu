@@ -13,9 +13,9 @@ int main() {
         const double t = (double)th;
         for (int variant = 0; variant < 3; ++variant) {
             mkb::RingSet s;
-            if (variant == 0) s = mkb::ring_decision_set([=](double a) { return a <= t; }, +1, false);
-            else if (variant == 1) s = mkb::ring_decision_set([=](double a) { return a >= t; }, -1, false);
-            else s = mkb::ring_decision_set([=](double a) { return a >= t; }, +1, true);
+            if (variant == 0) s = mkb::ring_decision_set([=](double a) { return a <= t; }, false);
+            else if (variant == 1) s = mkb::ring_decision_set([=](double a) { return a >= t; }, false);
+            else s = mkb::ring_decision_set([=](double a) { return a >= t; }, true);
             auto truth = [&](float x) {
                 double a = (double)acosf(x) * 57.29578;
                 if (a > 90.0) a = 180.0 - a;
