@@ -151,3 +151,23 @@ def test_waterbridge_reference_test_case(g_waterbridge):
     wb = waterbridge_calculate(mol, g["donors"], g["acceptors"], g["gol"], g["protein"], order=1, dist_threshold=2.6,
                                water=g["water"])
     assert [list(map(int, p)) for p in wb[0]] == _paths(g, "wb4")
+
+
+def test_edge_cases(oracle):
+    """no donors / no acceptors / zero frames / a donor that is its own acceptor / selections that exclude everything"""
+    from moleculekit_b200 import hbonds
+
+    rng = np.random.default_rng(5)
+    xyz = (rng.uniform(0, 6, size=(30, 3, 2))).astype(np.float32)
+    box = np.full((3, 2), 6.0, np.float32)
+    don = np.stack([np.arange(0, 20, 2), np.arange(1, 20, 2)], 1).astype(np.uint32)
+    acc = np.arange(0, 30, 3, dtype=np.uint32)          # includes donor heavy atoms (a_idx == d_idx_d is skipped)
+    ones, zeros = np.ones(30, np.uint32), np.zeros(30, np.uint32)
+    assert hbonds.calculate(don[:0], acc, xyz, box, ones, ones) == [[], []]
+    assert hbonds.calculate(don, acc[:0], xyz, box, ones, ones) == [[], []]
+    assert hbonds.calculate(don, acc, xyz[:, :, :0].copy(), box[:, :0].copy(), ones, ones) == []
+    assert hbonds.calculate(don, acc, xyz, box, zeros, ones, intra=True) == [[], []]
+    for intra, s1, s2 in ((True, ones, ones), (False, ones, zeros), (False, (np.arange(30) % 2).astype(np.uint32),
+                                                                   ((np.arange(30) + 1) % 2).astype(np.uint32))):
+        want = oracle.hbonds_calculate(don, acc, xyz, box, s1, s2, 4.0, 30.0, intra, False)
+        assert hbonds.calculate(don, acc, xyz, box, s1, s2, dist_threshold=4.0, angle_threshold=30.0, intra=intra) == want

@@ -100,3 +100,27 @@ def test_many_frames_vs_oracle(oracle):
         _check(fn(*args), wp, wd, wc)
         hits += len(wp)
     assert hits > 20000
+
+
+def test_edge_cases(oracle):
+    """empty partner lists, zero frames, rings of 3 atoms, a ring set against a single ring, NaN coordinates: same lists as
+    the oracle, no crash"""
+    from moleculekit_b200 import ringpairs
+
+    rng = np.random.default_rng(3)
+    xyz = (rng.uniform(0, 9, size=(40, 3, 3))).astype(np.float32)
+    box = np.full((3, 3), 9.0, np.float32)
+    ra = np.arange(12, dtype=np.uint32); st = np.array([0, 3, 6, 12], np.uint32)       # two 3-rings and a 6-ring
+    cat = np.arange(20, 30, dtype=np.uint32)
+    assert ringpairs.cationpi_calculate(ra, st, cat[:0], xyz, box, 5.0, 10.0) == ([[], [], []], [[], [], []])
+    assert ringpairs.pipi_calculate(ra, st, st, xyz[:, :, :0].copy(), box[:, :0].copy(), 9.0, 90.0, 9.0, 0.0) == ([], [])
+    for args, mode, fn in (((ra, st, st, xyz, box, 9.0, 90.0, 9.0, 0.0), 0, ringpairs.pipi_calculate),
+                           ((ra, st, cat, xyz, box, 9.0, 0.0), 1, ringpairs.cationpi_calculate),
+                           ((ra, st, np.stack([cat, cat[::-1]], 1).astype(np.uint32), xyz, box, 9.0, 0.0), 2,
+                            ringpairs.sigmahole_calculate)):
+        wc, wp, wd = _arrays(oracle.ring_interactions(mode, *args))
+        _check(fn(*args), wp, wd, wc)
+        assert len(wp) > 0
+    bad = xyz.copy(); bad[4, 1, 1] = np.nan
+    wc, wp, wd = _arrays(oracle.ring_interactions(1, ra, st, cat, bad, box, 9.0, 0.0))
+    _check(ringpairs.cationpi_calculate(ra, st, cat, bad, box, 9.0, 0.0), wp, wd, wc)

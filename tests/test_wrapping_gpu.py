@@ -339,3 +339,23 @@ def test_wrap_mirror_dispatches_on_boxangles(g_tric):
             warnings.simplefilter("ignore")
             wrap(m, wrapsel=sel, unitcell=unitcell)
         assert np.array_equal(_fbits(m.coords), _fbits(g[f"ref_{unitcell}"])), unitcell
+
+
+def test_triclinic_edge_cases(oracle):
+    """no groups (every atom is only centred), a single closing offset, zero frames, one atom"""
+    from moleculekit_b200.wrapping import wrap_compact_unitcell, wrap_triclinic_unitcell
+
+    rng = np.random.default_rng(9)
+    L = 15.0
+    xyz = rng.normal(0, 40, size=(11, 3, 4)).astype(np.float32)
+    bv = np.repeat(np.array([[L, 0, 0], [0, L, 0], [L / 2, L / 2, L * 2 ** 0.5 / 2]])[:, :, None], 4, axis=2)
+    cen = np.array([1.0, -2.0, 3.0], np.float32)
+    for groups in (np.zeros(0, np.uint32), np.array([11], np.uint32), np.array([0, 11], np.uint32), np.array([3, 7], np.uint32)):
+        for mode in (None, 0, 1):
+            want, got = xyz.copy(), xyz.copy()
+            _oracle_tric(oracle, mode, groups, want, bv, np.zeros(0, np.uint32), cen)
+            _gpu_tric(mode, groups, got, bv, np.zeros(0, np.uint32), cen)
+            assert np.array_equal(_fbits(got), _fbits(want)), (groups.tolist(), mode)
+    empty = xyz[:, :, :0].copy()
+    wrap_triclinic_unitcell(np.array([0, 11], np.uint32), empty, bv[:, :, :0].copy(), np.zeros(0, np.uint32), cen)
+    wrap_compact_unitcell(np.array([0, 1], np.uint32), xyz[:1].copy(), bv, np.zeros(0, np.uint32), cen, 1)
