@@ -237,6 +237,26 @@ __device__ __forceinline__ float4 lds_rec4(unsigned a) {
 #ifndef MKB_R_PIN
 #define MKB_R_PIN (MKB_R_PRE ? 2 : 0)
 #endif
+// MKB_R_OVF (needs MKB_R_PRE, MKB_R_FLUSH 2): the 5 A gate by floating-point OVERFLOW instead of FSETP + predicate.  The gate
+// d2 < cut2 does not depend on sigma, so the records carry the differences scaled by lambda = 2^64 / cut (the same for every
+// candidate): U = dx^2 + dy^2 + dz^2 in those units is d2 * 2^128 / cut2 and rounds to +inf exactly when the pair is outside
+// the gate (threshold 2^128 (1 - 2^-25): relative 3e-8, inside the band the float64 fix-up covers).  r = U * w with the
+// per-candidate w = 2^-128 cut2 / sigma^2 (one FMUL on the FMA pipe, inf stays inf) and the running minimum is an
+// UNPREDICATED FMNMX: per (candidate, voxel) 2 FMA-pipe + 1 ALU-pipe instruction instead of 1 + 2 -- the ALU pipe (one warp
+// instruction per two cycles) was the binding unit of the hot loop.  w is negative on the record that closes a run (|w| is a
+// free operand modifier); the run's mask and the close-the-group bit ride in the fourth word, so the run end needs no mask
+// byte load.  w is a denormal for sigma > 2.5 A (cut2 / sigma^2 < 4): FMUL handles denormals at full rate; w then keeps
+// 21 + log2(cut2 / sigma^2) bits.
+// MKB_R_MIN3: two candidates per FMNMX3 (min of three) while both lie inside the run.
+#ifndef MKB_R_OVF
+#define MKB_R_OVF MKB_R_PRE  // measured on C3: 0.834 -> 0.807 ms; with MKB_R_MIN3 0.785 ms; default
+#endif
+#ifndef MKB_R_MIN3
+#define MKB_R_MIN3 MKB_R_OVF
+#endif
+#if MKB_R_OVF && !(MKB_R_PRE && MKB_R_FLUSH == 2 && MKB_R_PIN >= 2)
+#error "MKB_R_OVF needs MKB_R_PRE, MKB_R_FLUSH 2 and MKB_R_PIN 2"
+#endif
 #ifndef MKB_R_EXP
 #define MKB_R_EXP 0  // timing experiments only (wrong results): 1 = no hot loop, 2 = no flush, 3 = no epilogue math
 #endif
@@ -303,6 +323,12 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
 #endif
     const float INF = __int_as_float(0x7f800000);
     bool pending = false;  // lanes 0..15: bulk copies still reading the stage
+#if MKB_R_OVF
+    // lambda = 2^64 / cut (voxel units): d2 == cut2 lands on 2^128, the float overflow threshold
+    double lam = UNIFORM ? 18446744073709551616.0 / sqrt((double)p.u.cut2v) : 0.0;
+    float lamf = (float)lam;
+    asm volatile("mov.b32 %0, %0;" : "+f"(lamf));
+#endif
 
     for (;;) {
         unsigned id = 0;
@@ -357,6 +383,12 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             continue;
         }
 
+#if MKB_R_OVF
+        if (!UNIFORM) {
+            lam = 18446744073709551616.0 / sqrt((double)cut2);
+            lamf = (float)lam;
+        }
+#endif
         for (int bzi = bz_begin; bzi < bz_end; ++bzi) {
             const int z0 = bzi * R_BZ;
             const int row_bytes = min(R_BZ, nz - z0) * 32;
@@ -478,7 +510,17 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     const double ex = (double)((int)(tg.z & 0xffffu) - cx) + ((double)f.x - 1.5);
                     const double ey = (double)((int)(tg.z >> 16) - cy) + ((double)f.y - 1.5);
                     const double ez = (double)((int)(tg.x >> 16) - cz) + ((double)f.z - 3.5);
-#if MKB_R_PRE
+#if MKB_R_OVF
+                    {
+                        const float xs = (float)(ex * lam);
+                        rec[pos] = make_float4(fmaf(-1.5f, lamf, -xs), fmaf(-0.5f, lamf, -xs), fmaf(0.5f, lamf, -xs), fmaf(1.5f, lamf, -xs));
+                        const float wt = ((cut2 * (sw * sw)) * 5.421010862427522e-20f) * 5.421010862427522e-20f;  // 2^-64 twice: exact
+                        const unsigned mh = m | 15u;
+                        const unsigned e0 = (hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu, e1 = (hist[mh >> 1] >> 16) & 0xffffu;
+                        recy[pos] = make_float4((float)(ey * lam), (float)(ez * lam), rk == 0 ? -wt : wt,
+                                                __uint_as_float(m | ((rk == 0 && e0 == e1) ? 0x100u : 0u)));
+                    }
+#elif MKB_R_PRE
                     {
                         const float xs = (float)(ex * dsw), ws = (float)dsw;  // the same roundings as the in-loop form
                         rec[pos] = make_float4(fmaf(-1.5f, ws, -xs), fmaf(-0.5f, ws, -xs), fmaf(0.5f, ws, -xs), fmaf(1.5f, ws, -xs));
@@ -526,6 +568,21 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
 #define MKB_LDREC(I) rec[I]
 #define MKB_LDRECY(I) recy[I]
 #endif
+#if MKB_R_OVF
+#define MKB_RUN_R(D, Y, R)                                                                        \
+    float R##0, R##1, R##2, R##3;                                                                 \
+    {                                                                                             \
+        const float dys = fmaf(fy, lamf, -Y.x), dzs = fmaf(fz, lamf, -Y.y);                       \
+        const float s2 = fmaf(dzs, dzs, dys * dys), w = fabsf(Y.z);                               \
+        R##0 = fmaf(D.x, D.x, s2) * w; R##1 = fmaf(D.y, D.y, s2) * w;                             \
+        R##2 = fmaf(D.z, D.z, s2) * w; R##3 = fmaf(D.w, D.w, s2) * w;                             \
+    }
+#define MKB_RUN_BODY(D, Y)                                                                        \
+    {                                                                                             \
+        MKB_RUN_R(D, Y, r)                                                                        \
+        m0 = fminf(m0, r0); m1 = fminf(m1, r1); m2 = fminf(m2, r2); m3 = fminf(m3, r3);           \
+    }
+#else
 #define MKB_RUN_BODY(D, Y)                                                                        \
     {                                                                                             \
         const float dys = fmaf(fy, Y.z, -Y.x), dzs = fmaf(fz, Y.z, -Y.y);                         \
@@ -536,6 +593,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
         MKB_GATED_MIN(m2, r2, Y.w);                                                               \
         MKB_GATED_MIN(m3, r3, Y.w);                                                               \
     }
+#endif
                     float4 a = MKB_LDREC(0), ya = MKB_LDRECY(0);
                     int i = 1;  // next record to load; i == np reads past the list (inside this warp's buffer), never used
 #if MKB_R_FLUSH == 2
@@ -545,6 +603,41 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     while (i <= np && MKB_R_EXP != 1) {
                         float m0 = INF, m1 = INF, m2 = INF, m3 = INF;
                         unsigned mask;
+#if MKB_R_OVF
+#pragma unroll 1
+                        for (;;) {
+                            const float4 b = MKB_LDREC(i), yb = MKB_LDRECY(i);
+#if MKB_R_MIN3
+                            MKB_RUN_R(a, ya, ra)
+                            if (ya.z < 0.0f) {  // the record that closes a run has a negative weight (warp-uniform)
+                                m0 = fminf(m0, ra0); m1 = fminf(m1, ra1); m2 = fminf(m2, ra2); m3 = fminf(m3, ra3);
+#else
+                            MKB_RUN_BODY(a, ya)
+                            if (ya.z < 0.0f) {
+#endif
+                                mask = __float_as_uint(ya.w);  // mask | close-the-group << 8
+                                a = b;
+                                ya = yb;
+                                i += 1;
+                                break;
+                            }
+                            a = MKB_LDREC(i + 1);
+                            ya = MKB_LDRECY(i + 1);
+#if MKB_R_MIN3
+                            MKB_RUN_R(b, yb, rb)
+                            m0 = fminf(fminf(m0, ra0), rb0); m1 = fminf(fminf(m1, ra1), rb1);
+                            m2 = fminf(fminf(m2, ra2), rb2); m3 = fminf(fminf(m3, ra3), rb3);
+#else
+                            MKB_RUN_BODY(b, yb)
+#endif
+                            i += 2;
+                            if (yb.z < 0.0f) {
+                                mask = __float_as_uint(yb.w);
+                                break;
+                            }
+                        }
+                        gclose = (mask & 0x100u) ? -1.0f : 1.0f;
+#else
 #pragma unroll 1
                         for (;;) {
                             const float4 b = MKB_LDREC(i), yb = MKB_LDRECY(i);
@@ -571,6 +664,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                                 break;
                             }
                         }
+#endif
 #else
 #define MKB_RUN_BODY(A, CW)                                                                       \
     {                                                                                             \
@@ -644,6 +738,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
 #endif
                     }
 #undef MKB_RUN_BODY
+#undef MKB_RUN_R
 #undef MKB_GATED_MIN
                 }
                 __syncwarp();
