@@ -77,6 +77,7 @@ struct RunParams {
     const unsigned *blk_rank;    // compact output (mkb_occupancy_grid_batch_compact): exclusive count of non-empty blocks; block
                                  // b with atoms in reach is one 4 KB record [4 x][4 y][8 z][8 ch] at out + 1024 * blk_rank[b],
                                  // empty blocks are not written at all; nullptr = the dense grid
+    int use_tmap;                // MKB_R_TMAP: the kernel's tensor-map argument describes `out` (dense, uniform, device memory)
     int sparse_dense;            // with blk_rank: keep the DENSE addressing (out may be mapped host memory) and only skip the empty
                                  // blocks -- the host zero-fills them meanwhile (mkb_occupancy_grid_batch_to_host)
     // uniform batches: descriptor of the first grid + strides (constant-bank operands)
@@ -258,13 +259,38 @@ __device__ __forceinline__ float4 lds_rec4(unsigned a) {
 // FMUL2, new on sm_100): one issue slot per two voxels.  (dy, dz) = (fy, fz) * lambda + (-y, -z) is one FFMA2, their squares one
 // FMUL2, U of the four voxels two FFMA2 (s2 broadcast), r = U * w two FMUL2 -- 7 FMA-pipe instructions per candidate instead
 // of 12.  Without a gate predicate the loop is bound by issue slots only.  The run-end flag moves to the sign bit of the tag
-// word (ISETP), w stays positive (no |w| modifier on a packed operand).  The first candidate of a run initialises the run
-// minima (no +inf set-up, no min for it).
+// word (ISETP), w stays positive (no |w| modifier on a packed operand).
 #ifndef MKB_R_X2
-#define MKB_R_X2 MKB_R_OVF  // measured on C3: 0.789 -> 0.758 ms (1); 2 = also peel the first candidate of a run: 0.776 ms (slower)
+#define MKB_R_X2 MKB_R_OVF  // measured on C3: 0.789 -> 0.758 ms; default
 #endif
 #if MKB_R_X2 && !MKB_R_OVF
 #error "MKB_R_X2 needs MKB_R_OVF"
+#endif
+// The phases around the hot loop are LATENCY bound with six warps per scheduler (ncu of the packed build: 65 % of the warp
+// samples lie outside hot loop + flush, which execute 58 % of the instructions; profiles/r02_fill_v10a_*).  Remedies:
+// MKB_R_ASYNC2 (needs MKB_R_OVF): the record pass gathers the per-atom data (rec_pos / rec_tag, two dependent L2 round trips
+//   per 32 candidates, one trip after the other) with cp.async straight into the candidate's SORTED slot -- all gathers of a
+//   round in flight at once, no registers -- and a second sub-pass turns the raw slots into records in place.
+// (Measured and dropped: a queue that runs two items ahead -- atomic and list offsets of the next items in flight during the
+//   current one -- 0.735 -> 0.757 ms: the second decode costs more issue slots than the hidden latency; peeling the first
+//   candidate of a run so that it initialises the minima: 0.758 -> 0.776 ms.)
+// MKB_R_TMAP: dense uniform device output leaves as ONE cp.async.bulk.tensor (4-D tiled tensor map over [grid][x][y][z * c], box
+//   1 x 4 x 4 x 64 floats) per block instead of 16 row copies -- ptxas serialises per-lane bulk copies through uniform registers
+//   (R2UR / UBLKCP in a 16-trip loop: 12 % of the warp samples); empty items are tensor copies from a zeroed 4 KB tile.
+// MKB_R_ENTPF: the list of the item's NEXT z block is requested right after the accumulators have gone to the stage: the epilogue
+//   needs few registers, so the R_CAP / 32 words per lane ride through it for free and the next block's histogram pass finds
+//   them loaded.
+#ifndef MKB_R_ASYNC2
+#define MKB_R_ASYNC2 MKB_R_OVF  // measured on C3: 0.762 -> 0.735 ms; default
+#endif
+#ifndef MKB_R_ENTPF
+#define MKB_R_ENTPF 0
+#endif
+#ifndef MKB_R_TMAP
+#define MKB_R_TMAP 1  // measured on C3: 0.762 -> 0.713 ms; with MKB_R_ASYNC2 0.690 ms = 49.4 % of HBM peak; default
+#endif
+#if MKB_R_ASYNC2 && !MKB_R_OVF
+#error "MKB_R_ASYNC2 needs MKB_R_OVF"
 #endif
 #if MKB_R_OVF && !(MKB_R_PRE && MKB_R_FLUSH == 2 && MKB_R_PIN >= 2)
 #error "MKB_R_OVF needs MKB_R_PRE, MKB_R_FLUSH 2 and MKB_R_PIN 2"
@@ -331,11 +357,27 @@ __device__ __forceinline__ void lds_2x64(unsigned a, f2_t &lo, f2_t &hi) {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(a));
 }
 
+__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+#if MKB_R_TMAP
+// one 4 x 4 x 8-voxel block (dense [x][y][z][c] tile in shared memory) -> the grid; coordinates (z * 8, y, x, grid); TMA clips
+// the part of the box that lies outside the grid
+__device__ __forceinline__ void tma_store_block(const CUtensorMap *tm, unsigned src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(tm), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3), "r"(src_smem)
+                 : "memory");
+}
+#define MKB_TMAP_PARAM , const __grid_constant__ CUtensorMap tmap
+#else
+#define MKB_TMAP_PARAM
+#endif
+
 #define RG(field) (UNIFORM ? p.u.field : __ldg(&gg->field))
 template <bool UNIFORM>
-__global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_kernel(const RunParams p) {
+__global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_kernel(const RunParams p MKB_TMAP_PARAM) {
     __shared__ __align__(128) unsigned char s_raw[R_WARPS][R_WARP_BYTES];
-    __shared__ __align__(128) float s_zero[64 * R_ZC];
+    __shared__ __align__(128) float s_zero[MKB_R_TMAP ? 1024 : 64 * R_ZC];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *const wb = s_raw[warp];
@@ -361,7 +403,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(wb);
     const unsigned zero_sa = (unsigned)__cvta_generic_to_shared(s_zero);
 
-    for (int i = threadIdx.x; i < 64 * R_ZC; i += R_WARPS * 32) s_zero[i] = 0.0f;
+    for (int i = threadIdx.x; i < (MKB_R_TMAP ? 1024 : 64 * R_ZC); i += R_WARPS * 32) s_zero[i] = 0.0f;
     for (int i = lane; i < 128; i += 32) hist[i] = 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -429,6 +471,13 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             if (p.blk_rank) {
             } else if (p.cmajor) {
                 for (int bzi = bz_begin; bzi < bz_end; ++bzi) store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, bzi * R_BZ + lz);
+#if MKB_R_TMAP
+            } else if (p.use_tmap) {
+                if (lane == 0) {
+                    for (int bzi = bz_begin; bzi < bz_end; ++bzi) tma_store_block(&tmap, zero_sa, bzi * (R_BZ * 8), y0, x0, gi);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+#endif
             } else {
                 if (row_ok) bulk_store_row(row_base + z0 * 8, zero_sa, (min(nz, bz_end * R_BZ) - z0) * 32);
                 if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -442,6 +491,10 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             lamf = (float)lam;
         }
 #endif
+#if MKB_R_ENTPF
+        unsigned eyn[R_CAP / 32];
+        bool have_next = false;  // warp-uniform: eyn holds the first R_CAP list words of block bzi (requested during the previous epilogue)
+#endif
         for (int bzi = bz_begin; bzi < bz_end; ++bzi) {
             const int z0 = bzi * R_BZ;
             const int row_bytes = min(R_BZ, nz - z0) * 32;
@@ -452,6 +505,13 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 if (p.blk_rank) {
                 } else if (p.cmajor) {
                     store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, z0 + lz);
+#if MKB_R_TMAP
+                } else if (p.use_tmap) {
+                    if (lane == 0) {
+                        tma_store_block(&tmap, zero_sa, z0 * 8, y0, x0, gi);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+#endif
                 } else {
                     if (row_ok) bulk_store_row(row_dst, zero_sa, row_bytes);
                     if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -471,52 +531,70 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 const int np = (int)min((unsigned)R_CAP, n - base);
                 const uint2 *const ent = p.blk_ent + ls + base;
                 // ---- pass 1: histogram of the channel masks, rank of every candidate inside its bin
-                unsigned ey[R_CAP / 32], ex_multi = 0;
+                unsigned ey[R_CAP / 32];
+#if MKB_R_ENTPF
+                if (base == 0 && have_next) {
 #pragma unroll
-                for (int u = 0; u < R_CAP / 32; ++u) {  // all loads of the round in flight together
-                    const int j = u * 32 + lane;
-                    ey[u] = j < np ? __ldg(&ent[j].y) : 0u;
+                    for (int u = 0; u < R_CAP / 32; ++u) ey[u] = eyn[u];
+                } else
+#endif
+                {
+#pragma unroll
+                    for (int u = 0; u < R_CAP / 32; ++u) {  // all loads of the round in flight together
+                        const int j = u * 32 + lane;
+                        ey[u] = j < np ? __ldg(&ent[j].y) : 0u;
+                    }
                 }
+                // the histogram trips carry no other code: the per-channel path of multi-sigma atoms (rare: user float channels) used
+                // to be inlined in each of the R_CAP / 32 unrolled trips -- 34 KB of code that the instruction cache had to skip
+                bool any_multi = false;
 #pragma unroll
                 for (int u = 0; u < R_CAP / 32; ++u) {
                     const int j0 = u * 32;
                     if (j0 >= np) break;
                     const int j = j0 + lane;
-                    uint2 e = make_uint2(0u, ey[u]);
+                    const uint2 e = make_uint2(0u, ey[u]);
                     const bool multi = (e.y & 0x100u) != 0;
-                    if (__any_sync(0xffffffffu, multi)) e.x = j < np ? __ldg(&ent[j].x) : 0u;
-                    (void)ex_multi;
-                    // atoms with several distinct sigmas (user float channels): whole-warp per-channel path; they stay in
-                    // the list under mask 0 (a run that updates no channel)
-                    for (unsigned bm = __ballot_sync(0xffffffffu, multi); bm; bm &= bm - 1) {
-                        const unsigned it = __shfl_sync(0xffffffffu, e.x, __ffs(bm) - 1);
-                        const float4 f = __ldg(p.rec_pos + it);
-                        const uint4 tg = __ldg(p.rec_tag + it);
-                        const float ax = (float)((int)(tg.z & 0xffffu) - cx) + (f.x - 1.5f), ay = (float)((int)(tg.z >> 16) - cy) + (f.y - 1.5f),
-                                    az = (float)((int)(tg.x >> 16) - cz) + (f.z - 3.5f);
-                        const float dy = ay - fy, dz = az - fz;
-                        const float s2 = fmaf(dz, dz, dy * dy);
-                        const double ivs = RG(inv_vs);
-                        float d2[4];
-#pragma unroll
-                        for (int k2 = 0; k2 < 4; ++k2) {
-                            const float dx = ax - ((float)k2 - 1.5f);
-                            d2[k2] = fmaf(dx, dx, s2);
-                        }
-#pragma unroll
-                        for (int h = 0; h < 8; ++h) {
-                            const double sv = __ldg(p.sigmas + (long long)tg.y * 8 + h) * ivs;
-                            if (sv == 0.0 || sv != sv) continue;
-                            const float w = (float)(1.0 / (sv * sv));
-#pragma unroll
-                            for (int k2 = 0; k2 < 4; ++k2)
-                                if (d2[k2] < cut2) acc[h][k2] = fminf(acc[h][k2], d2[k2] * w);
-                        }
-                    }
+                    any_multi |= multi;
                     if (j < np) {
                         const unsigned m = multi ? 0u : (e.y & 255u), sh = (m & 1u) * 16u;
                         const unsigned old = atomicAdd(&hist[m >> 1], 1u << sh);
                         rnk[j] = (unsigned char)((old >> sh) & 0xffffu);
+                    }
+                }
+                if (__any_sync(0xffffffffu, any_multi)) {
+#pragma unroll 1
+                    for (int j0 = 0; j0 < np; j0 += 32) {
+                        const int j = j0 + lane;
+                        const uint2 e = j < np ? __ldg(ent + j) : make_uint2(0u, 0u);
+                        const bool multi = (e.y & 0x100u) != 0;
+                    // atoms with several distinct sigmas (user float channels): whole-warp per-channel path; they stay in
+                        // the list under mask 0 (a run that updates no channel)
+                        for (unsigned bm = __ballot_sync(0xffffffffu, multi); bm; bm &= bm - 1) {
+                            const unsigned it = __shfl_sync(0xffffffffu, e.x, __ffs(bm) - 1);
+                            const float4 f = __ldg(p.rec_pos + it);
+                            const uint4 tg = __ldg(p.rec_tag + it);
+                            const float ax = (float)((int)(tg.z & 0xffffu) - cx) + (f.x - 1.5f), ay = (float)((int)(tg.z >> 16) - cy) + (f.y - 1.5f),
+                                        az = (float)((int)(tg.x >> 16) - cz) + (f.z - 3.5f);
+                            const float dy = ay - fy, dz = az - fz;
+                            const float s2 = fmaf(dz, dz, dy * dy);
+                            const double ivs = RG(inv_vs);
+                            float d2[4];
+#pragma unroll
+                            for (int k2 = 0; k2 < 4; ++k2) {
+                                const float dx = ax - ((float)k2 - 1.5f);
+                                d2[k2] = fmaf(dx, dx, s2);
+                            }
+#pragma unroll
+                            for (int h = 0; h < 8; ++h) {
+                                const double sv = __ldg(p.sigmas + (long long)tg.y * 8 + h) * ivs;
+                                if (sv == 0.0 || sv != sv) continue;
+                                const float w = (float)(1.0 / (sv * sv));
+#pragma unroll
+                                for (int k2 = 0; k2 < 4; ++k2)
+                                    if (d2[k2] < cut2) acc[h][k2] = fminf(acc[h][k2], d2[k2] * w);
+                            }
+                        }
                     }
                 }
                 __syncwarp();
@@ -551,6 +629,26 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 // ---- pass 2: records in run order, pre-scaled by 1/sigma (float64 rebase: one rounding per coordinate).
                 // The record that closes a run is stored NEGATED: every term of r is a square of a difference of record
                 // fields, so r is unchanged and the sign of .w is a free end-of-run flag.
+#if MKB_R_ASYNC2
+                // sub-pass a: the raw per-atom data of every candidate goes straight to its sorted slot (cp.async, all in flight)
+                for (int j = lane; j < np; j += 32) {
+                    const uint2 e = __ldg(ent + j);
+                    const unsigned m = (e.y & 0x100u) ? 0u : (e.y & 255u);
+                    const unsigned pos = ((hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu) - 1u - (unsigned)rnk[j];
+                    cp_async16(rec_sa + 16u * pos, p.rec_pos + e.x);
+                    cp_async16(rec_sa + (unsigned)(R_CAP * 16) + 16u * pos, p.rec_tag + e.x);
+                    msk[pos] = (unsigned char)m;
+                }
+                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                // sub-pass b: slot by slot in place (a lane reads and writes its own slots only)
+                for (int j = lane; j < np; j += 32) {
+                    const unsigned pos = (unsigned)j;
+                    const unsigned m = msk[pos];
+                    const unsigned rk = (((hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu) - 1u == pos) ? 0u : 1u;  // 0: closes its run
+                    const float4 f = rec[pos];
+                    const uint4 tg = *reinterpret_cast<const uint4 *>(recy + pos);
+#else
                 for (int j = lane; j < np; j += 32) {
                     const uint2 e = __ldg(ent + j);
                     const unsigned m = (e.y & 0x100u) ? 0u : (e.y & 255u);
@@ -558,6 +656,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     const unsigned pos = ((hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu) - 1u - rk;
                     const float4 f = __ldg(p.rec_pos + e.x);
                     const uint4 tg = __ldg(p.rec_tag + e.x);
+#endif
                     const float sw = __uint_as_float(tg.w);
                     const double dsw = rk == 0 ? -(double)sw : (double)sw;
                     const double ex = (double)((int)(tg.z & 0xffffu) - cx) + ((double)f.x - 1.5);
@@ -639,51 +738,6 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     float M0 = INF, M1 = INF, M2 = INF, M3 = INF, gclose;
 #pragma unroll 1
                     while (i <= np && MKB_R_EXP != 1) {
-#if MKB_R_X2 == 2
-                        float m0, m1, m2, m3;
-                        unsigned mask;
-                        {   // the first candidate (pair) of a run initialises the run minima
-                            float4 b = MKB_LDREC(i), yb = MKB_LDRECY(i);
-                            MKB_RUN_R2(a, ya, ra)
-                            if (__float_as_int(ya.w) < 0) {  // a run of one candidate
-                                m0 = ra0; m1 = ra1; m2 = ra2; m3 = ra3;
-                                mask = __float_as_uint(ya.w);
-                                a = b; ya = yb;
-                                i += 1;
-                            } else {
-                                a = MKB_LDREC(i + 1);
-                                ya = MKB_LDRECY(i + 1);
-                                MKB_RUN_R2(b, yb, rb)
-                                m0 = fminf(ra0, rb0); m1 = fminf(ra1, rb1); m2 = fminf(ra2, rb2); m3 = fminf(ra3, rb3);
-                                i += 2;
-                                mask = __float_as_uint(yb.w);
-                                if (__float_as_int(yb.w) >= 0) {
-#pragma unroll 1
-                                    for (;;) {
-                                        b = MKB_LDREC(i); yb = MKB_LDRECY(i);
-                                        MKB_RUN_R2(a, ya, rc)
-                                        if (__float_as_int(ya.w) < 0) {
-                                            m0 = fminf(m0, rc0); m1 = fminf(m1, rc1); m2 = fminf(m2, rc2); m3 = fminf(m3, rc3);
-                                            mask = __float_as_uint(ya.w);
-                                            a = b; ya = yb;
-                                            i += 1;
-                                            break;
-                                        }
-                                        a = MKB_LDREC(i + 1);
-                                        ya = MKB_LDRECY(i + 1);
-                                        MKB_RUN_R2(b, yb, rd)
-                                        m0 = fminf(fminf(m0, rc0), rd0); m1 = fminf(fminf(m1, rc1), rd1);
-                                        m2 = fminf(fminf(m2, rc2), rd2); m3 = fminf(fminf(m3, rc3), rd3);
-                                        i += 2;
-                                        if (__float_as_int(yb.w) < 0) {
-                                            mask = __float_as_uint(yb.w);
-                                            break;
-                                        }
-                                    }
-                                }
-                            }
-                        }
-#else
                         float m0 = INF, m1 = INF, m2 = INF, m3 = INF;
                         unsigned mask;
 #pragma unroll 1
@@ -709,7 +763,6 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                                 break;
                             }
                         }
-#endif
                         gclose = (mask & 0x100u) ? -1.0f : 1.0f;
 #elif MKB_R_PRE
 #if MKB_R_PIN >= 2
@@ -914,6 +967,23 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 stage[v] = make_float4(acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
                 stage[v + 1] = make_float4(acc[4][k], acc[5][k], acc[6][k], acc[7][k]);
             }
+#if MKB_R_ENTPF
+            have_next = false;
+            if (bzi + 1 < bz_end) {  // warp-uniform
+                const unsigned ls2 = __shfl_sync(0xffffffffu, my_start, bzi + 1 - bz_begin);
+                const unsigned n2 = __shfl_sync(0xffffffffu, my_start, bzi + 2 - bz_begin) - ls2;
+                if (n2 != 0) {
+                    have_next = true;
+                    const int np2 = (int)min((unsigned)R_CAP, n2);
+                    const uint2 *const ent2 = p.blk_ent + ls2;
+#pragma unroll
+                    for (int u = 0; u < R_CAP / 32; ++u) {
+                        const int j = u * 32 + lane;
+                        eyn[u] = j < np2 ? __ldg(&ent2[j].y) : 0u;
+                    }
+                }
+            }
+#endif
             __syncwarp();
 #pragma unroll 1
             for (int it = 0; it < 8; ++it) {
@@ -954,6 +1024,10 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             __syncwarp();
             if (p.blk_rank && !p.sparse_dense) {  // compact output: the whole 4 KB stage is one record, one bulk copy
                 if (lane == 0) bulk_store_row(p.out + 1024ll * __ldg(p.blk_rank + blk0 + (bzi - bz_begin)), stage_sa, 4096);
+#if MKB_R_TMAP
+            } else if (p.use_tmap) {
+                if (lane == 0) tma_store_block(&tmap, stage_sa, z0 * 8, y0, x0, gi);
+#endif
             } else if (row_ok) bulk_store_row(row_dst, stage_sa + lane * 256, row_bytes);
             if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             pending = true;

@@ -18,6 +18,7 @@
 //       Output: coalesced 32-byte (8-channel) streaming stores, 4 lanes = one 128-byte line.
 // HBM-bound gather-accumulate: no tensor cores (max of a transcendental is not a contraction).
 #include <cub/device/device_scan.cuh>
+#include <cuda.h>  // CUtensorMap (types only; the encoder is looked up through the runtime, libcuda is not linked)
 
 #include <cfloat>
 #include <cstdlib>
@@ -1536,6 +1537,35 @@ __global__ void __launch_bounds__(128) occ_points_kernel(const double *__restric
 
 }  // namespace mkb
 #include "occ_runs.cuh"
+
+#if MKB_R_TMAP
+// 4-D tiled tensor map over a uniform dense batch: [grid][x][y][z * 8 channels] float32, box = one 4 x 4 x 8-voxel block.
+// Returns false when the encoder is unavailable or rejects the layout (the caller keeps the row copies).
+static bool occ_make_tmap(CUtensorMap *tm, float *base, int nx, int ny, int nz, long long n_grids, long long grid_stride_vox) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            enc = (encode_fn)fn;
+        else
+            (void)cudaGetLastError();
+    }
+    if (!enc || ((uintptr_t)base & 15u)) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)nz * 8, (cuuint64_t)ny, (cuuint64_t)nx, (cuuint64_t)n_grids};
+    const cuuint64_t strides[3] = {(cuuint64_t)nz * 32, (cuuint64_t)ny * nz * 32, (cuuint64_t)grid_stride_vox * 32};  // bytes, dims 1..3
+    const cuuint32_t box[4] = {mkb::R_BZ * 8, 4, 4, 1}, estr[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 3; ++i)
+        if (strides[i] >= (1ull << 40)) return false;
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#endif
 namespace mkb {
 
 static int scan_u32(mkb_ctx *h, cudaStream_t st, unsigned *in, unsigned *out, long long n) {
@@ -1843,8 +1873,19 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             if (h->timing && c == 0) MKB_CUDA(h, cudaEventRecord(h->ev[1], st));
             const unsigned nctas = (unsigned)std::min<long long>((long long)h->sm_count * MKB_R_MIN_CTAS, cdiv((long long)rp.total_items, R_WARPS));
             if (nctas == 0) continue;
+            rp.use_tmap = 0;
+#if MKB_R_TMAP
+            CUtensorMap tmap;
+            memset(&tmap, 0, sizeof(tmap));
+            // dense uniform output in device memory (the to-host route writes mapped host memory: row copies)
+            if (uni && !rp.cmajor && !rp.blk_rank && !getenv("MKB_OCC_NO_TMAP"))
+                rp.use_tmap = occ_make_tmap(&tmap, out + g0d.out_offset * 8, g0d.dims[0], g0d.dims[1], g0d.dims[2], g1 - g0, nvox0) ? 1 : 0;
+            if (uni) occ_fill_runs_kernel<true><<<nctas, R_WARPS * 32, 0, st>>>(rp, tmap);
+            else occ_fill_runs_kernel<false><<<nctas, R_WARPS * 32, 0, st>>>(rp, tmap);
+#else
             if (uni) occ_fill_runs_kernel<true><<<nctas, R_WARPS * 32, 0, st>>>(rp);
             else occ_fill_runs_kernel<false><<<nctas, R_WARPS * 32, 0, st>>>(rp);
+#endif
             MKB_LAUNCHED(h);
         }
         if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));
