@@ -872,7 +872,7 @@ def run_ours(a):
     kname = _lib.last_fill_kernel(local) if hasattr(_lib, "last_fill_kernel") else "occ_fill_runs_kernel"
     try:
         if a.workload == "c3" and not a.batch:
-            fn = os.path.join(ROOT, "profiles", "r02_fill_v9_metrics.txt")  # capture of the shipped (v9) kernel
+            fn = os.path.join(ROOT, "profiles", "r02_fill_v10_metrics.txt")  # capture of the shipped (v10) kernel
             tr, kern_ok = 0.0, False
             for ln in open(fn):
                 if ln.startswith("# kernel:"):
@@ -881,7 +881,7 @@ def run_ours(a):
                 if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     tr += float(f[1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
             if kern_ok and tr:
-                traffic, traffic_source = tr, "committed ncu --set full capture of the same kernel and workload (profiles/r02_fill_v9_metrics.txt)"
+                traffic, traffic_source = tr, "committed ncu --set full capture of the same kernel and workload (profiles/r02_fill_v10_metrics.txt)"
     except Exception:
         traffic = None
     roofline = dict(bound="hbm", kernel=kname, achieved=achieved, peak=peak, unit="GB/s",

@@ -273,18 +273,13 @@ __device__ __forceinline__ float4 lds_rec4(unsigned a) {
 //   round in flight at once, no registers -- and a second sub-pass turns the raw slots into records in place.
 // (Measured and dropped: a queue that runs two items ahead -- atomic and list offsets of the next items in flight during the
 //   current one -- 0.735 -> 0.757 ms: the second decode costs more issue slots than the hidden latency; peeling the first
-//   candidate of a run so that it initialises the minima: 0.758 -> 0.776 ms.)
+//   candidate of a run so that it initialises the minima: 0.758 -> 0.776 ms; requesting the list words of the item's next z block
+//   during the epilogue: 0.689 -> 0.695 ms, the extra live registers spill.)
 // MKB_R_TMAP: dense uniform device output leaves as ONE cp.async.bulk.tensor (4-D tiled tensor map over [grid][x][y][z * c], box
 //   1 x 4 x 4 x 64 floats) per block instead of 16 row copies -- ptxas serialises per-lane bulk copies through uniform registers
 //   (R2UR / UBLKCP in a 16-trip loop: 12 % of the warp samples); empty items are tensor copies from a zeroed 4 KB tile.
-// MKB_R_ENTPF: the list of the item's NEXT z block is requested right after the accumulators have gone to the stage: the epilogue
-//   needs few registers, so the R_CAP / 32 words per lane ride through it for free and the next block's histogram pass finds
-//   them loaded.
 #ifndef MKB_R_ASYNC2
 #define MKB_R_ASYNC2 MKB_R_OVF  // measured on C3: 0.762 -> 0.735 ms; default
-#endif
-#ifndef MKB_R_ENTPF
-#define MKB_R_ENTPF 0
 #endif
 #ifndef MKB_R_TMAP
 #define MKB_R_TMAP 1  // measured on C3: 0.762 -> 0.713 ms; with MKB_R_ASYNC2 0.690 ms = 49.4 % of HBM peak; default
@@ -491,10 +486,6 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             lamf = (float)lam;
         }
 #endif
-#if MKB_R_ENTPF
-        unsigned eyn[R_CAP / 32];
-        bool have_next = false;  // warp-uniform: eyn holds the first R_CAP list words of block bzi (requested during the previous epilogue)
-#endif
         for (int bzi = bz_begin; bzi < bz_end; ++bzi) {
             const int z0 = bzi * R_BZ;
             const int row_bytes = min(R_BZ, nz - z0) * 32;
@@ -532,12 +523,6 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 const uint2 *const ent = p.blk_ent + ls + base;
                 // ---- pass 1: histogram of the channel masks, rank of every candidate inside its bin
                 unsigned ey[R_CAP / 32];
-#if MKB_R_ENTPF
-                if (base == 0 && have_next) {
-#pragma unroll
-                    for (int u = 0; u < R_CAP / 32; ++u) ey[u] = eyn[u];
-                } else
-#endif
                 {
 #pragma unroll
                     for (int u = 0; u < R_CAP / 32; ++u) {  // all loads of the round in flight together
@@ -967,23 +952,6 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 stage[v] = make_float4(acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
                 stage[v + 1] = make_float4(acc[4][k], acc[5][k], acc[6][k], acc[7][k]);
             }
-#if MKB_R_ENTPF
-            have_next = false;
-            if (bzi + 1 < bz_end) {  // warp-uniform
-                const unsigned ls2 = __shfl_sync(0xffffffffu, my_start, bzi + 1 - bz_begin);
-                const unsigned n2 = __shfl_sync(0xffffffffu, my_start, bzi + 2 - bz_begin) - ls2;
-                if (n2 != 0) {
-                    have_next = true;
-                    const int np2 = (int)min((unsigned)R_CAP, n2);
-                    const uint2 *const ent2 = p.blk_ent + ls2;
-#pragma unroll
-                    for (int u = 0; u < R_CAP / 32; ++u) {
-                        const int j = u * 32 + lane;
-                        eyn[u] = j < np2 ? __ldg(&ent2[j].y) : 0u;
-                    }
-                }
-            }
-#endif
             __syncwarp();
 #pragma unroll 1
             for (int it = 0; it < 8; ++it) {

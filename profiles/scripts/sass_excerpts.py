@@ -37,19 +37,24 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_sass_excerpts.txt"), "w") as f:
     for name, lines in fn.items():
         if "occ_fill_runs_kernelILb1" in name:
             f.write(f"\n## {name}: {len(lines)} instructions\n")
-            ub = [l for l in lines if "UBLKCP" in l]
-            f.write(f"# TMA bulk stores (cp.async.bulk.global.shared::cta) in the DEFAULT fill kernel: {len(ub)} UBLKCP\n")
+            ub = [l for l in lines if "UBLKCP" in l or "UTMASTG" in l]
+            f.write(f"# TMA stores in the DEFAULT fill kernel: {sum('UTMASTG' in l for l in ub)} UTMASTG (cp.async.bulk.tensor.4d: one 4 x 4 x 8-voxel block "
+                    f"per instruction), {sum('UBLKCP' in l for l in ub)} UBLKCP (cp.async.bulk row copies: compact / to-host / non-uniform batches)\n")
             f.write("\n".join(ub) + "\n")
-            # the hot loop: the two LDS.128 of the ping-pong records up to the run-end flush
-            # (v9: FSETP compares against |gate| -- the sign of the gate flags the end of a high-nibble group)
-            hot = [i for i, l in enumerate(lines) if "FSETP.GEU.AND" in l and ", |R" in l]
-            hot = [i for i in hot if hot[-1] - i < 120]
+            # the hot loop (v10): packed FFMA2 / FMUL2 from the first pair of LDS.128 up to the end of the two-level run-end flush
+            hot = [i for i, l in enumerate(lines) if "FFMA2" in l and "HI_LO, R" in l]
+            hot = [i for i in hot if i - hot[0] < 80]
             if hot:
-                lo = hot[0] - 16
-                hi = hot[-1] + 75
-                f.write("# hot loop (two candidates per trip; per candidate FFMA / FMUL x8, FSETP x5, predicated FMNMX x4, LDS.128 x2) and the\n"
-                        "# two-level run-end flush (low nibble: 16 predicated FMNMX + 4 folds; high nibble once per group)\n")
+                lo = max(0, hot[0] - 14)
+                hi = min(len(lines), hot[-1] + 95)
+                f.write("# hot loop (two candidates per trip; per candidate LDS.128 x2, FFMA2 x3, FMUL2 x3, FADD, ISETP on the tag; FMNMX3 x4 per pair --\n"
+                        "# the 5 A gate is the float overflow of FFMA2, no predicate) and the two-level run-end flush (low nibble: 16 predicated FMNMX + 4\n"
+                        "# folds; high nibble once per group)\n")
                 f.write("\n".join(lines[lo:hi]) + "\n")
+            ld = [i for i, l in enumerate(lines) if "LDGSTS" in l]
+            if ld:
+                f.write("# record pass: cp.async (LDGSTS) gathers of the per-atom data straight into the sorted slots\n")
+                f.write("\n".join(lines[max(0, ld[0] - 6):ld[-1] + 6]) + "\n")
         if "dist_kernelILi0ELb0" in name:
             f.write(f"\n## {name}: {len(lines)} instructions (K3 distances, bit-exact minimum image: FMUL/FADD/FSUB, no FFMA in the wrap)\n")
             f.write("\n".join(window(lines, lambda l: "MUFU.RSQ" in l, 45, 12)[:110]) + "\n")

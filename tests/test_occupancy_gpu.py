@@ -192,9 +192,12 @@ def test_full_size_c3_properties(vd, oracle):
 
 
 @pytest.mark.parametrize("envs", [("MKB_OCC_TILE",), ("MKB_OCC_TILE", "MKB_OCC_BULK_STORE"), ("MKB_OCC_GENERIC",), ("MKB_OCC_WARP",),
-                                  ("MKB_OCC_WARP32",)])
+                                  ("MKB_OCC_WARP32",), ("MKB_OCC_NO_TMAP",)])
 def test_alternative_kernel_paths_agree(vd, monkeypatch, envs):
-    """The tile kernel (quarter lists), its opt-in TMA bulk-store epilogue, the generic tile kernel and the one-voxel-per-lane
+    """MKB_OCC_NO_TMAP: the default run kernel with 16 bulk row copies per block instead of one TMA tensor store (the route of
+    non-uniform batches and of the compact / to-host transfers; the grid dims here are not multiples of the 4 x 4 x 8 block, so
+    the tensor store is clipped by the TMA unit and the row copies by hand).
+    The tile kernel (quarter lists), its opt-in TMA bulk-store epilogue, the generic tile kernel and the one-voxel-per-lane
     warp kernel (2x4x4 blocks) agree with the default two-voxels-per-lane warp kernel (ragged grid: dims not multiples of
     the block / tile sizes)."""
     from moleculekit_b200 import workloads
@@ -212,6 +215,8 @@ def test_alternative_kernel_paths_agree(vd, monkeypatch, envs):
             # different kernels place atoms in different local frames: each within 1e-5 of the float64 oracle, zero pattern identical
             assert np.array_equal(a != 0, b != 0)
             assert np.allclose(a, b, rtol=1.5e-5, atol=0)
+            if envs == ("MKB_OCC_NO_TMAP",):  # the same arithmetic, only the store differs
+                assert np.array_equal(a, b)
 
 
 def test_nonuniform_batch_buffer_mode(vd, oracle):
