@@ -1044,7 +1044,10 @@ __global__ void __launch_bounds__(128) occ_band_kernel(const float *__restrict__
         const float dy = (float)jy - f[1];
         const float A = fmaf(-dy, dy, cut2);
         if (A < -band || iy < 0 || iy >= ny) continue;
-        for (int jz = -W; jz <= W; ++jz) {
+        // z rows that can cross the sphere: |jz - f_z| <= sqrt(A + band) (a superset; the exact test follows per row)
+        const float zr = sqrtf(A + band) + 1e-3f;
+        const int jz_lo = max(-W, (int)ceilf(f[2] - zr)), jz_hi = min(W, (int)floorf(f[2] + zr));
+        for (int jz = jz_lo; jz <= jz_hi; ++jz) {
             const float dz = (float)jz - f[2];
             const float h2 = fmaf(-dz, dz, A);  // cut2 - s
             if (h2 < -band) continue;           // the row misses the sphere

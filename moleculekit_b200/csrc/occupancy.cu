@@ -1546,16 +1546,15 @@ static bool occ_make_tmap(CUtensorMap *tm, float *base, int nx, int ny, int nz, 
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static encode_fn enc = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
             enc = (encode_fn)fn;
         else
             (void)cudaGetLastError();
-    }
+    });
     if (!enc || ((uintptr_t)base & 15u)) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)nz * 8, (cuuint64_t)ny, (cuuint64_t)nx, (cuuint64_t)n_grids};
     const cuuint64_t strides[3] = {(cuuint64_t)nz * 32, (cuuint64_t)ny * nz * 32, (cuuint64_t)grid_stride_vox * 32};  // bytes, dims 1..3
