@@ -21,6 +21,12 @@
 //   * Persistent CTAs (7 x 148 x 4 warps) pull (x, y, 4 z-blocks) items from an atomic queue; results are staged in
 //     shared memory in the output layout and leave the SM as cp.async.bulk.global.shared::cta row copies (SASS UBLKCP);
 //     blocks without any atom in reach (~70 %) are bulk copies from a zeroed shared-memory line, no math.
+//
+// v10 (defaults below): the gate is the float OVERFLOW of d2 in units of cut2 / 2^128
+// (MKB_R_OVF: no FSETP, no predicate), the FMA-pipe work runs on packed float32 pairs (MKB_R_X2: FFMA2 / FMUL2), the record
+// pass gathers with cp.async into the sorted slots (MKB_R_ASYNC2) and a block of a dense uniform batch leaves as ONE TMA
+// tensor store (MKB_R_TMAP: cp.async.bulk.tensor.4d, SASS UTMASTG).  The older forms stay selectable at compile time for
+// A/B runs (MKB_NVCC_EXTRA="-DMKB_R_OVF=0 ..."); the descriptions above marked "FSETP gate" / "row copies" are theirs.
 #pragma once
 
 namespace mkb {
@@ -415,9 +421,13 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
     bool pending = false;  // lanes 0..15: bulk copies still reading the stage
 #if MKB_R_OVF
     // lambda = 2^64 / cut (voxel units): d2 == cut2 lands on 2^128, the float overflow threshold
-    double lam = UNIFORM ? 18446744073709551616.0 / sqrt((double)p.u.cut2v) : 0.0;
-    float lamf = (float)lam;
+    // The FLOAT is the root value and the double its exact image: with lamf = (float)lam ptxas kept only the double and
+    // re-converted it (F2F.F32.F64, a slow-pipe instruction the first FFMA2 then waits for) at the head of EVERY hot-loop trip.
+    // Atoms and voxels are scaled by the same number this way; cwf = 2^64 / lambda (= cut up to 6e-8) keeps r = U w exact.
+    float lamf = UNIFORM ? (float)(18446744073709551616.0 / sqrt((double)p.u.cut2v)) : 0.0f;
     asm volatile("mov.b32 %0, %0;" : "+f"(lamf));
+    double lam = (double)lamf;
+    float cwf = UNIFORM ? (float)(18446744073709551616.0 / lam) : 0.0f;
 #endif
 
     for (;;) {
@@ -482,8 +492,9 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
 
 #if MKB_R_OVF
         if (!UNIFORM) {
-            lam = 18446744073709551616.0 / sqrt((double)cut2);
-            lamf = (float)lam;
+            lamf = (float)(18446744073709551616.0 / sqrt((double)cut2));
+            lam = (double)lamf;
+            cwf = (float)(18446744073709551616.0 / lam);
         }
 #endif
         for (int bzi = bz_begin; bzi < bz_end; ++bzi) {
@@ -651,7 +662,8 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     {
                         const float xs = (float)(ex * lam);
                         rec[pos] = make_float4(fmaf(-1.5f, lamf, -xs), fmaf(-0.5f, lamf, -xs), fmaf(0.5f, lamf, -xs), fmaf(1.5f, lamf, -xs));
-                        const float wt = ((cut2 * (sw * sw)) * 5.421010862427522e-20f) * 5.421010862427522e-20f;  // 2^-64 twice: exact
+                        const float wh = (sw * cwf) * 5.421010862427522e-20f;  // (cut / sigma) 2^-64
+                        const float wt = wh * wh;                              // w = 1 / (sigma lambda)^2
                         const unsigned mh = m | 15u;
                         const unsigned e0 = (hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu, e1 = (hist[mh >> 1] >> 16) & 0xffffu;
 #if MKB_R_X2
