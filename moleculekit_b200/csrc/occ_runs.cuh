@@ -287,6 +287,10 @@ __device__ __forceinline__ float4 lds_rec4(unsigned a) {
 #ifndef MKB_R_ASYNC2
 #define MKB_R_ASYNC2 MKB_R_OVF  // measured on C3: 0.762 -> 0.735 ms; default
 #endif
+// MKB_R_SENTINEL (needs MKB_R_X2): the run loop ends on a bit of the last record's tag instead of a candidate count.
+#ifndef MKB_R_SENTINEL
+#define MKB_R_SENTINEL MKB_R_X2  // measured on C3: 0.669 -> 0.659 ms; default
+#endif
 #ifndef MKB_R_TMAP
 #define MKB_R_TMAP 1  // measured on C3: 0.762 -> 0.713 ms; with MKB_R_ASYNC2 0.690 ms = 49.4 % of HBM peak; default
 #endif
@@ -667,8 +671,11 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                         const unsigned mh = m | 15u;
                         const unsigned e0 = (hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu, e1 = (hist[mh >> 1] >> 16) & 0xffffu;
 #if MKB_R_X2
+                        // bit 9: the last record of the round (it closes a run) ends the run loop -- ptxas otherwise rebuilds the
+                        // candidate count (IADD, VIMNMX) for a compare at the end of every run
                         recy[pos] = make_float4(-(float)(ey * lam), -(float)(ez * lam), wt,
-                                                __uint_as_float(m | ((rk == 0 && e0 == e1) ? 0x100u : 0u) | (rk == 0 ? 0x80000000u : 0u)));
+                                                __uint_as_float(m | ((rk == 0 && e0 == e1) ? 0x100u : 0u) | (rk == 0 ? 0x80000000u : 0u) |
+                                                                (pos + 1u == (unsigned)np ? 0x200u : 0u)));
 #else
                         recy[pos] = make_float4((float)(ey * lam), (float)(ez * lam), rk == 0 ? -wt : wt,
                                                 __uint_as_float(m | ((rk == 0 && e0 == e1) ? 0x100u : 0u)));
@@ -715,6 +722,13 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
 #define MKB_GATED_MIN(M, R, CW) gated_min(M, R, CW)
 #endif
 #if MKB_R_X2
+#if MKB_R_SENTINEL
+#define MKB_RUN_LOOP_HEAD for (bool more_ = true; more_;)
+#define MKB_RUN_LOOP_TAIL more_ = (mask & 0x200u) == 0u;
+#else
+#define MKB_RUN_LOOP_HEAD while (i <= np && MKB_R_EXP != 1)
+#define MKB_RUN_LOOP_TAIL
+#endif
 #define MKB_LDREC(I) lds_rec4(rec_sa + 16u * (unsigned)(I))
 #define MKB_LDRECY(I) lds_rec4(rec_sa + (unsigned)(R_CAP * 16) + 16u * (unsigned)(I))
 #define MKB_RUN_R2(D, Y, R)                                                                       \
@@ -734,7 +748,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     int i = 1;  // next record to load; i == np reads past the list (inside this warp's buffer), never used
                     float M0 = INF, M1 = INF, M2 = INF, M3 = INF, gclose;
 #pragma unroll 1
-                    while (i <= np && MKB_R_EXP != 1) {
+                    MKB_RUN_LOOP_HEAD {
                         float m0 = INF, m1 = INF, m2 = INF, m3 = INF;
                         unsigned mask;
 #pragma unroll 1
@@ -937,7 +951,12 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                                 acc[h][2] = fminf(acc[h][2], m2); acc[h][3] = fminf(acc[h][3], m3);
                             }
 #endif
+#if MKB_R_X2
+                        MKB_RUN_LOOP_TAIL
+#endif
                     }
+#undef MKB_RUN_LOOP_HEAD
+#undef MKB_RUN_LOOP_TAIL
 #undef MKB_RUN_BODY
 #undef MKB_RUN_R
 #undef MKB_RUN_R2
