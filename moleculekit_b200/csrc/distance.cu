@@ -42,6 +42,33 @@ __device__ __forceinline__ float sq3(float dx, float dy, float dz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// packed float32 pairs (sm_100): a 64-bit register holds (lo, hi); used by the contact-map estimate of K3
+#ifndef MKB_K3_X2
+#define MKB_K3_X2 1  // measured on C4a contacts: 3.705 -> 3.538 ms, same booleans (23 distance GPU tests)
+#endif
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+    f2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+    f2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+    f2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 struct BoxF {
     float bx, by, bz, rx, ry, rz;
     float hx, hy, hz;  // b / 2
@@ -300,6 +327,50 @@ __global__ void MKB_K3_BOUNDS dist_kernel(const float4 *__restrict__ G1, const f
         unsigned char *const o8 = reinterpret_cast<unsigned char *>(out);
         long long idx = f * P + (SELF ? (i0 * n2 - (i0 * (i0 + 1)) / 2 + (j0 - i0 - 1)) : (i0 * n2 + j0));
         long long step = SELF ? n2 - i0 - 2 : n2;
+#if MKB_K3_X2
+        // The thread's two pairs of a row as PACKED float32 pairs (sm_100 add / mul / fma .f32x2): the estimate of pair_contact,
+        // operation for operation, on (pair 0, pair 1) -- half the FMA-pipe issue slots.  Only the ESTIMATE is packed: ptxas
+        // contracts packed mul + add into FFMA2 (even with .rn and -fmad=false), which an estimate tolerates (any nearest
+        // integer of a quotient good to 1e-6 satisfies the argument above) and the exact sequence would not.
+        if (!SELF && has1 && shortcut) {
+            const f2_t nbx = f2_pack(-b0.x, -b1.x), nby = f2_pack(-b0.y, -b1.y), nbz = f2_pack(-b0.z, -b1.z);
+            const f2_t M2 = f2_pack(12582912.0f, 12582912.0f), NM2 = f2_pack(-12582912.0f, -12582912.0f);
+            const float band = 4e-6f * threshold;
+            for (int r = 0; r < rows; ++r) {
+                const float4 a = __ldg(arow + r);
+                const unsigned ca = __float_as_uint(a.w);
+                const bool w0 = pbc && ca != cb0, w1 = pbc && ca != cb1;
+                bool c0, c1;
+                if (w0 == w1) {
+                    f2_t dx = f2_add(f2_pack(a.x, a.x), nbx), dy = f2_add(f2_pack(a.y, a.y), nby), dz = f2_add(f2_pack(a.z, a.z), nbz);
+                    float qm0 = 0.0f, qm1 = 0.0f;
+                    if (w0) {
+                        const f2_t qx = f2_mul(dx, f2_pack(bx.rx, bx.rx)), qy = f2_mul(dy, f2_pack(bx.ry, bx.ry)),
+                                   qz = f2_mul(dz, f2_pack(bx.rz, bx.rz));
+                        dx = f2_fma(f2_pack(-bx.bx, -bx.bx), f2_add(f2_add(qx, M2), NM2), dx);
+                        dy = f2_fma(f2_pack(-bx.by, -bx.by), f2_add(f2_add(qy, M2), NM2), dy);
+                        dz = f2_fma(f2_pack(-bx.bz, -bx.bz), f2_add(f2_add(qz, M2), NM2), dz);
+                        float x0, x1, y0, y1, z0, z1;
+                        f2_unpack(qx, x0, x1); f2_unpack(qy, y0, y1); f2_unpack(qz, z0, z1);
+                        qm0 = fmaxf(fmaxf(fabsf(x0), fabsf(y0)), fabsf(z0));
+                        qm1 = fmaxf(fmaxf(fabsf(x1), fabsf(y1)), fabsf(z1));
+                    }
+                    float e0, e1;
+                    f2_unpack(f2_fma(dx, dx, f2_fma(dy, dy, f2_mul(dz, dz))), e0, e1);
+                    // decided unless the estimate is within the band, not a number, or the magic rounding left its range
+                    c0 = (fabsf(e0 - threshold) > band && qm0 < 2097152.0f) ? (e0 <= threshold) : (pair_d2_fastwrap(a, b0, cb0, bx, pbc) <= threshold);
+                    c1 = (fabsf(e1 - threshold) > band && qm1 < 2097152.0f) ? (e1 <= threshold) : (pair_d2_fastwrap(a, b1, cb1, bx, pbc) <= threshold);
+                } else {
+                    c0 = pair_contact(a, b0, cb0, bx, pbc, threshold, shortcut);
+                    c1 = pair_contact(a, b1, cb1, bx, pbc, threshold, shortcut);
+                }
+                o8[idx] = c0 ? 1 : 0;
+                o8[idx + K3_COLS] = c1 ? 1 : 0;
+                idx += step;
+            }
+            return;
+        }
+#endif
 #pragma unroll 2
         for (int r = 0; r < rows; ++r) {
             const float4 a = __ldg(arow + r);
