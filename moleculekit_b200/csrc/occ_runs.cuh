@@ -1,46 +1,45 @@
-// occ_runs.cuh -- K1 v8, the default 8-channel fill: per-block candidate lists + persistent "mask-run" kernel with TMA
-// (cp.async.bulk) stores.  Included by occupancy.cu (after GridDev / occ_value).
-//
-// Replaces the inner loop of moleculekit/occupancy_utils/occupancy_utils.pyx:46-61.  What changed against v6
-// (occ_fill8v_kernel, 111 lane-instructions per in-gate (atom, voxel) pair, 16 predicated FMNMX per candidate):
+// occ_runs.cuh -- K1, the default 8-channel occupancy fill (v10): per-block candidate lists + a persistent "mask-run" kernel.
+// Included by occupancy.cu (after GridDev / occ_value).  Replaces the inner loop of
+// moleculekit/occupancy_utils/occupancy_utils.pyx:46-61.  DESIGN.md section 3 has the derivations, section 5 the
+// measurements of every step (v6 -> v10: 1.82 -> 0.66 ms per 256 pockets of BASELINE config 3); the superseded variants
+// (float-compare gate with predicated FMNMX, scalar FFMA hot loop, row-copy stores, in-register record gathers, jump-table
+// flush, FFMA.SAT gate ...) are in the git history of this file together with their compile-time selectors.
 //
 //   * K2' (occ_prep_kernel / occ_blk_fill_kernel): every atom is appended to the candidate list of each 4x4x8-voxel
 //     block it can reach (~16 blocks per atom at 1 A) -- count, scan, fill.  The fill kernel reads its list; no block
-//     re-scans cell rows any more (v7 spent half its time there: 860 atoms scanned per block to keep 190).
-//   * The hot loop tracks  r = d2 / sigma^2  (a MIN; q = 1/r) instead of max q = sigma^2 / d2: no reciprocal per pair.
-//     The record of a candidate is pre-scaled by 1/sigma -- (x, y, z)/sigma in the block-centre frame plus 1/sigma --
-//     so r of a voxel is two FFMAs:  dxs = fma(x_k, 1/sigma, -x_a/sigma);  r = fma(dxs, dxs, dys^2 + dzs^2).
-//   * One warp owns a block; a lane owns the 4 voxels of one x-row (they share dys, dzs).  The candidate is
-//     WARP-UNIFORM (one LDS.128 broadcast), so its channel mask is uniform too: candidates are counting-sorted by mask
-//     into runs (lane-parallel, shared-memory histogram), a run keeps ONE scalar running minimum per voxel (FSETP gate +
-//     predicated FMNMX), and the 8-channel update happens once per run, not once per pair.
-//   * The 5 A gate is a plain float compare in the loop.  Pairs whose d2 lies within 2e-6 (relative) of the gate
-//     -- where float32 could decide differently from the reference's float64 -- are found by a per-atom pre-pass
-//     (occ_band_kernel: the two lattice crossings of every (y, z) row of the cutoff sphere) and their voxels are
-//     recomputed in float64 with the reference's operation order by occ_fix_*_kernel after the fill.
-//   * Persistent CTAs (7 x 148 x 4 warps) pull (x, y, 4 z-blocks) items from an atomic queue; results are staged in
-//     shared memory in the output layout and leave the SM as cp.async.bulk.global.shared::cta row copies (SASS UBLKCP);
-//     blocks without any atom in reach (~70 %) are bulk copies from a zeroed shared-memory line, no math.
-//
-// v10 (defaults below): the gate is the float OVERFLOW of d2 in units of cut2 / 2^128
-// (MKB_R_OVF: no FSETP, no predicate), the FMA-pipe work runs on packed float32 pairs (MKB_R_X2: FFMA2 / FMUL2), the record
-// pass gathers with cp.async into the sorted slots (MKB_R_ASYNC2) and a block of a dense uniform batch leaves as ONE TMA
-// tensor store (MKB_R_TMAP: cp.async.bulk.tensor.4d, SASS UTMASTG).  The older forms stay selectable at compile time for
-// A/B runs (MKB_NVCC_EXTRA="-DMKB_R_OVF=0 ..."); the descriptions above marked "FSETP gate" / "row copies" are theirs.
+//     scans cell rows.
+//   * value = max_a [d2 < cut2] f(sigma^2 / d2) with f monotone: the kernel tracks  r = d2 / sigma^2  as a MIN and applies f
+//     once per voxel-channel; no reciprocal per pair.
+//   * One warp owns a block; a lane owns the 4 voxels of one x-row (they share dy, dz).  The candidate is WARP-UNIFORM (two
+//     LDS.128 broadcasts), so its channel mask is uniform too: candidates are counting-sorted by mask into runs (lane-parallel,
+//     shared-memory histogram), a run keeps ONE scalar running minimum per voxel, and the channel update happens once per
+//     run (low mask nibble) or once per group of runs that share the high nibble -- not once per pair.
+//   * The 5 A gate is the float OVERFLOW of d2: the records carry differences scaled by lambda = 2^64 / cut, so
+//     U = dx^2 + dy^2 + dz^2 = d2 2^128 / cut2 rounds to +inf exactly when the pair is outside the gate (threshold good to 3e-8;
+//     tests/test_gate_scheme_cpu.py restates the arithmetic).  r = U w with w = 1 / (sigma lambda)^2 (inf stays inf) and the
+//     minimum is an unpredicated FMNMX / FMNMX3 -- no compare, no predicate.  w is a denormal for sigma > 2.5 A
+//     (cut2 / sigma^2 < 4): FMUL handles denormals at full rate; w then keeps 21 + log2(cut2 / sigma^2) bits.
+//   * The FMA-pipe work runs on PACKED float32 pairs (fma.rn.f32x2 / mul.rn.f32x2, SASS FFMA2 / FMUL2, sm_100): (dy, dz), their
+//     squares, U and r of the four voxels take 7 issue slots per candidate; the epilogue evaluates two values per instruction.
+//   * Pairs whose d2 lies within 2e-6 (relative) of the gate -- where float32 could decide differently from the reference's
+//     float64 -- are found by a per-atom pre-pass (occ_band_kernel: the two lattice crossings of every (y, z) row of the
+//     cutoff sphere) and their voxels are recomputed in float64 with the reference's operation order by occ_fix_*_kernel.
+//   * Persistent CTAs (6 x 148 x 4 warps, 80 registers) pull (x, y, 4 z-blocks) items from an atomic queue.  The record pass
+//     gathers the per-atom data with cp.async straight into the candidates' sorted slots.  Results are staged in shared
+//     memory in the output layout; a block of a dense uniform batch leaves as ONE TMA tensor store (cp.async.bulk.tensor.4d,
+//     SASS UTMASTG; 4-D tensor map built per call), other outputs as cp.async.bulk row copies (UBLKCP); blocks without any
+//     atom in reach (~65 %) are copies from a zeroed shared-memory tile, no math.
+//   Measured and dropped in v10 (C3, ms per 256 pockets): a queue that runs two items ahead (0.735 -> 0.757: the second decode
+//   costs more issue slots than the latency it hides); peeling the first candidate of a run (0.758 -> 0.776); requesting the
+//   next z block's list words during the epilogue (0.689 -> 0.695, the extra live registers spill); 7 CTAs x 72 registers
+//   (0.699); 160 / 192 candidates per round (0.717 / 0.692); 2 z blocks per item (0.714).
 #pragma once
 
 namespace mkb {
 
 constexpr int R_BZ = 8;          // block = 4 x 4 x 8 voxels
-// MKB_R_PRE: the four x differences d_k = x_k / sigma - x_a / sigma of a candidate are the same in every lane, so the list
-// pass stores them in the record (32 bytes per candidate instead of 24) and the hot loop drops 4 of its 12 FMA-pipe
-// instructions per candidate; the mask moves to a byte array read once per run.
-// Measured on C3: 0.959 -> 0.911 ms (R_CAP 192 at 7 CTAs per SM and R_CAP 224 at 6 CTAs the same); default.
-#ifndef MKB_R_PRE
-#define MKB_R_PRE 1
-#endif
 #ifndef MKB_R_CAP
-#define MKB_R_CAP (MKB_R_PRE ? 224 : 256)
+#define MKB_R_CAP 224
 #endif
 constexpr int R_CAP = MKB_R_CAP;  // candidates per round (the 4 KB output stage aliases the records)
 #ifndef MKB_R_WARPS
@@ -48,21 +47,16 @@ constexpr int R_CAP = MKB_R_CAP;  // candidates per round (the 4 KB output stage
 #endif
 constexpr int R_WARPS = MKB_R_WARPS;
 #ifndef MKB_R_MIN_CTAS
-#define MKB_R_MIN_CTAS (MKB_R_PRE ? 6 : 7)  // 6 x 4 warps with 80 registers (two-level flush: 4 more live minima), R_CAP 224
+#define MKB_R_MIN_CTAS 6         // 6 x 4 warps with 80 registers
 #endif
 #ifndef MKB_R_ZC
 #define MKB_R_ZC 4               // consecutive z blocks per queue item
 #endif
 constexpr int R_ZC = MKB_R_ZC;
-// per warp: records 4096 | (gate, mask) 2048 | ranks 256 | histogram 512
-// (MKB_R_PRE: x records 16 | (y, z, 1/sigma, gate) records 16 | mask 1 | rank 1 per candidate, then the histogram)
-constexpr int R_WARP_BYTES = MKB_R_PRE ? ((R_CAP * 34 + 512 + 127) / 128) * 128 : R_CAP * 16 + R_CAP * 8 + R_CAP + 512;
-static_assert(R_CAP % 32 == 0 && R_CAP * (MKB_R_PRE ? 32 : 16) >= 4096 && R_WARP_BYTES % 128 == 0, "bad R_CAP");
-#ifndef MKB_R_FMA_GATE
-#define MKB_R_FMA_GATE 0
-#endif
-constexpr float R_GATE_BIG = 1099511627776.0f;       // 2^40
-constexpr float R_GATE_HUGE = 8.507059173023462e37f;  // 2^126: what an out-of-range pair adds to r (FMA gate variant)
+// per warp and candidate: x differences 16 | (-y, -z, w, tag) 16 | mask 1 | rank 1 bytes, then the 512-byte histogram
+constexpr int R_WARP_BYTES = ((R_CAP * 34 + 512 + 127) / 128) * 128;
+static_assert(R_CAP % 32 == 0 && R_CAP * 32 >= 4096 && R_WARP_BYTES % 128 == 0, "bad R_CAP");
+constexpr float R_GATE_HUGE = 8.507059173023462e37f;  // 2^126: the epilogue's "no atom reached this voxel-channel" bound
 constexpr float R_LIST_SLACK = 2e-4f;                 // relative slack of the block lists' reach test (float32 positions)
 
 struct RunParams {
@@ -83,7 +77,7 @@ struct RunParams {
     const unsigned *blk_rank;    // compact output (mkb_occupancy_grid_batch_compact): exclusive count of non-empty blocks; block
                                  // b with atoms in reach is one 4 KB record [4 x][4 y][8 z][8 ch] at out + 1024 * blk_rank[b],
                                  // empty blocks are not written at all; nullptr = the dense grid
-    int use_tmap;                // MKB_R_TMAP: the kernel's tensor-map argument describes `out` (dense, uniform, device memory)
+    int use_tmap;                // the kernel's tensor-map argument describes `out` (dense, uniform, device memory)
     int sparse_dense;            // with blk_rank: keep the DENSE addressing (out may be mapped host memory) and only skip the empty
                                  // blocks -- the host zero-fills them meanwhile (mkb_occupancy_grid_batch_to_host)
     // uniform batches: descriptor of the first grid + strides (constant-bank operands)
@@ -214,113 +208,14 @@ __device__ __forceinline__ void store_cmajor_zero(float *grid, int nx, int ny, i
             for (int h = 0; h < 8; ++h) __stcs(o + h * cs, 0.0f);
         }
 }
-// gate + running minimum: FSETP + predicated FMNMX (both on the ALU pipe), nothing else
-__device__ __forceinline__ void gated_min(float &m, float r, float cw) {
-    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p min.f32 %0, %0, %1;\n\t}" : "+f"(m) : "f"(r), "f"(cw));
-}
-// the same against |cw| (MKB_R_FLUSH 2 keeps a flag in the sign of the gate; the modifier is free in FSETP)
-__device__ __forceinline__ void gated_min_abs(float &m, float r, float cw) {
-    asm("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tabs.f32 t, %2;\n\tsetp.lt.f32 p, %1, t;\n\t@p min.f32 %0, %0, %1;\n\t}" : "+f"(m) : "f"(r), "f"(cw));
-}
-// record load through a pinned shared address (MKB_R_PIN >= 2).  Volatile: stays between the __syncwarp()s around the hot loop,
-// i.e. after the stores of the record pass and before the next round's.
+// record load through a pinned shared address (ptxas otherwise rebuilds the address from the lane / warp id at the head of every
+// run).  Volatile: stays between the __syncwarp()s around the hot loop, i.e. after the stores of the record pass and before
+// the next round's.
 __device__ __forceinline__ float4 lds_rec4(unsigned a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
-// run end: the run's four minima go into the channels of its mask.  MKB_R_FLUSH 0: 32 predicated FMNMX (compact; measured
-// faster than 1: one jump per mask nibble into code with only the live channels, which costs instruction-cache misses).
-// MKB_R_FLUSH 2 (needs MKB_R_PRE): two-level flush.  Candidates are sorted by mask value, so runs with the same HIGH nibble
-// are adjacent: a run end updates only channels 0..3 (16 predicated FMNMX) and folds its minima into four "high" minima
-// (4 FMNMX); channels 4..7 are updated once per group of runs that share the high nibble -- the record closing such a group
-// carries a negated gate.
-// Measured on C3 (with MKB_R_PRE): 0.913 -> 0.889 ms at 7 CTAs / 72 registers, 0.876 ms at 6 CTAs / 80 registers; default.
-#ifndef MKB_R_FLUSH
-#define MKB_R_FLUSH (MKB_R_PRE ? 2 : 0)
-#endif
-// MKB_R_PIN: 1 pins fy / fz, 2 also the record base (loads through a pinned shared address).  ptxas otherwise rebuilds them
-// from the lane / warp id at the head of every run.  Measured on C3: 0.879 -> 0.857 (1) -> 0.844 ms (2); default 2.
-#ifndef MKB_R_PIN
-#define MKB_R_PIN (MKB_R_PRE ? 2 : 0)
-#endif
-// MKB_R_OVF (needs MKB_R_PRE, MKB_R_FLUSH 2): the 5 A gate by floating-point OVERFLOW instead of FSETP + predicate.  The gate
-// d2 < cut2 does not depend on sigma, so the records carry the differences scaled by lambda = 2^64 / cut (the same for every
-// candidate): U = dx^2 + dy^2 + dz^2 in those units is d2 * 2^128 / cut2 and rounds to +inf exactly when the pair is outside
-// the gate (threshold 2^128 (1 - 2^-25): relative 3e-8, inside the band the float64 fix-up covers).  r = U * w with the
-// per-candidate w = 2^-128 cut2 / sigma^2 (one FMUL on the FMA pipe, inf stays inf) and the running minimum is an
-// UNPREDICATED FMNMX: per (candidate, voxel) 2 FMA-pipe + 1 ALU-pipe instruction instead of 1 + 2 -- the ALU pipe (one warp
-// instruction per two cycles) was the binding unit of the hot loop.  w is negative on the record that closes a run (|w| is a
-// free operand modifier); the run's mask and the close-the-group bit ride in the fourth word, so the run end needs no mask
-// byte load.  w is a denormal for sigma > 2.5 A (cut2 / sigma^2 < 4): FMUL handles denormals at full rate; w then keeps
-// 21 + log2(cut2 / sigma^2) bits.
-// MKB_R_MIN3: two candidates per FMNMX3 (min of three) while both lie inside the run.
-#ifndef MKB_R_OVF
-#define MKB_R_OVF MKB_R_PRE  // measured on C3: 0.834 -> 0.807 ms; with MKB_R_MIN3 0.785 ms; default
-#endif
-#ifndef MKB_R_MIN3
-#define MKB_R_MIN3 MKB_R_OVF
-#endif
-// MKB_R_X2 (needs MKB_R_OVF): the FMA-pipe work of the hot loop as PACKED float32 pairs (fma.rn.f32x2 / mul.rn.f32x2, SASS FFMA2 /
-// FMUL2, new on sm_100): one issue slot per two voxels.  (dy, dz) = (fy, fz) * lambda + (-y, -z) is one FFMA2, their squares one
-// FMUL2, U of the four voxels two FFMA2 (s2 broadcast), r = U * w two FMUL2 -- 7 FMA-pipe instructions per candidate instead
-// of 12.  Without a gate predicate the loop is bound by issue slots only.  The run-end flag moves to the sign bit of the tag
-// word (ISETP), w stays positive (no |w| modifier on a packed operand).
-#ifndef MKB_R_X2
-#define MKB_R_X2 MKB_R_OVF  // measured on C3: 0.789 -> 0.758 ms; default
-#endif
-#if MKB_R_X2 && !MKB_R_OVF
-#error "MKB_R_X2 needs MKB_R_OVF"
-#endif
-// The phases around the hot loop are LATENCY bound with six warps per scheduler (ncu of the packed build: 65 % of the warp
-// samples lie outside hot loop + flush, which execute 58 % of the instructions; profiles/r02_fill_v10a_*).  Remedies:
-// MKB_R_ASYNC2 (needs MKB_R_OVF): the record pass gathers the per-atom data (rec_pos / rec_tag, two dependent L2 round trips
-//   per 32 candidates, one trip after the other) with cp.async straight into the candidate's SORTED slot -- all gathers of a
-//   round in flight at once, no registers -- and a second sub-pass turns the raw slots into records in place.
-// (Measured and dropped: a queue that runs two items ahead -- atomic and list offsets of the next items in flight during the
-//   current one -- 0.735 -> 0.757 ms: the second decode costs more issue slots than the hidden latency; peeling the first
-//   candidate of a run so that it initialises the minima: 0.758 -> 0.776 ms; requesting the list words of the item's next z block
-//   during the epilogue: 0.689 -> 0.695 ms, the extra live registers spill.)
-// MKB_R_TMAP: dense uniform device output leaves as ONE cp.async.bulk.tensor (4-D tiled tensor map over [grid][x][y][z * c], box
-//   1 x 4 x 4 x 64 floats) per block instead of 16 row copies -- ptxas serialises per-lane bulk copies through uniform registers
-//   (R2UR / UBLKCP in a 16-trip loop: 12 % of the warp samples); empty items are tensor copies from a zeroed 4 KB tile.
-#ifndef MKB_R_ASYNC2
-#define MKB_R_ASYNC2 MKB_R_OVF  // measured on C3: 0.762 -> 0.735 ms; default
-#endif
-// MKB_R_SENTINEL (needs MKB_R_X2): the run loop ends on a bit of the last record's tag instead of a candidate count.
-#ifndef MKB_R_SENTINEL
-#define MKB_R_SENTINEL MKB_R_X2  // measured on C3: 0.669 -> 0.659 ms; default
-#endif
-#ifndef MKB_R_TMAP
-#define MKB_R_TMAP 1  // measured on C3: 0.762 -> 0.713 ms; with MKB_R_ASYNC2 0.690 ms = 49.4 % of HBM peak; default
-#endif
-#if MKB_R_ASYNC2 && !MKB_R_OVF
-#error "MKB_R_ASYNC2 needs MKB_R_OVF"
-#endif
-#if MKB_R_OVF && !(MKB_R_PRE && MKB_R_FLUSH == 2 && MKB_R_PIN >= 2)
-#error "MKB_R_OVF needs MKB_R_PRE, MKB_R_FLUSH 2 and MKB_R_PIN 2"
-#endif
-#ifndef MKB_R_EXP
-#define MKB_R_EXP 0  // timing experiments only (wrong results): 1 = no hot loop, 2 = no flush, 3 = no epilogue math
-#endif
-template <int M, int BASE>
-__device__ __forceinline__ void apply_nibble(float (&acc)[8][4], float m0, float m1, float m2, float m3) {
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-        if (M & (1 << b)) {
-            acc[BASE + b][0] = fminf(acc[BASE + b][0], m0); acc[BASE + b][1] = fminf(acc[BASE + b][1], m1);
-            acc[BASE + b][2] = fminf(acc[BASE + b][2], m2); acc[BASE + b][3] = fminf(acc[BASE + b][3], m3);
-        }
-}
-#define MKB_NIB_CASE(M, BASE) case M: apply_nibble<M, BASE>(acc, m0, m1, m2, m3); break;
-#define MKB_NIB_SWITCH(sel, BASE)                                                                          \
-    switch (sel) {                                                                                         \
-        MKB_NIB_CASE(1, BASE) MKB_NIB_CASE(2, BASE) MKB_NIB_CASE(3, BASE) MKB_NIB_CASE(4, BASE) MKB_NIB_CASE(5, BASE)       \
-        MKB_NIB_CASE(6, BASE) MKB_NIB_CASE(7, BASE) MKB_NIB_CASE(8, BASE) MKB_NIB_CASE(9, BASE) MKB_NIB_CASE(10, BASE)      \
-        MKB_NIB_CASE(11, BASE) MKB_NIB_CASE(12, BASE) MKB_NIB_CASE(13, BASE) MKB_NIB_CASE(14, BASE) MKB_NIB_CASE(15, BASE)  \
-        default: break;                                                                                    \
-    }
-
 // packed float32 pairs (sm_100): a 64-bit register holds (lo, hi)
 typedef unsigned long long f2_t;
 __device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
@@ -365,7 +260,6 @@ __device__ __forceinline__ void lds_2x64(unsigned a, f2_t &lo, f2_t &hi) {
 __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
-#if MKB_R_TMAP
 // one 4 x 4 x 8-voxel block (dense [x][y][z][c] tile in shared memory) -> the grid; coordinates (z * 8, y, x, grid); TMA clips
 // the part of the box that lies outside the grid
 __device__ __forceinline__ void tma_store_block(const CUtensorMap *tm, unsigned src_smem, int c0, int c1, int c2, int c3) {
@@ -373,57 +267,41 @@ __device__ __forceinline__ void tma_store_block(const CUtensorMap *tm, unsigned 
                  "r"(c2), "r"(c3), "r"(src_smem)
                  : "memory");
 }
-#define MKB_TMAP_PARAM , const __grid_constant__ CUtensorMap tmap
-#else
-#define MKB_TMAP_PARAM
-#endif
 
 #define RG(field) (UNIFORM ? p.u.field : __ldg(&gg->field))
 template <bool UNIFORM>
-__global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_kernel(const RunParams p MKB_TMAP_PARAM) {
+__global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_kernel(const RunParams p,
+                                                                                     const __grid_constant__ CUtensorMap tmap) {
     __shared__ __align__(128) unsigned char s_raw[R_WARPS][R_WARP_BYTES];
-    __shared__ __align__(128) float s_zero[MKB_R_TMAP ? 1024 : 64 * R_ZC];
+    __shared__ __align__(128) float s_zero[1024];  // one zeroed block (4 KB): the source of every store without atoms in reach
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *const wb = s_raw[warp];
-    float4 *const rec = reinterpret_cast<float4 *>(wb);                         // sorted candidates: (x, y, z)/sigma, 1/sigma
-#if MKB_R_PRE
-    float4 *const recy = reinterpret_cast<float4 *>(wb + R_CAP * 16);           // (y, z)/sigma, 1/sigma, gate in r units
+    float4 *const rec = reinterpret_cast<float4 *>(wb);                         // sorted candidates: the four x differences, x lambda
+    float4 *const recy = reinterpret_cast<float4 *>(wb + R_CAP * 16);           // (-y lambda, -z lambda, w, tag: mask | flags)
     unsigned char *const msk = wb + R_CAP * 32;                                 // channel mask of the sorted candidate
     unsigned char *const rnk = wb + R_CAP * 33;                                 // rank of a candidate inside its mask bin
     unsigned *const hist = reinterpret_cast<unsigned *>(wb + R_CAP * 34);       // 256 x 16-bit bins in 128 words
-    // the run-end mask load goes through an address the compiler cannot rematerialise (it would rebuild it from S2R
-    // SR_TID / SR_CgaCtaId at every run end: ten instructions and two slow special-register reads per run)
-    unsigned msk_sa = (unsigned)__cvta_generic_to_shared(msk);
-    asm volatile("mov.b32 %0, %0;" : "+r"(msk_sa));
-#if MKB_R_PIN >= 2
-    unsigned rec_sa = (unsigned)__cvta_generic_to_shared(wb);  // same for the record base: the hot loop loads through it
+    // the hot loop loads through an address the compiler cannot rematerialise (it would rebuild it from S2R SR_TID /
+    // SR_CgaCtaId at the head of every run: ten instructions and two slow special-register reads)
+    unsigned rec_sa = (unsigned)__cvta_generic_to_shared(wb);
     asm volatile("mov.b32 %0, %0;" : "+r"(rec_sa));
-#endif
-#else
-    float2 *const cwv = reinterpret_cast<float2 *>(wb + R_CAP * 16);            // gate in r units (cut2 / sigma^2), channel mask bits
-    unsigned char *const rnk = wb + R_CAP * 24;                                 // rank of a candidate inside its mask bin
-    unsigned *const hist = reinterpret_cast<unsigned *>(wb + R_CAP * 25);       // 256 x 16-bit bins in 128 words
-#endif
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(wb);
     const unsigned zero_sa = (unsigned)__cvta_generic_to_shared(s_zero);
 
-    for (int i = threadIdx.x; i < (MKB_R_TMAP ? 1024 : 64 * R_ZC); i += R_WARPS * 32) s_zero[i] = 0.0f;
+    for (int i = threadIdx.x; i < 1024; i += R_WARPS * 32) s_zero[i] = 0.0f;
     for (int i = lane; i < 128; i += 32) hist[i] = 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     const int ly = lane >> 3, lz = lane & 7;
     float fy = (float)ly - 1.5f, fz = (float)lz - 3.5f;  // block frame: origin at the block centre
-#if MKB_R_PIN
     // ptxas rebuilds fy / fz from the lane id (SHF, LOP3, I2FP, FADD) at the head of every run instead of keeping two registers
     // alive: an opaque move pins them (8 instructions per run, 3 % of the kernel)
     asm volatile("mov.b32 %0, %0;" : "+f"(fy));
     asm volatile("mov.b32 %0, %0;" : "+f"(fz));
-#endif
     const float INF = __int_as_float(0x7f800000);
     bool pending = false;  // lanes 0..15: bulk copies still reading the stage
-#if MKB_R_OVF
     // lambda = 2^64 / cut (voxel units): d2 == cut2 lands on 2^128, the float overflow threshold
     // The FLOAT is the root value and the double its exact image: with lamf = (float)lam ptxas kept only the double and
     // re-converted it (F2F.F32.F64, a slow-pipe instruction the first FFMA2 then waits for) at the head of EVERY hot-loop trip.
@@ -432,7 +310,6 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
     asm volatile("mov.b32 %0, %0;" : "+f"(lamf));
     double lam = (double)lamf;
     float cwf = UNIFORM ? (float)(18446744073709551616.0 / lam) : 0.0f;
-#endif
 
     for (;;) {
         unsigned id = 0;
@@ -480,13 +357,11 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             if (p.blk_rank) {
             } else if (p.cmajor) {
                 for (int bzi = bz_begin; bzi < bz_end; ++bzi) store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, bzi * R_BZ + lz);
-#if MKB_R_TMAP
             } else if (p.use_tmap) {
                 if (lane == 0) {
                     for (int bzi = bz_begin; bzi < bz_end; ++bzi) tma_store_block(&tmap, zero_sa, bzi * (R_BZ * 8), y0, x0, gi);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-#endif
             } else {
                 if (row_ok) bulk_store_row(row_base + z0 * 8, zero_sa, (min(nz, bz_end * R_BZ) - z0) * 32);
                 if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -494,13 +369,11 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             continue;
         }
 
-#if MKB_R_OVF
         if (!UNIFORM) {
             lamf = (float)(18446744073709551616.0 / sqrt((double)cut2));
             lam = (double)lamf;
             cwf = (float)(18446744073709551616.0 / lam);
         }
-#endif
         for (int bzi = bz_begin; bzi < bz_end; ++bzi) {
             const int z0 = bzi * R_BZ;
             const int row_bytes = min(R_BZ, nz - z0) * 32;
@@ -511,13 +384,11 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 if (p.blk_rank) {
                 } else if (p.cmajor) {
                     store_cmajor_zero(p.out + out_offset * 8, nx, ny, nz, x0, y0 + ly, z0 + lz);
-#if MKB_R_TMAP
                 } else if (p.use_tmap) {
                     if (lane == 0) {
                         tma_store_block(&tmap, zero_sa, z0 * 8, y0, x0, gi);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-#endif
                 } else {
                     if (row_ok) bulk_store_row(row_dst, zero_sa, row_bytes);
                     if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -626,10 +497,8 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     pending = false;
                 }
                 __syncwarp();
-                // ---- pass 2: records in run order, pre-scaled by 1/sigma (float64 rebase: one rounding per coordinate).
-                // The record that closes a run is stored NEGATED: every term of r is a square of a difference of record
-                // fields, so r is unchanged and the sign of .w is a free end-of-run flag.
-#if MKB_R_ASYNC2
+                // ---- pass 2: records in run order, scaled by lambda (float64 rebase: one rounding per coordinate); the tag of the
+                // record that closes a run carries the run's mask and the flags of the run loop.
                 // sub-pass a: the raw per-atom data of every candidate goes straight to its sorted slot (cp.async, all in flight)
                 for (int j = lane; j < np; j += 32) {
                     const uint2 e = __ldg(ent + j);
@@ -648,64 +517,21 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     const unsigned rk = (((hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu) - 1u == pos) ? 0u : 1u;  // 0: closes its run
                     const float4 f = rec[pos];
                     const uint4 tg = *reinterpret_cast<const uint4 *>(recy + pos);
-#else
-                for (int j = lane; j < np; j += 32) {
-                    const uint2 e = __ldg(ent + j);
-                    const unsigned m = (e.y & 0x100u) ? 0u : (e.y & 255u);
-                    const unsigned rk = rnk[j];
-                    const unsigned pos = ((hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu) - 1u - rk;
-                    const float4 f = __ldg(p.rec_pos + e.x);
-                    const uint4 tg = __ldg(p.rec_tag + e.x);
-#endif
-                    const float sw = __uint_as_float(tg.w);
-                    const double dsw = rk == 0 ? -(double)sw : (double)sw;
+                    const float sw = __uint_as_float(tg.w);  // 1 / sigma (voxel units)
                     const double ex = (double)((int)(tg.z & 0xffffu) - cx) + ((double)f.x - 1.5);
                     const double ey = (double)((int)(tg.z >> 16) - cy) + ((double)f.y - 1.5);
                     const double ez = (double)((int)(tg.x >> 16) - cz) + ((double)f.z - 3.5);
-#if MKB_R_OVF
-                    {
-                        const float xs = (float)(ex * lam);
-                        rec[pos] = make_float4(fmaf(-1.5f, lamf, -xs), fmaf(-0.5f, lamf, -xs), fmaf(0.5f, lamf, -xs), fmaf(1.5f, lamf, -xs));
-                        const float wh = (sw * cwf) * 5.421010862427522e-20f;  // (cut / sigma) 2^-64
-                        const float wt = wh * wh;                              // w = 1 / (sigma lambda)^2
-                        const unsigned mh = m | 15u;
-                        const unsigned e0 = (hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu, e1 = (hist[mh >> 1] >> 16) & 0xffffu;
-#if MKB_R_X2
-                        // bit 9: the last record of the round (it closes a run) ends the run loop -- ptxas otherwise rebuilds the
-                        // candidate count (IADD, VIMNMX) for a compare at the end of every run
-                        recy[pos] = make_float4(-(float)(ey * lam), -(float)(ez * lam), wt,
-                                                __uint_as_float(m | ((rk == 0 && e0 == e1) ? 0x100u : 0u) | (rk == 0 ? 0x80000000u : 0u) |
-                                                                (pos + 1u == (unsigned)np ? 0x200u : 0u)));
-#else
-                        recy[pos] = make_float4((float)(ey * lam), (float)(ez * lam), rk == 0 ? -wt : wt,
-                                                __uint_as_float(m | ((rk == 0 && e0 == e1) ? 0x100u : 0u)));
-#endif
-                    }
-#elif MKB_R_PRE
-                    {
-                        const float xs = (float)(ex * dsw), ws = (float)dsw;  // the same roundings as the in-loop form
-                        rec[pos] = make_float4(fmaf(-1.5f, ws, -xs), fmaf(-0.5f, ws, -xs), fmaf(0.5f, ws, -xs), fmaf(1.5f, ws, -xs));
-                        float gate = cut2 * (sw * sw);
-#if MKB_R_FLUSH == 2
-                        {   // last run of its high nibble: no candidate in the bins m + 1 .. m | 15 (hist holds END offsets)
-                            const unsigned mh = m | 15u;
-                            const unsigned e0 = (hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu, e1 = (hist[mh >> 1] >> 16) & 0xffffu;
-                            if (rk == 0 && e0 == e1) gate = -gate;
-                        }
-#endif
-                        recy[pos] = make_float4((float)(ey * dsw), (float)(ez * dsw), ws, gate);
-                        msk[pos] = (unsigned char)m;
-                    }
-#else
-                    rec[pos] = make_float4((float)(ex * dsw), (float)(ey * dsw), (float)(ez * dsw), (float)dsw);
-#endif
-                    // the candidate's mask rides with its gate: the record that closes a run hands the run's mask to the flush
-#if MKB_R_PRE
-#elif MKB_R_FMA_GATE
-                    cwv[pos] = make_float2(-(cut2 * (sw * sw)) * R_GATE_BIG, __uint_as_float(m));  // FMA-pipe gate: sat((r - cw) 2^40)
-#else
-                    cwv[pos] = make_float2(cut2 * (sw * sw), __uint_as_float(m));
-#endif
+                    const float xs = (float)(ex * lam);
+                    rec[pos] = make_float4(fmaf(-1.5f, lamf, -xs), fmaf(-0.5f, lamf, -xs), fmaf(0.5f, lamf, -xs), fmaf(1.5f, lamf, -xs));
+                    const float wh = (sw * cwf) * 5.421010862427522e-20f;  // (cut / sigma) 2^-64
+                    const float wt = wh * wh;                              // w = 1 / (sigma lambda)^2
+                    // tag: mask | bit 8: the run also closes its group (no candidate in the bins m + 1 .. m | 15; hist holds END
+                    // offsets) | bit 9: last record of the round | bit 31: the record closes its run
+                    const unsigned mh = m | 15u;
+                    const unsigned e0 = (hist[m >> 1] >> ((m & 1u) * 16u)) & 0xffffu, e1 = (hist[mh >> 1] >> 16) & 0xffffu;
+                    recy[pos] = make_float4(-(float)(ey * lam), -(float)(ez * lam), wt,
+                                            __uint_as_float(m | ((rk == 0 && e0 == e1) ? 0x100u : 0u) | (rk == 0 ? 0x80000000u : 0u) |
+                                                            (pos + 1u == (unsigned)np ? 0x200u : 0u)));
                 }
                 __syncwarp();
                 *reinterpret_cast<uint4 *>(hist + 4 * lane) = make_uint4(0u, 0u, 0u, 0u);
@@ -714,21 +540,6 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                 // ---- the hot loop: one warp-uniform candidate per half trip, 4 voxels per lane; two records in flight
                 // (a / b ping-pong, the next one is loaded before the current one is evaluated)
                 {
-#if MKB_R_FMA_GATE
-#define MKB_GATED_MIN(M, R, CW) M = fminf(M, fmaf(__saturatef(fmaf(R, R_GATE_BIG, CW)), R_GATE_HUGE, R))
-#elif MKB_R_FLUSH == 2
-#define MKB_GATED_MIN(M, R, CW) gated_min_abs(M, R, CW)
-#else
-#define MKB_GATED_MIN(M, R, CW) gated_min(M, R, CW)
-#endif
-#if MKB_R_X2
-#if MKB_R_SENTINEL
-#define MKB_RUN_LOOP_HEAD for (bool more_ = true; more_;)
-#define MKB_RUN_LOOP_TAIL more_ = (mask & 0x200u) == 0u;
-#else
-#define MKB_RUN_LOOP_HEAD while (i <= np && MKB_R_EXP != 1)
-#define MKB_RUN_LOOP_TAIL
-#endif
 #define MKB_LDREC(I) lds_rec4(rec_sa + 16u * (unsigned)(I))
 #define MKB_LDRECY(I) lds_rec4(rec_sa + (unsigned)(R_CAP * 16) + 16u * (unsigned)(I))
 #define MKB_RUN_R2(D, Y, R)                                                                       \
@@ -746,9 +557,11 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                     const f2_t fyz = f2_pack(fy, fz), lam2 = f2_pack(lamf, lamf);
                     float4 a = MKB_LDREC(0), ya = MKB_LDRECY(0);
                     int i = 1;  // next record to load; i == np reads past the list (inside this warp's buffer), never used
-                    float M0 = INF, M1 = INF, M2 = INF, M3 = INF, gclose;
+                    float M0 = INF, M1 = INF, M2 = INF, M3 = INF;
+                    // one trip per run; bit 9 of the tag marks the last record of the round (ptxas otherwise rebuilds the candidate
+                    // count for a compare at the end of every run)
 #pragma unroll 1
-                    MKB_RUN_LOOP_HEAD {
+                    for (bool more = true; more;) {
                         float m0 = INF, m1 = INF, m2 = INF, m3 = INF;
                         unsigned mask;
 #pragma unroll 1
@@ -757,7 +570,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                             MKB_RUN_R2(a, ya, ra)
                             if (__float_as_int(ya.w) < 0) {  // the tag of the record that closes a run has its sign bit set (warp-uniform)
                                 m0 = fminf(m0, ra0); m1 = fminf(m1, ra1); m2 = fminf(m2, ra2); m3 = fminf(m3, ra3);
-                                mask = __float_as_uint(ya.w);  // mask | close-the-group << 8
+                                mask = __float_as_uint(ya.w);  // mask | close-the-group << 8 | last-of-the-round << 9
                                 a = b;
                                 ya = yb;
                                 i += 1;
@@ -774,159 +587,6 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                                 break;
                             }
                         }
-                        gclose = (mask & 0x100u) ? -1.0f : 1.0f;
-#elif MKB_R_PRE
-#if MKB_R_PIN >= 2
-#define MKB_LDREC(I) lds_rec4(rec_sa + 16u * (unsigned)(I))
-#define MKB_LDRECY(I) lds_rec4(rec_sa + (unsigned)(R_CAP * 16) + 16u * (unsigned)(I))
-#else
-#define MKB_LDREC(I) rec[I]
-#define MKB_LDRECY(I) recy[I]
-#endif
-#if MKB_R_OVF
-#define MKB_RUN_R(D, Y, R)                                                                        \
-    float R##0, R##1, R##2, R##3;                                                                 \
-    {                                                                                             \
-        const float dys = fmaf(fy, lamf, -Y.x), dzs = fmaf(fz, lamf, -Y.y);                       \
-        const float s2 = fmaf(dzs, dzs, dys * dys), w = fabsf(Y.z);                               \
-        R##0 = fmaf(D.x, D.x, s2) * w; R##1 = fmaf(D.y, D.y, s2) * w;                             \
-        R##2 = fmaf(D.z, D.z, s2) * w; R##3 = fmaf(D.w, D.w, s2) * w;                             \
-    }
-#define MKB_RUN_BODY(D, Y)                                                                        \
-    {                                                                                             \
-        MKB_RUN_R(D, Y, r)                                                                        \
-        m0 = fminf(m0, r0); m1 = fminf(m1, r1); m2 = fminf(m2, r2); m3 = fminf(m3, r3);           \
-    }
-#else
-#define MKB_RUN_BODY(D, Y)                                                                        \
-    {                                                                                             \
-        const float dys = fmaf(fy, Y.z, -Y.x), dzs = fmaf(fz, Y.z, -Y.y);                         \
-        const float s2 = fmaf(dzs, dzs, dys * dys);                                               \
-        const float r0 = fmaf(D.x, D.x, s2), r1 = fmaf(D.y, D.y, s2), r2 = fmaf(D.z, D.z, s2), r3 = fmaf(D.w, D.w, s2); \
-        MKB_GATED_MIN(m0, r0, Y.w);                                                               \
-        MKB_GATED_MIN(m1, r1, Y.w);                                                               \
-        MKB_GATED_MIN(m2, r2, Y.w);                                                               \
-        MKB_GATED_MIN(m3, r3, Y.w);                                                               \
-    }
-#endif
-                    float4 a = MKB_LDREC(0), ya = MKB_LDRECY(0);
-                    int i = 1;  // next record to load; i == np reads past the list (inside this warp's buffer), never used
-#if MKB_R_FLUSH == 2
-                    float M0 = INF, M1 = INF, M2 = INF, M3 = INF, gclose;
-#endif
-#pragma unroll 1
-                    while (i <= np && MKB_R_EXP != 1) {
-                        float m0 = INF, m1 = INF, m2 = INF, m3 = INF;
-                        unsigned mask;
-#if MKB_R_OVF
-#pragma unroll 1
-                        for (;;) {
-                            const float4 b = MKB_LDREC(i), yb = MKB_LDRECY(i);
-#if MKB_R_MIN3
-                            MKB_RUN_R(a, ya, ra)
-                            if (ya.z < 0.0f) {  // the record that closes a run has a negative weight (warp-uniform)
-                                m0 = fminf(m0, ra0); m1 = fminf(m1, ra1); m2 = fminf(m2, ra2); m3 = fminf(m3, ra3);
-#else
-                            MKB_RUN_BODY(a, ya)
-                            if (ya.z < 0.0f) {
-#endif
-                                mask = __float_as_uint(ya.w);  // mask | close-the-group << 8
-                                a = b;
-                                ya = yb;
-                                i += 1;
-                                break;
-                            }
-                            a = MKB_LDREC(i + 1);
-                            ya = MKB_LDRECY(i + 1);
-#if MKB_R_MIN3
-                            MKB_RUN_R(b, yb, rb)
-                            m0 = fminf(fminf(m0, ra0), rb0); m1 = fminf(fminf(m1, ra1), rb1);
-                            m2 = fminf(fminf(m2, ra2), rb2); m3 = fminf(fminf(m3, ra3), rb3);
-#else
-                            MKB_RUN_BODY(b, yb)
-#endif
-                            i += 2;
-                            if (yb.z < 0.0f) {
-                                mask = __float_as_uint(yb.w);
-                                break;
-                            }
-                        }
-                        gclose = (mask & 0x100u) ? -1.0f : 1.0f;
-#else
-#pragma unroll 1
-                        for (;;) {
-                            const float4 b = MKB_LDREC(i), yb = MKB_LDRECY(i);
-                            MKB_RUN_BODY(a, ya)
-                            if (ya.z < 0.0f) {  // the record that closes a run is negated (warp-uniform)
-                                asm volatile("ld.shared.u8 %0, [%1+-1];" : "=r"(mask) : "r"(msk_sa + i));
-#if MKB_R_FLUSH == 2
-                                gclose = ya.w;
-#endif
-                                a = b;
-                                ya = yb;
-                                i += 1;
-                                break;
-                            }
-                            a = MKB_LDREC(i + 1);
-                            ya = MKB_LDRECY(i + 1);
-                            MKB_RUN_BODY(b, yb)
-                            i += 2;
-                            if (yb.z < 0.0f) {
-                                asm volatile("ld.shared.u8 %0, [%1+-2];" : "=r"(mask) : "r"(msk_sa + i));
-#if MKB_R_FLUSH == 2
-                                gclose = yb.w;
-#endif
-                                break;
-                            }
-                        }
-#endif
-#else
-#define MKB_RUN_BODY(A, CW)                                                                       \
-    {                                                                                             \
-        const float dys = fmaf(fy, A.w, -A.y), dzs = fmaf(fz, A.w, -A.z);                         \
-        const float s2 = fmaf(dzs, dzs, dys * dys);                                               \
-        const float d0 = fmaf(-1.5f, A.w, -A.x), d1 = fmaf(-0.5f, A.w, -A.x);                     \
-        const float d2 = fmaf(0.5f, A.w, -A.x), d3 = fmaf(1.5f, A.w, -A.x);                       \
-        const float r0 = fmaf(d0, d0, s2), r1 = fmaf(d1, d1, s2), r2 = fmaf(d2, d2, s2), r3 = fmaf(d3, d3, s2); \
-        MKB_GATED_MIN(m0, r0, CW);                                                                \
-        MKB_GATED_MIN(m1, r1, CW);                                                                \
-        MKB_GATED_MIN(m2, r2, CW);                                                                \
-        MKB_GATED_MIN(m3, r3, CW);                                                                \
-    }
-                    float4 a = rec[0];
-                    float2 cwa = cwv[0];
-                    int i = 1;  // next record to load; i == np reads past the list (inside this warp's buffer), never used
-#pragma unroll 1
-                    while (i <= np && MKB_R_EXP != 1) {
-                        float m0 = INF, m1 = INF, m2 = INF, m3 = INF;
-                        unsigned mask;
-#pragma unroll 1
-                        for (;;) {
-                            const float4 b = rec[i];
-                            const float2 cwb = cwv[i];
-                            MKB_RUN_BODY(a, cwa.x)
-                            if (a.w < 0.0f) {  // the record that closes a run is negated (warp-uniform)
-                                mask = __float_as_uint(cwa.y);
-                                a = b;
-                                cwa = cwb;
-                                i += 1;
-                                break;
-                            }
-                            a = rec[i + 1];
-                            cwa = cwv[i + 1];
-                            MKB_RUN_BODY(b, cwb.x)
-                            i += 2;
-                            if (b.w < 0.0f) {
-                                mask = __float_as_uint(cwb.y);
-                                break;
-                            }
-                        }
-#endif
-                        if (MKB_R_EXP == 2) mask = 0u;
-#if MKB_R_FLUSH == 1
-                        MKB_NIB_SWITCH(mask & 15u, 0)
-                        MKB_NIB_SWITCH(mask >> 4, 4)
-#elif MKB_R_FLUSH == 2
 #pragma unroll
                         for (int h = 0; h < 4; ++h)
                             if (mask & (1u << h)) {
@@ -934,7 +594,7 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                                 acc[h][2] = fminf(acc[h][2], m2); acc[h][3] = fminf(acc[h][3], m3);
                             }
                         M0 = fminf(M0, m0); M1 = fminf(M1, m1); M2 = fminf(M2, m2); M3 = fminf(M3, m3);
-                        if (gclose < 0.0f) {  // warp-uniform: the group of runs sharing this high nibble ends here
+                        if (mask & 0x100u) {  // warp-uniform: the group of runs sharing this high nibble ends here
 #pragma unroll
                             for (int h = 4; h < 8; ++h)
                                 if (mask & (1u << h)) {
@@ -943,26 +603,11 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
                                 }
                             M0 = INF; M1 = INF; M2 = INF; M3 = INF;
                         }
-#else
-#pragma unroll
-                        for (int h = 0; h < 8; ++h)
-                            if (mask & (1u << h)) {
-                                acc[h][0] = fminf(acc[h][0], m0); acc[h][1] = fminf(acc[h][1], m1);
-                                acc[h][2] = fminf(acc[h][2], m2); acc[h][3] = fminf(acc[h][3], m3);
-                            }
-#endif
-#if MKB_R_X2
-                        MKB_RUN_LOOP_TAIL
-#endif
+                        more = (mask & 0x200u) == 0u;
                     }
-#undef MKB_RUN_LOOP_HEAD
-#undef MKB_RUN_LOOP_TAIL
-#undef MKB_RUN_BODY
-#undef MKB_RUN_R
 #undef MKB_RUN_R2
 #undef MKB_LDREC
 #undef MKB_LDRECY
-#undef MKB_GATED_MIN
                 }
                 __syncwarp();
             }
@@ -987,10 +632,10 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
 #pragma unroll 1
             for (int it = 0; it < 8; ++it) {
                 float4 v = stage[it * 32 + lane];
-                const float LIVE = 0.5f * R_GATE_HUGE;  // r of a voxel-channel no atom reached: +inf (or 2^126 with the FMA gate)
+                const float LIVE = 0.5f * R_GATE_HUGE;  // r of a voxel-channel no atom reached: +inf
                 const bool live = fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < LIVE;
-                if (MKB_R_EXP != 3 && __any_sync(0xffffffffu, live)) {
-#if MKB_R_X2 && MKB_VALUE_SHORT
+                if (__any_sync(0xffffffffu, live)) {
+#if MKB_VALUE_SHORT
                     occ_value_x2(v.x, v.y);
                     occ_value_x2(v.z, v.w);
 #else
@@ -1023,10 +668,8 @@ __global__ void __launch_bounds__(R_WARPS * 32, MKB_R_MIN_CTAS) occ_fill_runs_ke
             __syncwarp();
             if (p.blk_rank && !p.sparse_dense) {  // compact output: the whole 4 KB stage is one record, one bulk copy
                 if (lane == 0) bulk_store_row(p.out + 1024ll * __ldg(p.blk_rank + blk0 + (bzi - bz_begin)), stage_sa, 4096);
-#if MKB_R_TMAP
             } else if (p.use_tmap) {
                 if (lane == 0) tma_store_block(&tmap, stage_sa, z0 * 8, y0, x0, gi);
-#endif
             } else if (row_ok) bulk_store_row(row_dst, stage_sa + lane * 256, row_bytes);
             if (lane < 16) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             pending = true;

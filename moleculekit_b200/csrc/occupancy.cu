@@ -1538,7 +1538,6 @@ __global__ void __launch_bounds__(128) occ_points_kernel(const double *__restric
 }  // namespace mkb
 #include "occ_runs.cuh"
 
-#if MKB_R_TMAP
 // 4-D tiled tensor map over a uniform dense batch: [grid][x][y][z * 8 channels] float32, box = one 4 x 4 x 8-voxel block.
 // Returns false when the encoder is unavailable or rejects the layout (the caller keeps the row copies).
 static bool occ_make_tmap(CUtensorMap *tm, float *base, int nx, int ny, int nz, long long n_grids, long long grid_stride_vox) {
@@ -1564,7 +1563,6 @@ static bool occ_make_tmap(CUtensorMap *tm, float *base, int nx, int ny, int nz, 
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-#endif
 namespace mkb {
 
 static int scan_u32(mkb_ctx *h, cudaStream_t st, unsigned *in, unsigned *out, long long n) {
@@ -1873,7 +1871,6 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
             const unsigned nctas = (unsigned)std::min<long long>((long long)h->sm_count * MKB_R_MIN_CTAS, cdiv((long long)rp.total_items, R_WARPS));
             if (nctas == 0) continue;
             rp.use_tmap = 0;
-#if MKB_R_TMAP
             CUtensorMap tmap;
             memset(&tmap, 0, sizeof(tmap));
             // dense uniform output in device memory (the to-host route writes mapped host memory: row copies)
@@ -1881,10 +1878,6 @@ static int occupancy_grid_batch_impl(mkb_handle_t h, void *stream, const float *
                 rp.use_tmap = occ_make_tmap(&tmap, out + g0d.out_offset * 8, g0d.dims[0], g0d.dims[1], g0d.dims[2], g1 - g0, nvox0) ? 1 : 0;
             if (uni) occ_fill_runs_kernel<true><<<nctas, R_WARPS * 32, 0, st>>>(rp, tmap);
             else occ_fill_runs_kernel<false><<<nctas, R_WARPS * 32, 0, st>>>(rp, tmap);
-#else
-            if (uni) occ_fill_runs_kernel<true><<<nctas, R_WARPS * 32, 0, st>>>(rp);
-            else occ_fill_runs_kernel<false><<<nctas, R_WARPS * 32, 0, st>>>(rp);
-#endif
             MKB_LAUNCHED(h);
         }
         if (h->timing) MKB_CUDA(h, cudaEventRecord(h->ev[2], st));

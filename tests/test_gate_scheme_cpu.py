@@ -1,4 +1,4 @@
-"""Host-side check of the ARITHMETIC of the v10 fill kernel's gate (csrc/occ_runs.cuh, MKB_R_OVF).
+"""Host-side check of the ARITHMETIC of the v10 fill kernel's gate (csrc/occ_runs.cuh).
 
 The kernel decides `d2 < cut2` by float32 overflow: differences are scaled by lambda = 2^64 / cut, so U = dx^2 + dy^2 + dz^2 rounds to
 +inf exactly when the pair is outside the gate, and r = U * w with w = 1 / (sigma lambda)^2.  This test restates those float32
